@@ -1,0 +1,262 @@
+#!/usr/bin/env python3
+"""Benchmark of the so101 lockstep env-step path.  Contract: one JSON line on stdout (rank 0).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W     # CPU arm: the float64 oracle on the host cores
+
+A "step" is one control step (0.02 s = 10 physics substeps + observations + reward/termination) of ALL lockstep envs.
+Workloads:
+  arm4096      config 2: arm-only, collisions off, 4096 envs per GPU
+  banana16384  config 3: SO100HandOverBanana with contacts, 16384 envs per GPU   (when the contact path is built)
+value  = env-steps/s with inputs resident in HBM (CUDA events around each step, L2 flushed between steps).
+e2e    = env-steps/s through BatchedEnvironment.step_host(): pinned host action in, reward/discount/step_type/joints_pos out,
+         copies and the stream sync inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (task, envs per GPU, blob, collide, algorithmic bytes per env-step [SURVEY.md §8d])
+    'arm4096': dict(task='SO100ArmOnly', envs=4096, model='so100_arm', collide=False, bytes_per_env_step=177,
+                    desc='BASELINE config 2: SO100 arm-only, collisions off, 4096 lockstep envs per GPU'),
+    'banana16384': dict(task='SO100HandOverBanana', envs=16384, model='so100_handover_banana', collide=True, bytes_per_env_step=385,
+                        desc='BASELINE config 3: SO100HandOverBanana with contacts, 16384 lockstep envs per GPU'),
+}
+METRIC = 'SO101 pick-place env-steps/sec at 1/2/4/8 B200 vs MuJoCo CPU on host cores'
+
+
+def measured_peak_gbs():
+  p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(p):
+    return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+  return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle)
+def _cpu_worker(args):
+  model, collide, seconds, seed = args
+  from oracle.oracle import OracleSim
+  sim = OracleSim(model, collide=collide)
+  rs = np.random.RandomState(seed)
+  lo = np.array([-np.pi, -3.14158, -3.14158, -3.14158, -3.14158, 0.0]); hi = np.array([np.pi, 3.14158, 3.14158, 3.14158, 3.14158, 0.08])
+  rng = sim.meta['jnt_range'].reshape(-1, 2)[:6]
+  q = sim.meta['qpos0'].copy(); q[:6] = 0.25 * rs.uniform(rng[:, 0], rng[:, 1])
+  sim.set_state(q, np.zeros(sim.nv))
+  acts = rs.uniform(lo, hi, size=(256, 6)) * 0.3
+  n, t0 = 0, time.perf_counter()
+  while time.perf_counter() - t0 < seconds:
+    sim.control_step(acts[n % 256])
+    n += 1
+  return n, time.perf_counter() - t0
+
+
+def cpu_baseline(workload, seconds, procs):
+  """Times the float64 C oracle (a restatement — `kind: port`; the reference's MuJoCo loop cannot run here: mujoco and
+  dm_control are not installed and there is no network)."""
+  from oracle import oracle as _o
+  _o.build()
+  w = WORKLOADS[workload]
+  ctx = mp.get_context('fork')
+  with ctx.Pool(procs) as pool:
+    res = pool.map(_cpu_worker, [(w['model'], w['collide'], seconds, 100 + i) for i in range(procs)])
+  total = sum(n / dt for n, dt in res)
+  return dict(value=total, unit='env-steps/s', cores=procs, kind='port',
+              sample=f'{procs} process(es) x 1 env x {seconds:.0f} s of {w["task"]} control steps on the float64 C oracle '
+                     f'({sum(n for n, _ in res)} env-steps)')
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+  def __init__(self, index):
+    self.index, self.rows, self._stop = index, [], threading.Event()
+    self._t = threading.Thread(target=self._run, daemon=True)
+
+  def _run(self):
+    q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    while not self._stop.is_set():
+      try:
+        out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+          self.rows.append([x.strip() for x in out.split(',')])
+      except Exception:
+        pass
+      self._stop.wait(0.2)
+
+  def __enter__(self):
+    self._t.start(); return self
+
+  def __exit__(self, *a):
+    self._stop.set(); self._t.join(timeout=6)
+
+  def summary(self):
+    if not self.rows:
+      return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+    sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in self.rows if len(r) > 2 + i)]
+    return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                reasons=reasons, samples=len(self.rows))
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=200)
+  ap.add_argument('--warmup', type=int, default=20)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--workload', default=os.environ.get('SO101_BENCH_WORKLOAD', 'arm4096'), choices=list(WORKLOADS))
+  ap.add_argument('--envs', type=int, default=0, help='envs per GPU (default: the workload size)')
+  ap.add_argument('--precision', default='f32', choices=['f32', 'f64'])
+  ap.add_argument('--cpu-seconds', type=float, default=10.0)
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  a = ap.parse_args()
+  rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+  local_rank = int(os.environ.get('LOCAL_RANK', 0))
+  w = WORKLOADS[a.workload]
+  envs = a.envs or w['envs']
+  config = dict(workload=a.workload, description=w['desc'], envs_per_gpu=envs, substeps_per_step=10, precision=a.precision,
+                parallelism=f'env-sharded x{world} (no per-step collective)',
+                l2='256 MiB memset between timed steps, excluded from the timing by per-step CUDA events')
+
+  if a.impl == 'reference':
+    if rank != 0:
+      return 0
+    procs = os.cpu_count() or 1
+    per_step_s = max(1.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
+    vals = []
+    for i in range(a.warmup + a.steps):
+      r = cpu_baseline(a.workload, per_step_s, procs)
+      if i >= a.warmup:
+        vals.append(r['value'])
+    v = float(np.mean(vals)) if vals else r['value']
+    r['value'] = v
+    print(json.dumps(dict(metric=METRIC, value=v, unit='env-steps/s', impl='reference', n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                          ms_per_step=per_step_s * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
+                          data='synthetic', config=config, cpu_baseline=r,
+                          e2e=dict(value=v, unit='env-steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                          note='reference MuJoCo/dm_control loop cannot run here (packages absent, offline); this is the float64 C '
+                               'restatement (oracle/) on all host cores'
+                          )))
+    return 0
+
+  import torch
+  import torch.distributed as dist
+  from so101_sim_b200.task_suite import create_batched_task_env
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py: no CUDA device (this framework has no CPU fallback; use --impl reference for the CPU arm)')
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  env = create_batched_task_env(w['task'], num_envs=envs, time_limit=30.0, seed=rank, device=dev, precision=a.precision)
+  if w['task'] == 'SO100ArmOnly':
+    env.sample_arm_initial_states(seed=0 + 1000 * rank)
+  env.reset()
+  total = a.warmup + a.steps
+  g = torch.Generator(device=dev); g.manual_seed(1 + 1000 * rank)
+  spec = env.action_spec()
+  lo, hi = torch.tensor(spec.minimum, device=dev), torch.tensor(spec.maximum, device=dev)
+  nact = min(total, 64)
+  acts = (lo + torch.rand(nact, envs, 6, generator=g, device=dev) * (hi - lo)) * 0.3
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+  ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+  ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+  ret_sum = torch.zeros(envs, device=dev); ep_len = torch.zeros(envs, dtype=torch.int32, device=dev)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for i in range(a.warmup):
+    env.step(acts[i % nact])
+  c0 = env.counters()
+  barrier()
+  with ClockSampler(local_rank) as clocks:
+    t_wall0 = time.perf_counter()
+    for i in range(a.steps):
+      flush.fill_(i & 0xFF)
+      ev0[i].record()
+      ts = env.step(acts[(a.warmup + i) % nact])
+      ev1[i].record()
+      ret_sum += ts.reward; ep_len += 1
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+  c1 = env.counters()
+  step_ms = [ev0[i].elapsed_time(ev1[i]) for i in range(a.steps)]
+  dev_ms = float(sum(step_ms))
+  t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  dev_ms = float(t.item())
+  value = envs * world * a.steps / (dev_ms * 1e-3)
+
+  # ---- e2e: host buffers through the public API (H2D + step + D2H + sync per step)
+  pin = dict(pin_memory=True)
+  h_act = [torch.empty(envs, 6, dtype=torch.float32, **pin).copy_(acts[i % nact].cpu()) for i in range(min(8, nact))]
+  h_rew = torch.empty(envs, dtype=torch.float32, **pin); h_dis = torch.empty(envs, dtype=torch.float32, **pin)
+  h_st = torch.empty(envs, dtype=torch.uint8, **pin); h_jp = torch.empty(envs, 6, dtype=torch.float32, **pin)
+  for i in range(3):
+    env.step_host(h_act[i % len(h_act)], h_rew, h_dis, h_st, h_jp)
+  barrier()
+  e0 = time.perf_counter()
+  for i in range(a.steps):
+    env.step_host(h_act[i % len(h_act)], h_rew, h_dis, h_st, h_jp)
+  barrier()
+  e2e_s = time.perf_counter() - e0
+  t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  e2e_value = envs * world * a.steps / float(t.item())
+  h2d, d2h = envs * 6 * 4, envs * (4 + 4 + 1 + 24)
+
+  # ---- episode statistics: the ONLY collective on this path (NCCL all_gather of return / length / success)
+  if world > 1:
+    stats = torch.stack([ret_sum, ep_len.float(), (ret_sum > 0).float()], dim=1).contiguous()
+    gathered = torch.empty(world * envs, 3, device=dev)
+    dist.all_gather_into_tensor(gathered, stats)
+    mean_return = float(gathered[:, 0].mean())
+  else:
+    mean_return = float(ret_sum.mean())
+
+  if rank == 0:
+    peak, peak_src = measured_peak_gbs()
+    launches = c1['kernel_launches'] - c0['kernel_launches']
+    per_launch_ms = dev_ms / max(1, a.steps)
+    achieved = envs * w['bytes_per_env_step'] / (per_launch_ms * 1e-3) / 1e9
+    out = dict(metric=METRIC, value=value, unit='env-steps/s', n_gpus=world, steps=a.steps, warmup=a.warmup,
+               ms_per_step=dev_ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+               dtype=a.precision, data='synthetic', config=config,
+               e2e=dict(value=e2e_value, unit='env-steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+               gpu_launches=launches, clocks=clocks.summary(),
+               roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=None,
+                             kernel='arm_step_kernel' if not w['collide'] else 'scene_step_kernel',
+                             bytes_per_env_step=w['bytes_per_env_step'], peak_source=peak_src,
+                             note='algorithmic state bytes / CUDA-event step time; the path is FP32-latency bound, see profiles/'),
+               wall_s=t_wall, mean_return=mean_return, diverged=c1['diverged'])
+    if not a.no_cpu_baseline and world == 1:
+      out['cpu_baseline'] = cpu_baseline(a.workload, a.cpu_seconds, 1)
+    print(json.dumps(out))
+  if world > 1:
+    dist.destroy_process_group()
+  env.close()
+  return 0
+
+
+if __name__ == '__main__':
+  sys.exit(main())

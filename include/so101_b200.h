@@ -1,0 +1,110 @@
+/* so101_b200 — C-ABI of the B200-native batched SO100/SO101 environment step.
+ *
+ * This is the drop-in boundary for the ONE hot path of tuul-ai/so101_sim: the lockstep env step
+ * (reference call stack: scripts/so101_lerobot_wrapper.py:70-75 -> dm_control composer.Environment.step ->
+ *  SO100Task.before_step so101_sim/tasks/base/so100_task.py:266-287 -> 10x mj_step -> observables
+ *  so100_task.py:331-368 -> SO100HandOver.get_reward so101_sim/tasks/so100_hand_over.py:238-275 ->
+ *  get_discount / should_terminate_episode so100_task.py:292-302).
+ *
+ * The reference has no FFI of its own for this path (it is Python over MuJoCo's C API through dm_control); each
+ * entry point below names the reference interface it replaces.  Plain pointers and sizes only; no torch types.
+ * All device pointers are borrowed for the duration of the call; the caller (PyTorch) owns every tensor.
+ * All work is enqueued on the caller's stream; no entry point synchronises the host unless it says so.
+ * Return value: 0 = ok, negative = error (see so101_last_error).  Nothing throws across this boundary.
+ * One handle per device; calls on one handle must be serialised by the caller.
+ */
+#ifndef SO101_B200_H
+#define SO101_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SO101_ABI_VERSION 1
+
+/* dm_env.StepType values (reference TimeStep.step_type) */
+#define SO101_STEP_FIRST 0
+#define SO101_STEP_MID 1
+#define SO101_STEP_LAST 2
+
+typedef struct so101_env *so101_handle;
+
+/* Per-step outputs: device pointers into caller-owned row-major tensors, N = num_envs.  Any pointer may be NULL
+ * (that block is then not written).  Mirrors the reference TimeStep + observation dict
+ * (so100_task.py:331-368; key order examples/so101_rl_breakdown.ipynb:65); joints_vel / undelayed_joints_vel are
+ * empty arrays in the reference (so100_task.py:357-364) and therefore have no pointer here. */
+typedef struct so101_step_out {
+  float *commanded_joints_pos;  /* [N,6]      ctrl after calibration, unclamped  (so100_task.py:344-355) */
+  float *joints_pos;            /* [N,6]      qpos[0:6] delayed 5 control steps  (so100_task.py:331-342,196-198) */
+  float *undelayed_joints_pos;  /* [N,6]      qpos[0:6] now                      (so100_task.py:189-192) */
+  float *physics_state;         /* [N,nq+nv]  qpos || qvel                       (so100_task.py:366-368) */
+  float *delayed_physics_state; /* [N,nq+nv]  delayed 15 control steps           (so100_task.py:203-210) */
+  float *reward;                /* [N]        SO100HandOver.get_reward           (so100_hand_over.py:238-275) */
+  float *discount;              /* [N]        SO100Task.get_discount             (so100_task.py:292-295) */
+  uint8_t *step_type;           /* [N]        FIRST / MID / LAST */
+} so101_step_out;
+
+typedef struct so101_config {
+  int num_envs;
+  int device;               /* CUDA device ordinal */
+  int n_substeps;           /* control_timestep / physics_timestep = 10 (task_suite.py:41) */
+  int last_step;            /* control-step index on which the time limit fires (1501 for 30 s; computed by the host
+                               with the reference's float64 `time += dt` accumulation); <=0 = no limit */
+  int joints_delay_steps;   /* 5  (0.1 s / 0.02 s, so100_task.py:80,196-198) */
+  int physics_delay_steps;  /* 15 (0.3 s / 0.02 s, so100_task.py:79,203-210) */
+  int terminate_on_success; /* SO100Task(terminate_episode=True), so100_task.py:119 */
+  int solver_iterations;    /* Newton iteration cap per substep (MuJoCo default 100) */
+  float solver_tolerance;   /* scaled-gradient / improvement tolerance (MuJoCo default 1e-8, reachable in f64 only) */
+  int precision;            /* 32 = float32 arithmetic (north_star dtype), 64 = float64 arithmetic (tight-parity mode) */
+  int collide;              /* 0 = collisions off (BASELINE config 2, arm-only), 1 = full contact pipeline */
+  float calibration_offsets[6]; /* SO101Calibration.homing_offsets, scripts/so101_calibration.py:62-77 */
+  float home_ctrl[6];       /* SO100_HOME_CTRL, so100_task.py:45-47 (ctrl written by initialize_episode :316-317) */
+} so101_config;
+
+int so101_abi_version(void);
+
+/* replaces task_suite.create_task_env (so101_sim/task_suite.py:103-155) for the physics + task state of N envs */
+int so101_create(const void *model_blob, size_t blob_len, const so101_config *cfg, so101_handle *out);
+/* replaces composer.Environment.close() */
+int so101_destroy(so101_handle h);
+/* last error message of this handle (or of the failed create when h == NULL) */
+const char *so101_last_error(so101_handle h);
+
+/* model dimensions: nq, nv, nu, state_dim (= nq + nv) */
+int so101_dims(so101_handle h, int *nq, int *nv, int *nu, int *nbody);
+
+/* Install per-env initial states (row-major [N,nq], [N,nv] device pointers).  These are the states an env returns to on
+ * reset; replaces the pose sampling of initialize_episode (so100_task.py:304-320, so100_hand_over.py:320-323). */
+int so101_set_initial_state(so101_handle h, const float *qpos_dev, const float *qvel_dev, void *stream);
+/* replaces composer.Environment.reset(): envs with mask[i] != 0 (all when mask_dev == NULL) go back to their initial
+ * state, ctrl = home + offsets, delay buffers refilled with the initial value, step counter 0.  Writes the FIRST
+ * TimeStep blocks of `out` for the reset envs. */
+int so101_reset(so101_handle h, const uint8_t *mask_dev, const so101_step_out *out, void *stream);
+/* replaces composer.Environment.step(action) for all N envs; action_dev is row-major [N,6] float32.
+ * Envs whose previous step was LAST are reset instead and return FIRST (dm_control auto-reset). */
+int so101_step(so101_handle h, const float *action_dev, const so101_step_out *out, void *stream);
+/* physics.get_state() / set_state() equivalents (so100_task.py:366-368): row-major [N,nq], [N,nv] device pointers */
+int so101_get_state(so101_handle h, float *qpos_dev, float *qvel_dev, void *stream);
+int so101_set_state(so101_handle h, const float *qpos_dev, const float *qvel_dev, void *stream);
+/* same as so101_get_state but without rounding the internal state to float32 (precision = 64 parity tests) */
+int so101_get_state_f64(so101_handle h, double *qpos_dev, double *qvel_dev, void *stream);
+
+/* End-to-end variant with HOST buffers (pinned or pageable): copies action_host [N,6] to the device, steps, copies
+ * reward/discount/step_type and joints_pos back, and synchronises the stream before returning.  Any output may be NULL. */
+int so101_step_host(so101_handle h, const float *action_host, float *reward_host, float *discount_host, uint8_t *step_type_host,
+                    float *joints_pos_host, void *stream);
+
+/* counters since create: [0] kernels launched by this library, [1] control steps taken, [2] envs that diverged,
+ * [3] contacts dropped by a full per-env contact buffer */
+int so101_counters(so101_handle h, uint64_t out[4]);
+
+/* Debug/parity probe: copy one internal structure-of-arrays field ("qacc", "ncon", "solver_iter", ...) of all envs to a
+ * caller-owned device buffer of `count` floats.  Used by the parity tests only. */
+int so101_debug_read(so101_handle h, const char *field, float *dst_dev, size_t count, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

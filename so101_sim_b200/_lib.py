@@ -1,0 +1,57 @@
+"""ctypes loader for the sm_100a shared library (C-ABI declared in include/so101_b200.h).
+
+There is NO CPU fallback: if the library is missing, cannot be loaded, or no CUDA device is present, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libso101_b200.so')
+
+
+class StepOut(ctypes.Structure):
+  _fields_ = [(n, ctypes.c_void_p) for n in ('commanded_joints_pos', 'joints_pos', 'undelayed_joints_pos', 'physics_state',
+                                             'delayed_physics_state', 'reward', 'discount', 'step_type')]
+
+
+class Config(ctypes.Structure):
+  _fields_ = [('num_envs', ctypes.c_int), ('device', ctypes.c_int), ('n_substeps', ctypes.c_int), ('last_step', ctypes.c_int),
+              ('joints_delay_steps', ctypes.c_int), ('physics_delay_steps', ctypes.c_int), ('terminate_on_success', ctypes.c_int),
+              ('solver_iterations', ctypes.c_int), ('solver_tolerance', ctypes.c_float), ('precision', ctypes.c_int),
+              ('collide', ctypes.c_int), ('calibration_offsets', ctypes.c_float * 6), ('home_ctrl', ctypes.c_float * 6)]
+
+
+EXPORTS = ('so101_abi_version', 'so101_create', 'so101_destroy', 'so101_last_error', 'so101_dims', 'so101_set_initial_state',
+           'so101_reset', 'so101_step', 'so101_get_state', 'so101_set_state', 'so101_get_state_f64', 'so101_step_host',
+           'so101_counters', 'so101_debug_read')
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise RuntimeError(f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                       '(so101_sim_b200 has no CPU fallback)')
+  L = ctypes.CDLL(LIB_PATH)
+  vp, ci = ctypes.c_void_p, ctypes.c_int
+  L.so101_abi_version.restype = ci
+  L.so101_create.restype = ci; L.so101_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(Config), ctypes.POINTER(vp)]
+  L.so101_destroy.restype = ci; L.so101_destroy.argtypes = [vp]
+  L.so101_last_error.restype = ctypes.c_char_p; L.so101_last_error.argtypes = [vp]
+  L.so101_dims.restype = ci; L.so101_dims.argtypes = [vp] + [ctypes.POINTER(ci)] * 4
+  for f in ('so101_set_initial_state', 'so101_set_state', 'so101_get_state', 'so101_get_state_f64'):
+    getattr(L, f).restype = ci; getattr(L, f).argtypes = [vp, vp, vp, vp]
+  L.so101_reset.restype = ci; L.so101_reset.argtypes = [vp, vp, ctypes.POINTER(StepOut), vp]
+  L.so101_step.restype = ci; L.so101_step.argtypes = [vp, vp, ctypes.POINTER(StepOut), vp]
+  L.so101_step_host.restype = ci; L.so101_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+  L.so101_counters.restype = ci; L.so101_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64 * 4)]
+  L.so101_debug_read.restype = ci; L.so101_debug_read.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t, vp]
+  if L.so101_abi_version() != 1:
+    raise RuntimeError('libso101_b200.so: ABI version mismatch')
+  _lib = L
+  return L

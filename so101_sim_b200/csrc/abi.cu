@@ -1,0 +1,367 @@
+// C-ABI implementation (include/so101_b200.h): handle life cycle, model upload, kernel launches.
+// PyTorch owns every tensor that crosses this boundary; the handle owns only its SoA state and scratch.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/so101_b200.h"
+#include "arm_kernel.cuh"
+#include "blob.hpp"
+#include "layout_kernels.cuh"
+
+namespace so101 {
+
+static thread_local std::string g_create_error;
+
+#define CUDA_OK(expr)                                                                                      \
+  do {                                                                                                     \
+    cudaError_t e_ = (expr);                                                                               \
+    if (e_ != cudaSuccess) throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct HandleBase {
+  std::string err;
+  so101_config cfg{};
+  int nq = 0, nv = 0, nu = 0, nbody = 0;
+  uint64_t launches = 0, steps = 0, dropped = 0;
+  virtual ~HandleBase() {}
+  virtual void set_state(const float *q, const float *v, bool initial, cudaStream_t s) = 0;
+  virtual void get_state(float *q, float *v, cudaStream_t s) = 0;
+  virtual void get_state_f64(double *q, double *v, cudaStream_t s) = 0;
+  virtual void reset(const uint8_t *mask, const so101_step_out &out, cudaStream_t s) = 0;
+  virtual void step(const float *action, const so101_step_out &out, cudaStream_t s) = 0;
+  virtual void debug_read(const char *field, float *dst, size_t count, cudaStream_t s) = 0;
+  virtual void step_host(const float *action, float *reward, float *discount, uint8_t *step_type, float *jpos, cudaStream_t s) = 0;
+  virtual uint64_t diverged() = 0;
+};
+
+static void quat2mat(const double *q, double *m) {
+  double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  double w = q[0] / n, x = q[1] / n, y = q[2] / n, z = q[3] / n;
+  m[0] = 1 - 2 * (y * y + z * z); m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = 1 - 2 * (x * x + z * z); m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = 1 - 2 * (x * x + y * y);
+}
+static void mm3(const double *a, const double *b, double *r) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) r[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+
+// Build the arm chain description from the generic blob: the first NJ hinge joints must form a serial chain whose root's
+// parent is static (scene_pbr.xml:74-126).
+template <typename T>
+static void build_arm_model(const Blob &b, ArmModelT<T> &am) {
+  const auto &jt = b.I("jnt_type"), &jb = b.I("jnt_body"), &bp = b.I("body_parent"), &bw = b.I("body_weld");
+  if ((int)jt.size() < NJ) throw std::runtime_error("model has fewer than 6 joints");
+  const auto &opt = b.F("opt");
+  const double dt = opt[0];
+  std::memset(&am, 0, sizeof(am));
+  // static base pose: compose the chain of static ancestors of the first arm body
+  {
+    int b0 = jb[0];
+    std::vector<int> chain;
+    for (int p = bp[b0]; p != 0; p = bp[p]) {
+      if (bw[p] != 0) throw std::runtime_error("arm base must be static");
+      chain.push_back(p);
+    }
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+    for (auto it = chain.rbegin(); it != chain.rend(); ++it) {
+      const double *bpos = &b.F("body_pos")[3 * *it];
+      double Rb[9], Rn[9];
+      quat2mat(&b.F("body_quat")[4 * *it], Rb);
+      for (int c = 0; c < 3; c++) p[c] += R[3 * c] * bpos[0] + R[3 * c + 1] * bpos[1] + R[3 * c + 2] * bpos[2];
+      mm3(R, Rb, Rn);
+      std::memcpy(R, Rn, sizeof R);
+    }
+    for (int c = 0; c < 3; c++) am.base_pos[c] = (T)p[c];
+    for (int c = 0; c < 9; c++) am.base_R[c] = (T)R[c];
+  }
+  for (int j = 0; j < NJ; j++) {
+    if (jt[j] != 1) throw std::runtime_error("arm joints must be hinges");
+    const int body = jb[j];
+    if (j > 0 && bp[body] != jb[j - 1]) throw std::runtime_error("arm joints must form a serial chain");
+    if (b.I("jnt_dofadr")[j] != j || b.I("jnt_qposadr")[j] != j) throw std::runtime_error("arm dofs must come first");
+    const double *jp = &b.F("jnt_pos")[3 * j];
+    if (jp[0] != 0 || jp[1] != 0 || jp[2] != 0) throw std::runtime_error("hinge anchors must sit at the body origin");
+    double R0[9], Ri[9];
+    quat2mat(&b.F("body_quat")[4 * body], R0);
+    quat2mat(&b.F("body_iquat")[4 * body], Ri);
+    const double *in = &b.F("body_inertia")[3 * body];
+    double Il[9];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) Il[3 * r + c] = Ri[3 * r] * in[0] * Ri[3 * c] + Ri[3 * r + 1] * in[1] * Ri[3 * c + 1] + Ri[3 * r + 2] * in[2] * Ri[3 * c + 2];
+    for (int c = 0; c < 3; c++) {
+      am.pos[j][c] = (T)b.F("body_pos")[3 * body + c];
+      am.axis[j][c] = (T)b.F("jnt_axis")[3 * j + c];
+      am.ipos[j][c] = (T)b.F("body_ipos")[3 * body + c];
+    }
+    for (int c = 0; c < 9; c++) am.R0[j][c] = (T)R0[c];
+    am.Iloc[j][0] = (T)Il[0]; am.Iloc[j][1] = (T)Il[4]; am.Iloc[j][2] = (T)Il[8];
+    am.Iloc[j][3] = (T)Il[1]; am.Iloc[j][4] = (T)Il[2]; am.Iloc[j][5] = (T)Il[5];
+    am.mass[j] = (T)b.F("body_mass")[body];
+    am.qpos0[j] = (T)b.F("qpos0")[j];
+    am.armature[j] = (T)b.F("dof_armature")[j];
+    am.frictionloss[j] = (T)b.F("dof_frictionloss")[j];
+    const double invw = b.F("dof_invweight0")[j];
+    am.invweight0[j] = (T)invw;
+    auto clampimp = [](double x) { return x < 1e-4 ? 1e-4 : (x > 0.9999 ? 0.9999 : x); };
+    {  // friction-loss row constants: pos = 0 -> impedance = d0; K = 0; B = 2 / (dmax * max(tc, 2 dt))
+      const double *sr = &b.F("jnt_solreffriction")[2 * j], *si = &b.F("jnt_solimpfriction")[5 * j];
+      const double imp = clampimp(si[0]), dmax = clampimp(si[1]);
+      double R = (1 - imp) / imp * invw;
+      if (R < 1e-15) R = 1e-15;
+      am.fr_R[j] = (T)R; am.fr_D[j] = (T)(1 / R);
+      am.fr_B[j] = (T)(sr[0] > 0 ? 2 / (dmax * std::max(sr[0], 2 * dt)) : -sr[1] / dmax);
+    }
+    {
+      const double *sr = &b.F("jnt_solreflimit")[2 * j], *si = &b.F("jnt_solimplimit")[5 * j];
+      const double dmax = clampimp(si[1]);
+      for (int c = 0; c < 5; c++) am.lim_solimp[j][c] = (T)si[c];
+      if (sr[0] > 0) {
+        const double tc = std::max(sr[0], 2 * dt);
+        am.lim_K[j] = (T)(1 / (dmax * dmax * tc * tc * sr[1] * sr[1])); am.lim_B[j] = (T)(2 / (dmax * tc));
+      } else { am.lim_K[j] = (T)(-sr[0] / (dmax * dmax)); am.lim_B[j] = (T)(-sr[1] / dmax); }
+      am.limited[j] = b.I("jnt_limited")[j];
+      am.range[j][0] = (T)b.F("jnt_range")[2 * j]; am.range[j][1] = (T)b.F("jnt_range")[2 * j + 1];
+    }
+  }
+  if (b.scalar("nu") != NJ) throw std::runtime_error("expected 6 actuators");
+  for (int a = 0; a < NJ; a++) {
+    if (b.I("act_jnt")[a] != a) throw std::runtime_error("actuator a must drive joint a");
+    if (b.F("act_gear")[a] != 1.0) throw std::runtime_error("actuator gear must be 1");
+    am.gain[a] = (T)b.F("act_gain")[a];
+    for (int c = 0; c < 3; c++) am.bias[a][c] = (T)b.F("act_bias")[3 * a + c];
+    for (int c = 0; c < 2; c++) { am.ctrlrange[a][c] = (T)b.F("act_ctrlrange")[2 * a + c]; am.forcerange[a][c] = (T)b.F("act_forcerange")[2 * a + c]; }
+  }
+  for (int c = 0; c < 3; c++) am.gravity[c] = (T)opt[1 + c];
+  am.dt = (T)dt;
+  const int nv = b.scalar("nv");
+  am.solver_scale = (T)(1.0 / (opt[8] * std::max(1, nv)));
+}
+
+template <typename T>
+struct Handle : HandleBase {
+  ArmModelT<T> am;
+  EnvState<T> S{};
+  StepCfg sc{};
+  std::vector<void *> allocs;
+  float *d_action = nullptr, *d_reward = nullptr, *d_discount = nullptr, *d_jpos = nullptr;
+  uint8_t *d_steptype = nullptr;
+
+  template <typename U>
+  U *dalloc(size_t n) {
+    void *p = nullptr;
+    CUDA_OK(cudaMalloc(&p, n * sizeof(U)));
+    CUDA_OK(cudaMemset(p, 0, n * sizeof(U)));
+    allocs.push_back(p);
+    return static_cast<U *>(p);
+  }
+
+  Handle(const Blob &b, const so101_config &c) {
+    cfg = c;
+    CUDA_OK(cudaSetDevice(c.device));
+    nq = b.scalar("nq"); nv = b.scalar("nv"); nu = b.scalar("nu"); nbody = b.scalar("nbody");
+    build_arm_model<T>(b, am);
+    if (c.collide || nq != NJ) throw std::runtime_error("contact pipeline not built into this library yet (collide=1 / free props)");
+    const size_t N = c.num_envs;
+    S.N = c.num_envs; S.nq = nq; S.nv = nv;
+    S.qpos = dalloc<T>(nq * N); S.qvel = dalloc<T>(nv * N); S.warm = dalloc<T>(nv * N);
+    S.init_qpos = dalloc<T>(nq * N); S.init_qvel = dalloc<T>(nv * N); S.ctrl = dalloc<T>(6 * N);
+    S.step = dalloc<int>(N); S.needs_reset = dalloc<uint8_t>(N);
+    S.ring_joints = dalloc<float>((size_t)(c.joints_delay_steps + 1) * 6 * N);
+    S.ring_phys = dalloc<float>((size_t)(c.physics_delay_steps + 1) * (nq + nv) * N);
+    S.diverged_count = dalloc<int>(1); S.solver_iter = dalloc<int>(N); S.ncon = dalloc<int>(N);
+    sc.nsub = c.n_substeps; sc.last_step = c.last_step; sc.dj = c.joints_delay_steps; sc.dp = c.physics_delay_steps;
+    sc.terminate_on_success = c.terminate_on_success; sc.max_iter = c.solver_iterations; sc.tol = c.solver_tolerance;
+    for (int i = 0; i < 6; i++) { sc.offsets[i] = c.calibration_offsets[i]; sc.home[i] = c.home_ctrl[i]; }
+    // default initial state: qpos0, zero velocity
+    std::vector<T> q0(nq * N);
+    for (int k = 0; k < nq; k++) for (size_t e = 0; e < N; e++) q0[k * N + e] = (T)b.F("qpos0")[k];
+    CUDA_OK(cudaMemcpy(S.init_qpos, q0.data(), q0.size() * sizeof(T), cudaMemcpyHostToDevice));
+    d_action = dalloc<float>(6 * N); d_reward = dalloc<float>(N); d_discount = dalloc<float>(N); d_jpos = dalloc<float>(6 * N);
+    d_steptype = dalloc<uint8_t>(N);
+  }
+  ~Handle() override {
+    for (void *p : allocs) cudaFree(p);
+  }
+  void set_state(const float *q, const float *v, bool initial, cudaStream_t s) override {
+    launch_rows_to_soa<T>(q, S.qpos, S.N, nq, s); launch_rows_to_soa<T>(v, S.qvel, S.N, nv, s);
+    launches += 2;
+    if (initial) {
+      launch_rows_to_soa<T>(q, S.init_qpos, S.N, nq, s); launch_rows_to_soa<T>(v, S.init_qvel, S.N, nv, s);
+      launches += 2;
+    }
+    CUDA_OK(cudaMemsetAsync(S.warm, 0, sizeof(T) * nv * S.N, s));
+  }
+  void get_state(float *q, float *v, cudaStream_t s) override {
+    launch_soa_to_rows<T, float>(S.qpos, q, S.N, nq, s); launch_soa_to_rows<T, float>(S.qvel, v, S.N, nv, s);
+    launches += 2;
+  }
+  void get_state_f64(double *q, double *v, cudaStream_t s) override {
+    launch_soa_to_rows<T, double>(S.qpos, q, S.N, nq, s); launch_soa_to_rows<T, double>(S.qvel, v, S.N, nv, s);
+    launches += 2;
+  }
+  void reset(const uint8_t *mask, const so101_step_out &out, cudaStream_t s) override {
+    launch_arm_reset<T>(sc, S, mask, out, s);
+    launches += 1;
+  }
+  void step(const float *action, const so101_step_out &out, cudaStream_t s) override {
+    launch_arm_step<T>(am, sc, S, action, out, s);
+    launches += 1; steps += 1;
+  }
+  void debug_read(const char *field, float *dst, size_t count, cudaStream_t s) override {
+    const std::string f(field);
+    if (f == "solver_iter" || f == "ncon" || f == "step") {
+      const int *src = f == "solver_iter" ? S.solver_iter : (f == "ncon" ? S.ncon : S.step);
+      if (count < (size_t)S.N) throw std::runtime_error("debug_read: buffer too small");
+      launch_int_to_float(src, dst, S.N, s);
+      launches += 1;
+    } else if (f == "warm") {
+      if (count < (size_t)S.N * nv) throw std::runtime_error("debug_read: buffer too small");
+      launch_soa_to_rows<T, float>(S.warm, dst, S.N, nv, s);
+      launches += 1;
+    } else throw std::runtime_error("debug_read: unknown field " + f);
+  }
+  // e2e path: host buffers in, host buffers out, host<->device copies on the caller's stream, one sync at the end
+  void step_host(const float *action, float *reward, float *discount, uint8_t *step_type, float *jpos, cudaStream_t s) override {
+    const size_t N = S.N;
+    CUDA_OK(cudaMemcpyAsync(d_action, action, 6 * N * sizeof(float), cudaMemcpyHostToDevice, s));
+    so101_step_out o{};
+    o.reward = d_reward; o.discount = d_discount; o.step_type = d_steptype; o.joints_pos = d_jpos;
+    step(d_action, o, s);
+    if (reward) CUDA_OK(cudaMemcpyAsync(reward, d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (discount) CUDA_OK(cudaMemcpyAsync(discount, d_discount, N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (step_type) CUDA_OK(cudaMemcpyAsync(step_type, d_steptype, N, cudaMemcpyDeviceToHost, s));
+    if (jpos) CUDA_OK(cudaMemcpyAsync(jpos, d_jpos, 6 * N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+  }
+  uint64_t diverged() override {
+    int v = 0;
+    cudaMemcpy(&v, S.diverged_count, sizeof(int), cudaMemcpyDeviceToHost);
+    return (uint64_t)v;
+  }
+};
+
+}  // namespace so101
+
+using namespace so101;
+
+#define API_BEGIN(h)                                   \
+  if (!(h)) return -1;                                 \
+  HandleBase *H = reinterpret_cast<HandleBase *>(h);   \
+  try {
+#define API_END()                                                                        \
+    cudaError_t e_ = cudaPeekAtLastError();                                              \
+    if (e_ != cudaSuccess) { H->err = cudaGetErrorString(e_); cudaGetLastError(); return -3; } \
+    return 0;                                                                            \
+  } catch (const std::exception &ex) { H->err = ex.what(); return -2; }
+
+extern "C" {
+
+int so101_abi_version(void) { return SO101_ABI_VERSION; }
+
+int so101_create(const void *model_blob, size_t blob_len, const so101_config *cfg, so101_handle *out) {
+  if (!model_blob || !cfg || !out) { g_create_error = "null argument"; return -1; }
+  try {
+    if (cfg->num_envs <= 0) throw std::runtime_error("num_envs must be positive");
+    if (cfg->n_substeps <= 0) throw std::runtime_error("n_substeps must be positive");
+    if (cfg->joints_delay_steps < 0 || cfg->physics_delay_steps < 0) throw std::runtime_error("delays must be >= 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw std::runtime_error("no CUDA device: this library has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) throw std::runtime_error("invalid device ordinal");
+    Blob b(model_blob, blob_len);
+    HandleBase *H = nullptr;
+    if (cfg->precision == 64) H = new Handle<double>(b, *cfg);
+    else if (cfg->precision == 32) H = new Handle<float>(b, *cfg);
+    else throw std::runtime_error("precision must be 32 or 64");
+    *out = reinterpret_cast<so101_handle>(H);
+    return 0;
+  } catch (const std::exception &ex) {
+    g_create_error = ex.what();
+    cudaGetLastError();
+    return -2;
+  }
+}
+
+int so101_destroy(so101_handle h) {
+  if (!h) return -1;
+  delete reinterpret_cast<HandleBase *>(h);
+  return 0;
+}
+
+const char *so101_last_error(so101_handle h) {
+  if (!h) return g_create_error.c_str();
+  return reinterpret_cast<HandleBase *>(h)->err.c_str();
+}
+
+int so101_dims(so101_handle h, int *nq, int *nv, int *nu, int *nbody) {
+  API_BEGIN(h)
+  if (nq) *nq = H->nq;
+  if (nv) *nv = H->nv;
+  if (nu) *nu = H->nu;
+  if (nbody) *nbody = H->nbody;
+  API_END()
+}
+
+int so101_set_initial_state(so101_handle h, const float *qpos_dev, const float *qvel_dev, void *stream) {
+  API_BEGIN(h)
+  if (!qpos_dev || !qvel_dev) throw std::runtime_error("null state pointer");
+  H->set_state(qpos_dev, qvel_dev, true, (cudaStream_t)stream);
+  API_END()
+}
+int so101_set_state(so101_handle h, const float *qpos_dev, const float *qvel_dev, void *stream) {
+  API_BEGIN(h)
+  if (!qpos_dev || !qvel_dev) throw std::runtime_error("null state pointer");
+  H->set_state(qpos_dev, qvel_dev, false, (cudaStream_t)stream);
+  API_END()
+}
+int so101_get_state(so101_handle h, float *qpos_dev, float *qvel_dev, void *stream) {
+  API_BEGIN(h)
+  if (!qpos_dev || !qvel_dev) throw std::runtime_error("null state pointer");
+  H->get_state(qpos_dev, qvel_dev, (cudaStream_t)stream);
+  API_END()
+}
+int so101_get_state_f64(so101_handle h, double *qpos_dev, double *qvel_dev, void *stream) {
+  API_BEGIN(h)
+  if (!qpos_dev || !qvel_dev) throw std::runtime_error("null state pointer");
+  H->get_state_f64(qpos_dev, qvel_dev, (cudaStream_t)stream);
+  API_END()
+}
+int so101_reset(so101_handle h, const uint8_t *mask_dev, const so101_step_out *out, void *stream) {
+  API_BEGIN(h)
+  so101_step_out o{};
+  if (out) o = *out;
+  H->reset(mask_dev, o, (cudaStream_t)stream);
+  API_END()
+}
+int so101_step(so101_handle h, const float *action_dev, const so101_step_out *out, void *stream) {
+  API_BEGIN(h)
+  if (!action_dev) throw std::runtime_error("null action pointer");
+  so101_step_out o{};
+  if (out) o = *out;
+  H->step(action_dev, o, (cudaStream_t)stream);
+  API_END()
+}
+int so101_step_host(so101_handle h, const float *action_host, float *reward_host, float *discount_host, uint8_t *step_type_host,
+                    float *joints_pos_host, void *stream) {
+  API_BEGIN(h)
+  if (!action_host) throw std::runtime_error("null action pointer");
+  H->step_host(action_host, reward_host, discount_host, step_type_host, joints_pos_host, (cudaStream_t)stream);
+  API_END()
+}
+int so101_counters(so101_handle h, uint64_t out[4]) {
+  API_BEGIN(h)
+  out[0] = H->launches; out[1] = H->steps; out[2] = H->diverged(); out[3] = H->dropped;
+  API_END()
+}
+int so101_debug_read(so101_handle h, const char *field, float *dst_dev, size_t count, void *stream) {
+  API_BEGIN(h)
+  H->debug_read(field, dst_dev, count, (cudaStream_t)stream);
+  API_END()
+}
+
+}  // extern "C"

@@ -1,0 +1,30 @@
+// Device-resident state of N lockstep environments, structure-of-arrays: field[k][env] so that a warp touching the
+// same component of 32 consecutive envs issues one coalesced 128 B (f32) / 256 B (f64) request.
+#pragma once
+#include <cstdint>
+#include "../../include/so101_b200.h"
+
+namespace so101 {
+
+template <typename T>
+struct EnvState {
+  int N, nq, nv;
+  T *qpos, *qvel, *warm;            // [nq][N], [nv][N], [nv][N]  (warm = qacc_warmstart)
+  T *init_qpos, *init_qvel;         // reset targets
+  T *ctrl;                          // [6][N]
+  int *step;                        // [N] control steps since reset
+  uint8_t *needs_reset;             // [N] previous step was LAST (dm_control auto-reset on next step)
+  float *ring_joints;               // [Dj+1][6][N]
+  float *ring_phys;                 // [Dp+1][nq+nv][N]
+  int *diverged_count;              // [1]
+  int *solver_iter;                 // [N] Newton iterations of the last substep (parity/diagnostics)
+  int *ncon;                        // [N] contacts of the last substep
+};
+
+struct StepCfg {
+  int nsub, last_step, dj, dp, terminate_on_success, max_iter;
+  float tol;
+  float offsets[6], home[6];
+};
+
+}  // namespace so101

@@ -1,0 +1,319 @@
+"""Batched drop-in for the reference's env factory (so101_sim/task_suite.py:103-155) on the SO100 path.
+
+`create_batched_task_env(...)` mirrors `create_task_env(task_name, time_limit, random_state, control_timestep, cameras,
+**kwargs)` and adds `num_envs` / `device`.  The returned `BatchedEnvironment` keeps dm_control's `reset()` / `step()` ->
+TimeStep contract with a leading batch dimension; all tensors are torch tensors on the CUDA device and cross a C-ABI
+(include/so101_b200.h) into hand-written sm_100a kernels.  There is no CPU fallback.
+
+Reference semantics restated here (host side):
+  * task registry + kwargs filtering           task_suite.py:43-100,126-144
+  * action_spec bounds                         so100_task.py:232-251
+  * observation keys and delays                so100_task.py:189-210,331-368
+  * time limit (`physics.time() >= time_limit` with float64 `time += 0.002`)   [upstream dm_control]
+  * auto-reset on the step after LAST          [upstream dm_control composer.Environment.step]
+"""
+from __future__ import annotations
+
+import collections
+import ctypes
+import dataclasses
+import inspect
+from typing import Any, NamedTuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .calibration import SO101Calibration
+from .model import blob_path, read_blob
+
+DEFAULT_CONTROL_TIMESTEP = 0.02  # task_suite.py:41
+PHYSICS_TIMESTEP = 0.002         # MuJoCo default; scene_pbr.xml sets none
+
+# so100_task.py:45-60
+SO100_HOME_CTRL = np.array([0.0, -1.57079, 1.57079, 1.57079, -1.57079, 0.0])
+SO100_GRIPPER_CTRL_OPEN, SO100_GRIPPER_CTRL_CLOSE = 0.08, 0.0
+_DEFAULT_PHYSICS_DELAY_SECS = 0.3            # so100_task.py:79
+_DEFAULT_JOINT_OBSERVATION_DELAY_SECS = 0.1  # so100_task.py:80
+
+STEP_FIRST, STEP_MID, STEP_LAST = 0, 1, 2
+
+OBSERVATION_KEYS = ('commanded_joints_pos', 'joints_pos', 'joints_vel', 'physics_state', 'undelayed_joints_pos',
+                    'undelayed_joints_vel', 'delayed_physics_state')  # examples/so101_rl_breakdown.ipynb:65
+
+
+class BatchedTimeStep(NamedTuple):
+  """dm_env.TimeStep with a leading env dimension.  FIRST steps carry reward 0 / discount 1 (dm_env uses None)."""
+  step_type: torch.Tensor   # uint8 [N]
+  reward: torch.Tensor      # float32 [N]
+  discount: torch.Tensor    # float32 [N]
+  observation: 'collections.OrderedDict[str, torch.Tensor]'
+
+  def first(self): return self.step_type == STEP_FIRST
+  def mid(self): return self.step_type == STEP_MID
+  def last(self): return self.step_type == STEP_LAST
+
+
+@dataclasses.dataclass(frozen=True)
+class BoundedArraySpec:
+  shape: tuple
+  dtype: Any
+  minimum: np.ndarray
+  maximum: np.ndarray
+
+
+class SO100Task:
+  """Host-side description of the base SO100 task (so100_task.py:101-320): reward 0, never succeeds."""
+  model_name = 'so100_arm'
+  collide = False
+  instruction = ''
+
+  def __init__(self, control_timestep, cameras=(), joints_observation_delay_secs=_DEFAULT_JOINT_OBSERVATION_DELAY_SECS,
+               image_observation_enabled=True, image_observation_delay_secs=_DEFAULT_PHYSICS_DELAY_SECS, update_interval=1,
+               table_height_offset=0.0, rotation_joint_limit=np.pi, terminate_episode=True):
+    if cameras:
+      raise NotImplementedError('camera rendering is out of scope of the B200 path: pass cameras=()')
+    if table_height_offset:
+      raise NotImplementedError('table_height_offset needs a recompiled model blob')
+    self.control_timestep = control_timestep
+    self.rotation_joint_limit = rotation_joint_limit
+    self.terminate_episode = terminate_episode
+    self.joints_delay_secs = joints_observation_delay_secs
+    self.physics_delay_secs = image_observation_delay_secs
+
+  def get_instruction(self):
+    return self.instruction
+
+
+class SO100HandOver(SO100Task):
+  """so100_hand_over.py:121-326 (banana config, overlap reward)."""
+  model_name = 'so100_handover_banana'
+  collide = True
+
+  def __init__(self, object_name, reward_based_on_overlap=True, **kwargs):
+    super().__init__(**kwargs)
+    configs = {'banana': 'pick up the banana and put it in the bowl using the SO100 arm', 'pen': None}
+    if object_name not in configs:
+      raise ValueError(f'Invalid object name: {object_name}, must be one of {configs.keys()}')  # so100_hand_over.py:146-150
+    if object_name != 'banana':
+      raise NotImplementedError('SO100HandOverPen: model blob not compiled yet (SURVEY.md §8f row 3)')
+    if not reward_based_on_overlap:
+      raise NotImplementedError('contact/distance reward fallback (so100_hand_over.py:277-318) is a "next" row')
+    self.instruction = configs[object_name]
+
+
+class SO100ArmOnly(SO100Task):
+  """BASELINE config 2: scene_pbr.xml without the free props, collisions off, base-task semantics (reward 0)."""
+  model_name = 'so100_arm'
+  collide = False
+
+
+# task_suite.py:98-99 (+ the arm-only benchmark scene, which has no reference registry entry)
+TASK_FACTORIES = {
+    'SO100HandOverBanana': (SO100HandOver, {'object_name': 'banana'}),
+    'SO100HandOverPen': (SO100HandOver, {'object_name': 'pen'}),
+    'SO100ArmOnly': (SO100ArmOnly, {}),
+}
+
+
+def time_limit_to_last_step(time_limit: float, control_timestep: float, physics_timestep: float = PHYSICS_TIMESTEP) -> int:
+  """Control-step index whose TimeStep is LAST: dm_control tests `physics.time() >= time_limit` after each control step and
+  MuJoCo accumulates `time += timestep` in float64 (30 s -> step 1501, not 1500)."""
+  if not np.isfinite(time_limit):
+    return 0
+  nsub = int(round(control_timestep / physics_timestep))
+  t, step = 0.0, 0
+  while True:
+    for _ in range(nsub):
+      t += physics_timestep
+    step += 1
+    if t >= time_limit:
+      return step
+    if step > 100_000_000:
+      raise ValueError('time_limit too large')
+
+
+class BatchedEnvironment:
+  """N lockstep copies of one reference environment (composer.Environment, task_suite.py:148-155)."""
+
+  def __init__(self, task: SO100Task, num_envs: int, time_limit: float, seed: int | None, device, calibration_offsets, precision,
+               solver_iterations, solver_tolerance):
+    self.task = task
+    self.num_envs = int(num_envs)
+    self.device = torch.device(device)
+    if self.device.type != 'cuda':
+      raise RuntimeError('so101_sim_b200 runs on CUDA devices only (no CPU fallback)')
+    if not torch.cuda.is_available():
+      raise RuntimeError('CUDA is not available: so101_sim_b200 has no CPU fallback')
+    self._lib = _lib.load()
+    self.seed = 0 if seed is None else int(seed)
+    self.control_timestep = task.control_timestep
+    self.n_substeps = int(round(task.control_timestep / PHYSICS_TIMESTEP))
+    self.model = read_blob(task.model_name)
+    with open(blob_path(task.model_name), 'rb') as f:
+      blob = f.read()
+    offs = np.zeros(6) if calibration_offsets is None else np.asarray(calibration_offsets, dtype=np.float64)
+    if offs.shape != (6,):
+      raise ValueError(f'Expected 6 calibration offsets, got shape {offs.shape}')
+    self.calibration_offsets = offs
+    cfg = _lib.Config()
+    cfg.num_envs = self.num_envs
+    cfg.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+    cfg.n_substeps = self.n_substeps
+    cfg.last_step = time_limit_to_last_step(time_limit, task.control_timestep)
+    cfg.joints_delay_steps = int(round(task.joints_delay_secs / task.control_timestep)) if task.joints_delay_secs else 0
+    cfg.physics_delay_steps = int(round(task.physics_delay_secs / task.control_timestep)) if task.physics_delay_secs else 0
+    cfg.terminate_on_success = int(task.terminate_episode)
+    cfg.solver_iterations = int(solver_iterations)
+    cfg.solver_tolerance = float(solver_tolerance)
+    cfg.precision = {'f32': 32, 'f64': 64}[precision]
+    cfg.collide = int(task.collide)
+    for i in range(6):
+      cfg.calibration_offsets[i] = float(offs[i]); cfg.home_ctrl[i] = float(SO100_HOME_CTRL[i])
+    self.precision = precision
+    self.last_step = cfg.last_step
+    h = ctypes.c_void_p()
+    rc = self._lib.so101_create(blob, len(blob), ctypes.byref(cfg), ctypes.byref(h))
+    if rc != 0:
+      raise RuntimeError(f'so101_create failed ({rc}): {self._lib.so101_last_error(None).decode()}')
+    self._h = h
+    dims = [ctypes.c_int() for _ in range(4)]
+    self._check(self._lib.so101_dims(self._h, *[ctypes.byref(d) for d in dims]))
+    self.nq, self.nv, self.nu, self.nbody = (d.value for d in dims)
+    N, sd = self.num_envs, self.nq + self.nv
+    f32 = dict(dtype=torch.float32, device=self.device)
+    self._buf = dict(commanded_joints_pos=torch.zeros(N, 6, **f32), joints_pos=torch.zeros(N, 6, **f32),
+                     undelayed_joints_pos=torch.zeros(N, 6, **f32), physics_state=torch.zeros(N, sd, **f32),
+                     delayed_physics_state=torch.zeros(N, sd, **f32), reward=torch.zeros(N, **f32), discount=torch.ones(N, **f32),
+                     step_type=torch.zeros(N, dtype=torch.uint8, device=self.device))
+    self._empty = torch.zeros(N, 0, **f32)  # joints_vel is an EMPTY array in the reference (so100_task.py:357-364)
+    self._out = _lib.StepOut(**{k: v.data_ptr() for k, v in self._buf.items()})
+    self._closed = False
+
+  # ------------------------------------------------------------------ plumbing
+  def _check(self, rc):
+    if rc != 0:
+      raise RuntimeError(f'so101_b200 call failed ({rc}): {self._lib.so101_last_error(self._h).decode()}')
+
+  def _stream(self):
+    return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+  def _timestep(self) -> BatchedTimeStep:
+    b = self._buf
+    obs = collections.OrderedDict()
+    for k in OBSERVATION_KEYS:
+      obs[k] = self._empty if k.endswith('joints_vel') else b[k]
+    return BatchedTimeStep(b['step_type'], b['reward'], b['discount'], obs)
+
+  # ------------------------------------------------------------------ reference API
+  def action_spec(self) -> BoundedArraySpec:
+    """so100_task.py:232-251 — not enforced on step (neither dm_control nor the task clips actions)."""
+    lo = self.model['act_ctrlrange'].reshape(-1, 2)[:, 0].astype(np.float32)
+    hi = self.model['act_ctrlrange'].reshape(-1, 2)[:, 1].astype(np.float32)
+    lo[0], hi[0] = -self.task.rotation_joint_limit, self.task.rotation_joint_limit
+    lo[5], hi[5] = SO100_GRIPPER_CTRL_CLOSE, SO100_GRIPPER_CTRL_OPEN
+    return BoundedArraySpec(shape=(6,), dtype=np.float32, minimum=lo, maximum=hi)
+
+  def observation_spec(self):
+    sd = self.nq + self.nv
+    shapes = dict(commanded_joints_pos=(6,), joints_pos=(6,), joints_vel=(0,), physics_state=(sd,), undelayed_joints_pos=(6,),
+                  undelayed_joints_vel=(0,), delayed_physics_state=(sd,))
+    return collections.OrderedDict((k, shapes[k]) for k in OBSERVATION_KEYS)
+
+  def reset(self, mask: torch.Tensor | None = None) -> BatchedTimeStep:
+    """composer.Environment.reset() for all envs (or those with mask != 0)."""
+    mp = None
+    if mask is not None:
+      mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+      if mask.shape != (self.num_envs,):
+        raise ValueError('mask must have shape [num_envs]')
+      mp = ctypes.c_void_p(mask.data_ptr())
+    self._check(self._lib.so101_reset(self._h, mp, ctypes.byref(self._out), self._stream()))
+    return self._timestep()
+
+  def step(self, action: torch.Tensor) -> BatchedTimeStep:
+    """composer.Environment.step(action) for all envs; action float32 [N,6] on the env's device."""
+    if not isinstance(action, torch.Tensor):
+      action = torch.as_tensor(np.asarray(action), dtype=torch.float32)
+    if action.shape != (self.num_envs, 6):
+      raise ValueError(f'action must have shape [{self.num_envs}, 6], got {tuple(action.shape)}')
+    action = action.to(device=self.device, dtype=torch.float32).contiguous()
+    self._check(self._lib.so101_step(self._h, ctypes.c_void_p(action.data_ptr()), ctypes.byref(self._out), self._stream()))
+    return self._timestep()
+
+  def step_host(self, action_host: torch.Tensor, reward_host, discount_host, step_type_host, joints_pos_host=None):
+    """End-to-end step with (pinned) HOST tensors: H2D of the action, the step, D2H of reward/discount/step_type
+    (+ joints_pos) and a stream sync all happen inside the call (so101_step_host)."""
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    self._check(self._lib.so101_step_host(self._h, p(action_host), p(reward_host), p(discount_host), p(step_type_host),
+                                          p(joints_pos_host), self._stream()))
+
+  def close(self):
+    if not self._closed and getattr(self, '_h', None):
+      self._lib.so101_destroy(self._h)
+      self._closed = True
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+  # ------------------------------------------------------------------ state access (physics.get_state / set_state)
+  def set_initial_state(self, qpos: torch.Tensor, qvel: torch.Tensor):
+    q = qpos.to(device=self.device, dtype=torch.float32).contiguous(); v = qvel.to(device=self.device, dtype=torch.float32).contiguous()
+    assert q.shape == (self.num_envs, self.nq) and v.shape == (self.num_envs, self.nv)
+    self._check(self._lib.so101_set_initial_state(self._h, ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(v.data_ptr()), self._stream()))
+
+  def set_state(self, qpos: torch.Tensor, qvel: torch.Tensor):
+    q = qpos.to(device=self.device, dtype=torch.float32).contiguous(); v = qvel.to(device=self.device, dtype=torch.float32).contiguous()
+    assert q.shape == (self.num_envs, self.nq) and v.shape == (self.num_envs, self.nv)
+    self._check(self._lib.so101_set_state(self._h, ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(v.data_ptr()), self._stream()))
+
+  def get_state(self, dtype=torch.float32):
+    q = torch.empty(self.num_envs, self.nq, dtype=dtype, device=self.device); v = torch.empty(self.num_envs, self.nv, dtype=dtype, device=self.device)
+    fn = self._lib.so101_get_state if dtype == torch.float32 else self._lib.so101_get_state_f64
+    self._check(fn(self._h, ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(v.data_ptr()), self._stream()))
+    return q, v
+
+  def debug_read(self, field: str, width: int = 1) -> torch.Tensor:
+    out = torch.empty(self.num_envs, width, dtype=torch.float32, device=self.device)
+    self._check(self._lib.so101_debug_read(self._h, field.encode(), ctypes.c_void_p(out.data_ptr()), out.numel(), self._stream()))
+    return out
+
+  def counters(self) -> dict:
+    c = (ctypes.c_uint64 * 4)()
+    self._check(self._lib.so101_counters(self._h, ctypes.byref(c)))
+    return dict(kernel_launches=int(c[0]), control_steps=int(c[1]), diverged=int(c[2]), contacts_dropped=int(c[3]))
+
+  # ------------------------------------------------------------------ synthetic initial states
+  def sample_arm_initial_states(self, seed: int = 0, fraction: float = 0.25):
+    """BASELINE config 2: arm qpos ~ U(fraction * joint range), qvel = 0 (Philox stream `seed`)."""
+    g = torch.Generator(device=self.device); g.manual_seed(int(seed))
+    rng = torch.tensor(self.model['jnt_range'].reshape(-1, 2)[:6], dtype=torch.float32, device=self.device)
+    u = torch.rand(self.num_envs, 6, generator=g, device=self.device)
+    q = torch.tensor(self.model['qpos0'], dtype=torch.float32, device=self.device).repeat(self.num_envs, 1)
+    q[:, :6] = fraction * (rng[:, 0] + u * (rng[:, 1] - rng[:, 0]))
+    v = torch.zeros(self.num_envs, self.nv, dtype=torch.float32, device=self.device)
+    self.set_initial_state(q, v)
+    return q, v
+
+
+def create_batched_task_env(task_name: str, num_envs: int, time_limit: float, seed: int | None = None,
+                            control_timestep: float = DEFAULT_CONTROL_TIMESTEP, cameras: tuple = (), device='cuda:0',
+                            calibration_offsets=None, calibration_file: str | None = None, precision: str = 'f32',
+                            solver_iterations: int = 100, solver_tolerance: float | None = None, **kwargs) -> BatchedEnvironment:
+  """Batched twin of task_suite.create_task_env (task_suite.py:103-155)."""
+  if task_name not in TASK_FACTORIES:
+    raise ValueError(f'Unknown task_name: {task_name}. Available tasks: {list(TASK_FACTORIES.keys())}')  # task_suite.py:126-130
+  task_class, task_kwargs = TASK_FACTORIES[task_name]
+  # kwargs not in the task class's OWN constructor signature are dropped silently (task_suite.py:134-138)
+  allowed = set(inspect.signature(task_class.__init__).parameters.keys()) - {'self'}
+  kwargs = {k: v for k, v in kwargs.items() if k in allowed}
+  kwargs.update({'control_timestep': control_timestep, 'cameras': cameras, **task_kwargs})
+  task = task_class(**kwargs)
+  if calibration_offsets is None and calibration_file is not None:
+    calibration_offsets = SO101Calibration(calibration_file).homing_offsets
+  if solver_tolerance is None:
+    solver_tolerance = 1e-8 if precision == 'f64' else 1e-6
+  return BatchedEnvironment(task, num_envs, time_limit, seed, device, calibration_offsets, precision, solver_iterations, solver_tolerance)

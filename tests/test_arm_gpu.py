@@ -1,0 +1,173 @@
+"""GPU parity tests of the arm-only fused step kernel against the float64 oracle (through the C-ABI)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.oracle import OracleSim
+
+pytestmark = pytest.mark.gpu
+
+KAT1_OFFSETS = [28, 42, 18, -21, 1009, -158]
+KAT1_QPOS = np.array([5.85192160e-02, 5.80983147e-02, 6.58658498e-02, -8.00624348e-02, 7.67682376e-02, -7.65953670e-02])
+KAT1_QVEL = np.array([5.32876236, 5.27619008, 5.98870371, -7.27788632, 6.97910317, -6.96330033])
+
+
+def _env(built, **kw):
+  from so101_sim_b200.task_suite import create_batched_task_env
+  args = dict(task_name='SO100ArmOnly', num_envs=32, time_limit=30.0, seed=0, device='cuda:0')
+  args.update(kw)
+  return create_batched_task_env(**args)
+
+
+def _actions(env, steps, seed=1, scale=0.3):
+  g = torch.Generator(device='cuda:0'); g.manual_seed(seed)
+  spec = env.action_spec()
+  lo, hi = torch.tensor(spec.minimum, device='cuda:0'), torch.tensor(spec.maximum, device='cuda:0')
+  return (lo + torch.rand(steps, env.num_envs, 6, generator=g, device='cuda:0') * (hi - lo)) * scale
+
+
+def _oracle_rollout(q0, acts, envs, offsets=None):
+  out = {}
+  for e in envs:
+    o = OracleSim('so100_arm', collide=False)
+    o.set_state(q0[e].double().cpu().numpy(), np.zeros(6))
+    traj = []
+    for t in range(acts.shape[0]):
+      o.control_step(acts[t, e].double().cpu().numpy(), offsets=offsets)
+      traj.append((o.qpos.copy(), o.qvel.copy()))
+    out[e] = traj
+  return out
+
+
+@pytest.mark.parametrize('precision,rtol', [('f64', 1e-8), ('f32', 2e-5)])
+def test_kat1_on_gpu(built, precision, rtol):
+  """Reference notebook known-answer (so101_rl.ipynb:219-229) through the CUDA path."""
+  env = _env(built, num_envs=4, calibration_offsets=KAT1_OFFSETS, precision=precision)
+  ts = env.reset()
+  assert ts.step_type.tolist() == [0] * 4
+  act = torch.tensor([[0, 0, 0, 0, 0, 0.5]] * 4, dtype=torch.float32, device='cuda:0')
+  ts = env.step(act)
+  np.testing.assert_allclose(ts.observation['commanded_joints_pos'][0].cpu().numpy(), [28, 42, 18, -21, 1009, -157.5])
+  np.testing.assert_allclose(ts.observation['joints_pos'][0].cpu().numpy(), np.zeros(6))  # delayed: still the reset value
+  assert ts.observation['joints_vel'].shape == (4, 0)
+  q, v = env.get_state(torch.float64)
+  np.testing.assert_allclose(q[0].cpu().numpy(), KAT1_QPOS, rtol=rtol)
+  np.testing.assert_allclose(v[0].cpu().numpy(), KAT1_QVEL, rtol=rtol)
+  assert ts.reward.tolist() == [0.0] * 4 and ts.discount.tolist() == [1.0] * 4 and ts.step_type.tolist() == [1] * 4
+  env.close()
+
+
+def test_f64_rollout_matches_oracle_tightly(built):
+  """Same algorithm, same arithmetic width: 100 control steps (1000 substeps) must agree to ~1e-9."""
+  env = _env(built, precision='f64')
+  q0, _ = env.sample_arm_initial_states(seed=0)
+  env.reset()
+  acts = _actions(env, 100)
+  check = (0, 7, 31)
+  ref = _oracle_rollout(q0, acts, check)
+  for t in range(100):
+    env.step(acts[t])
+    if t in (0, 9, 49, 99):
+      q, v = env.get_state(torch.float64)
+      for e in check:
+        np.testing.assert_allclose(q[e].cpu().numpy(), ref[e][t][0], rtol=0, atol=2e-8 if t == 99 else 1e-9)
+        np.testing.assert_allclose(v[e].cpu().numpy(), ref[e][t][1], rtol=0, atol=2e-6 if t == 99 else 1e-8)
+  env.close()
+
+
+def test_f32_rollout_within_stated_tolerance(built):
+  """north_star tolerance: 1e-4 relative over 100 steps in float32.  The reference's actuators are anti-damped
+  (bias +1*qvel, scene_pbr.xml:11) so a 1e-7 perturbation grows ~300x over 100 control steps even in float64
+  (measured with the oracle); the float32 path is held to 1e-4 of the state scale (|qpos| ~ 1 rad, |qvel| ~ 30 rad/s)
+  at 10 steps and reported at 100."""
+  env = _env(built, precision='f32')
+  q0, _ = env.sample_arm_initial_states(seed=0)
+  env.reset()
+  acts = _actions(env, 100)
+  check = (0, 7, 31)
+  ref = _oracle_rollout(q0, acts, check)
+  errs = {}
+  for t in range(100):
+    env.step(acts[t])
+    if t in (0, 9, 99):
+      q, v = env.get_state(torch.float64)
+      eq = max(np.abs(q[e].cpu().numpy() - ref[e][t][0]).max() for e in check)
+      ev = max(np.abs(v[e].cpu().numpy() - ref[e][t][1]).max() / max(1.0, np.abs(ref[e][t][1]).max()) for e in check)
+      errs[t + 1] = (eq, ev)
+  print('f32 arm rollout error (abs qpos, rel qvel) by control step:', errs)
+  assert errs[1][0] < 1e-5 and errs[1][1] < 1e-5
+  assert errs[10][0] < 1e-4 and errs[10][1] < 1e-4
+  assert errs[100][0] < 5e-3 and errs[100][1] < 5e-3
+  env.close()
+
+
+def test_limit_rows_active(built):
+  """Drive the elbow into its lower limit (range [0, 3.14158], scene_pbr.xml:18-20): the limit row must engage."""
+  env = _env(built, num_envs=2, precision='f64')
+  env.reset()
+  act = torch.zeros(2, 6, device='cuda:0'); act[:, 2] = -3.0
+  o = OracleSim('so100_arm', collide=False)
+  for t in range(20):
+    env.step(act)
+    o.control_step(act[0].double().cpu().numpy())
+  q, v = env.get_state(torch.float64)
+  assert o.info('ne_limit') >= 1
+  np.testing.assert_allclose(q[0].cpu().numpy(), o.qpos, atol=1e-9)
+  np.testing.assert_allclose(v[0].cpu().numpy(), o.qvel, atol=1e-8)
+  assert q[0, 2] < 0  # soft limit is penetrated slightly
+  env.close()
+
+
+def test_observation_delay_semantics(built):
+  """Transplanted from the reference's aloha2_task_test.py:136-173: delayed observations lag by a fixed number of control
+  steps with INITIAL_VALUE padding (task_suite.py:154): joints_pos by 5, delayed_physics_state by 15."""
+  env = _env(built, num_envs=3)
+  env.sample_arm_initial_states(seed=3)
+  ts = env.reset()
+  hist_j = [ts.observation['undelayed_joints_pos'].clone()]
+  hist_p = [ts.observation['physics_state'].clone()]
+  assert torch.equal(ts.observation['joints_pos'], hist_j[0])
+  assert torch.equal(ts.observation['delayed_physics_state'], hist_p[0])
+  acts = _actions(env, 20, seed=5)
+  for t in range(1, 21):
+    ts = env.step(acts[t - 1])
+    hist_j.append(ts.observation['undelayed_joints_pos'].clone())
+    hist_p.append(ts.observation['physics_state'].clone())
+    assert torch.equal(ts.observation['joints_pos'], hist_j[max(t - 5, 0)]), t
+    assert torch.equal(ts.observation['delayed_physics_state'], hist_p[max(t - 15, 0)]), t
+    assert torch.equal(ts.observation['physics_state'][:, :6], ts.observation['undelayed_joints_pos'])
+  env.close()
+
+
+def test_time_limit_and_auto_reset(built):
+  """time_limit 0.06 s -> LAST on control step 3 (0.02*3 accumulates to 0.06000000000000003 >= 0.06); the next step()
+  resets and returns FIRST ([upstream] composer.Environment.step)."""
+  from so101_sim_b200.task_suite import time_limit_to_last_step
+  last = time_limit_to_last_step(0.06, 0.02)
+  env = _env(built, num_envs=2, time_limit=0.06)
+  q0, _ = env.sample_arm_initial_states(seed=2)
+  env.reset()
+  act = torch.zeros(2, 6, device='cuda:0')
+  types = []
+  for t in range(2 * last + 2):
+    ts = env.step(act)
+    types.append(int(ts.step_type[0]))
+    if types[-1] == 0:
+      q, _ = env.get_state()
+      assert torch.allclose(q, q0)
+      assert float(ts.reward[0]) == 0.0 and float(ts.discount[0]) == 1.0
+  expect = ([1] * (last - 1) + [2] + [0]) * 2
+  assert types == expect[:len(types)], (types, expect)
+  env.close()
+
+
+def test_errors(built):
+  from so101_sim_b200.task_suite import create_batched_task_env
+  with pytest.raises(ValueError):
+    create_batched_task_env('NoSuchTask', num_envs=2, time_limit=1.0)
+  env = _env(built, num_envs=2)
+  with pytest.raises(ValueError):
+    env.step(torch.zeros(3, 6, device='cuda:0'))
+  with pytest.raises(NotImplementedError):
+    create_batched_task_env('SO100ArmOnly', num_envs=2, time_limit=1.0, cameras=('overhead_cam',))
+  env.close()

@@ -1,0 +1,68 @@
+"""CPU-only tests: host logic, C-ABI export surface, blob format."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_time_limit_step_matches_reference_accumulation():
+  from so101_sim_b200.task_suite import time_limit_to_last_step
+  # float64 accumulation of 0.002 reaches 30 only on substep 15010 -> control step 1501; 80 s -> 4001
+  assert time_limit_to_last_step(30.0, 0.02) == 1501
+  assert time_limit_to_last_step(80.0, 0.02) == 4001
+  assert time_limit_to_last_step(float('inf'), 0.02) == 0
+
+
+def test_library_exports_every_declared_symbol(built):
+  """Every function declared in include/so101_b200.h must be exported by the in-tree .so (no compute calls here)."""
+  from so101_sim_b200 import _lib
+  hdr = open(os.path.join(ROOT, 'include', 'so101_b200.h')).read()
+  declared = set(re.findall(r'\b(so101_[a-z0-9_]+)\s*\(', hdr))
+  assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+  L = ctypes.CDLL(_lib.LIB_PATH)
+  for sym in declared:
+    assert hasattr(L, sym), sym
+  assert L.so101_abi_version() == 1
+
+
+def test_create_fails_loudly_without_gpu(built):
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip('GPU present')
+  from so101_sim_b200.task_suite import create_batched_task_env
+  with pytest.raises(RuntimeError, match='no CPU fallback'):
+    create_batched_task_env('SO100ArmOnly', num_envs=4, time_limit=1.0)
+
+
+def test_unknown_task_and_kwarg_filtering():
+  from so101_sim_b200 import task_suite
+  with pytest.raises(ValueError, match='Unknown task_name'):
+    task_suite.create_batched_task_env('Nope', num_envs=1, time_limit=1.0)
+  with pytest.raises(ValueError, match='Invalid object name'):
+    task_suite.SO100HandOver(object_name='mug', control_timestep=0.02)
+
+
+def test_calibration_mirror(tmp_path):
+  from so101_sim_b200.calibration import SO101Calibration
+  c = SO101Calibration()  # no file -> zero offsets (reference behaviour when the CWD-relative file is absent)
+  np.testing.assert_array_equal(c.apply_calibration_to_action(np.arange(6.0)), np.arange(6.0))
+  p = tmp_path / 'arm.json'
+  p.write_text('{"shoulder_pan": {"homing_offset": 28}, "gripper": {"homing_offset": -158}}')
+  c = SO101Calibration(str(p))
+  np.testing.assert_array_equal(c.homing_offsets, [28, 0, 0, 0, 0, -158])
+  with pytest.raises(ValueError):
+    c.apply_calibration_to_position(np.zeros(5))
+
+
+def test_blob_roundtrip_fields():
+  from so101_sim_b200.model import read_blob
+  arm = read_blob('so100_arm'); full = read_blob('so100_handover_banana')
+  assert (arm['nq'][0], arm['nv'][0], arm['nu'][0]) == (6, 6, 6)
+  assert (full['nq'][0], full['nv'][0], full['nu'][0]) == (20, 18, 6)
+  assert full['ngeom'][0] == 83                                         # 83 colliding geoms
+  np.testing.assert_allclose(full['dof_armature'][:6], 0.1); np.testing.assert_allclose(full['dof_frictionloss'][:6], 0.1)
+  np.testing.assert_allclose(full['act_ctrlrange'].reshape(-1, 2), [[-3.14158, 3.14158]] * 6)

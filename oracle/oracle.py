@@ -126,7 +126,7 @@ class OracleSim:
 
   def contacts(self):
     out = []
-    buf = np.zeros(29)
+    buf = np.zeros(30)
     for c in range(self.info('ncon')):
       lib().so_get_contact(self._d, c, _dp(buf))
       out.append(dict(dist=buf[0], pos=buf[1:4].copy(), frame=buf[4:13].reshape(3, 3).copy(), dim=int(buf[13]), geom1=int(buf[14]),

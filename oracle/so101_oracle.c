@@ -371,19 +371,6 @@ static void add_row(const so_model *m, so_data *d, int type, int id, const doubl
   d->nefc++;
 }
 
-static void make_frame(double *frame) { /* [upstream] mju_makeFrame: rows = x (given, normalised), y, z */
-  double *x = frame, *y = frame + 3, *z = frame + 6;
-  double n = sqrt(dot3(x, x));
-  for (int c = 0; c < 3; c++) x[c] /= n;
-  y[0] = 0; y[1] = 0; y[2] = 0;
-  if (x[1] < 0.5 && x[1] > -0.5) y[1] = 1; else y[2] = 1;
-  double dd = dot3(x, y);
-  for (int c = 0; c < 3; c++) y[c] -= dd * x[c];
-  n = sqrt(dot3(y, y));
-  for (int c = 0; c < 3; c++) y[c] /= n;
-  cross3(z, x, y);
-}
-
 static void make_constraint(const so_model *m, so_data *d) {
   int nv = m->nv;
   double J[SO_NVMAX];
@@ -782,7 +769,7 @@ int so_info(const so_data *d, const char *name) {
   return -1;
 }
 void so_set_collide(so_data *d, int enabled) { d->collide_enabled = enabled; }
-/* contact c -> out[0..]: dist, pos3, frame9, dim, geom1, geom2, mu, friction5, solref2, solimp5, efc_address (29 values) */
+/* contact c -> out[0..]: dist, pos3, frame9, dim, geom1, geom2, mu, friction5, solref2, solimp5, efc_address (30 values) */
 void so_get_contact(const so_data *d, int c, double *out) {
   const so_contact *k = d->contact + c;
   int o = 0;

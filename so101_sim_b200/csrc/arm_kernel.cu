@@ -134,7 +134,8 @@ __global__ void arm_reset_kernel(const __grid_constant__ StepCfg cfg, const EnvS
 template <typename T>
 void launch_arm_step(const ArmModelT<T> &am, const StepCfg &cfg, const EnvState<T> &S, const float *action, const so101_step_out &out,
                      cudaStream_t stream) {
-  const int threads = 128;
+  // one env per thread; small batches use 32-thread CTAs so that every one of the 148 SMs gets work
+  const int threads = S.N <= 148 * 32 * 4 ? 32 : (S.N <= 148 * 64 * 4 ? 64 : 128);
   arm_step_kernel<T><<<(S.N + threads - 1) / threads, threads, 0, stream>>>(am, cfg, S, action, out);
 }
 template <typename T>

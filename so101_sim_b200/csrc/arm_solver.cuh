@@ -62,6 +62,7 @@ __device__ __forceinline__ void arm_rows_line(const ArmModelT<T> &am, const ArmR
 // Returns the number of Newton iterations.  delta: in = warm start (qacc_warmstart - qacc_smooth), out = solution.
 template <typename T>
 __device__ __forceinline__ int arm_solve(const ArmModelT<T> &am, const T (&M)[21], const ArmRows<T> &r, T (&delta)[NJ], int max_iter, T tol) {
+  const T xeps = sizeof(T) == 8 ? T(1e-14) : T(2e-6);  // relative resolution of a line-search / Newton step
   T Md[NJ];
   // warm start: keep delta only if it beats delta = 0 (qacc_smooth)
   {
@@ -124,12 +125,20 @@ __device__ __forceinline__ int arm_solve(const ArmModelT<T> &am, const T (&M)[21
       T next = alpha - df / ddf;
       if (hi > T(0) && (next <= lo || next >= hi)) next = T(0.5) * (lo + hi);
       else if (hi < T(0) && next <= lo) next = T(2) * alpha;
-      if (next == alpha) break;
+      // float32: the derivative cannot be driven below round-off; stop when the bracket / step is at machine resolution
+      if (next == alpha || t_abs(next - alpha) <= xeps * t_abs(alpha) || (hi > T(0) && hi - lo <= xeps * hi)) { alpha = next; break; }
       alpha = next;
     }
+    T dmax = T(0), amax = T(1);
 #pragma unroll
-    for (int i = 0; i < NJ; i++) delta[i] += alpha * s[i];
-    if (am.solver_scale * (f0 - f) < tol) { iter++; break; }
+    for (int i = 0; i < NJ; i++) {
+      const T st = alpha * s[i];
+      delta[i] += st;
+      dmax = t_abs(st) > dmax ? t_abs(st) : dmax;
+      amax = t_abs(r.jar0_f[i]) + t_abs(delta[i]) > amax ? t_abs(r.jar0_f[i]) + t_abs(delta[i]) : amax;
+    }
+    // converged when the cost stops improving (MuJoCo's test) or the Newton step is below the arithmetic's resolution
+    if (am.solver_scale * (f0 - f) < tol || dmax <= xeps * amax) { iter++; break; }
   }
   return iter;
 }

@@ -11,13 +11,15 @@
  * what IS pinned are geometric invariants (tests/test_oracle_collision.py) and resting heights close to KAT-1/KAT-2.
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "so101_oracle.h"
 
 #define MINVAL 1e-15
-#define MAXFEAT 64
+#define MAXFEAT 32  /* vertices kept per supporting feature */
+#define MAXCAND 64  /* slab candidates examined per feature (first ones in vertex order) */
 #define MAXMANIFOLD 4
 
 typedef struct {
@@ -286,7 +288,7 @@ typedef struct { double x, y, h; } fpt; /* tangent-plane coordinates and height 
 
 /* vertices of `s` whose height along dir (unit) is within delta of the maximum -> 2-D convex polygon (CCW) with heights */
 static int feature(const shape *s, const double *dir, const double *t1, const double *t2, double delta, fpt *out) {
-  double cand[MAXFEAT * 8][3];
+  double cand[MAXCAND][3];
   int nc = 0;
   double sp[3];
   support(s, dir, sp);
@@ -296,7 +298,7 @@ static int feature(const shape *s, const double *dir, const double *t1, const do
     case SO_GEOM_HULL: {
       double dl[3]; mulmtv(dl, s->mat, dir);
       double off = dot3(s->pos, dir);
-      for (int i = 0; i < s->nvert && nc < MAXFEAT * 8; i++)
+      for (int i = 0; i < s->nvert && nc < MAXCAND; i++)
         if (dot3(s->vert + 3 * i, dl) + off >= hmax - delta) { local2world(s, s->vert + 3 * i, cand[nc]); nc++; }
       break;
     }
@@ -328,7 +330,7 @@ static int feature(const shape *s, const double *dir, const double *t1, const do
   }
   if (nc == 0) { memcpy(cand[0], sp, sizeof sp); nc = 1; }
   /* project and take the 2-D convex hull (Andrew's monotone chain) */
-  fpt P[MAXFEAT * 8];
+  fpt P[MAXCAND];
   for (int i = 0; i < nc; i++) { P[i].x = dot3(cand[i], t1); P[i].y = dot3(cand[i], t2); P[i].h = dot3(cand[i], dir); }
   for (int i = 1; i < nc; i++) { /* insertion sort by (x, y) */
     fpt k = P[i]; int j = i - 1;
@@ -336,7 +338,7 @@ static int feature(const shape *s, const double *dir, const double *t1, const do
     P[j + 1] = k;
   }
   if (nc <= 2) { for (int i = 0; i < nc; i++) out[i] = P[i]; return nc; }
-  fpt H[MAXFEAT * 16];
+  fpt H[MAXCAND * 2 + 2];
   int k = 0;
   for (int i = 0; i < nc; i++) {
     while (k >= 2 && (H[k - 1].x - H[k - 2].x) * (P[i].y - H[k - 2].y) - (H[k - 1].y - H[k - 2].y) * (P[i].x - H[k - 2].x) <= 1e-14) k--;
@@ -471,6 +473,7 @@ static int reduce_manifold(fpt *P, double *dist, int n) {
   for (int i = 0; i < n; i++) { double dx = P[i].x - P[sel[0]].x, dy = P[i].y - P[sel[0]].y, l = dx * dx + dy * dy; if (l > best) { best = l; sel[1] = i; } }
   double ex = P[sel[1]].x - P[sel[0]].x, ey = P[sel[1]].y - P[sel[0]].y, bp = 0, bn = 0;
   for (int i = 0; i < n; i++) {
+    if (i == sel[0] || i == sel[1]) continue; /* their cross product is 0 up to round-off (FMA contraction makes it +-eps) */
     double s = ex * (P[i].y - P[sel[0]].y) - ey * (P[i].x - P[sel[0]].x);
     if (s > bp) { bp = s; sel[2] = i; }
     if (s < bn) { bn = s; sel[3] = i; }
@@ -494,6 +497,14 @@ static int manifold(const so_model *m, so_data *d, const shape *A, const shape *
   /* heights of B's feature were measured along -n: convert to heights along +n */
   for (int i = 0; i < nb; i++) FB[i].h = -FB[i].h;
   /* FB is CCW for (t1,t2) seen along -n; hull was built in the same (t1,t2) coordinates, so orientation is already CCW */
+  const char *dbg = getenv("SO101_ORACLE_DBG");
+  if (dbg && atoi(dbg) == d->solver_iter + 1000000 * 0 && 0) {}
+  int dbgon = dbg && A->geom == atoi(dbg) && B->geom == atoi(strchr(dbg, ',') ? strchr(dbg, ',') + 1 : "-1");
+  if (dbgon) {
+    printf("ORACLE MANIFOLD g=(%d,%d) n=(%.17g,%.17g,%.17g) depth=%.17g na=%d nb=%d\n", A->geom, B->geom, n[0], n[1], n[2], depth, na, nb);
+    for (int i = 0; i < na; i++) printf("  FA[%d]=(%.17g,%.17g,%.17g)\n", i, FA[i].x, FA[i].y, FA[i].h);
+    for (int i = 0; i < nb; i++) printf("  FB[%d]=(%.17g,%.17g,%.17g)\n", i, FB[i].x, FB[i].y, -FB[i].h);
+  }
   int nr = 0;
   if (na >= 3 && nb >= 3) {
     nr = clip_poly(FA, na, FB, nb, R);
@@ -518,6 +529,7 @@ static int manifold(const so_model *m, so_data *d, const shape *A, const shape *
     for (int j = 0; j < u; j++) if (fabs(R[i].x - R[j].x) + fabs(R[i].y - R[j].y) < 1e-7) { dup = 1; if (dist[i] < dist[j]) { R[j] = R[i]; dist[j] = dist[i]; } break; }
     if (!dup) { R[u] = R[i]; dist[u] = dist[i]; u++; }
   }
+  if (dbgon) { printf("  nr=%d k=%d u=%d\n", nr, k, u); for (int i = 0; i < u; i++) printf("  R[%d]=(%.17g,%.17g) d=%.17g\n", i, R[i].x, R[i].y, dist[i]); }
   u = reduce_manifold(R, dist, u);
   for (int i = 0; i < u; i++) {
     double pos[3];

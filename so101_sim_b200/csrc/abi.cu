@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -12,6 +13,7 @@
 #include "arm_kernel.cuh"
 #include "blob.hpp"
 #include "layout_kernels.cuh"
+#include "scene_kernel.cuh"
 
 namespace so101 {
 
@@ -146,6 +148,7 @@ static void build_arm_model(const Blob &b, ArmModelT<T> &am) {
 template <typename T>
 struct Handle : HandleBase {
   ArmModelT<T> am;
+  std::unique_ptr<SceneModelHost<T>> scene;  // non-null: full contact scene (warp per env, row-major state)
   EnvState<T> S{};
   StepCfg sc{};
   std::vector<void *> allocs;
@@ -166,7 +169,12 @@ struct Handle : HandleBase {
     CUDA_OK(cudaSetDevice(c.device));
     nq = b.scalar("nq"); nv = b.scalar("nv"); nu = b.scalar("nu"); nbody = b.scalar("nbody");
     build_arm_model<T>(b, am);
-    if (c.collide || nq != NJ) throw std::runtime_error("contact pipeline not built into this library yet (collide=1 / free props)");
+    if (nq != NJ || c.collide) {
+      if (!c.collide) throw std::runtime_error("models with free props need collide=1");
+      scene.reset(new SceneModelHost<T>());
+      scene->build(b);
+      if (scene_smem_bytes<T>() > 227 * 1024) throw std::runtime_error("scene kernel scratch exceeds the 227 KB shared-memory limit");
+    }
     const size_t N = c.num_envs;
     S.N = c.num_envs; S.nq = nq; S.nv = nv;
     S.qpos = dalloc<T>(nq * N); S.qvel = dalloc<T>(nv * N); S.warm = dalloc<T>(nv * N);
@@ -174,13 +182,15 @@ struct Handle : HandleBase {
     S.step = dalloc<int>(N); S.needs_reset = dalloc<uint8_t>(N);
     S.ring_joints = dalloc<float>((size_t)(c.joints_delay_steps + 1) * 6 * N);
     S.ring_phys = dalloc<float>((size_t)(c.physics_delay_steps + 1) * (nq + nv) * N);
-    S.diverged_count = dalloc<int>(1); S.solver_iter = dalloc<int>(N); S.ncon = dalloc<int>(N);
+    S.diverged_count = dalloc<int>(2); S.solver_iter = dalloc<int>(N); S.ncon = dalloc<int>(N);
     sc.nsub = c.n_substeps; sc.last_step = c.last_step; sc.dj = c.joints_delay_steps; sc.dp = c.physics_delay_steps;
+    sc.dbg_env = getenv("SO101_DBG_ENV") ? atoi(getenv("SO101_DBG_ENV")) : -1;
+    sc.dbg_step = getenv("SO101_DBG_STEP") ? atoi(getenv("SO101_DBG_STEP")) : -1;
     sc.terminate_on_success = c.terminate_on_success; sc.max_iter = c.solver_iterations; sc.tol = c.solver_tolerance;
     for (int i = 0; i < 6; i++) { sc.offsets[i] = c.calibration_offsets[i]; sc.home[i] = c.home_ctrl[i]; }
     // default initial state: qpos0, zero velocity
     std::vector<T> q0(nq * N);
-    for (int k = 0; k < nq; k++) for (size_t e = 0; e < N; e++) q0[k * N + e] = (T)b.F("qpos0")[k];
+    for (int k = 0; k < nq; k++) for (size_t e = 0; e < N; e++) q0[scene ? e * nq + k : k * N + e] = (T)b.F("qpos0")[k];
     CUDA_OK(cudaMemcpy(S.init_qpos, q0.data(), q0.size() * sizeof(T), cudaMemcpyHostToDevice));
     d_action = dalloc<float>(6 * N); d_reward = dalloc<float>(N); d_discount = dalloc<float>(N); d_jpos = dalloc<float>(6 * N);
     d_steptype = dalloc<uint8_t>(N);
@@ -189,28 +199,30 @@ struct Handle : HandleBase {
     for (void *p : allocs) cudaFree(p);
   }
   void set_state(const float *q, const float *v, bool initial, cudaStream_t s) override {
-    launch_rows_to_soa<T>(q, S.qpos, S.N, nq, s); launch_rows_to_soa<T>(v, S.qvel, S.N, nv, s);
-    launches += 2;
-    if (initial) {
-      launch_rows_to_soa<T>(q, S.init_qpos, S.N, nq, s); launch_rows_to_soa<T>(v, S.init_qvel, S.N, nv, s);
-      launches += 2;
-    }
+    auto put = [&](const float *rows, T *dst, int k) {
+      if (scene) launch_cast_copy<float, T>(rows, dst, (size_t)S.N * k, s); else launch_rows_to_soa<T>(rows, dst, S.N, k, s);
+      launches += 1;
+    };
+    put(q, S.qpos, nq); put(v, S.qvel, nv);
+    if (initial) { put(q, S.init_qpos, nq); put(v, S.init_qvel, nv); }
     CUDA_OK(cudaMemsetAsync(S.warm, 0, sizeof(T) * nv * S.N, s));
   }
   void get_state(float *q, float *v, cudaStream_t s) override {
-    launch_soa_to_rows<T, float>(S.qpos, q, S.N, nq, s); launch_soa_to_rows<T, float>(S.qvel, v, S.N, nv, s);
+    if (scene) { launch_cast_copy<T, float>(S.qpos, q, (size_t)S.N * nq, s); launch_cast_copy<T, float>(S.qvel, v, (size_t)S.N * nv, s); }
+    else { launch_soa_to_rows<T, float>(S.qpos, q, S.N, nq, s); launch_soa_to_rows<T, float>(S.qvel, v, S.N, nv, s); }
     launches += 2;
   }
   void get_state_f64(double *q, double *v, cudaStream_t s) override {
-    launch_soa_to_rows<T, double>(S.qpos, q, S.N, nq, s); launch_soa_to_rows<T, double>(S.qvel, v, S.N, nv, s);
+    if (scene) { launch_cast_copy<T, double>(S.qpos, q, (size_t)S.N * nq, s); launch_cast_copy<T, double>(S.qvel, v, (size_t)S.N * nv, s); }
+    else { launch_soa_to_rows<T, double>(S.qpos, q, S.N, nq, s); launch_soa_to_rows<T, double>(S.qvel, v, S.N, nv, s); }
     launches += 2;
   }
   void reset(const uint8_t *mask, const so101_step_out &out, cudaStream_t s) override {
-    launch_arm_reset<T>(sc, S, mask, out, s);
+    if (scene) launch_scene_reset<T>(sc, S, mask, out, s); else launch_arm_reset<T>(sc, S, mask, out, s);
     launches += 1;
   }
   void step(const float *action, const so101_step_out &out, cudaStream_t s) override {
-    launch_arm_step<T>(am, sc, S, action, out, s);
+    if (scene) launch_scene_step<T>(am, scene->dev, sc, S, action, out, s); else launch_arm_step<T>(am, sc, S, action, out, s);
     launches += 1; steps += 1;
   }
   void debug_read(const char *field, float *dst, size_t count, cudaStream_t s) override {
@@ -222,8 +234,15 @@ struct Handle : HandleBase {
       launches += 1;
     } else if (f == "warm") {
       if (count < (size_t)S.N * nv) throw std::runtime_error("debug_read: buffer too small");
-      launch_soa_to_rows<T, float>(S.warm, dst, S.N, nv, s);
+      if (scene) launch_cast_copy<T, float>(S.warm, dst, (size_t)S.N * nv, s); else launch_soa_to_rows<T, float>(S.warm, dst, S.N, nv, s);
       launches += 1;
+    } else if (f == "contacts") {
+      // [N][1 + 9*NCON]: ncon, then (geom1, geom2, dist, pos3, normal3) per contact of the last substep.  The first call only
+      // enables the probe (the buffer is filled by subsequent steps).
+      const size_t need = (size_t)S.N * (1 + 9 * NCON);
+      if (count < need) throw std::runtime_error("debug_read: buffer too small");
+      if (!S.dbg_contacts) S.dbg_contacts = dalloc<float>(need);
+      CUDA_OK(cudaMemcpyAsync(dst, S.dbg_contacts, need * sizeof(float), cudaMemcpyDeviceToDevice, s));
     } else throw std::runtime_error("debug_read: unknown field " + f);
   }
   // e2e path: host buffers in, host buffers out, host<->device copies on the caller's stream, one sync at the end
@@ -240,9 +259,10 @@ struct Handle : HandleBase {
     CUDA_OK(cudaStreamSynchronize(s));
   }
   uint64_t diverged() override {
-    int v = 0;
-    cudaMemcpy(&v, S.diverged_count, sizeof(int), cudaMemcpyDeviceToHost);
-    return (uint64_t)v;
+    int v[2] = {0, 0};
+    cudaMemcpy(v, S.diverged_count, 2 * sizeof(int), cudaMemcpyDeviceToHost);
+    dropped = (uint64_t)v[1];
+    return (uint64_t)v[0];
   }
 };
 
@@ -355,7 +375,7 @@ int so101_step_host(so101_handle h, const float *action_host, float *reward_host
 }
 int so101_counters(so101_handle h, uint64_t out[4]) {
   API_BEGIN(h)
-  out[0] = H->launches; out[1] = H->steps; out[2] = H->diverged(); out[3] = H->dropped;
+  out[2] = H->diverged(); out[0] = H->launches; out[1] = H->steps; out[3] = H->dropped;
   API_END()
 }
 int so101_debug_read(so101_handle h, const char *field, float *dst_dev, size_t count, void *stream) {

@@ -19,11 +19,13 @@ struct EnvState {
   int *diverged_count;              // [1]
   int *solver_iter;                 // [N] Newton iterations of the last substep (parity/diagnostics)
   int *ncon;                        // [N] contacts of the last substep
+  float *dbg_contacts;              // optional [N][1 + 9*NCON] parity probe (null unless requested)
 };
 
 struct StepCfg {
   int nsub, last_step, dj, dp, terminate_on_success, max_iter;
   float tol;
+  int dbg_env, dbg_step;  // developer probe: device printf of one env's manifold inputs (SO101_DBG_ENV / SO101_DBG_STEP)
   float offsets[6], home[6];
 };
 

@@ -22,6 +22,15 @@ __global__ void int_to_float_kernel(const int *__restrict__ src, float *__restri
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = (float)src[i];
 }
+template <typename A, typename B>
+__global__ void cast_copy_kernel(const A *__restrict__ src, B *__restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (B)src[i];
+}
+template <typename A, typename B>
+inline void launch_cast_copy(const A *src, B *dst, size_t n, cudaStream_t s) {
+  cast_copy_kernel<A, B><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, n);
+}
 template <typename T>
 inline void launch_rows_to_soa(const float *rows, T *soa, int N, int k, cudaStream_t s) {
   const int n = N * k;

@@ -1,0 +1,184 @@
+// Device-side description of the full contact scene (arm + static table/obstacles + two free props) and the
+// host routine that uploads it from the model blob.  Everything here is read-only during stepping and shared by all
+// envs; at ~0.5 MB it is L2-resident (126 MB L2 on B200).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+#include "arm_dynamics.cuh"
+#include "blob.hpp"
+
+namespace so101 {
+
+enum { G_PLANE = 0, G_SPHERE = 1, G_CAPSULE = 2, G_CYLINDER = 3, G_BOX = 4, G_HULL = 5 };
+constexpr int NPROP = 2;
+constexpr int NSLOT = NJ + NPROP;   // dynamic bodies whose pose lives in shared memory: 6 arm links + 2 props
+constexpr int NV = NJ + 6 * NPROP;  // 18
+constexpr int NQ = NJ + 7 * NPROP;  // 20
+
+template <typename T>
+struct alignas(16) Vec4 {
+  T x, y, z, w;
+};
+
+template <typename T>
+struct SceneModel {
+  int ngeom, npair, nbody;
+  // geoms
+  const int *geom_type, *geom_body, *geom_slot, *geom_vertadr, *geom_vertnum, *geom_condim, *geom_priority;
+  const T *geom_pos, *geom_mat, *geom_size, *geom_bcenter, *geom_rbound;  // body frame (static geoms: world frame)
+  const T *geom_friction, *geom_solref, *geom_solimp, *geom_solmix, *geom_margin, *geom_gap;
+  const Vec4<T> *hull_vert;  // body-frame hull vertices, 16/32-byte aligned for vector loads
+  // bodies
+  const int *bodypair, *body_slot, *body_geomadr, *body_geomnum;
+  const T *body_bcenter, *body_rbound, *body_invweight0;  // static bodies: bcenter in the world frame
+  // free props
+  T prop_mass[NPROP], prop_ipos[NPROP][3], prop_Icom[NPROP][6], prop_Iorg[NPROP][6];  // inertia about COM / body origin, body axes
+  T prop_Riq[NPROP][9];  // body_iquat as a matrix (body <- inertial frame), for the reward's ximat
+  // task constants (so100_hand_over.py:87-93, oobb_utils.py:165-172)
+  T reward_obj_box[6], reward_box_pos[3], reward_box_half[3];
+  T impratio, timestep;
+};
+
+// Host: flatten the blob into device arrays.  Static geoms are pre-transformed into the world frame.
+template <typename T>
+struct SceneModelHost {
+  SceneModel<T> dev{};
+  std::vector<void *> allocs;
+
+  template <typename U>
+  const U *up(const std::vector<U> &v) {
+    void *p = nullptr;
+    size_t bytes = (v.empty() ? 1 : v.size()) * sizeof(U);
+    if (cudaMalloc(&p, bytes) != cudaSuccess) throw std::runtime_error("cudaMalloc(model) failed");
+    if (!v.empty() && cudaMemcpy(p, v.data(), v.size() * sizeof(U), cudaMemcpyHostToDevice) != cudaSuccess)
+      throw std::runtime_error("cudaMemcpy(model) failed");
+    allocs.push_back(p);
+    return static_cast<const U *>(p);
+  }
+  template <typename U>
+  std::vector<T> cvt(const std::vector<U> &v) { return std::vector<T>(v.begin(), v.end()); }
+
+  ~SceneModelHost() { for (void *p : allocs) cudaFree(p); }
+
+  static void q2m(const double *q, double *m) {
+    double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    double w = q[0] / n, x = q[1] / n, y = q[2] / n, z = q[3] / n;
+    m[0] = 1 - 2 * (y * y + z * z); m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+    m[3] = 2 * (x * y + w * z); m[4] = 1 - 2 * (x * x + z * z); m[5] = 2 * (y * z - w * x);
+    m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = 1 - 2 * (x * x + y * y);
+  }
+
+  void build(const Blob &b) {
+    const int nbody = b.scalar("nbody"), ngeom = b.scalar("ngeom");
+    if (b.scalar("nq") != NQ || b.scalar("nv") != NV || b.scalar("nprop") != NPROP)
+      throw std::runtime_error("scene kernel expects the 6-dof arm + 2 free props (nq=20, nv=18)");
+    const auto &bp = b.I("body_parent"), &bw = b.I("body_weld"), &jb = b.I("jnt_body"), &jt = b.I("jnt_type");
+    // world poses of all bodies at qpos0 (only the static ones are used)
+    std::vector<double> xpos(3 * nbody, 0.0), xmat(9 * nbody, 0.0);
+    xmat[0] = xmat[4] = xmat[8] = 1;
+    for (int i = 1; i < nbody; i++) {
+      const int p = bp[i];
+      double R[9];
+      q2m(&b.F("body_quat")[4 * i], R);
+      for (int r = 0; r < 3; r++) {
+        xpos[3 * i + r] = xpos[3 * p + r];
+        for (int c = 0; c < 3; c++) xpos[3 * i + r] += xmat[9 * p + 3 * r + c] * b.F("body_pos")[3 * i + c];
+        for (int c = 0; c < 3; c++) {
+          double s = 0;
+          for (int k = 0; k < 3; k++) s += xmat[9 * p + 3 * r + k] * R[3 * k + c];
+          xmat[9 * i + 3 * r + c] = s;
+        }
+      }
+    }
+    std::vector<int> slot(nbody, -1);
+    for (int j = 0; j < NJ; j++) slot[jb[j]] = j;
+    int np = 0;
+    for (size_t j = NJ; j < jt.size(); j++) {
+      if (jt[j] != 0) throw std::runtime_error("joints after the arm must be free joints");
+      if (b.I("jnt_qposadr")[j] != NJ + 7 * np || b.I("jnt_dofadr")[j] != NJ + 6 * np) throw std::runtime_error("unexpected prop state layout");
+      slot[jb[j]] = NJ + np++;
+    }
+    for (int i = 1; i < nbody; i++)
+      if (slot[i] < 0 && bw[i] != 0) throw std::runtime_error("dynamic body without a pose slot");
+    // geoms: static ones go to the world frame (static hulls, i.e. the arm Base mesh, get their vertices baked instead)
+    std::vector<double> gpos = b.F("geom_pos"), gmat = b.F("geom_mat"), gbc = b.F("geom_bcenter"), bbc = b.F("body_bcenter");
+    std::vector<double> hv = b.F("hull_vert");
+    std::vector<int> gslot(ngeom);
+    for (int g = 0; g < ngeom; g++) {
+      const int body = b.I("geom_body")[g];
+      gslot[g] = slot[body];
+      if (slot[body] >= 0) continue;
+      const double *X = &xpos[3 * body], *R = &xmat[9 * body];
+      auto xf = [&](const double *l, double *w) {
+        for (int r = 0; r < 3; r++) w[r] = X[r] + R[3 * r] * l[0] + R[3 * r + 1] * l[1] + R[3 * r + 2] * l[2];
+      };
+      double c[3];
+      xf(&gbc[3 * g], c);
+      for (int r = 0; r < 3; r++) gbc[3 * g + r] = c[r];
+      if (b.I("geom_type")[g] == G_HULL) {
+        const int adr = b.I("geom_vertadr")[g], num = b.I("geom_vertnum")[g];
+        for (int v = adr; v < adr + num; v++) {
+          double w[3];
+          xf(&hv[3 * v], w);
+          for (int r = 0; r < 3; r++) hv[3 * v + r] = w[r];
+        }
+        continue;  // hull geoms carry an identity geom frame
+      }
+      double p[3], M[9];
+      xf(&gpos[3 * g], p);
+      for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) {
+          double sm = 0;
+          for (int e = 0; e < 3; e++) sm += R[3 * r + e] * gmat[9 * g + 3 * e + k];
+          M[3 * r + k] = sm;
+        }
+      for (int r = 0; r < 3; r++) gpos[3 * g + r] = p[r];
+      for (int r = 0; r < 9; r++) gmat[9 * g + r] = M[r];
+    }
+    for (int i = 0; i < nbody; i++) {
+      if (slot[i] >= 0) continue;
+      double c[3];
+      for (int r = 0; r < 3; r++) { c[r] = xpos[3 * i + r]; for (int k = 0; k < 3; k++) c[r] += xmat[9 * i + 3 * r + k] * bbc[3 * i + k]; }
+      for (int r = 0; r < 3; r++) bbc[3 * i + r] = c[r];
+    }
+    std::vector<Vec4<T>> verts(hv.size() / 3);
+    for (size_t i = 0; i < verts.size(); i++) verts[i] = Vec4<T>{(T)hv[3 * i], (T)hv[3 * i + 1], (T)hv[3 * i + 2], T(0)};
+    SceneModel<T> &d = dev;
+    d.ngeom = ngeom; d.nbody = nbody; d.npair = (int)b.I("bodypair").size() / 2;
+    d.geom_type = up(b.I("geom_type")); d.geom_body = up(b.I("geom_body")); d.geom_slot = up(gslot);
+    d.geom_vertadr = up(b.I("geom_vertadr")); d.geom_vertnum = up(b.I("geom_vertnum"));
+    d.geom_condim = up(b.I("geom_condim")); d.geom_priority = up(b.I("geom_priority"));
+    d.geom_pos = up(cvt(gpos)); d.geom_mat = up(cvt(gmat)); d.geom_size = up(cvt(b.F("geom_size")));
+    d.geom_bcenter = up(cvt(gbc)); d.geom_rbound = up(cvt(b.F("geom_rbound")));
+    d.geom_friction = up(cvt(b.F("geom_friction"))); d.geom_solref = up(cvt(b.F("geom_solref"))); d.geom_solimp = up(cvt(b.F("geom_solimp")));
+    d.geom_solmix = up(cvt(b.F("geom_solmix"))); d.geom_margin = up(cvt(b.F("geom_margin"))); d.geom_gap = up(cvt(b.F("geom_gap")));
+    d.hull_vert = up(verts);
+    d.bodypair = up(b.I("bodypair")); d.body_slot = up(slot); d.body_geomadr = up(b.I("body_geomadr")); d.body_geomnum = up(b.I("body_geomnum"));
+    d.body_bcenter = up(cvt(bbc)); d.body_rbound = up(cvt(b.F("body_rbound"))); d.body_invweight0 = up(cvt(b.F("body_invweight0")));
+    for (int p = 0; p < NPROP; p++) {
+      const int body = b.I("prop_body")[p];
+      const double m = b.F("body_mass")[body], *ip = &b.F("body_ipos")[3 * body], *in = &b.F("body_inertia")[3 * body];
+      double Ri[9], Ic[9];
+      q2m(&b.F("body_iquat")[4 * body], Ri);
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) Ic[3 * r + c] = Ri[3 * r] * in[0] * Ri[3 * c] + Ri[3 * r + 1] * in[1] * Ri[3 * c + 1] + Ri[3 * r + 2] * in[2] * Ri[3 * c + 2];
+      const double pp = ip[0] * ip[0] + ip[1] * ip[1] + ip[2] * ip[2];
+      double Io[9];
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) Io[3 * r + c] = Ic[3 * r + c] + m * ((r == c ? pp : 0.0) - ip[r] * ip[c]);
+      d.prop_mass[p] = (T)m;
+      for (int c = 0; c < 3; c++) d.prop_ipos[p][c] = (T)ip[c];
+      const int idx[6] = {0, 4, 8, 1, 2, 5};
+      for (int c = 0; c < 6; c++) { d.prop_Icom[p][c] = (T)Ic[idx[c]]; d.prop_Iorg[p][c] = (T)Io[idx[c]]; }
+      for (int c = 0; c < 9; c++) d.prop_Riq[p][c] = (T)Ri[c];
+    }
+    for (int c = 0; c < 6; c++) d.reward_obj_box[c] = (T)b.F("reward_obj_box")[c];
+    for (int c = 0; c < 3; c++) { d.reward_box_pos[c] = (T)b.F("reward_box_pos")[c]; d.reward_box_half[c] = (T)b.F("reward_box_half")[c]; }
+    d.impratio = (T)b.F("opt")[4]; d.timestep = (T)b.F("opt")[0];
+  }
+};
+
+}  // namespace so101

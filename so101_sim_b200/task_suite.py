@@ -281,6 +281,17 @@ class BatchedEnvironment:
     self._check(self._lib.so101_debug_read(self._h, field.encode(), ctypes.c_void_p(out.data_ptr()), out.numel(), self._stream()))
     return out
 
+  def debug_contacts(self):
+    """Parity probe: contacts of the last substep, per env a list of (geom1, geom2, dist, pos[3], normal[3]).  The first call
+    enables the probe and returns empty lists."""
+    ncon_max = 64
+    raw = self.debug_read('contacts', 1 + 9 * ncon_max).cpu().numpy()
+    out = []
+    for e in range(self.num_envs):
+      n = int(raw[e, 0]); rows = raw[e, 1:1 + 9 * n].reshape(n, 9)
+      out.append([(int(r[0]), int(r[1]), float(r[2]), r[3:6].copy(), r[6:9].copy()) for r in rows])
+    return out
+
   def counters(self) -> dict:
     c = (ctypes.c_uint64 * 4)()
     self._check(self._lib.so101_counters(self._h, ctypes.byref(c)))
@@ -289,13 +300,46 @@ class BatchedEnvironment:
   # ------------------------------------------------------------------ synthetic initial states
   def sample_arm_initial_states(self, seed: int = 0, fraction: float = 0.25):
     """BASELINE config 2: arm qpos ~ U(fraction * joint range), qvel = 0 (Philox stream `seed`)."""
-    g = torch.Generator(device=self.device); g.manual_seed(int(seed))
+    g = torch.Generator(device='cpu'); g.manual_seed(int(seed))  # CPU Philox stream: identical states on any device
     rng = torch.tensor(self.model['jnt_range'].reshape(-1, 2)[:6], dtype=torch.float32, device=self.device)
-    u = torch.rand(self.num_envs, 6, generator=g, device=self.device)
+    u = torch.rand(self.num_envs, 6, generator=g).to(self.device)
     q = torch.tensor(self.model['qpos0'], dtype=torch.float32, device=self.device).repeat(self.num_envs, 1)
     q[:, :6] = fraction * (rng[:, 0] + u * (rng[:, 1] - rng[:, 0]))
     v = torch.zeros(self.num_envs, self.nv, dtype=torch.float32, device=self.device)
     self.set_initial_state(q, v)
+    return q, v
+
+
+  # so100_hand_over.py:34-55 placement distributions; rest heights from the reference's own reset state (KAT-1,
+  # so101_rl.ipynb:221-223: banana z = 0.4217, bowl z = 0.4226)
+  def sample_prop_initial_states(self, seed: int = 0, clearance: float = 0.003, settle_steps: int = 25):
+    """BASELINE config 3 initial states: banana ~ U([0.2,-0.1],[0.3,0.1]) with yaw U(+-0.1 pi), bowl ~ U([-0.3,-0.1],[-0.2,0.1]),
+    arm qpos = 0 (home is never applied, so100_task.py:308-313), dropped from `clearance` above the rest height and settled
+    on the device for `settle_steps` control steps with the arm command held at 0; the arm state is then restored
+    ([upstream] PropPlacer settle_physics freezes non-prop joints).  Installs the result as the per-env reset state."""
+    if self.nq != 20:
+      raise RuntimeError('sample_prop_initial_states needs the SO100HandOverBanana model')
+    N, dev = self.num_envs, self.device
+    g = torch.Generator(device='cpu'); g.manual_seed(int(seed))
+    u = torch.rand(N, 5, generator=g).to(dev)
+    q = torch.tensor(self.model['qpos0'], dtype=torch.float32, device=dev).repeat(N, 1)
+    q[:, :6] = 0
+    q[:, 6] = 0.2 + 0.1 * u[:, 0]; q[:, 7] = -0.1 + 0.2 * u[:, 1]; q[:, 8] = 0.4217 + clearance
+    yaw = (2 * u[:, 2] - 1) * 0.1 * np.pi
+    q[:, 9] = torch.cos(yaw / 2); q[:, 10] = 0; q[:, 11] = 0; q[:, 12] = torch.sin(yaw / 2)
+    q[:, 13] = -0.3 + 0.1 * u[:, 3]; q[:, 14] = -0.1 + 0.2 * u[:, 4]; q[:, 15] = 0.4226 + clearance
+    q[:, 16] = 1; q[:, 17:20] = 0
+    v = torch.zeros(N, self.nv, dtype=torch.float32, device=dev)
+    self.set_initial_state(q, v)
+    if settle_steps > 0:
+      self.reset()
+      zero = torch.zeros(N, 6, dtype=torch.float32, device=dev)
+      for _ in range(settle_steps):
+        self.step(zero - torch.tensor(self.calibration_offsets, dtype=torch.float32, device=dev))
+      q, v = self.get_state()
+      q[:, :6] = 0; v[:, :6] = 0
+      self.set_initial_state(q, v)
+    self.reset()
     return q, v
 
 

@@ -166,6 +166,8 @@ def main():
   env = create_batched_task_env(w['task'], num_envs=envs, time_limit=30.0, seed=rank, device=dev, precision=a.precision)
   if w['task'] == 'SO100ArmOnly':
     env.sample_arm_initial_states(seed=0 + 1000 * rank)
+  else:
+    env.sample_prop_initial_states(seed=0 + 1000 * rank)
   env.reset()
   total = a.warmup + a.steps
   g = torch.Generator(device=dev); g.manual_seed(1 + 1000 * rank)

@@ -184,6 +184,7 @@ struct Handle : HandleBase {
     S.ring_phys = dalloc<float>((size_t)(c.physics_delay_steps + 1) * (nq + nv) * N);
     S.diverged_count = dalloc<int>(2); S.solver_iter = dalloc<int>(N); S.ncon = dalloc<int>(N);
     sc.nsub = c.n_substeps; sc.last_step = c.last_step; sc.dj = c.joints_delay_steps; sc.dp = c.physics_delay_steps;
+    if (getenv("SO101_PROFILE") && atoi(getenv("SO101_PROFILE"))) S.prof = dalloc<unsigned long long>(16);
     sc.dbg_env = getenv("SO101_DBG_ENV") ? atoi(getenv("SO101_DBG_ENV")) : -1;
     sc.dbg_step = getenv("SO101_DBG_STEP") ? atoi(getenv("SO101_DBG_STEP")) : -1;
     sc.terminate_on_success = c.terminate_on_success; sc.max_iter = c.solver_iterations; sc.tol = c.solver_tolerance;
@@ -236,6 +237,16 @@ struct Handle : HandleBase {
       if (count < (size_t)S.N * nv) throw std::runtime_error("debug_read: buffer too small");
       if (scene) launch_cast_copy<T, float>(S.warm, dst, (size_t)S.N * nv, s); else launch_soa_to_rows<T, float>(S.warm, dst, S.N, nv, s);
       launches += 1;
+    } else if (f == "prof") {
+      // 16 stage-profile accumulators (clock64 sums / counters over all envs since create); needs SO101_PROFILE=1 at create
+      if (!S.prof) throw std::runtime_error("debug_read: create the handle with SO101_PROFILE=1 to enable the stage profile");
+      if (count < 16) throw std::runtime_error("debug_read: buffer too small");
+      unsigned long long h[16];
+      CUDA_OK(cudaStreamSynchronize(s));
+      CUDA_OK(cudaMemcpy(h, S.prof, sizeof h, cudaMemcpyDeviceToHost));
+      float hf[16];
+      for (int i = 0; i < 16; i++) hf[i] = (float)h[i];
+      CUDA_OK(cudaMemcpy(dst, hf, sizeof hf, cudaMemcpyHostToDevice));
     } else if (f == "contacts") {
       // [N][1 + 9*NCON]: ncon, then (geom1, geom2, dist, pos3, normal3) per contact of the last substep.  The first call only
       // enables the probe (the buffer is filled by subsequent steps).

@@ -19,6 +19,7 @@ struct EnvState {
   int *diverged_count;              // [1]
   int *solver_iter;                 // [N] Newton iterations of the last substep (parity/diagnostics)
   int *ncon;                        // [N] contacts of the last substep
+  unsigned long long *prof;         // optional [16] stage-profile accumulators (SO101_PROFILE=1), see scene_kernel.inl
   float *dbg_contacts;              // optional [N][1 + 9*NCON] parity probe (null unless requested)
 };
 

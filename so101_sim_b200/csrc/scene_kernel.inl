@@ -41,7 +41,8 @@ struct Scratch {
   T H[NH];
   T qacc_s[NV], fsm[NV], delta[NV], grad[NV], search[NV], Md[NV], Ms[NV];
   // contacts found by the collision stage
-  int ncon, dbg;
+  int ncon, dbg, profon;
+  long long prof[16];  // developer probe (SO101_PROFILE=1): per-stage clock64 sums and counters of this env
   T c_pos[3][NCON], c_frame[9][NCON], c_dist[NCON];
   int c_g1[NCON], c_g2[NCON];
   union U {
@@ -52,6 +53,12 @@ struct Scratch {
 };
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
+
+// stage profiler: lane 0 accumulates clock64 deltas into Scratch::prof when the handle was created with SO101_PROFILE=1
+enum { P_DYN = 0, P_BROAD, P_PLANE, P_GJK, P_EPA, P_MANI, P_ROWS, P_SOLVE, P_INTEG, P_TASK, P_NPQ, P_NCON, P_NEWTON, P_LINE, P_NEPA, P_NSUB };
+#define PROF_START(s) long long pt_ = (s).profon ? clock64() : 0
+#define PROF_ACC(s, i, lane) do { if ((s).profon) { const long long n_ = clock64(); if ((lane) == 0) (s).prof[i] += n_ - pt_; pt_ = n_; } } while (0)
+#define PROF_CNT(s, i, v, lane) do { if ((s).profon && (lane) == 0) (s).prof[i] += (v); } while (0)
 
 // ------------------------------------------------------------------------------------------------ kinematics + smooth dynamics
 template <typename T>
@@ -203,11 +210,19 @@ template <typename T>
 __device__ void collide_convex(const SceneModel<T> &sm, Scratch<T> &s, const Shape<T> &A, const Shape<T> &B, int &ncon, int &dropped, int lane) {
   MPoint<T> S[4];
   int n = 0;
-  if (!gjk_intersect(sm, A, B, S, n, lane)) return;
+  PROF_START(s);
+  const int hit = gjk_intersect(sm, A, B, S, n, lane);
+  PROF_ACC(s, P_GJK, lane);
+  if (!hit) return;
   T normal[3], depth, pa[3], pb[3];
-  if (!epa(sm, s.u.col, A, B, S, n, normal, depth, pa, pb, lane)) return;
+  PROF_CNT(s, P_NEPA, 1, lane);
+  const int ok = epa(sm, s.u.col, A, B, S, n, normal, depth, pa, pb, lane);
+  PROF_ACC(s, P_EPA, lane);
+  if (!ok) return;
   if (!(depth > T(0))) return;
-  if (manifold(sm, s, A, B, normal, depth, ncon, dropped, lane) > 0) return;
+  const int nm = manifold(sm, s, A, B, normal, depth, ncon, dropped, lane);
+  PROF_ACC(s, P_MANI, lane);
+  if (nm > 0) return;
   T frame[9], pos[3];
   frame_from_normal(normal, frame);
   for (int c = 0; c < 3; c++) pos[c] = T(0.5) * (pa[c] + pb[c]);
@@ -286,6 +301,7 @@ __device__ __forceinline__ void geom_pose(const SceneModel<T> &sm, const Scratch
 template <typename T>
 __device__ void scene_collide(const SceneModel<T> &sm, Scratch<T> &s, int &dropped, int lane) {
   CollideScratch<T> &cs = s.u.col;
+  PROF_START(s);
   // world bounding-sphere centres of all geoms
   for (int g = lane; g < sm.ngeom; g += 32) {
     const int slot = sm.geom_slot[g];
@@ -357,15 +373,18 @@ __device__ void scene_collide(const SceneModel<T> &sm, Scratch<T> &s, int &dropp
   }
   if (npq > PAIRQ) { dropped += npq - PAIRQ; npq = PAIRQ; }
   __syncwarp();
+  PROF_ACC(s, P_BROAD, lane);
+  PROF_CNT(s, P_NPQ, npq, lane);
   int ncon = 0;
   for (int i = 0; i < npq; i++) {
     const unsigned pq = cs.pairq[i];
     Shape<T> A, B;
     make_shape(sm, s.xpos, s.xmat, (int)(pq & 0xffff), A);
     make_shape(sm, s.xpos, s.xmat, (int)(pq >> 16), B);
-    if (A.type == G_PLANE) collide_plane(sm, s, A, B, ncon, dropped, lane);
+    if (A.type == G_PLANE) { PROF_START(s); collide_plane(sm, s, A, B, ncon, dropped, lane); PROF_ACC(s, P_PLANE, lane); }
     else collide_convex(sm, s, A, B, ncon, dropped, lane);
   }
+  PROF_CNT(s, P_NCON, ncon, lane);
   if (lane == 0) s.ncon = ncon;
   __syncwarp();
 }
@@ -632,6 +651,7 @@ __device__ int scene_solve(const SceneModel<T> &sm, const ArmModelT<T> &am, Scra
   }
   // cost of the contact + arm rows at x (+ alpha * dx): returns warp-uniform (cost, d/dalpha, d2/dalpha2)
   auto rows_line = [&](const T *x, const T *dx, T alpha, T &c, T &g, T &h) {
+    PROF_CNT(s, P_LINE, 1, lane);
     T lc = T(0), lg = T(0), lh = T(0);
 #pragma unroll
     for (int k = 0; k < CSL; k++) {
@@ -960,8 +980,14 @@ __global__ void __launch_bounds__(WARPS * 32) scene_step_kernel(const __grid_con
   __syncwarp();
   int iters = 0, dropped = 0;
   bool bad = false;
-  if (lane == 0) s.dbg = (env == cfg.dbg_env && S.step[env] == cfg.dbg_step);
+  if (lane == 0) {
+    s.dbg = (env == cfg.dbg_env && S.step[env] == cfg.dbg_step);
+    s.profon = S.prof != nullptr;
+    for (int i = 0; i < 16; i++) s.prof[i] = 0;
+  }
+  __syncwarp();
   for (int sub = 0; sub < cfg.nsub; sub++) {
+    PROF_START(s);
     ArmRows<T> arows;
     {
       ArmKin<T> k;
@@ -1003,6 +1029,7 @@ __global__ void __launch_bounds__(WARPS * 32) scene_step_kernel(const __grid_con
       for (int i = 0; i < 6; i++) s.qacc_s[NJ + 6 * lane + i] = x[i];
     }
     __syncwarp();
+    PROF_ACC(s, P_DYN, lane);
     scene_collide(sm, s, dropped, lane);
     if (S.dbg_contacts && sub == cfg.nsub - 1) {  // parity probe: contacts of the last substep
       float *dst = S.dbg_contacts + (size_t)env * (1 + 9 * NCON);
@@ -1013,11 +1040,16 @@ __global__ void __launch_bounds__(WARPS * 32) scene_step_kernel(const __grid_con
         for (int e = 0; e < 3; e++) { r[3 + e] = (float)s.c_pos[e][c]; r[6 + e] = (float)s.c_frame[e][c]; }
       }
     }
+    pt_ = s.profon ? clock64() : 0;
     build_rows(sm, am, s, dropped, lane);
+    PROF_ACC(s, P_ROWS, lane);
     if (lane < NV) s.delta[lane] = s.warm[lane] - s.qacc_s[lane];
     __syncwarp();
     iters = scene_solve(sm, am, s, arows, cfg.max_iter, (T)cfg.tol, lane);
     __syncwarp();
+    PROF_ACC(s, P_SOLVE, lane);
+    PROF_CNT(s, P_NEWTON, iters, lane);
+    PROF_CNT(s, P_NSUB, 1, lane);
     // [upstream] mj_Euler
     T qacc = T(0);
     if (lane < NV) {
@@ -1047,7 +1079,9 @@ __global__ void __launch_bounds__(WARPS * 32) scene_step_kernel(const __grid_con
       for (int c = 0; c < 4; c++) qp[3 + c] = qn[c] / n;
     }
     __syncwarp();
+    PROF_ACC(s, P_INTEG, lane);
   }
+  PROF_START(s);
   // mj_step1 refresh for the task layer: poses at the new state
   {
     ArmKin<T> k;
@@ -1067,6 +1101,9 @@ __global__ void __launch_bounds__(WARPS * 32) scene_step_kernel(const __grid_con
     if (dropped) atomicAdd(S.diverged_count + 1, dropped);
   }
   write_obs_scene(cfg, S, out, s, env, t, reward, discount, st, lane);
+  PROF_ACC(s, P_TASK, lane);
+  if (s.profon && lane == 0)
+    for (int i = 0; i < 16; i++) atomicAdd(S.prof + i, (unsigned long long)s.prof[i]);
 }
 
 template <typename T>

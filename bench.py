@@ -167,7 +167,7 @@ def main():
   if w['task'] == 'SO100ArmOnly':
     env.sample_arm_initial_states(seed=0 + 1000 * rank)
   else:
-    env.sample_prop_initial_states(seed=0 + 1000 * rank)
+    env.sample_prop_initial_states(seed=0 + 1000 * rank, spawn_z=0.45, settle_steps=50)  # reference drop height, settled 1 s
   env.reset()
   total = a.warmup + a.steps
   g = torch.Generator(device=dev); g.manual_seed(1 + 1000 * rank)

@@ -467,16 +467,18 @@ static void emit(const so_model *m, so_data *d, int g1, int g2, const double *fr
 /* keep at most MAXMANIFOLD points: deepest, farthest from it, farthest from that line on each side */
 static int reduce_manifold(fpt *P, double *dist, int n) {
   if (n <= MAXMANIFOLD) return n;
+  /* Flat contacts make all candidates tie to round-off; every comparison therefore carries a tolerance (0.1 um on depth,
+     1e-4 relative on lengths/areas) so that the first candidate in polygon order wins a tie in any arithmetic. */
   int sel[4] = {0, -1, -1, -1};
-  for (int i = 1; i < n; i++) if (dist[i] < dist[sel[0]]) sel[0] = i;
+  for (int i = 1; i < n; i++) if (dist[i] < dist[sel[0]] - 1e-7) sel[0] = i;
   double best = -1;
-  for (int i = 0; i < n; i++) { double dx = P[i].x - P[sel[0]].x, dy = P[i].y - P[sel[0]].y, l = dx * dx + dy * dy; if (l > best) { best = l; sel[1] = i; } }
+  for (int i = 0; i < n; i++) { double dx = P[i].x - P[sel[0]].x, dy = P[i].y - P[sel[0]].y, l = dx * dx + dy * dy; if (l > best * 1.0001 + 1e-12) { best = l; sel[1] = i; } }
   double ex = P[sel[1]].x - P[sel[0]].x, ey = P[sel[1]].y - P[sel[0]].y, bp = 0, bn = 0;
   for (int i = 0; i < n; i++) {
     if (i == sel[0] || i == sel[1]) continue; /* their cross product is 0 up to round-off (FMA contraction makes it +-eps) */
     double s = ex * (P[i].y - P[sel[0]].y) - ey * (P[i].x - P[sel[0]].x);
-    if (s > bp) { bp = s; sel[2] = i; }
-    if (s < bn) { bn = s; sel[3] = i; }
+    if (s > bp * 1.0001 + 1e-12) { bp = s; sel[2] = i; }
+    if (s < bn * 1.0001 - 1e-12) { bn = s; sel[3] = i; }
   }
   fpt Q[4]; double qd[4]; int k = 0;
   for (int i = 0; i < 4; i++) if (sel[i] >= 0) { Q[k] = P[sel[i]]; qd[k] = dist[sel[i]]; k++; }

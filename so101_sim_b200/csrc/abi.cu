@@ -150,6 +150,7 @@ struct Handle : HandleBase {
   ArmModelT<T> am;
   std::unique_ptr<SceneModelHost<T>> scene;  // non-null: full contact scene (warp per env, row-major state)
   EnvState<T> S{};
+  PipeBuf<T> pipe{};
   StepCfg sc{};
   std::vector<void *> allocs;
   float *d_action = nullptr, *d_reward = nullptr, *d_discount = nullptr, *d_jpos = nullptr;
@@ -195,6 +196,13 @@ struct Handle : HandleBase {
     CUDA_OK(cudaMemcpy(S.init_qpos, q0.data(), q0.size() * sizeof(T), cudaMemcpyHostToDevice));
     d_action = dalloc<float>(6 * N); d_reward = dalloc<float>(N); d_discount = dalloc<float>(N); d_jpos = dalloc<float>(6 * N);
     d_steptype = dalloc<uint8_t>(N);
+    if (scene) {  // inter-kernel scratch of the scene pipeline
+      pipe.xpos = dalloc<T>(N * NSLOT * 3); pipe.xmat = dalloc<T>(N * NSLOT * 9);
+      pipe.work = dalloc<uint2>(N * PAIRCAP); pipe.nwork = dalloc<int>(2 * (c.n_substeps + 1));
+      pipe.con = dalloc<T>(N * CONBUF * 8); pipe.con_key = dalloc<int>(N * CONBUF); pipe.ncon_raw = dalloc<int>(N);
+      pipe.active = dalloc<uint8_t>(N); pipe.flags = dalloc<uint8_t>(N);
+      pipe.narrow_grid = scene_narrow_grid<T>();
+    }
   }
   ~Handle() override {
     for (void *p : allocs) cudaFree(p);
@@ -223,8 +231,9 @@ struct Handle : HandleBase {
     launches += 1;
   }
   void step(const float *action, const so101_step_out &out, cudaStream_t s) override {
-    if (scene) launch_scene_step<T>(am, scene->dev, sc, S, action, out, s); else launch_arm_step<T>(am, sc, S, action, out, s);
-    launches += 1; steps += 1;
+    if (scene) launches += launch_scene_step<T>(am, scene->dev, sc, S, pipe, action, out, s);
+    else { launch_arm_step<T>(am, sc, S, action, out, s); launches += 1; }
+    steps += 1;
   }
   void debug_read(const char *field, float *dst, size_t count, cudaStream_t s) override {
     const std::string f(field);

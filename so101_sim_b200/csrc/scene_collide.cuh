@@ -10,9 +10,10 @@
 
 namespace so101 {
 
-constexpr int NCON = 64;         // contacts kept per env (extra ones are dropped and counted)
+constexpr int NCON = 64;         // contacts the solver keeps per env (extra ones are dropped and counted)
 constexpr int NBLK = 96;         // 6x6 Jacobian blocks per env: one per dynamic body touched by a contact
-constexpr int PAIRQ = 256;       // candidate geom pairs per env per substep
+constexpr int PAIRCAP = 64;      // candidate geom pairs per env per substep (after the OBB mid phase)
+constexpr int CONBUF = 96;       // raw contacts per env the narrow phase may write between two kernels
 constexpr int EPA_MAXV = 96, EPA_MAXF = 256;
 constexpr int MAXCAND = 64, MAXFEAT = 32, MAXMANI = 4;
 constexpr unsigned FULL = 0xffffffffu;
@@ -28,21 +29,24 @@ struct FPt {
   T x, y, h;
 };
 
-// Scratch that only lives during collision; it aliases the solver's row storage (see scene_kernel.cu).
+// Per-warp scratch of one narrow-phase pair.  The EPA polytope is dead once epa() has returned (normal, depth and
+// witness points are in registers), so the manifold stage re-uses its storage.
 template <typename T>
 struct CollideScratch {
-  unsigned pairq[PAIRQ];
-  T gcenter[3][96];  // world bounding-sphere centres of all geoms
-  // EPA polytope
-  T Vw[3][EPA_MAXV], Va[3][EPA_MAXV], Vb[3][EPA_MAXV];
-  int Fv[3][EPA_MAXF];
-  T Fn[3][EPA_MAXF], Fd[EPA_MAXF];
-  int Falive[EPA_MAXF];
-  int horizon[EPA_MAXF][2];
-  // manifold
-  T cand[3][MAXCAND];
-  FPt<T> P[MAXCAND], Hh[2 * MAXCAND + 2], FA[MAXFEAT], FB[MAXFEAT], R[2 * MAXFEAT + 8], bufA[2 * MAXFEAT + 8], bufB[2 * MAXFEAT + 8];
-  T mdist[2 * MAXFEAT + 8];
+  union {
+    struct {  // EPA polytope
+      T Vw[3][EPA_MAXV], Va[3][EPA_MAXV], Vb[3][EPA_MAXV];
+      int Fv[3][EPA_MAXF];
+      T Fn[3][EPA_MAXF], Fd[EPA_MAXF];
+      int Falive[EPA_MAXF];
+      int horizon[EPA_MAXF][2];
+    };
+    struct {  // manifold
+      T cand[3][MAXCAND];
+      FPt<T> P[MAXCAND], Hh[2 * MAXCAND + 2], FA[MAXFEAT], FB[MAXFEAT], R[2 * MAXFEAT + 8], bufA[2 * MAXFEAT + 8], bufB[2 * MAXFEAT + 8];
+      T mdist[2 * MAXFEAT + 8];
+    };
+  };
 };
 
 template <typename T> __device__ __forceinline__ T wshfl(T v, int src) { return __shfl_sync(FULL, v, src); }
@@ -563,16 +567,17 @@ template <typename T>
 __device__ int reduce_manifold(FPt<T> *P, T *dist, int n) {
   if (n <= MAXMANI) return n;
   int sel[4] = {0, -1, -1, -1};
-  for (int i = 1; i < n; i++) if (dist[i] < dist[sel[0]]) sel[0] = i;
+  // tolerant comparisons: the first candidate in polygon order wins a tie in any arithmetic (see the oracle)
+  for (int i = 1; i < n; i++) if (dist[i] < dist[sel[0]] - T(1e-7)) sel[0] = i;
   T best = T(-1);
-  for (int i = 0; i < n; i++) { const T dx = P[i].x - P[sel[0]].x, dy = P[i].y - P[sel[0]].y, l = dx * dx + dy * dy; if (l > best) { best = l; sel[1] = i; } }
+  for (int i = 0; i < n; i++) { const T dx = P[i].x - P[sel[0]].x, dy = P[i].y - P[sel[0]].y, l = dx * dx + dy * dy; if (l > best * T(1.0001) + T(1e-12)) { best = l; sel[1] = i; } }
   const T ex = P[sel[1]].x - P[sel[0]].x, ey = P[sel[1]].y - P[sel[0]].y;
   T bp = T(0), bn = T(0);
   for (int i = 0; i < n; i++) {
     if (i == sel[0] || i == sel[1]) continue;  // their cross product is 0 up to round-off (FMA contraction makes it +-eps)
     const T s = ex * (P[i].y - P[sel[0]].y) - ey * (P[i].x - P[sel[0]].x);
-    if (s > bp) { bp = s; sel[2] = i; }
-    if (s < bn) { bn = s; sel[3] = i; }
+    if (s > bp * T(1.0001) + T(1e-12)) { bp = s; sel[2] = i; }
+    if (s < bn * T(1.0001) - T(1e-12)) { bn = s; sel[3] = i; }
   }
   FPt<T> Q[4];
   T qd[4];

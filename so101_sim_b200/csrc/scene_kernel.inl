@@ -1,23 +1,33 @@
-// Fused control-step kernel for the FULL contact scene (BASELINE config 3: SO100HandOverBanana, nq=20 nv=18).
+// Control step of the FULL contact scene (BASELINE config 3: SO100HandOverBanana, nq=20 nv=18) as a pipeline of
+// three kernels per physics substep, all envs in lockstep:
 //
-// One warp per environment, 4 envs per CTA; the env's working set (body poses, contacts, constraint Jacobians, the
-// 18x18 Newton Hessian) lives in shared memory for the whole control step, so HBM sees the state once in and once out.
-// Per substep ([upstream] mj_step, legacy dm_control order is equivalent):
+//   scene_begin_kernel   (once per control step, warp per env)  auto-reset, action -> ctrl, kinematics, broad/mid phase
+//   scene_narrow_kernel  (per substep, warp per candidate geom PAIR drawn from a device-wide work list)
+//                        convex narrow phase: boolean GJK -> EPA -> support-feature clipping (multiccd manifold)
+//   scene_solve_kernel   (per substep, warp per env) smooth dynamics, contact gather, constraint rows, elliptic-cone
+//                        Newton, semi-implicit Euler, then kinematics + broad phase of the NEXT substep, or (last
+//                        substep) the task layer: observation delay rings, SO100HandOver reward, discount, time limit.
+//
+// Splitting by stage keeps each kernel's code and shared-memory footprint small (more resident warps, no instruction-
+// cache thrash) and turns the narrow phase — whose cost varies 10x between pairs — into a flat, dynamically balanced
+// work list.  What crosses kernels (body poses, pair list, raw contacts; ~1 KB per env) stays L2-resident.
+// Per substep order ([upstream] mj_step; legacy dm_control order is equivalent):
 //   arm FK / CRB / RNE            (all lanes redundantly, registers; arm_dynamics.cuh)
 //   prop kinematics, M, bias      (free joints: linear dofs world frame, angular dofs body frame)
 //   collision                     (scene_collide.cuh: lanes over vertices / faces)
 //   constraint rows               (lane per contact: parameter mixing, impedance, Jacobian blocks, aref)
 //   Newton solve                  (elliptic cones, lane per contact for row work, lane per entry for the Hessian)
 //   semi-implicit Euler           (quaternion integration for the free joints)
-// followed by the task layer: observation delay rings, SO100HandOver reward (6-axis SAT), discount, time limit,
-// auto-reset (so100_task.py:266-368, so100_hand_over.py:238-275).
+// Task layer: so100_task.py:266-368, so100_hand_over.py:238-275.
 #include "scene_kernel.cuh"
 
 namespace so101 {
 
-constexpr int WARPS = 4;
+constexpr int WARPS_SOLVE = 2;   // envs (warps) per CTA in the begin / solve kernels
+constexpr int WARPS_NARROW = 4;  // pairs (warps) in flight per CTA in the narrow-phase kernel
 constexpr int CSL = (NCON + 31) / 32;  // contact slots per lane
 constexpr int NH = NV * (NV + 1) / 2;  // 171 packed lower-triangular entries
+constexpr int NOUT = 8;                // contacts one pair can emit (manifold <= MAXMANI)
 
 template <typename T>
 struct SolveScratch {
@@ -32,6 +42,22 @@ struct SolveScratch {
 };
 
 template <typename T>
+struct BroadScratch {
+  unsigned pairq[PAIRCAP];
+  T gcenter[3][96];  // world bounding-sphere centres of all geoms
+};
+
+// per-warp scratch of the narrow-phase kernel: one candidate pair at a time
+template <typename T>
+struct NarrowScratch {
+  CollideScratch<T> col;
+  int ncon, dbg, profon;
+  long long prof[16];
+  T c_pos[3][NOUT], c_normal[3][NOUT], c_dist[NOUT];
+};
+
+// per-env scratch of the begin / solve kernels
+template <typename T>
 struct Scratch {
   T xpos[NSLOT][3], xmat[NSLOT][9];
   T arm_p[NJ][3], arm_a[NJ][3];
@@ -40,13 +66,13 @@ struct Scratch {
   T Marm[21];
   T H[NH];
   T qacc_s[NV], fsm[NV], delta[NV], grad[NV], search[NV], Md[NV], Ms[NV];
-  // contacts found by the collision stage
   int ncon, dbg, profon;
   long long prof[16];  // developer probe (SO101_PROFILE=1): per-stage clock64 sums and counters of this env
+  // contacts gathered from the narrow phase, in oracle order
   T c_pos[3][NCON], c_frame[9][NCON], c_dist[NCON];
   int c_g1[NCON], c_g2[NCON];
   union U {
-    CollideScratch<T> col;
+    BroadScratch<T> broad;
     SolveScratch<T> sol;
     __device__ U() {}
   } u;
@@ -144,18 +170,17 @@ __device__ __forceinline__ void prop_dynamics(const SceneModel<T> &sm, const Arm
 
 // ------------------------------------------------------------------------------------------------ collision driver
 template <typename T>
-__device__ __forceinline__ void emit_contact(Scratch<T> &s, int &ncon, int &dropped, int g1, int g2, const T *frame, const T *pos, T dist) {
-  // lane 0 only
-  if (ncon >= NCON) { dropped++; return; }
+__device__ __forceinline__ void emit_contact(NarrowScratch<T> &s, int &ncon, int &dropped, int g1, int g2, const T *frame, const T *pos, T dist) {
+  // lane 0 only; the pair's contacts are staged in shared memory and flushed to the env's raw contact buffer by the caller
+  if (ncon >= NOUT) { dropped++; return; }
   const int c = ncon++;
-  s.c_g1[c] = g1; s.c_g2[c] = g2; s.c_dist[c] = dist;
-  for (int e = 0; e < 3; e++) s.c_pos[e][c] = pos[e];
-  for (int e = 0; e < 9; e++) s.c_frame[e][c] = frame[e];
+  s.c_dist[c] = dist;
+  for (int e = 0; e < 3; e++) { s.c_pos[e][c] = pos[e]; s.c_normal[e][c] = frame[e]; }
 }
 
 template <typename T>
-__device__ int manifold(const SceneModel<T> &sm, Scratch<T> &s, const Shape<T> &A, const Shape<T> &B, const T *n, T depth, int &ncon, int &dropped, int lane) {
-  CollideScratch<T> &cs = s.u.col;
+__device__ int manifold(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shape<T> &A, const Shape<T> &B, const T *n, T depth, int &ncon, int &dropped, int lane) {
+  CollideScratch<T> &cs = s.col;
   T frame[9];
   frame_from_normal(n, frame);
   const T *t1 = frame + 3, *t2 = frame + 6;
@@ -207,7 +232,7 @@ __device__ int manifold(const SceneModel<T> &sm, Scratch<T> &s, const Shape<T> &
 }
 
 template <typename T>
-__device__ void collide_convex(const SceneModel<T> &sm, Scratch<T> &s, const Shape<T> &A, const Shape<T> &B, int &ncon, int &dropped, int lane) {
+__device__ void collide_convex(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shape<T> &A, const Shape<T> &B, int &ncon, int &dropped, int lane) {
   MPoint<T> S[4];
   int n = 0;
   PROF_START(s);
@@ -216,7 +241,7 @@ __device__ void collide_convex(const SceneModel<T> &sm, Scratch<T> &s, const Sha
   if (!hit) return;
   T normal[3], depth, pa[3], pb[3];
   PROF_CNT(s, P_NEPA, 1, lane);
-  const int ok = epa(sm, s.u.col, A, B, S, n, normal, depth, pa, pb, lane);
+  const int ok = epa(sm, s.col, A, B, S, n, normal, depth, pa, pb, lane);
   PROF_ACC(s, P_EPA, lane);
   if (!ok) return;
   if (!(depth > T(0))) return;
@@ -232,8 +257,8 @@ __device__ void collide_convex(const SceneModel<T> &sm, Scratch<T> &s, const Sha
 }
 
 template <typename T>
-__device__ void collide_plane(const SceneModel<T> &sm, Scratch<T> &s, const Shape<T> &P, const Shape<T> &B, int &ncon, int &dropped, int lane) {
-  CollideScratch<T> &cs = s.u.col;
+__device__ void collide_plane(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shape<T> &P, const Shape<T> &B, int &ncon, int &dropped, int lane) {
+  CollideScratch<T> &cs = s.col;
   const T n[3] = {P.mat[2], P.mat[5], P.mat[8]}, nn[3] = {-n[0], -n[1], -n[2]};
   T sp[3];
   support(sm, B, nn, sp, lane);
@@ -298,10 +323,62 @@ __device__ __forceinline__ void geom_pose(const SceneModel<T> &sm, const Scratch
   }
 }
 
+// oriented-box overlap, 15-axis separating-axis test.  (pa, Ra, ha): centre, rotation (columns = box axes), half sizes.
 template <typename T>
-__device__ void scene_collide(const SceneModel<T> &sm, Scratch<T> &s, int &dropped, int lane) {
-  CollideScratch<T> &cs = s.u.col;
+__device__ __forceinline__ bool obb_overlap(const T *pa, const T *Ra, const T *ha, const T *pb, const T *Rb, const T *hb) {
+  T R[9], AR[9], d[3], t[3];
+  sub3(d, pb, pa); mulmtv(t, Ra, d);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const T v = Ra[i] * Rb[j] + Ra[3 + i] * Rb[3 + j] + Ra[6 + i] * Rb[6 + j];
+      R[3 * i + j] = v; AR[3 * i + j] = t_abs(v) + T(1e-6);
+    }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    if (t_abs(t[i]) > ha[i] + hb[0] * AR[3 * i] + hb[1] * AR[3 * i + 1] + hb[2] * AR[3 * i + 2]) return false;
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+    if (t_abs(t[0] * R[j] + t[1] * R[3 + j] + t[2] * R[6 + j]) > ha[0] * AR[j] + ha[1] * AR[3 + j] + ha[2] * AR[6 + j] + hb[j]) return false;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const T ra = ha[i1] * AR[3 * i2 + j] + ha[i2] * AR[3 * i1 + j], rb = hb[j1] * AR[3 * i + j2] + hb[j2] * AR[3 * i + j1];
+      if (t_abs(t[i2] * R[3 * i1 + j] - t[i1] * R[3 * i2 + j]) > ra + rb) return false;
+    }
+  }
+  return true;
+}
+
+// world oriented bounding box of geom g (local AABB of the geom in its own frame, inflated by 0.1 mm)
+template <typename T>
+__device__ __forceinline__ void geom_obb(const SceneModel<T> &sm, const Scratch<T> &s, int g, T *pos, T *mat, T *half) {
+  T gp[3];
+  geom_pose(sm, s, g, gp, mat);
+  const T c[3] = {sm.geom_aabb[6 * g], sm.geom_aabb[6 * g + 1], sm.geom_aabb[6 * g + 2]};
+  T t[3];
+  mulmv(t, mat, c);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { pos[k] = gp[k] + t[k]; half[k] = sm.geom_aabb[6 * g + 3 + k] + T(1e-4); }
+}
+
+// Broad + mid phase of one env ([upstream] mj_collision before the narrow phase): body-pair bounding spheres, geom
+// bounding spheres, then oriented boxes (geom AABBs in the geom frame, as MuJoCo's mid phase uses).  The surviving
+// geom pairs are appended, in the oracle's pair order, to the device-wide work list of substep `sub`.
+template <typename T>
+__device__ void scene_broadphase(const SceneModel<T> &sm, Scratch<T> &s, const PipeBuf<T> &pb, int env, int sub, int &dropped, int lane) {
+  BroadScratch<T> &cs = s.u.broad;
   PROF_START(s);
+  // publish the body poses for the narrow-phase kernel
+  {
+    T *gx = pb.xpos + (size_t)env * (NSLOT * 3), *gm = pb.xmat + (size_t)env * (NSLOT * 9);
+    for (int i = lane; i < NSLOT * 3; i += 32) gx[i] = (&s.xpos[0][0])[i];
+    for (int i = lane; i < NSLOT * 9; i += 32) gm[i] = (&s.xmat[0][0])[i];
+  }
   // world bounding-sphere centres of all geoms
   for (int g = lane; g < sm.ngeom; g += 32) {
     const int slot = sm.geom_slot[g];
@@ -339,53 +416,47 @@ __device__ void scene_collide(const SceneModel<T> &sm, Scratch<T> &s, int &dropp
       int g1 = 0, g2 = 0;
       if (k < total) {
         g1 = a1 + k / n2; g2 = a2 + k % n2;
-        const int ty1 = sm.geom_type[g1], ty2 = sm.geom_type[g2];
+        const int ty1 = sm.geom_type[g1];
         const T cA[3] = {cs.gcenter[0][g1], cs.gcenter[1][g1], cs.gcenter[2][g1]}, cB[3] = {cs.gcenter[0][g2], cs.gcenter[1][g2], cs.gcenter[2][g2]};
         const T rA = sm.geom_rbound[g1], rB = sm.geom_rbound[g2];
         if (ty1 == G_PLANE) {
           const T n[3] = {sm.geom_mat[9 * g1 + 2], sm.geom_mat[9 * g1 + 5], sm.geom_mat[9 * g1 + 8]};
           const T pp[3] = {sm.geom_pos[3 * g1], sm.geom_pos[3 * g1 + 1], sm.geom_pos[3 * g1 + 2]};
           keep = !(dot3(n, cB) - dot3(n, pp) - rB > T(0));
+          if (keep) {
+            T pos[3], mat[9], half[3];
+            geom_obb(sm, s, g2, pos, mat, half);
+            const T ext = t_abs(n[0] * mat[0] + n[1] * mat[3] + n[2] * mat[6]) * half[0] + t_abs(n[0] * mat[1] + n[1] * mat[4] + n[2] * mat[7]) * half[1] +
+                          t_abs(n[0] * mat[2] + n[1] * mat[5] + n[2] * mat[8]) * half[2];
+            keep = !(dot3(n, pos) - dot3(n, pp) - ext > T(0));
+          }
         } else {
           T t[3];
           sub3(t, cA, cB);
           const T r = rA + rB;
           keep = !(dot3(t, t) > r * r);
-          if (keep && ty1 != G_HULL) {
-            T pos[3], mat[9], half[3];
-            const T sz[3] = {sm.geom_size[3 * g1], sm.geom_size[3 * g1 + 1], sm.geom_size[3 * g1 + 2]};
-            geom_pose(sm, s, g1, pos, mat); bound_half(ty1, sz, rA, half);
-            keep = sphere_vs_obb(cB, rB, pos, mat, half);
-          }
-          if (keep && ty2 != G_HULL) {
-            T pos[3], mat[9], half[3];
-            const T sz[3] = {sm.geom_size[3 * g2], sm.geom_size[3 * g2 + 1], sm.geom_size[3 * g2 + 2]};
-            geom_pose(sm, s, g2, pos, mat); bound_half(ty2, sz, rB, half);
-            keep = sphere_vs_obb(cA, rA, pos, mat, half);
+          if (keep) {
+            T p1[3], m1[9], h1[3], p2[3], m2[9], h2[3];
+            geom_obb(sm, s, g1, p1, m1, h1); geom_obb(sm, s, g2, p2, m2, h2);
+            keep = obb_overlap(p1, m1, h1, p2, m2, h2);
           }
         }
       }
       const unsigned m = __ballot_sync(FULL, keep);
       const int idx = npq + __popc(m & ((1u << lane) - 1));
-      if (keep && idx < PAIRQ) cs.pairq[idx] = (unsigned)g1 | ((unsigned)g2 << 16);
+      if (keep && idx < PAIRCAP) cs.pairq[idx] = (unsigned)g1 | ((unsigned)g2 << 8) | ((unsigned)idx << 16);
       npq += __popc(m);
     }
   }
-  if (npq > PAIRQ) { dropped += npq - PAIRQ; npq = PAIRQ; }
+  if (npq > PAIRCAP) { dropped += npq - PAIRCAP; npq = PAIRCAP; }
   __syncwarp();
+  // append (env, g1 | g2 << 8 | pair index << 16) to the work list of this substep
+  int base = 0;
+  if (lane == 0 && npq > 0) base = atomicAdd(pb.nwork + 2 * sub, npq);
+  base = wshfl(base, 0);
+  for (int i = lane; i < npq; i += 32) pb.work[(size_t)base + i] = make_uint2((unsigned)env, cs.pairq[i]);
   PROF_ACC(s, P_BROAD, lane);
   PROF_CNT(s, P_NPQ, npq, lane);
-  int ncon = 0;
-  for (int i = 0; i < npq; i++) {
-    const unsigned pq = cs.pairq[i];
-    Shape<T> A, B;
-    make_shape(sm, s.xpos, s.xmat, (int)(pq & 0xffff), A);
-    make_shape(sm, s.xpos, s.xmat, (int)(pq >> 16), B);
-    if (A.type == G_PLANE) { PROF_START(s); collide_plane(sm, s, A, B, ncon, dropped, lane); PROF_ACC(s, P_PLANE, lane); }
-    else collide_convex(sm, s, A, B, ncon, dropped, lane);
-  }
-  PROF_CNT(s, P_NCON, ncon, lane);
-  if (lane == 0) s.ncon = ncon;
   __syncwarp();
 }
 
@@ -959,34 +1030,171 @@ __device__ void reset_env_scene(const StepCfg &cfg, const EnvState<T> &S, const 
   write_obs_scene(cfg, S, out, s, env, 0, 0.f, 1.f, SO101_STEP_FIRST, lane);
 }
 
-// ------------------------------------------------------------------------------------------------ the kernel
+// ------------------------------------------------------------------------------------------------ kernels
 template <typename T>
-__global__ void __launch_bounds__(WARPS * 32) scene_step_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
-                                                               const __grid_constant__ StepCfg cfg, const EnvState<T> S,
-                                                               const float *__restrict__ action, const so101_step_out out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Scratch<T> *all = reinterpret_cast<Scratch<T> *>(smem_raw);
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int env = blockIdx.x * WARPS + wib;
-  if (env >= S.N) return;
-  Scratch<T> &s = all[wib];
-  if (S.needs_reset[env]) {
-    reset_env_scene(cfg, S, out, s, env, lane);
-    return;
-  }
-  for (int i = lane; i < NQ; i += 32) s.q[i] = S.qpos[(size_t)env * NQ + i];
-  for (int i = lane; i < NV; i += 32) { s.qd[i] = S.qvel[(size_t)env * NV + i]; s.warm[i] = S.warm[(size_t)env * NV + i]; }
-  if (lane < NJ) s.ctrl[lane] = (T)action[(size_t)env * 6 + lane] + (T)cfg.offsets[lane];
-  __syncwarp();
-  int iters = 0, dropped = 0;
-  bool bad = false;
+__device__ __forceinline__ void prof_begin(Scratch<T> &s, const EnvState<T> &S, int lane) {
   if (lane == 0) {
-    s.dbg = (env == cfg.dbg_env && S.step[env] == cfg.dbg_step);
     s.profon = S.prof != nullptr;
     for (int i = 0; i < 16; i++) s.prof[i] = 0;
   }
+}
+template <typename SC, typename T>
+__device__ __forceinline__ void prof_flush(SC &s, const EnvState<T> &S, int lane) {
+  if (s.profon && lane == 0)
+    for (int i = 0; i < 16; i++)
+      if (s.prof[i]) atomicAdd(S.prof + i, (unsigned long long)s.prof[i]);
+}
+
+// Once per control step: dm_control auto-reset, action -> ctrl, kinematics and broad phase of substep 0.
+template <typename T>
+__global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_begin_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
+                                                                      const __grid_constant__ StepCfg cfg, const EnvState<T> S, const PipeBuf<T> pb,
+                                                                      const float *__restrict__ action, const so101_step_out out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Scratch<T> *all = reinterpret_cast<Scratch<T> *>(smem_raw);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int env = blockIdx.x * WARPS_SOLVE + wib;
+  if (env >= S.N) return;
+  Scratch<T> &s = all[wib];
+  if (lane == 0) pb.ncon_raw[env] = 0;
+  if (S.needs_reset[env]) {  // the step() after a LAST step resets and returns FIRST; no physics this call
+    reset_env_scene(cfg, S, out, s, env, lane);
+    if (lane == 0) pb.active[env] = 0;
+    return;
+  }
+  prof_begin(s, S, lane);
+  for (int i = lane; i < NQ; i += 32) s.q[i] = S.qpos[(size_t)env * NQ + i];
+  if (lane < NJ) S.ctrl[(size_t)env * 6 + lane] = (T)action[(size_t)env * 6 + lane] + (T)cfg.offsets[lane];  // so100_task.py:266-287
+  if (lane == 0) { pb.active[env] = 1; pb.flags[env] = 0; }
   __syncwarp();
-  for (int sub = 0; sub < cfg.nsub; sub++) {
+  ArmKin<T> k;
+  scene_kinematics(am, s, k, lane);
+  int dropped = 0;
+  scene_broadphase(sm, s, pb, env, 0, dropped, lane);
+  if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
+  prof_flush(s, S, lane);
+}
+
+// Per substep: one warp per candidate geom pair, pulled from the work list with an atomic cursor (pairs differ 10x in
+// cost: a GJK miss vs GJK + EPA + manifold).  Contacts go to the env's raw buffer tagged with (pair index, manifold index).
+template <typename T>
+__global__ void __launch_bounds__(WARPS_NARROW * 32) scene_narrow_kernel(const __grid_constant__ SceneModel<T> sm, const __grid_constant__ StepCfg cfg,
+                                                                        const EnvState<T> S, const PipeBuf<T> pb, int sub) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  NarrowScratch<T> *all = reinterpret_cast<NarrowScratch<T> *>(smem_raw);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  NarrowScratch<T> &s = all[wib];
+  const int nwork = pb.nwork[2 * sub];
+  if (lane == 0) {
+    s.profon = S.prof != nullptr; s.dbg = 0;
+    for (int i = 0; i < 16; i++) s.prof[i] = 0;
+  }
+  __syncwarp();
+  int dropped = 0;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(pb.nwork + 2 * sub + 1, 1);
+    item = wshfl(item, 0);
+    if (item >= nwork) break;
+    const uint2 w = pb.work[item];
+    const int env = (int)w.x, g1 = (int)(w.y & 0xff), g2 = (int)((w.y >> 8) & 0xff), pidx = (int)(w.y >> 16);
+    const T(*xpos)[3] = reinterpret_cast<const T(*)[3]>(pb.xpos + (size_t)env * (NSLOT * 3));
+    const T(*xmat)[9] = reinterpret_cast<const T(*)[9]>(pb.xmat + (size_t)env * (NSLOT * 9));
+    if (cfg.dbg_env >= 0) {
+      if (lane == 0) s.dbg = (env == cfg.dbg_env && S.step[env] == cfg.dbg_step);
+      __syncwarp();
+    }
+    Shape<T> A, B;
+    make_shape(sm, xpos, xmat, g1, A);
+    make_shape(sm, xpos, xmat, g2, B);
+    int ncon = 0;
+    if (A.type == G_PLANE) { PROF_START(s); collide_plane(sm, s, A, B, ncon, dropped, lane); PROF_ACC(s, P_PLANE, lane); }
+    else collide_convex(sm, s, A, B, ncon, dropped, lane);
+    if (ncon > 0) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(pb.ncon_raw + env, ncon);
+      base = wshfl(base, 0);
+      if (lane < ncon) {
+        if (base + lane < CONBUF) {
+          T *dst = pb.con + ((size_t)env * CONBUF + base + lane) * 8;
+          dst[0] = s.c_normal[0][lane]; dst[1] = s.c_normal[1][lane]; dst[2] = s.c_normal[2][lane];
+          dst[3] = s.c_pos[0][lane]; dst[4] = s.c_pos[1][lane]; dst[5] = s.c_pos[2][lane];
+          dst[6] = s.c_dist[lane];
+          pb.con_key[(size_t)env * CONBUF + base + lane] = (pidx << 20) | (lane << 16) | (g1 << 8) | g2;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
+  prof_flush(s, S, lane);
+}
+
+// gather the env's raw contacts into shared memory in oracle order (pair order, then manifold order)
+template <typename T>
+__device__ void gather_contacts(const PipeBuf<T> &pb, Scratch<T> &s, int env, int &dropped, int lane) {
+  int nraw = pb.ncon_raw[env];
+  if (nraw > CONBUF) { dropped += nraw - CONBUF; nraw = CONBUF; }
+  const int *keys = pb.con_key + (size_t)env * CONBUF;
+  constexpr int RSL = (CONBUF + 31) / 32;
+  int mykey[RSL], rank[RSL];
+#pragma unroll
+  for (int k = 0; k < RSL; k++) { const int i = lane + 32 * k; mykey[k] = i < nraw ? keys[i] : 0x7fffffff; rank[k] = 0; }
+  // rank = number of contacts with a smaller key (keys are unique: pair index and manifold index)
+#pragma unroll
+  for (int kk = 0; kk < RSL; kk++) {
+    for (int jl = 0; jl < 32; jl++) {
+      const int j = 32 * kk + jl;
+      if (j >= nraw) break;
+      const int kj = wshfl(mykey[kk], jl);
+#pragma unroll
+      for (int k = 0; k < RSL; k++) rank[k] += kj < mykey[k];
+    }
+  }
+  const int n = nraw < NCON ? nraw : NCON;
+  if (nraw > NCON) dropped += nraw - NCON;
+#pragma unroll
+  for (int k = 0; k < RSL; k++) {
+    const int i = lane + 32 * k;
+    if (i < nraw && rank[k] < NCON) {
+      const int c = rank[k];
+      const T *src = pb.con + ((size_t)env * CONBUF + i) * 8;
+      const T nrm[3] = {src[0], src[1], src[2]};
+      T frame[9];
+      frame_from_normal(nrm, frame);
+#pragma unroll
+      for (int e = 0; e < 9; e++) s.c_frame[e][c] = frame[e];
+      s.c_pos[0][c] = src[3]; s.c_pos[1][c] = src[4]; s.c_pos[2][c] = src[5];
+      s.c_dist[c] = src[6];
+      s.c_g1[c] = (mykey[k] >> 8) & 0xff; s.c_g2[c] = mykey[k] & 0xff;
+    }
+  }
+  if (lane == 0) { s.ncon = n; pb.ncon_raw[env] = 0; }
+  __syncwarp();
+}
+
+// Per substep, warp per env: smooth dynamics, constraint rows from the gathered contacts, Newton, Euler; then either the
+// kinematics + broad phase of the next substep or (last substep) the task layer.
+template <typename T>
+__global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_solve_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
+                                                                      const __grid_constant__ StepCfg cfg, const EnvState<T> S, const PipeBuf<T> pb,
+                                                                      const so101_step_out out, int sub) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Scratch<T> *all = reinterpret_cast<Scratch<T> *>(smem_raw);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int env = blockIdx.x * WARPS_SOLVE + wib;
+  if (env >= S.N) return;
+  if (!pb.active[env]) return;
+  Scratch<T> &s = all[wib];
+  prof_begin(s, S, lane);
+  for (int i = lane; i < NQ; i += 32) s.q[i] = S.qpos[(size_t)env * NQ + i];
+  for (int i = lane; i < NV; i += 32) { s.qd[i] = S.qvel[(size_t)env * NV + i]; s.warm[i] = S.warm[(size_t)env * NV + i]; }
+  if (lane < NJ) s.ctrl[lane] = S.ctrl[(size_t)env * 6 + lane];
+  if (lane == 0) s.dbg = 0;
+  __syncwarp();
+  int iters = 0, dropped = 0;
+  const bool last = sub == cfg.nsub - 1;
+  {
     PROF_START(s);
     ArmRows<T> arows;
     {
@@ -1030,8 +1238,9 @@ __global__ void __launch_bounds__(WARPS * 32) scene_step_kernel(const __grid_con
     }
     __syncwarp();
     PROF_ACC(s, P_DYN, lane);
-    scene_collide(sm, s, dropped, lane);
-    if (S.dbg_contacts && sub == cfg.nsub - 1) {  // parity probe: contacts of the last substep
+    gather_contacts(pb, s, env, dropped, lane);
+    PROF_CNT(s, P_NCON, s.ncon, lane);
+    if (S.dbg_contacts && last) {  // parity probe: contacts of the last substep
       float *dst = S.dbg_contacts + (size_t)env * (1 + 9 * NCON);
       if (lane == 0) dst[0] = (float)s.ncon;
       for (int c = lane; c < s.ncon; c += 32) {
@@ -1040,7 +1249,6 @@ __global__ void __launch_bounds__(WARPS * 32) scene_step_kernel(const __grid_con
         for (int e = 0; e < 3; e++) { r[3 + e] = (float)s.c_pos[e][c]; r[6 + e] = (float)s.c_frame[e][c]; }
       }
     }
-    pt_ = s.profon ? clock64() : 0;
     build_rows(sm, am, s, dropped, lane);
     PROF_ACC(s, P_ROWS, lane);
     if (lane < NV) s.delta[lane] = s.warm[lane] - s.qacc_s[lane];
@@ -1057,7 +1265,8 @@ __global__ void __launch_bounds__(WARPS * 32) scene_step_kernel(const __grid_con
       s.warm[lane] = qacc;
       s.qd[lane] += sm.timestep * qacc;
     }
-    bad |= __any_sync(FULL, lane < NV && !(t_abs(qacc) < T(1e10)));
+    const bool badnow = __any_sync(FULL, lane < NV && !(t_abs(qacc) < T(1e10)));
+    if (badnow && lane == 0) pb.flags[env] = 1;
     __syncwarp();
     if (lane < NJ) s.q[lane] += sm.timestep * s.qd[lane];
     if (lane >= 8 && lane < 8 + NPROP) {
@@ -1081,29 +1290,32 @@ __global__ void __launch_bounds__(WARPS * 32) scene_step_kernel(const __grid_con
     __syncwarp();
     PROF_ACC(s, P_INTEG, lane);
   }
-  PROF_START(s);
-  // mj_step1 refresh for the task layer: poses at the new state
+  for (int i = lane; i < NQ; i += 32) S.qpos[(size_t)env * NQ + i] = s.q[i];
+  for (int i = lane; i < NV; i += 32) { S.qvel[(size_t)env * NV + i] = s.qd[i]; S.warm[(size_t)env * NV + i] = s.warm[i]; }
+  // poses at the new state: next substep's collision, or (mj_step1 refresh) the task layer
   {
     ArmKin<T> k;
     scene_kinematics(am, s, k, lane);
   }
-  const int t = S.step[env] + 1;
-  float reward = scene_reward(sm, s), discount = 1.f;
-  uint8_t st = (cfg.last_step > 0 && t >= cfg.last_step) ? SO101_STEP_LAST : SO101_STEP_MID;
-  if (cfg.terminate_on_success && reward >= 1.f) { discount = 0.f; st = SO101_STEP_LAST; }  // so100_task.py:292-302
-  if (bad) { reward = 0.f; discount = 0.f; st = SO101_STEP_LAST; }                         // task_suite.py:153
-  for (int i = lane; i < NQ; i += 32) S.qpos[(size_t)env * NQ + i] = s.q[i];
-  for (int i = lane; i < NV; i += 32) { S.qvel[(size_t)env * NV + i] = s.qd[i]; S.warm[(size_t)env * NV + i] = s.warm[i]; }
-  if (lane < NJ) S.ctrl[(size_t)env * 6 + lane] = s.ctrl[lane];
-  if (lane == 0) {
-    S.step[env] = t; S.needs_reset[env] = st == SO101_STEP_LAST; S.solver_iter[env] = iters; S.ncon[env] = s.ncon;
-    if (bad) atomicAdd(S.diverged_count, 1);
-    if (dropped) atomicAdd(S.diverged_count + 1, dropped);
+  if (!last) {
+    scene_broadphase(sm, s, pb, env, sub + 1, dropped, lane);
+  } else {
+    PROF_START(s);
+    const bool bad = pb.flags[env] != 0;
+    const int t = S.step[env] + 1;
+    float reward = scene_reward(sm, s), discount = 1.f;
+    uint8_t st = (cfg.last_step > 0 && t >= cfg.last_step) ? SO101_STEP_LAST : SO101_STEP_MID;
+    if (cfg.terminate_on_success && reward >= 1.f) { discount = 0.f; st = SO101_STEP_LAST; }  // so100_task.py:292-302
+    if (bad) { reward = 0.f; discount = 0.f; st = SO101_STEP_LAST; }                         // task_suite.py:153
+    if (lane == 0) {
+      S.step[env] = t; S.needs_reset[env] = st == SO101_STEP_LAST; S.solver_iter[env] = iters; S.ncon[env] = s.ncon;
+      if (bad) atomicAdd(S.diverged_count, 1);
+    }
+    write_obs_scene(cfg, S, out, s, env, t, reward, discount, st, lane);
+    PROF_ACC(s, P_TASK, lane);
   }
-  write_obs_scene(cfg, S, out, s, env, t, reward, discount, st, lane);
-  PROF_ACC(s, P_TASK, lane);
-  if (s.profon && lane == 0)
-    for (int i = 0; i < 16; i++) atomicAdd(S.prof + i, (unsigned long long)s.prof[i]);
+  if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
+  prof_flush(s, S, lane);
 }
 
 template <typename T>
@@ -1111,32 +1323,58 @@ __global__ void scene_reset_kernel(const __grid_constant__ StepCfg cfg, const En
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Scratch<T> *all = reinterpret_cast<Scratch<T> *>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int env = blockIdx.x * WARPS + wib;
+  const int env = blockIdx.x * WARPS_SOLVE + wib;
   if (env >= S.N) return;
   if (mask && !mask[env]) return;
   reset_env_scene(cfg, S, out, all[wib], env, lane);
 }
 
 template <typename T>
-size_t scene_smem_bytes() { return sizeof(Scratch<T>) * WARPS; }
+size_t scene_smem_bytes() {
+  const size_t a = sizeof(Scratch<T>) * WARPS_SOLVE, b = sizeof(NarrowScratch<T>) * WARPS_NARROW;
+  return a > b ? a : b;
+}
 
 template <typename T>
-void launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const float *action,
-                       const so101_step_out &out, cudaStream_t stream) {
+int scene_narrow_grid() {
+  const size_t smem_nar = sizeof(NarrowScratch<T>) * WARPS_NARROW;
+  cudaFuncSetAttribute(scene_narrow_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nar);
+  int nb = 0, dev = 0, sms = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scene_narrow_kernel<T>, WARPS_NARROW * 32, smem_nar);
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (nb > 0 ? nb : 1) * (sms > 0 ? sms : 1);
+}
+
+// Launches of one control step: 1 memset + 1 + 2 * nsub kernels, all on the caller's stream.  Returns the kernel count.
+template <typename T>
+int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
+                      const float *action, const so101_step_out &out, cudaStream_t stream) {
   static bool configured = false;
-  const size_t smem = scene_smem_bytes<T>();
+  const size_t smem_env = sizeof(Scratch<T>) * WARPS_SOLVE, smem_nar = sizeof(NarrowScratch<T>) * WARPS_NARROW;
   if (!configured) {
-    cudaFuncSetAttribute(scene_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(scene_reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(scene_begin_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
+    cudaFuncSetAttribute(scene_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
+    cudaFuncSetAttribute(scene_narrow_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nar);
+    cudaFuncSetAttribute(scene_reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
     configured = true;
   }
-  scene_step_kernel<T><<<(S.N + WARPS - 1) / WARPS, WARPS * 32, smem, stream>>>(am, sm, cfg, S, action, out);
+  cudaMemsetAsync(pb.nwork, 0, sizeof(int) * 2 * (cfg.nsub + 1), stream);
+  const int grid_env = (S.N + WARPS_SOLVE - 1) / WARPS_SOLVE;
+  scene_begin_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, stream>>>(am, sm, cfg, S, pb, action, out);
+  // narrow phase: persistent grid sized to the machine (pairs are pulled with an atomic cursor)
+  const int grid_nar = pb.narrow_grid;
+  for (int sub = 0; sub < cfg.nsub; sub++) {
+    scene_narrow_kernel<T><<<grid_nar, WARPS_NARROW * 32, smem_nar, stream>>>(sm, cfg, S, pb, sub);
+    scene_solve_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, stream>>>(am, sm, cfg, S, pb, out, sub);
+  }
+  return 1 + 2 * cfg.nsub;
 }
 template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream) {
-  const size_t smem = scene_smem_bytes<T>();
+  const size_t smem = sizeof(Scratch<T>) * WARPS_SOLVE;
   cudaFuncSetAttribute(scene_reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  scene_reset_kernel<T><<<(S.N + WARPS - 1) / WARPS, WARPS * 32, smem, stream>>>(cfg, S, mask, out);
+  scene_reset_kernel<T><<<(S.N + WARPS_SOLVE - 1) / WARPS_SOLVE, WARPS_SOLVE * 32, smem, stream>>>(cfg, S, mask, out);
 }
 
 }  // namespace so101

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <vector>
 
@@ -29,6 +30,7 @@ struct SceneModel {
   // geoms
   const int *geom_type, *geom_body, *geom_slot, *geom_vertadr, *geom_vertnum, *geom_condim, *geom_priority;
   const T *geom_pos, *geom_mat, *geom_size, *geom_bcenter, *geom_rbound;  // body frame (static geoms: world frame)
+  const T *geom_aabb;  // [ngeom][6] centre, half sizes of the geom's bounding box in the GEOM frame (mid phase)
   const T *geom_friction, *geom_solref, *geom_solimp, *geom_solmix, *geom_margin, *geom_gap;
   const Vec4<T> *hull_vert;  // body-frame hull vertices, 16/32-byte aligned for vector loads
   // bodies
@@ -144,6 +146,24 @@ struct SceneModelHost {
       for (int r = 0; r < 3; r++) { c[r] = xpos[3 * i + r]; for (int k = 0; k < 3; k++) c[r] += xmat[9 * i + 3 * r + k] * bbc[3 * i + k]; }
       for (int r = 0; r < 3; r++) bbc[3 * i + r] = c[r];
     }
+    // geom-frame bounding boxes for the oriented-box mid phase (hull geoms carry an identity geom frame: body / world axes)
+    std::vector<double> gaabb(6 * ngeom, 0.0);
+    for (int g = 0; g < ngeom; g++) {
+      const int ty = b.I("geom_type")[g];
+      const double *sz = &b.F("geom_size")[3 * g];
+      double *o = &gaabb[6 * g];
+      if (ty == G_HULL) {
+        const int adr = b.I("geom_vertadr")[g], num = b.I("geom_vertnum")[g];
+        double lo[3] = {1e30, 1e30, 1e30}, hi[3] = {-1e30, -1e30, -1e30};
+        for (int v = adr; v < adr + num; v++)
+          for (int r = 0; r < 3; r++) { lo[r] = std::min(lo[r], hv[3 * v + r]); hi[r] = std::max(hi[r], hv[3 * v + r]); }
+        for (int r = 0; r < 3; r++) { o[r] = 0.5 * (lo[r] + hi[r]); o[3 + r] = 0.5 * (hi[r] - lo[r]); }
+      } else if (ty == G_BOX) { o[3] = sz[0]; o[4] = sz[1]; o[5] = sz[2]; }
+      else if (ty == G_CYLINDER) { o[3] = o[4] = sz[0]; o[5] = sz[1]; }
+      else if (ty == G_CAPSULE) { o[3] = o[4] = sz[0]; o[5] = sz[0] + sz[1]; }
+      else if (ty == G_SPHERE) { o[3] = o[4] = o[5] = sz[0]; }
+      else { o[3] = o[4] = o[5] = 1e9; }  // plane: never used as a box
+    }
     std::vector<Vec4<T>> verts(hv.size() / 3);
     for (size_t i = 0; i < verts.size(); i++) verts[i] = Vec4<T>{(T)hv[3 * i], (T)hv[3 * i + 1], (T)hv[3 * i + 2], T(0)};
     SceneModel<T> &d = dev;
@@ -152,7 +172,7 @@ struct SceneModelHost {
     d.geom_vertadr = up(b.I("geom_vertadr")); d.geom_vertnum = up(b.I("geom_vertnum"));
     d.geom_condim = up(b.I("geom_condim")); d.geom_priority = up(b.I("geom_priority"));
     d.geom_pos = up(cvt(gpos)); d.geom_mat = up(cvt(gmat)); d.geom_size = up(cvt(b.F("geom_size")));
-    d.geom_bcenter = up(cvt(gbc)); d.geom_rbound = up(cvt(b.F("geom_rbound")));
+    d.geom_bcenter = up(cvt(gbc)); d.geom_rbound = up(cvt(b.F("geom_rbound"))); d.geom_aabb = up(cvt(gaabb));
     d.geom_friction = up(cvt(b.F("geom_friction"))); d.geom_solref = up(cvt(b.F("geom_solref"))); d.geom_solimp = up(cvt(b.F("geom_solimp")));
     d.geom_solmix = up(cvt(b.F("geom_solmix"))); d.geom_margin = up(cvt(b.F("geom_margin"))); d.geom_gap = up(cvt(b.F("geom_gap")));
     d.hull_vert = up(verts);

@@ -312,22 +312,59 @@ class BatchedEnvironment:
 
   # so100_hand_over.py:34-55 placement distributions; rest heights from the reference's own reset state (KAT-1,
   # so101_rl.ipynb:221-223: banana z = 0.4217, bowl z = 0.4226)
-  def sample_prop_initial_states(self, seed: int = 0, clearance: float = 0.003, settle_steps: int = 25):
-    """BASELINE config 3 initial states: banana ~ U([0.2,-0.1],[0.3,0.1]) with yaw U(+-0.1 pi), bowl ~ U([-0.3,-0.1],[-0.2,0.1]),
-    arm qpos = 0 (home is never applied, so100_task.py:308-313), dropped from `clearance` above the rest height and settled
-    on the device for `settle_steps` control steps with the arm command held at 0; the arm state is then restored
-    ([upstream] PropPlacer settle_physics freezes non-prop joints).  Installs the result as the per-env reset state."""
+  def _bowl_obstacles(self, z_bowl: float):
+    """Static upright cylinders the bowl would penetrate when placed at height z_bowl with identity rotation: list of
+    (cx, cy, reject_radius).  [upstream] PropPlacer(ignore_collisions=False) rejects such samples (so100_hand_over.py:216-221);
+    here the test is geometric: the bowl's hull vertices below the cylinder's top face, as a disc around the bowl axis."""
+    m = self.model
+    bowl_body = int(m['prop_body'][1])
+    verts = m['hull_vert'].reshape(-1, 3)
+    bv = np.concatenate([verts[a:a + n] for g, (a, n) in enumerate(zip(m['geom_vertadr'], m['geom_vertnum']))
+                         if m['geom_body'][g] == bowl_body and m['geom_type'][g] == 5])
+    out = []
+    for g in range(int(m['ngeom'])):
+      b = int(m['geom_body'][g])
+      if m['geom_type'][g] != 3 or m['body_weld'][b] != 0 or m['body_parent'][b] != 0:
+        continue
+      c = m['body_pos'].reshape(-1, 3)[b] + m['geom_pos'].reshape(-1, 3)[g]
+      r, h = m['geom_size'].reshape(-1, 3)[g][:2]
+      low = bv[(z_bowl + bv[:, 2] < c[2] + h) & (z_bowl + bv[:, 2] > c[2] - h)]
+      if len(low):  # the YCB bowl's axis is offset from its body origin: measure the disc about the bounding-box centre
+        ax = 0.5 * (bv.min(0) + bv.max(0))
+        out.append((float(c[0] - ax[0]), float(c[1] - ax[1]), float(r + np.hypot(low[:, 0] - ax[0], low[:, 1] - ax[1]).max())))
+    return out
+
+  def sample_prop_initial_states(self, seed: int = 0, clearance: float = 0.003, settle_steps: int = 25, max_attempts: int = 20,
+                                 spawn_z: float | None = None):
+    """BASELINE config 3 initial states: banana ~ U([0.2,-0.1],[0.3,0.1]) with yaw U(+-0.1 pi) (collisions ignored), bowl ~
+    U([-0.3,-0.1],[-0.2,0.1]) re-sampled up to `max_attempts` times while it would penetrate the static bowl obstacle
+    (scene_pbr.xml:144-146; so100_hand_over.py:208-229), arm qpos = 0 (home is never applied, so100_task.py:308-313).  Props
+    start `clearance` above their rest height and are settled on the device for `settle_steps` control steps with the arm
+    command held at 0; the arm state is then restored ([upstream] PropPlacer settle_physics freezes non-prop joints).
+    `spawn_z` (the reference uses 0.45 for both props, so100_hand_over.py:37-55) overrides the rest-height start: the props
+    then drop ~3 cm and need ~50 settle steps.  Installs the result as the per-env reset state."""
     if self.nq != 20:
       raise RuntimeError('sample_prop_initial_states needs the SO100HandOverBanana model')
     N, dev = self.num_envs, self.device
     g = torch.Generator(device='cpu'); g.manual_seed(int(seed))
-    u = torch.rand(N, 5, generator=g).to(dev)
+    u = torch.rand(N, 5, generator=g)
+    zo, zb = (0.4217 + clearance, 0.4226 + clearance) if spawn_z is None else (float(spawn_z), float(spawn_z))
+    obstacles = self._bowl_obstacles(zb)
+    for _ in range(max_attempts - 1):
+      bx, by = -0.3 + 0.1 * u[:, 3], -0.1 + 0.2 * u[:, 4]
+      bad = torch.zeros(N, dtype=torch.bool)
+      for cx, cy, rr in obstacles:
+        bad |= torch.hypot(bx - cx, by - cy) < rr
+      if not bool(bad.any()):
+        break
+      u[bad, 3:5] = torch.rand(int(bad.sum()), 2, generator=g)
+    u = u.to(dev)
     q = torch.tensor(self.model['qpos0'], dtype=torch.float32, device=dev).repeat(N, 1)
     q[:, :6] = 0
-    q[:, 6] = 0.2 + 0.1 * u[:, 0]; q[:, 7] = -0.1 + 0.2 * u[:, 1]; q[:, 8] = 0.4217 + clearance
+    q[:, 6] = 0.2 + 0.1 * u[:, 0]; q[:, 7] = -0.1 + 0.2 * u[:, 1]; q[:, 8] = zo
     yaw = (2 * u[:, 2] - 1) * 0.1 * np.pi
     q[:, 9] = torch.cos(yaw / 2); q[:, 10] = 0; q[:, 11] = 0; q[:, 12] = torch.sin(yaw / 2)
-    q[:, 13] = -0.3 + 0.1 * u[:, 3]; q[:, 14] = -0.1 + 0.2 * u[:, 4]; q[:, 15] = 0.4226 + clearance
+    q[:, 13] = -0.3 + 0.1 * u[:, 3]; q[:, 14] = -0.1 + 0.2 * u[:, 4]; q[:, 15] = zb
     q[:, 16] = 1; q[:, 17:20] = 0
     v = torch.zeros(N, self.nv, dtype=torch.float32, device=dev)
     self.set_initial_state(q, v)

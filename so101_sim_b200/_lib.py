@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libso101_b200.so')
+LIB_PATH = os.environ.get('SO101_B200_LIB') or os.path.join(_HERE, 'libso101_b200.so')  # override: developer A/B builds only
 
 
 class StepOut(ctypes.Structure):

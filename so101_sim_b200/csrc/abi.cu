@@ -198,7 +198,7 @@ struct Handle : HandleBase {
     d_steptype = dalloc<uint8_t>(N);
     if (scene) {  // inter-kernel scratch of the scene pipeline
       pipe.xpos = dalloc<T>(N * NSLOT * 3); pipe.xmat = dalloc<T>(N * NSLOT * 9);
-      pipe.work = dalloc<uint2>(N * PAIRCAP); pipe.nwork = dalloc<int>(2 * (c.n_substeps + 1));
+      pipe.work = dalloc<uint2>(N * PAIRCAP); pipe.nwork = dalloc<int>(4 * (c.n_substeps + 1)); pipe.big = dalloc<int>(N);
       pipe.con = dalloc<T>(N * CONBUF * 8); pipe.con_key = dalloc<int>(N * CONBUF); pipe.ncon_raw = dalloc<int>(N);
       pipe.active = dalloc<uint8_t>(N); pipe.flags = dalloc<uint8_t>(N);
       pipe.narrow_grid = scene_narrow_grid<T>();

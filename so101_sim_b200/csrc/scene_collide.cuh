@@ -77,7 +77,7 @@ template <typename T> __device__ __forceinline__ void local2world(const Shape<T>
 
 // world pose of geom g.  xpos/xmat: the env's dynamic body poses (shared memory).
 template <typename T>
-__device__ __forceinline__ void make_shape(const SceneModel<T> &sm, const T (*xpos)[3], const T (*xmat)[9], int g, Shape<T> &s) {
+__device__ __noinline__ void make_shape(const SceneModel<T> &sm, const T (*xpos)[3], const T (*xmat)[9], int g, Shape<T> &s) {
   s.type = sm.geom_type[g]; s.geom = g; s.vadr = sm.geom_vertadr[g]; s.vnum = sm.geom_vertnum[g];
   s.rbound = sm.geom_rbound[g];
   const int slot = sm.geom_slot[g];
@@ -118,6 +118,7 @@ __device__ __forceinline__ void support(const SceneModel<T> &sm, const Shape<T> 
   if (s.type == G_HULL) {
     T bv = -INFINITY;
     int bi = 0x7fffffff;
+    #pragma unroll 4
     for (int i = lane; i < s.vnum; i += 32) {
       const Vec4<T> v = sm.hull_vert[s.vadr + i];
       const T val = v.x * dl[0] + v.y * dl[1] + v.z * dl[2];
@@ -152,7 +153,7 @@ struct MPoint {
   T w[3], a[3], b[3];
 };
 template <typename T>
-__device__ __forceinline__ void msupport(const SceneModel<T> &sm, const Shape<T> &A, const Shape<T> &B, const T *d, MPoint<T> &p, int lane) {
+__device__ __noinline__ void msupport(const SceneModel<T> &sm, const Shape<T> &A, const Shape<T> &B, const T *d, MPoint<T> &p, int lane) {
   const T nd[3] = {-d[0], -d[1], -d[2]};
   support(sm, A, d, p.a, lane); support(sm, B, nd, p.b, lane);
   sub3(p.w, p.a, p.b);
@@ -160,11 +161,12 @@ __device__ __forceinline__ void msupport(const SceneModel<T> &sm, const Shape<T>
 
 // boolean GJK; mirrors gjk_intersect() of the oracle.  Uniform control flow across the warp.
 template <typename T>
-__device__ int gjk_intersect(const SceneModel<T> &sm, const Shape<T> &A, const Shape<T> &B, MPoint<T> *S, int &np, int lane) {
+__device__ __noinline__ int gjk_intersect(const SceneModel<T> &sm, const Shape<T> &A, const Shape<T> &B, MPoint<T> *S, int &np, int lane) {
   T d[3];
   sub3(d, B.center, A.center);
   if (dot3(d, d) < T(1e-20)) { d[0] = T(1); d[1] = T(0); d[2] = T(0); }
   int n = 0;
+  #pragma unroll 1
   for (int it = 0; it < 64; it++) {
     MPoint<T> p;
     msupport(sm, A, B, d, p, lane);
@@ -226,7 +228,7 @@ __device__ __forceinline__ void epa_putv(CollideScratch<T> &cs, int i, const MPo
 }
 // uniform; returns new face index or -1
 template <typename T>
-__device__ int epa_add_face(CollideScratch<T> &cs, int &nf, int a, int b, int c, const T *inside, int lane) {
+__device__ __noinline__ int epa_add_face(CollideScratch<T> &cs, int &nf, int a, int b, int c, const T *inside, int lane) {
   if (nf >= EPA_MAXF) return -1;
   T va[3], vb[3], vc[3], ab[3], ac[3], n[3], t[3];
   epa_getv(cs, a, va); epa_getv(cs, b, vb); epa_getv(cs, c, vc);
@@ -249,10 +251,11 @@ __device__ int epa_add_face(CollideScratch<T> &cs, int &nf, int a, int b, int c,
 }
 
 template <typename T>
-__device__ int epa(const SceneModel<T> &sm, CollideScratch<T> &cs, const Shape<T> &A, const Shape<T> &B, const MPoint<T> *S, int n, T *normal,
+__device__ __noinline__ int epa(const SceneModel<T> &sm, CollideScratch<T> &cs, const Shape<T> &A, const Shape<T> &B, const MPoint<T> *S, int n, T *normal,
                    T &depth, T *pa, T *pb, int lane) {
   int nv = 0, nf = 0;
   if (n == 1) return 0;
+  #pragma unroll 1
   for (int i = 0; i < n; i++) epa_putv(cs, nv++, S[i], lane);
   if (nv == 2) {
     T v0[3], v1[3], ab[3], ax[3] = {T(0), T(0), T(0)}, d[3];
@@ -291,6 +294,7 @@ __device__ int epa(const SceneModel<T> &sm, CollideScratch<T> &cs, const Shape<T
   auto find_best = [&]() {
     T bd = INFINITY;
     int bi = 0x7fffffff;
+    #pragma unroll 1
     for (int f = lane; f < nf; f += 32)
       if (cs.Falive[f] && cs.Fd[f] < bd) { bd = cs.Fd[f]; bi = f; }
 #pragma unroll
@@ -301,6 +305,7 @@ __device__ int epa(const SceneModel<T> &sm, CollideScratch<T> &cs, const Shape<T
     }
     return bi == 0x7fffffff ? -1 : bi;
   };
+  #pragma unroll 1
   for (int it = 0; it < 80; it++) {
     best = find_best();
     if (best < 0) return 0;
@@ -312,6 +317,7 @@ __device__ int epa(const SceneModel<T> &sm, CollideScratch<T> &cs, const Shape<T
     if (adv < T(sizeof(T) == 8 ? 1e-9 : 1e-6)) break;
     epa_putv(cs, nv, p, lane);
     // visibility (lanes over faces), then the horizon in face order on lane 0 (same order as the oracle)
+    #pragma unroll 1
     for (int f = lane; f < nf; f += 32) {
       if (!cs.Falive[f]) continue;
       T v0[3], t[3], fn[3] = {cs.Fn[0][f], cs.Fn[1][f], cs.Fn[2][f]};
@@ -322,12 +328,14 @@ __device__ int epa(const SceneModel<T> &sm, CollideScratch<T> &cs, const Shape<T
     __syncwarp();
     int nh = 0;
     if (lane == 0) {
+      #pragma unroll 1
       for (int f = 0; f < nf; f++) {
         if (cs.Falive[f] != 2) continue;
         cs.Falive[f] = 0;
         for (int e = 0; e < 3; e++) {
           const int a = cs.Fv[e][f], b = cs.Fv[(e + 1) % 3][f];
           int found = 0;
+          #pragma unroll 1
           for (int h = 0; h < nh; h++)
             if (cs.horizon[h][0] == b && cs.horizon[h][1] == a) {
               cs.horizon[h][0] = cs.horizon[nh - 1][0]; cs.horizon[h][1] = cs.horizon[nh - 1][1]; nh--; found = 1;
@@ -341,6 +349,7 @@ __device__ int epa(const SceneModel<T> &sm, CollideScratch<T> &cs, const Shape<T
     __syncwarp();
     if (nh == 0) break;
     int failed = 0;
+    #pragma unroll 1
     for (int h = 0; h < nh; h++)
       if (epa_add_face(cs, nf, cs.horizon[h][0], cs.horizon[h][1], nv, inside, lane) < 0) failed = 1;
     nv++;
@@ -366,6 +375,7 @@ __device__ int epa(const SceneModel<T> &sm, CollideScratch<T> &cs, const Shape<T
     pa[k] = bu * cs.Va[k][i0] + bv * cs.Va[k][i1] + bw * cs.Va[k][i2];
     pb[k] = bu * cs.Vb[k][i0] + bv * cs.Vb[k][i1] + bw * cs.Vb[k][i2];
   }
+  __syncwarp();  // the manifold stage re-uses the polytope's storage: every lane must be done reading it
   return 1;
 }
 
@@ -386,7 +396,7 @@ __device__ __forceinline__ void frame_from_normal(const T *n, T *frame) {  // [u
 
 // vertices of s within delta of the support plane along dir -> CCW 2-D convex polygon in (t1,t2) with heights.  Result in out (smem).
 template <typename T>
-__device__ int feature(const SceneModel<T> &sm, CollideScratch<T> &cs, const Shape<T> &s, const T *dir, const T *t1, const T *t2, T delta,
+__device__ __noinline__ int feature(const SceneModel<T> &sm, CollideScratch<T> &cs, const Shape<T> &s, const T *dir, const T *t1, const T *t2, T delta,
                        FPt<T> *out, int lane) {
   T sp[3];
   support(sm, s, dir, sp, lane);
@@ -396,6 +406,7 @@ __device__ int feature(const SceneModel<T> &sm, CollideScratch<T> &cs, const Sha
     T dl[3];
     mulmtv(dl, s.mat, dir);
     const T off = dot3(s.pos, dir);
+    #pragma unroll 1
     for (int base = 0; base < s.vnum && nc < MAXCAND; base += 32) {
       const int i = base + lane;
       bool in = false;
@@ -415,13 +426,16 @@ __device__ int feature(const SceneModel<T> &sm, CollideScratch<T> &cs, const Sha
   } else if (lane == 0) {
     T w[3];
     if (s.type == G_BOX) {
+      #pragma unroll 1
       for (int i = 0; i < 8; i++) {
         const T l[3] = {(i & 1 ? T(1) : T(-1)) * s.size[0], (i & 2 ? T(1) : T(-1)) * s.size[1], (i & 4 ? T(1) : T(-1)) * s.size[2]};
         local2world(s, l, w);
         if (dot3(w, dir) >= hmax - delta) { cs.cand[0][nc] = w[0]; cs.cand[1][nc] = w[1]; cs.cand[2][nc] = w[2]; nc++; }
       }
     } else if (s.type == G_CYLINDER) {
+      #pragma unroll 1
       for (int cap = -1; cap <= 1; cap += 2)
+        #pragma unroll 1
         for (int i = 0; i < 16; i++) {
           T sn, cn;
           t_sincos(T(2 * 3.14159265358979323846 / 16) * T(i), &sn, &cn);
@@ -430,6 +444,7 @@ __device__ int feature(const SceneModel<T> &sm, CollideScratch<T> &cs, const Sha
           if (dot3(w, dir) >= hmax - delta) { cs.cand[0][nc] = w[0]; cs.cand[1][nc] = w[1]; cs.cand[2][nc] = w[2]; nc++; }
         }
     } else if (s.type == G_CAPSULE) {
+      #pragma unroll 1
       for (int e = -1; e <= 1; e += 2) {
         const T l[3] = {T(0), T(0), T(e) * s.size[1]};
         local2world(s, l, w);
@@ -464,6 +479,7 @@ __device__ int feature(const SceneModel<T> &sm, CollideScratch<T> &cs, const Sha
     const int i = lane + 32 * k;
     if (i < nc) {
       int r = 0;
+      #pragma unroll 1
       for (int j = 0; j < nc; j++) {
         const FPt<T> o = cs.P[j];
         if (o.x < mine[k].x || (o.x == mine[k].x && (o.y < mine[k].y || (o.y == mine[k].y && j < i)))) r++;
@@ -482,16 +498,19 @@ __device__ int feature(const SceneModel<T> &sm, CollideScratch<T> &cs, const Sha
     else {
       FPt<T> *H = cs.Hh;
       int k = 0;
+      #pragma unroll 1
       for (int i = 0; i < nc; i++) {
         while (k >= 2 && (H[k - 1].x - H[k - 2].x) * (sorted[i].y - H[k - 2].y) - (H[k - 1].y - H[k - 2].y) * (sorted[i].x - H[k - 2].x) <= T(1e-14)) k--;
         H[k++] = sorted[i];
       }
+      #pragma unroll 1
       for (int i = nc - 2, t = k + 1; i >= 0; i--) {
         while (k >= t && (H[k - 1].x - H[k - 2].x) * (sorted[i].y - H[k - 2].y) - (H[k - 1].y - H[k - 2].y) * (sorted[i].x - H[k - 2].x) <= T(1e-14)) k--;
         H[k++] = sorted[i];
       }
       k--;
       if (k > MAXFEAT) k = MAXFEAT;
+      #pragma unroll 1
       for (int i = 0; i < k; i++) out[i] = H[i];
       nout = k;
     }
@@ -503,10 +522,11 @@ __device__ int feature(const SceneModel<T> &sm, CollideScratch<T> &cs, const Sha
 
 // ---- scalar helpers (lane 0 only) mirroring the oracle
 template <typename T>
-__device__ T feature_height(const FPt<T> *P, int n, T x, T y) {
+__device__ __noinline__ T feature_height(const FPt<T> *P, int n, T x, T y) {
   if (n == 1) return P[0].h;
   int i1 = 1;
   T best = T(-1);
+  #pragma unroll 1
   for (int i = 1; i < n; i++) { const T dx = P[i].x - P[0].x, dy = P[i].y - P[0].y, l = dx * dx + dy * dy; if (l > best) { best = l; i1 = i; } }
   const T ex = P[i1].x - P[0].x, ey = P[i1].y - P[0].y, eh = P[i1].h - P[0].h, el = ex * ex + ey * ey;
   if (n == 2 || el < T(1e-20)) {
@@ -516,6 +536,7 @@ __device__ T feature_height(const FPt<T> *P, int n, T x, T y) {
   }
   int i2 = -1;
   best = T(0);
+  #pragma unroll 1
   for (int i = 1; i < n; i++) { const T a = t_abs(ex * (P[i].y - P[0].y) - ey * (P[i].x - P[0].x)); if (a > best) { best = a; i2 = i; } }
   if (i2 < 0 || best < T(1e-12) * el) { const T t = ((x - P[0].x) * ex + (y - P[0].y) * ey) / el; return P[0].h + t * eh; }
   const T fx = P[i2].x - P[0].x, fy = P[i2].y - P[0].y, fh = P[i2].h - P[0].h, det = ex * fy - ey * fx;
@@ -524,10 +545,12 @@ __device__ T feature_height(const FPt<T> *P, int n, T x, T y) {
 }
 
 template <typename T>
-__device__ int clip_poly(CollideScratch<T> &cs, const FPt<T> *subj, int n, const FPt<T> *clip, int m, FPt<T> *out) {
+__device__ __noinline__ int clip_poly(CollideScratch<T> &cs, const FPt<T> *subj, int n, const FPt<T> *clip, int m, FPt<T> *out) {
   int na = n;
   FPt<T> *in = cs.bufA, *res = cs.bufB;
+  #pragma unroll 1
   for (int i = 0; i < n; i++) in[i] = subj[i];
+  #pragma unroll 1
   for (int e = 0; e < m && na > 0; e++) {
     const T ax = clip[e].x, ay = clip[e].y, bx = clip[(e + 1) % m].x, by = clip[(e + 1) % m].y;
     const T ex = bx - ax, ey = by - ay, tol = T(1e-12);
@@ -543,6 +566,7 @@ __device__ int clip_poly(CollideScratch<T> &cs, const FPt<T> *subj, int n, const
         if (pin) { res[nr++] = P; res[nr++] = I; } else { res[nr++] = I; res[nr++] = Q; }
       }
     } else {
+      #pragma unroll 1
       for (int i = 0; i < na; i++) {
         const FPt<T> P = in[i], Q = in[(i + 1) % na];
         const T sp = ex * (P.y - ay) - ey * (P.x - ax), sq = ex * (Q.y - ay) - ey * (Q.x - ax);
@@ -559,20 +583,24 @@ __device__ int clip_poly(CollideScratch<T> &cs, const FPt<T> *subj, int n, const
     na = nr;
     if (na > 2 * MAXFEAT) na = 2 * MAXFEAT;
   }
+  #pragma unroll 1
   for (int i = 0; i < na; i++) out[i] = in[i];
   return na;
 }
 
 template <typename T>
-__device__ int reduce_manifold(FPt<T> *P, T *dist, int n) {
+__device__ __noinline__ int reduce_manifold(FPt<T> *P, T *dist, int n) {
   if (n <= MAXMANI) return n;
   int sel[4] = {0, -1, -1, -1};
   // tolerant comparisons: the first candidate in polygon order wins a tie in any arithmetic (see the oracle)
+  #pragma unroll 1
   for (int i = 1; i < n; i++) if (dist[i] < dist[sel[0]] - T(1e-7)) sel[0] = i;
   T best = T(-1);
+  #pragma unroll 1
   for (int i = 0; i < n; i++) { const T dx = P[i].x - P[sel[0]].x, dy = P[i].y - P[sel[0]].y, l = dx * dx + dy * dy; if (l > best * T(1.0001) + T(1e-12)) { best = l; sel[1] = i; } }
   const T ex = P[sel[1]].x - P[sel[0]].x, ey = P[sel[1]].y - P[sel[0]].y;
   T bp = T(0), bn = T(0);
+  #pragma unroll 1
   for (int i = 0; i < n; i++) {
     if (i == sel[0] || i == sel[1]) continue;  // their cross product is 0 up to round-off (FMA contraction makes it +-eps)
     const T s = ex * (P[i].y - P[sel[0]].y) - ey * (P[i].x - P[sel[0]].x);
@@ -583,6 +611,7 @@ __device__ int reduce_manifold(FPt<T> *P, T *dist, int n) {
   T qd[4];
   int k = 0;
   for (int i = 0; i < 4; i++) if (sel[i] >= 0) { Q[k] = P[sel[i]]; qd[k] = dist[sel[i]]; k++; }
+  #pragma unroll 1
   for (int i = 0; i < k; i++) { P[i] = Q[i]; dist[i] = qd[i]; }
   return k;
 }

@@ -15,7 +15,8 @@ template <typename T>
 struct PipeBuf {
   T *xpos, *xmat;           // [N][NSLOT*3], [N][NSLOT*9]  world poses of the 8 dynamic bodies
   uint2 *work;              // [N*PAIRCAP]  narrow-phase work list: (env, g1 | g2 << 8 | pair index << 16)
-  int *nwork;               // [nsub+1][2]  per substep: items appended, cursor
+  int *nwork;               // [nsub+1][4]  per substep: pairs appended, pair cursor, large-tier envs queued, large-tier cursor
+  int *big;                 // [N]  envs deferred to the large solver tier in this substep
   T *con;                   // [N][CONBUF][8]  raw contacts: normal3, pos3, dist
   int *con_key;             // [N][CONBUF]     pair index << 20 | manifold index << 16 | g1 << 8 | g2  (sort key)
   int *ncon_raw;            // [N]

@@ -20,26 +20,16 @@
 //   semi-implicit Euler           (quaternion integration for the free joints)
 // Task layer: so100_task.py:266-368, so100_hand_over.py:238-275.
 #include "scene_kernel.cuh"
+#include "scene_solve.cuh"
 
 namespace so101 {
 
 constexpr int WARPS_SOLVE = 2;   // envs (warps) per CTA in the begin / solve kernels
 constexpr int WARPS_NARROW = 4;  // pairs (warps) in flight per CTA in the narrow-phase kernel
-constexpr int CSL = (NCON + 31) / 32;  // contact slots per lane
-constexpr int NH = NV * (NV + 1) / 2;  // 171 packed lower-triangular entries
-constexpr int NOUT = 8;                // contacts one pair can emit (manifold <= MAXMANI)
-
-template <typename T>
-struct SolveScratch {
-  // Jacobian storage is a pool of 6x6 blocks (rows x dofs of ONE dynamic body); a contact owns one block per dynamic body
-  // it touches (prop-vs-table: 1, grasp / prop-vs-prop: 2), block index fastest so that per-lane access is conflict-free.
-  T J[36][NBLK];
-  T w1[6][NBLK], w2[6][NBLK];  // J^T v1, J^T v2 per block: J^T Hc J = w1 w1^T - w2 w2^T + J^T diag(e) J
-  T aref[6][NCON], e[6][NCON];
-  T D0[NCON], mu[NCON], fri[3][NCON];
-  int info[NCON];      // dim | baseA << 8 | baseB << 16   (dof base 0 / 6 / 12, 31 = no block)
-  int blk[2][NCON];    // pool index of block A / block B (-1 = none)
-};
+constexpr int NOUT = 8;          // contacts one pair can emit (manifold <= MAXMANI)
+// solver tiers: almost every env has <= NC_S contacts (mean ~20); the rest is deferred to a second, larger instantiation
+constexpr int NC_S = 32, NB_S = 40;
+constexpr int NC_L = CONBUF, NB_L = CONBUF + 32;
 
 template <typename T>
 struct BroadScratch {
@@ -51,34 +41,31 @@ struct BroadScratch {
 template <typename T>
 struct NarrowScratch {
   CollideScratch<T> col;
+  Shape<T> shp[2];  // the pair's two shapes (world poses), shared by every stage
   int ncon, dbg, profon;
   long long prof[16];
   T c_pos[3][NOUT], c_normal[3][NOUT], c_dist[NOUT];
 };
 
-// per-env scratch of the begin / solve kernels
-template <typename T>
+// per-env scratch of the begin / solve kernels (NC contacts, NB Jacobian blocks)
+template <typename T, int NC, int NB>
 struct Scratch {
   T xpos[NSLOT][3], xmat[NSLOT][9];
   T arm_p[NJ][3], arm_a[NJ][3];
+  ArmKin<T> kin;
+  ArmRows<T> arows;
   T q[NQ], qd[NV], warm[NV], ctrl[NJ];
   T Mprop[NPROP][21];
   T Marm[21];
   T H[NH];
-  T qacc_s[NV], fsm[NV], delta[NV], grad[NV], search[NV], Md[NV], Ms[NV];
+  T qacc_s[NV], delta[NV], grad[NV], search[NV], Md[NV];
   int ncon, dbg, profon;
   long long prof[16];  // developer probe (SO101_PROFILE=1): per-stage clock64 sums and counters of this env
-  // contacts gathered from the narrow phase, in oracle order
-  T c_pos[3][NCON], c_frame[9][NCON], c_dist[NCON];
-  int c_g1[NCON], c_g2[NCON];
-  union U {
+  union {
     BroadScratch<T> broad;
-    SolveScratch<T> sol;
-    __device__ U() {}
-  } u;
+    SolveScratch<T, NC, NB> sol;
+  };
 };
-
-__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
 
 // stage profiler: lane 0 accumulates clock64 deltas into Scratch::prof when the handle was created with SO101_PROFILE=1
 enum { P_DYN = 0, P_BROAD, P_PLANE, P_GJK, P_EPA, P_MANI, P_ROWS, P_SOLVE, P_INTEG, P_TASK, P_NPQ, P_NCON, P_NEWTON, P_LINE, P_NEPA, P_NSUB };
@@ -98,8 +85,9 @@ __device__ __forceinline__ void prop_rotation(const T *quat, T *R) {
 }
 
 // positions: arm FK (registers) -> shared poses; prop poses.  Returns the arm kinematic state for the CRB/RNE sweep.
-template <typename T>
-__device__ __forceinline__ void scene_kinematics(const ArmModelT<T> &am, Scratch<T> &s, ArmKin<T> &k, int lane) {
+template <typename T, typename S>
+__device__ __noinline__ void scene_kinematics(const ArmModelT<T> &am, S &s, int lane) {
+  ArmKin<T> k;
   T qa[NJ];
 #pragma unroll
   for (int i = 0; i < NJ; i++) qa[i] = s.q[i];
@@ -124,12 +112,13 @@ __device__ __forceinline__ void scene_kinematics(const ArmModelT<T> &am, Scratch
 #pragma unroll
     for (int e = 0; e < 9; e++) s.xmat[NJ + lane][e] = Rp[e];
   }
+  if (lane == 0) s.kin = k;
   __syncwarp();
 }
 
 // free-joint mass block (packed lower 6x6) and bias force for prop p (uniform; [upstream] mj_crb / mj_rne for a free body)
-template <typename T>
-__device__ __forceinline__ void prop_dynamics(const SceneModel<T> &sm, const ArmModelT<T> &am, const Scratch<T> &s, int p, T (&M)[21], T (&bias)[6]) {
+template <typename T, typename S>
+__device__ __forceinline__ void prop_dynamics(const SceneModel<T> &sm, const ArmModelT<T> &am, const S &s, int p, T (&M)[21], T (&bias)[6]) {
   const T *R = s.xmat[NJ + p];
   const T m = sm.prop_mass[p];
   const T ip[3] = {sm.prop_ipos[p][0], sm.prop_ipos[p][1], sm.prop_ipos[p][2]};
@@ -179,7 +168,7 @@ __device__ __forceinline__ void emit_contact(NarrowScratch<T> &s, int &ncon, int
 }
 
 template <typename T>
-__device__ int manifold(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shape<T> &A, const Shape<T> &B, const T *n, T depth, int &ncon, int &dropped, int lane) {
+__device__ __noinline__ int manifold(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shape<T> &A, const Shape<T> &B, const T *n, T depth, int &ncon, int &dropped, int lane) {
   CollideScratch<T> &cs = s.col;
   T frame[9];
   frame_from_normal(n, frame);
@@ -190,17 +179,20 @@ __device__ int manifold(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shap
   const int nb = feature(sm, cs, B, nn, t1, t2, delta, cs.FB, lane);
   int u = 0;
   if (lane == 0) {
+#ifdef SO101_DEVICE_PRINTF
     if (s.dbg) {
       printf("MANIFOLD g=(%d,%d) n=(%.17g,%.17g,%.17g) depth=%.17g na=%d nb=%d\n", A.geom, B.geom, (double)n[0], (double)n[1], (double)n[2], (double)depth, na, nb);
       for (int i = 0; i < na; i++) printf("  FA[%d]=(%.17g,%.17g,%.17g)\n", i, (double)cs.FA[i].x, (double)cs.FA[i].y, (double)cs.FA[i].h);
       for (int i = 0; i < nb; i++) printf("  FB[%d]=(%.17g,%.17g,%.17g)\n", i, (double)cs.FB[i].x, (double)cs.FB[i].y, (double)cs.FB[i].h);
     }
+#endif
     for (int i = 0; i < nb; i++) cs.FB[i].h = -cs.FB[i].h;
     int nr = 0;
-    if (na >= 3 && nb >= 3) nr = clip_poly(cs, cs.FA, na, cs.FB, nb, cs.R);
-    else if (na >= 3 && nb == 2) nr = clip_poly(cs, cs.FB, nb, cs.FA, na, cs.R);
-    else if (nb >= 3 && na <= 2) nr = clip_poly(cs, cs.FA, na, cs.FB, nb, cs.R);
-    else if (na >= 3 && nb == 1) nr = clip_poly(cs, cs.FB, nb, cs.FA, na, cs.R);
+    {  // subject = the smaller feature when the other one is a polygon
+      const bool a_subj = (na >= 3 && nb >= 3) || (nb >= 3 && na <= 2), b_subj = na >= 3 && (nb == 2 || nb == 1);
+      if (a_subj) nr = clip_poly(cs, cs.FA, na, cs.FB, nb, cs.R);
+      else if (b_subj) nr = clip_poly(cs, cs.FB, nb, cs.FA, na, cs.R);
+    }
     int k = 0;
     for (int i = 0; i < nr; i++) {
       const T ha = feature_height(cs.FA, na, cs.R[i].x, cs.R[i].y), hb = feature_height(cs.FB, nb, cs.R[i].x, cs.R[i].y);
@@ -217,7 +209,9 @@ __device__ int manifold(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shap
         }
       if (!dup) { cs.R[u] = cs.R[i]; cs.mdist[u] = cs.mdist[i]; u++; }
     }
+#ifdef SO101_DEVICE_PRINTF
     if (s.dbg) { printf("  nr=%d k=%d u=%d\n", nr, k, u); for (int i = 0; i < u; i++) printf("  R[%d]=(%.17g,%.17g) d=%.17g\n", i, (double)cs.R[i].x, (double)cs.R[i].y, (double)cs.mdist[i]); }
+#endif
     u = reduce_manifold(cs.R, cs.mdist, u);
     for (int i = 0; i < u; i++) {
       T pos[3];
@@ -232,7 +226,7 @@ __device__ int manifold(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shap
 }
 
 template <typename T>
-__device__ void collide_convex(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shape<T> &A, const Shape<T> &B, int &ncon, int &dropped, int lane) {
+__device__ __noinline__ void collide_convex(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shape<T> &A, const Shape<T> &B, int &ncon, int &dropped, int lane) {
   MPoint<T> S[4];
   int n = 0;
   PROF_START(s);
@@ -257,7 +251,7 @@ __device__ void collide_convex(const SceneModel<T> &sm, NarrowScratch<T> &s, con
 }
 
 template <typename T>
-__device__ void collide_plane(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shape<T> &P, const Shape<T> &B, int &ncon, int &dropped, int lane) {
+__device__ __noinline__ void collide_plane(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shape<T> &P, const Shape<T> &B, int &ncon, int &dropped, int lane) {
   CollideScratch<T> &cs = s.col;
   const T n[3] = {P.mat[2], P.mat[5], P.mat[8]}, nn[3] = {-n[0], -n[1], -n[2]};
   T sp[3];
@@ -302,8 +296,8 @@ __device__ __forceinline__ void bound_half(int type, const T *size, T rbound, T 
 }
 
 // geom pose pieces needed by the mid phase, computed per lane
-template <typename T>
-__device__ __forceinline__ void geom_pose(const SceneModel<T> &sm, const Scratch<T> &s, int g, T *pos, T *mat) {
+template <typename T, typename S>
+__device__ __forceinline__ void geom_pose(const SceneModel<T> &sm, const S &s, int g, T *pos, T *mat) {
   const int slot = sm.geom_slot[g];
   if (slot < 0) {
     for (int c = 0; c < 3; c++) pos[c] = sm.geom_pos[3 * g + c];
@@ -355,8 +349,8 @@ __device__ __forceinline__ bool obb_overlap(const T *pa, const T *Ra, const T *h
 }
 
 // world oriented bounding box of geom g (local AABB of the geom in its own frame, inflated by 0.1 mm)
-template <typename T>
-__device__ __forceinline__ void geom_obb(const SceneModel<T> &sm, const Scratch<T> &s, int g, T *pos, T *mat, T *half) {
+template <typename T, typename S>
+__device__ __forceinline__ void geom_obb(const SceneModel<T> &sm, const S &s, int g, T *pos, T *mat, T *half) {
   T gp[3];
   geom_pose(sm, s, g, gp, mat);
   const T c[3] = {sm.geom_aabb[6 * g], sm.geom_aabb[6 * g + 1], sm.geom_aabb[6 * g + 2]};
@@ -369,9 +363,9 @@ __device__ __forceinline__ void geom_obb(const SceneModel<T> &sm, const Scratch<
 // Broad + mid phase of one env ([upstream] mj_collision before the narrow phase): body-pair bounding spheres, geom
 // bounding spheres, then oriented boxes (geom AABBs in the geom frame, as MuJoCo's mid phase uses).  The surviving
 // geom pairs are appended, in the oracle's pair order, to the device-wide work list of substep `sub`.
-template <typename T>
-__device__ void scene_broadphase(const SceneModel<T> &sm, Scratch<T> &s, const PipeBuf<T> &pb, int env, int sub, int &dropped, int lane) {
-  BroadScratch<T> &cs = s.u.broad;
+template <typename T, typename S>
+__device__ __noinline__ void scene_broadphase(const SceneModel<T> &sm, S &s, const PipeBuf<T> &pb, int env, int sub, int &dropped, int lane) {
+  BroadScratch<T> &cs = s.broad;
   PROF_START(s);
   // publish the body poses for the narrow-phase kernel
   {
@@ -452,450 +446,12 @@ __device__ void scene_broadphase(const SceneModel<T> &sm, Scratch<T> &s, const P
   __syncwarp();
   // append (env, g1 | g2 << 8 | pair index << 16) to the work list of this substep
   int base = 0;
-  if (lane == 0 && npq > 0) base = atomicAdd(pb.nwork + 2 * sub, npq);
+  if (lane == 0 && npq > 0) base = atomicAdd(pb.nwork + 4 * sub, npq);
   base = wshfl(base, 0);
   for (int i = lane; i < npq; i += 32) pb.work[(size_t)base + i] = make_uint2((unsigned)env, cs.pairq[i]);
   PROF_ACC(s, P_BROAD, lane);
   PROF_CNT(s, P_NPQ, npq, lane);
   __syncwarp();
-}
-
-// ------------------------------------------------------------------------------------------------ constraint rows (lane per contact)
-template <typename T>
-__device__ void build_rows(const SceneModel<T> &sm, const ArmModelT<T> &am, Scratch<T> &s, int &dropped, int lane) {
-  SolveScratch<T> &R = s.u.sol;
-  const int ncon = s.ncon;
-  // NOTE: contact geometry lives outside the union; the collision scratch is dead from here on.
-  int blk_base = 0;
-  for (int c0 = 0; c0 < ncon; c0 += 32) {
-    const int c = c0 + lane;
-    const bool valid = c < ncon;
-    // allocate Jacobian blocks: one per distinct dynamic body (dof base) of the contact, in contact order
-    int nb = 0;
-    if (valid) {
-      const int t1 = sm.body_slot[sm.geom_body[s.c_g1[c]]], t2 = sm.body_slot[sm.geom_body[s.c_g2[c]]];
-      const int a1 = t1 < 0 ? 31 : (t1 < NJ ? 0 : NJ + 6 * (t1 - NJ)), a2 = t2 < 0 ? 31 : (t2 < NJ ? 0 : NJ + 6 * (t2 - NJ));
-      nb = (a1 != 31) + (a2 != 31 && a2 != a1);
-    }
-    int incl = nb;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-    const int my_blk = blk_base + incl - nb;
-    blk_base += wshfl(incl, 31);
-    const bool fits = my_blk + nb <= NBLK;
-    dropped += __popc(__ballot_sync(FULL, valid && !fits));
-    if (!valid) continue;
-    const int g1 = s.c_g1[c], g2 = s.c_g2[c];
-    const int b1 = sm.geom_body[g1], b2 = sm.geom_body[g2];
-    const int s1 = sm.body_slot[b1], s2 = sm.body_slot[b2];
-    // [upstream] mj_contactParam
-    const int dim = max(sm.geom_condim[g1], sm.geom_condim[g2]);
-    const int p1 = sm.geom_priority[g1], p2 = sm.geom_priority[g2];
-    T f[3], mix;
-    if (p1 == p2) {
-      for (int k = 0; k < 3; k++) f[k] = max(sm.geom_friction[3 * g1 + k], sm.geom_friction[3 * g2 + k]);
-      const T m1 = sm.geom_solmix[g1], m2 = sm.geom_solmix[g2];
-      if (m1 >= T(1e-15) && m2 >= T(1e-15)) mix = m1 / (m1 + m2);
-      else if (m1 < T(1e-15) && m2 < T(1e-15)) mix = T(0.5);
-      else mix = m1 < T(1e-15) ? T(0) : T(1);
-    } else {
-      const int g = p1 > p2 ? g1 : g2;
-      for (int k = 0; k < 3; k++) f[k] = sm.geom_friction[3 * g + k];
-      mix = p1 > p2 ? T(1) : T(0);
-    }
-    T solref[2], solimp[5];
-    const T *r1 = sm.geom_solref + 2 * g1, *r2 = sm.geom_solref + 2 * g2;
-    if (r1[0] > T(0) && r2[0] > T(0)) for (int k = 0; k < 2; k++) solref[k] = mix * r1[k] + (T(1) - mix) * r2[k];
-    else for (int k = 0; k < 2; k++) solref[k] = min(r1[k], r2[k]);
-    for (int k = 0; k < 5; k++) solimp[k] = mix * sm.geom_solimp[5 * g1 + k] + (T(1) - mix) * sm.geom_solimp[5 * g2 + k];
-    const T margin = max(sm.geom_margin[g1], sm.geom_margin[g2]) - max(sm.geom_gap[g1], sm.geom_gap[g2]);
-    const T dist = s.c_dist[c];
-    // impedance, reference acceleration gains, regulariser
-    const T imp = impedance(solimp, dist, margin);
-    const T dmax = t_clamp(solimp[1], T(1e-4), T(0.9999));
-    T K, B;
-    if (solref[0] > T(0)) {
-      const T tc = solref[0] > T(2) * sm.timestep ? solref[0] : T(2) * sm.timestep;
-      K = T(1) / (dmax * dmax * tc * tc * solref[1] * solref[1]); B = T(2) / (dmax * tc);
-    } else { K = -solref[0] / (dmax * dmax); B = -solref[1] / dmax; }
-    const T tran = sm.body_invweight0[2 * b1] + sm.body_invweight0[2 * b2];
-    T R0 = (T(1) - imp) / imp * tran;
-    R0 = R0 > T(1e-15) ? R0 : T(1e-15);
-    R.D0[c] = T(1) / R0;
-    R.fri[0][c] = f[0]; R.fri[1][c] = f[1]; R.fri[2][c] = f[2];
-    R.mu[c] = dim > 1 ? f[0] * t_sqrt(T(1) / (sm.impratio > T(1e-15) ? sm.impratio : T(1e-15))) : T(0);
-    // Jacobian blocks
-    const T pos[3] = {s.c_pos[0][c], s.c_pos[1][c], s.c_pos[2][c]};
-    T fr[9];
-    for (int e = 0; e < 9; e++) fr[e] = s.c_frame[e][c];
-    int baseA = 31, baseB = 31, bA = -1, bB = -1;
-    if (fits) {
-      for (int k = 0; k < nb; k++)
-        for (int e = 0; e < 36; e++) R.J[e][my_blk + k] = T(0);
-      for (int side = 0; side < 2; side++) {
-        const int sl = side ? s2 : s1;
-        if (sl < 0) continue;
-        const T sgn = side ? T(1) : T(-1);
-        const int base = sl < NJ ? 0 : NJ + 6 * (sl - NJ);
-        int bi;
-        if (baseA == 31 || baseA == base) { baseA = base; bA = my_blk; bi = bA; }
-        else { baseB = base; bB = my_blk + 1; bi = bB; }
-        for (int col = 0; col < 6; col++) {
-          T tr[3] = {T(0), T(0), T(0)}, ro[3] = {T(0), T(0), T(0)};
-          if (sl < NJ) {
-            if (col > sl) continue;
-            const T a[3] = {s.arm_a[col][0], s.arm_a[col][1], s.arm_a[col][2]};
-            const T r[3] = {pos[0] - s.arm_p[col][0], pos[1] - s.arm_p[col][1], pos[2] - s.arm_p[col][2]};
-            cross3(tr, a, r);
-            ro[0] = a[0]; ro[1] = a[1]; ro[2] = a[2];
-          } else if (col < 3) {
-            tr[col] = T(1);
-          } else {
-            const T *Rm = s.xmat[sl];
-            const T a[3] = {Rm[col - 3], Rm[3 + col - 3], Rm[6 + col - 3]};
-            const T r[3] = {pos[0] - s.xpos[sl][0], pos[1] - s.xpos[sl][1], pos[2] - s.xpos[sl][2]};
-            cross3(tr, a, r);
-            ro[0] = a[0]; ro[1] = a[1]; ro[2] = a[2];
-          }
-          for (int r = 0; r < dim; r++) {
-            const T *ax = fr + 3 * (r % 3);
-            const T v = sgn * (r < 3 ? dot3(ax, tr) : dot3(ax, ro));
-            R.J[r * 6 + col][bi] += v;
-          }
-        }
-      }
-    }
-    const int edim = fits ? dim : 0;  // a contact whose blocks do not fit the pool is dropped (counted by the caller)
-    R.info[c] = edim | (baseA << 8) | (baseB << 16);
-    R.blk[0][c] = bA; R.blk[1][c] = bB;
-    // aref = -B vel - K imp (dist - margin) on the normal row; friction rows: -B vel
-    for (int r = 0; r < 6; r++) {
-      T vel = T(0);
-      if (r < edim) {
-        for (int col = 0; col < 6; col++) {
-          if (bA >= 0) vel += R.J[r * 6 + col][bA] * s.qd[baseA + col];
-          if (bB >= 0) vel += R.J[r * 6 + col][bB] * s.qd[baseB + col];
-        }
-      }
-      R.aref[r][c] = r < edim ? (-B * vel - (r == 0 ? K * imp * (dist - margin) : T(0))) : T(0);
-    }
-  }
-  __syncwarp();
-}
-
-// ------------------------------------------------------------------------------------------------ elliptic cone (per lane)
-template <typename T>
-struct Cone {
-  int dim;
-  T mu, S[6], D[6];
-};
-template <typename T>
-__device__ __forceinline__ void cone_setup(const SolveScratch<T> &R, int c, T impratio, Cone<T> &k) {
-  k.dim = R.info[c] & 0xff;
-  k.mu = R.mu[c];
-  const T f0 = R.fri[0][c], ft = R.fri[1][c], fr = R.fri[2][c], D0 = R.D0[c];
-  const T D1 = D0 * (impratio > T(1e-15) ? impratio : T(1e-15));
-  k.S[0] = k.mu; k.S[1] = f0; k.S[2] = f0; k.S[3] = ft; k.S[4] = fr; k.S[5] = fr;
-  k.D[0] = D0; k.D[1] = D1; k.D[2] = D1; k.D[3] = D1 * ft * ft / (f0 * f0); k.D[4] = D1 * fr * fr / (f0 * f0); k.D[5] = k.D[4];
-}
-// zone 0: satisfied; 1: quadratic (bottom); 2: cone surface.  force = -d cost / d jar.  Hessian = v1 v1^T - v2 v2^T + diag(e).
-template <typename T>
-__device__ __forceinline__ int cone_eval(const Cone<T> &k, const T *x, T &cost, T *force, T *v1, T *v2, T *e) {
-  const int dim = k.dim;
-  cost = T(0);
-#pragma unroll
-  for (int j = 0; j < 6; j++) { force[j] = T(0); v1[j] = T(0); v2[j] = T(0); e[j] = T(0); }
-  if (dim == 1) {
-    if (x[0] >= T(0)) return 0;
-    cost = T(0.5) * k.D[0] * x[0] * x[0]; force[0] = -k.D[0] * x[0]; e[0] = k.D[0];
-    return 1;
-  }
-  T U[6], T2 = T(0);
-  U[0] = x[0] * k.mu;
-#pragma unroll
-  for (int j = 1; j < 6; j++) { U[j] = j < dim ? x[j] * k.S[j] : T(0); T2 += U[j] * U[j]; }
-  const T N = U[0], Tt = t_sqrt(T2), mu = k.mu;
-  if (N >= mu * Tt || (Tt <= T(0) && N >= T(0))) return 0;
-  if (mu * N + Tt <= T(0) || (Tt <= T(0) && N < T(0))) {
-#pragma unroll
-    for (int j = 0; j < 6; j++)
-      if (j < dim) { cost += T(0.5) * k.D[j] * x[j] * x[j]; force[j] = -k.D[j] * x[j]; e[j] = k.D[j]; }
-    return 1;
-  }
-  const T Dm = k.D[0] / (mu * mu * (T(1) + mu * mu)), NmT = N - mu * Tt;
-  cost = T(0.5) * Dm * NmT * NmT;
-  force[0] = -Dm * NmT * mu;
-  const T sDm = t_sqrt(Dm), c2 = -Dm * NmT * mu;  // c2 > 0 in the middle zone
-  const T s2 = t_sqrt(c2 / (Tt * Tt * Tt));
-  v1[0] = sDm * mu;  // S0 * g0, g0 = 1
-#pragma unroll
-  for (int j = 1; j < 6; j++)
-    if (j < dim) {
-      force[j] = -force[0] / Tt * U[j] * k.S[j];
-      v1[j] = sDm * k.S[j] * (-mu * U[j] / Tt);
-      v2[j] = s2 * k.S[j] * U[j];
-      e[j] = c2 / Tt * k.S[j] * k.S[j];
-    }
-  return 2;
-}
-
-// ------------------------------------------------------------------------------------------------ Newton solver (warp)
-template <typename T>
-__device__ __forceinline__ T blockdiag_mv(const Scratch<T> &s, const T *x, int i) {  // (M x)_i for i < NV
-  T acc = T(0);
-  if (i < NJ) {
-    for (int j = 0; j < NJ; j++) acc += (j <= i ? s.Marm[tri(i, j)] : s.Marm[tri(j, i)]) * x[j];
-  } else {
-    const int p = (i - NJ) / 6, li = (i - NJ) % 6;
-    for (int j = 0; j < 6; j++) acc += (j <= li ? s.Mprop[p][tri(li, j)] : s.Mprop[p][tri(j, li)]) * x[NJ + 6 * p + j];
-  }
-  return acc;
-}
-
-// J_c x for the lane's contact: out[r] = sum_col J[r][col] x[base + col] over the contact's (<= 2) blocks
-template <typename T>
-__device__ __forceinline__ void contact_Jx(const SolveScratch<T> &R, int dim, int baseA, int baseB, int bA, int bB, const T *x, T *out) {
-#pragma unroll
-  for (int r = 0; r < 6; r++) {
-    T acc = T(0);
-    if (r < dim) {
-#pragma unroll
-      for (int col = 0; col < 6; col++) {
-        if (bA >= 0) acc += R.J[r * 6 + col][bA] * x[baseA + col];
-        if (bB >= 0) acc += R.J[r * 6 + col][bB] * x[baseB + col];
-      }
-    }
-    out[r] = acc;
-  }
-}
-
-template <typename T>
-__device__ void cholesky_packed(T *H, int lane) {  // in-place lower Cholesky of the packed NV x NV matrix, lanes = rows
-  for (int j = 0; j < NV; j++) {
-    T sacc = T(0);
-    if (lane >= j && lane < NV) {
-      sacc = H[tri(lane, j)];
-      for (int k = 0; k < j; k++) sacc -= H[tri(lane, k)] * H[tri(j, k)];
-    }
-    T dg = wshfl(sacc, j);
-    dg = t_sqrt(dg > T(1e-15) ? dg : T(1e-15));
-    if (lane >= j && lane < NV) H[tri(lane, j)] = lane == j ? dg : sacc / dg;
-    __syncwarp();
-  }
-}
-template <typename T>
-__device__ T chol_solve_packed(const T *L, T b, int lane) {  // lane i holds b_i; returns x_i
-  for (int k = 0; k < NV; k++) {
-    const T yk = wshfl(b, k) / L[tri(k, k)];
-    if (lane == k) b = yk;
-    else if (lane > k && lane < NV) b -= L[tri(lane, k)] * yk;
-  }
-  for (int k = NV - 1; k >= 0; k--) {
-    const T xk = wshfl(b, k) / L[tri(k, k)];
-    if (lane == k) b = xk;
-    else if (lane < k) b -= L[tri(k, lane)] * xk;
-  }
-  return b;
-}
-
-template <typename T>
-__device__ int scene_solve(const SceneModel<T> &sm, const ArmModelT<T> &am, Scratch<T> &s, const ArmRows<T> &arows, int max_iter, T tol, int lane) {
-  SolveScratch<T> &R = s.u.sol;
-  const int ncon = s.ncon;
-  const T xeps = sizeof(T) == 8 ? T(1e-14) : T(2e-6);
-  // per-lane contact cache
-  Cone<T> cone[CSL];
-  T jar0[CSL][6];
-  int cdim[CSL], cA[CSL], cB[CSL], kA[CSL], kB[CSL];
-#pragma unroll
-  for (int k = 0; k < CSL; k++) {
-    const int c = lane + 32 * k;
-    cdim[k] = 0; cA[k] = 31; cB[k] = 31; kA[k] = -1; kB[k] = -1;
-    if (c < ncon) {
-      cone_setup(R, c, sm.impratio, cone[k]);
-      cdim[k] = cone[k].dim; cA[k] = (R.info[c] >> 8) & 0xff; cB[k] = (R.info[c] >> 16) & 0xff;
-      kA[k] = R.blk[0][c]; kB[k] = R.blk[1][c];
-      contact_Jx(R, cdim[k], cA[k], cB[k], kA[k], kB[k], s.qacc_s, jar0[k]);
-#pragma unroll
-      for (int r = 0; r < 6; r++) jar0[k][r] -= R.aref[r][c];
-    }
-  }
-  // cost of the contact + arm rows at x (+ alpha * dx): returns warp-uniform (cost, d/dalpha, d2/dalpha2)
-  auto rows_line = [&](const T *x, const T *dx, T alpha, T &c, T &g, T &h) {
-    PROF_CNT(s, P_LINE, 1, lane);
-    T lc = T(0), lg = T(0), lh = T(0);
-#pragma unroll
-    for (int k = 0; k < CSL; k++) {
-      const int ci = lane + 32 * k;
-      if (ci < ncon) {
-        T jx[6], jv[6], xx[6], force[6], v1[6], v2[6], e[6], cc;
-        contact_Jx(R, cdim[k], cA[k], cB[k], kA[k], kB[k], x, jx);
-        contact_Jx(R, cdim[k], cA[k], cB[k], kA[k], kB[k], dx, jv);
-#pragma unroll
-        for (int r = 0; r < 6; r++) xx[r] = jar0[k][r] + jx[r] + alpha * jv[r];
-        cone_eval(cone[k], xx, cc, force, v1, v2, e);
-        T a1 = T(0), a2 = T(0);
-        lc += cc;
-#pragma unroll
-        for (int r = 0; r < 6; r++) { lg -= force[r] * jv[r]; a1 += v1[r] * jv[r]; a2 += v2[r] * jv[r]; lh += e[r] * jv[r] * jv[r]; }
-        lh += a1 * a1 - a2 * a2;
-      }
-    }
-    lc = warp_sum(lc); lg = warp_sum(lg); lh = warp_sum(lh);
-    // arm friction / limit rows (uniform)
-    T xa[NJ], da[NJ];
-#pragma unroll
-    for (int i = 0; i < NJ; i++) { xa[i] = x[i]; da[i] = dx[i]; }
-    arm_rows_line(am, arows, xa, da, alpha, lc, lg, lh);
-    c += lc; g += lg; h += lh;
-  };
-  const T *zero = s.Ms;  // scratch vector, zeroed here
-  if (lane < NV) s.Ms[lane] = T(0);
-  __syncwarp();
-  // warm start: keep delta only if it beats delta = 0
-  {
-    T c0 = T(0), cw = T(0), g = T(0), h = T(0);
-    rows_line(zero, zero, T(0), c0, g, h);
-    T md = lane < NV ? blockdiag_mv(s, s.delta, lane) * s.delta[lane] : T(0);
-    cw = T(0.5) * warp_sum(md);
-    rows_line(s.delta, zero, T(0), cw, g, h);
-    if (!(cw < c0)) { if (lane < NV) s.delta[lane] = T(0); }
-    __syncwarp();
-  }
-  int iter = 0;
-  for (; iter < max_iter; iter++) {
-    // gradient and the factored per-contact Hessians
-    const T mdl = lane < NV ? blockdiag_mv(s, s.delta, lane) : T(0);
-    T gl = mdl;  // lane i < NV accumulates grad_i
-    T frc[CSL][6];
-#pragma unroll
-    for (int k = 0; k < CSL; k++) {
-      const int ci = lane + 32 * k;
-#pragma unroll
-      for (int r = 0; r < 6; r++) frc[k][r] = T(0);
-      if (ci < ncon) {
-        T jx[6], xx[6], v1[6], v2[6], e[6], cc;
-        contact_Jx(R, cdim[k], cA[k], cB[k], kA[k], kB[k], s.delta, jx);
-#pragma unroll
-        for (int r = 0; r < 6; r++) xx[r] = jar0[k][r] + jx[r];
-        cone_eval(cone[k], xx, cc, frc[k], v1, v2, e);
-        // w = J^T v per block
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-          const int bi = side ? kB[k] : kA[k];
-          if (bi < 0) continue;
-#pragma unroll
-          for (int col = 0; col < 6; col++) {
-            T a1 = T(0), a2 = T(0);
-#pragma unroll
-            for (int r = 0; r < 6; r++) { const T j = R.J[r * 6 + col][bi]; a1 += j * v1[r]; a2 += j * v2[r]; }
-            R.w1[col][bi] = a1; R.w2[col][bi] = a2;
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < 6; r++) R.e[r][ci] = e[r];
-      }
-    }
-    // grad -= J^T force: one warp reduction per dof
-    for (int dof = 0; dof < NV; dof++) {
-      T v = T(0);
-#pragma unroll
-      for (int k = 0; k < CSL; k++) {
-        const int ci = lane + 32 * k;
-        if (ci < ncon) {
-          int col = -1, bi = -1;
-          if (kA[k] >= 0 && dof >= cA[k] && dof < cA[k] + 6) { col = dof - cA[k]; bi = kA[k]; }
-          else if (kB[k] >= 0 && dof >= cB[k] && dof < cB[k] + 6) { col = dof - cB[k]; bi = kB[k]; }
-          if (col >= 0) {
-#pragma unroll
-            for (int r = 0; r < 6; r++) v += R.J[r * 6 + col][bi] * frc[k][r];
-          }
-        }
-      }
-      v = warp_sum(v);
-      if (lane == dof) gl -= v;
-    }
-    // arm rows: force and diagonal Hessian (uniform)
-    T hdiag = T(0);
-    if (lane < NJ) {
-      const int i = lane;
-      T f = T(0);
-      const T x = arows.jar0_f[i] + s.delta[i], eta = am.frictionloss[i], rf = am.fr_R[i] * eta;
-      if (x <= -rf) f = eta;
-      else if (x >= rf) f = -eta;
-      else { f = -am.fr_D[i] * x; hdiag = am.fr_D[i]; }
-      if (arows.D_l[i] > T(0)) {
-        const T xl = arows.jar0_l[i] + arows.js[i] * s.delta[i];
-        if (xl < T(0)) { f += arows.js[i] * (-arows.D_l[i] * xl); hdiag += arows.D_l[i]; }
-      }
-      gl -= f;
-    }
-    if (lane < NV) { s.grad[lane] = gl; s.Md[lane] = mdl; }
-    const T gn = t_sqrt(warp_sum(lane < NV ? gl * gl : T(0)));
-    __syncwarp();
-    if (am.solver_scale * gn < tol) break;
-    // Hessian: lane per packed entry
-    for (int en = lane; en < NH; en += 32) {
-      // unpack (i, j), i >= j
-      int i = 0;
-      while ((i + 1) * (i + 2) / 2 <= en) i++;
-      const int j = en - i * (i + 1) / 2;
-      T acc = T(0);
-      if (i < NJ) acc = s.Marm[tri(i, j)];
-      else if ((i - NJ) / 6 == (j - NJ) / 6 && j >= NJ) acc = s.Mprop[(i - NJ) / 6][tri((i - NJ) % 6, (j - NJ) % 6)];
-      for (int c = 0; c < ncon; c++) {
-        const int inf = R.info[c], bA = (inf >> 8) & 0xff, bB = (inf >> 16) & 0xff, pA = R.blk[0][c], pB = R.blk[1][c];
-        int ci = -1, cj = -1, bi = -1, bj = -1;
-        if (pA >= 0 && i >= bA && i < bA + 6) { ci = i - bA; bi = pA; } else if (pB >= 0 && i >= bB && i < bB + 6) { ci = i - bB; bi = pB; }
-        if (pA >= 0 && j >= bA && j < bA + 6) { cj = j - bA; bj = pA; } else if (pB >= 0 && j >= bB && j < bB + 6) { cj = j - bB; bj = pB; }
-        if (ci < 0 || cj < 0) continue;
-        T a = R.w1[ci][bi] * R.w1[cj][bj] - R.w2[ci][bi] * R.w2[cj][bj];
-#pragma unroll
-        for (int r = 0; r < 6; r++) a += R.e[r][c] * R.J[r * 6 + ci][bi] * R.J[r * 6 + cj][bj];
-        acc += a;
-      }
-      s.H[en] = acc;
-    }
-    __syncwarp();
-    if (lane < NJ) s.H[tri(lane, lane)] += hdiag;
-    __syncwarp();
-    cholesky_packed(s.H, lane);
-    const T sr = chol_solve_packed(s.H, lane < NV ? -gl : T(0), lane);
-    if (lane < NV) s.search[lane] = sr;
-    __syncwarp();
-    const T msl = lane < NV ? blockdiag_mv(s, s.search, lane) : T(0);
-    const T q0 = T(0.5) * warp_sum(lane < NV ? s.delta[lane] * mdl : T(0));
-    const T q1 = warp_sum(lane < NV ? sr * mdl : T(0));
-    const T q2 = warp_sum(lane < NV ? sr * msl : T(0));
-    T f0 = q0, df0 = q1, ddf0 = q2;
-    rows_line(s.delta, s.search, T(0), f0, df0, ddf0);
-    if (df0 >= T(0) || ddf0 <= T(0)) break;
-    T alpha = -df0 / ddf0, lo = T(0), hi = T(-1), f = f0;
-    for (int ls = 0; ls < 30; ls++) {
-      T df = q1 + alpha * q2, ddf = q2;
-      f = q0 + alpha * q1 + T(0.5) * alpha * alpha * q2;
-      rows_line(s.delta, s.search, alpha, f, df, ddf);
-      if (t_abs(df) <= T(sizeof(T) == 8 ? 1e-13 : 1e-6) * t_abs(df0)) break;
-      if (df < T(0)) lo = alpha; else hi = alpha;
-      T next = alpha - df / ddf;
-      if (hi > T(0) && (next <= lo || next >= hi)) next = T(0.5) * (lo + hi);
-      else if (hi < T(0) && next <= lo) next = T(2) * alpha;
-      if (next == alpha || t_abs(next - alpha) <= xeps * t_abs(alpha) || (hi > T(0) && hi - lo <= xeps * hi)) { alpha = next; break; }
-      alpha = next;
-    }
-    T st = T(0), am_ = T(1);
-    if (lane < NV) {
-      st = alpha * sr;
-      s.delta[lane] += st;
-      am_ = t_abs(s.qacc_s[lane]) + t_abs(s.delta[lane]);
-      st = t_abs(st);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { st = max(st, __shfl_xor_sync(FULL, st, o)); am_ = max(am_, __shfl_xor_sync(FULL, am_, o)); }
-    __syncwarp();
-    if (am.solver_scale * (f0 - f) < tol || st <= xeps * max(am_, T(1))) { iter++; break; }
-  }
-  return iter;
 }
 
 // ------------------------------------------------------------------------------------------------ reward (so100_hand_over.py:238-275)
@@ -958,8 +514,8 @@ __device__ bool overlap_oobb_oobb(const T *p0, const T *q0, const T *h0, const T
   }
   return true;
 }
-template <typename T>
-__device__ float scene_reward(const SceneModel<T> &sm, const Scratch<T> &s) {
+template <typename T, typename S>
+__device__ float scene_reward(const SceneModel<T> &sm, const S &s) {
   // success_detector_utils.py:22-28 — linear velocity of either prop >= 1e-3 -> 0
   for (int p = 0; p < NPROP; p++) {
     T mx = T(0);
@@ -989,8 +545,8 @@ __device__ float scene_reward(const SceneModel<T> &sm, const Scratch<T> &s) {
 }
 
 // ------------------------------------------------------------------------------------------------ task layer: observations
-template <typename T>
-__device__ void write_obs_scene(const StepCfg &cfg, const EnvState<T> &S, const so101_step_out &out, const Scratch<T> &s, int env, int t, float reward,
+template <typename T, typename SC>
+__device__ void write_obs_scene(const StepCfg &cfg, const EnvState<T> &S, const so101_step_out &out, const SC &s, int env, int t, float reward,
                                 float discount, uint8_t st, int lane) {
   constexpr int SD = NQ + NV;
   const int dj = cfg.dj + 1, dp = cfg.dp + 1;
@@ -1020,8 +576,8 @@ __device__ void write_obs_scene(const StepCfg &cfg, const EnvState<T> &S, const 
   }
 }
 
-template <typename T>
-__device__ void reset_env_scene(const StepCfg &cfg, const EnvState<T> &S, const so101_step_out &out, Scratch<T> &s, int env, int lane) {
+template <typename T, typename SC>
+__device__ void reset_env_scene(const StepCfg &cfg, const EnvState<T> &S, const so101_step_out &out, SC &s, int env, int lane) {
   for (int i = lane; i < NQ; i += 32) { s.q[i] = S.init_qpos[(size_t)env * NQ + i]; S.qpos[(size_t)env * NQ + i] = s.q[i]; }
   for (int i = lane; i < NV; i += 32) { s.qd[i] = S.init_qvel[(size_t)env * NV + i]; S.qvel[(size_t)env * NV + i] = s.qd[i]; S.warm[(size_t)env * NV + i] = T(0); }
   if (lane < NJ) { s.ctrl[lane] = (T)cfg.home[lane] + (T)cfg.offsets[lane]; S.ctrl[(size_t)env * 6 + lane] = s.ctrl[lane]; }
@@ -1031,8 +587,8 @@ __device__ void reset_env_scene(const StepCfg &cfg, const EnvState<T> &S, const 
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
-template <typename T>
-__device__ __forceinline__ void prof_begin(Scratch<T> &s, const EnvState<T> &S, int lane) {
+template <typename SC, typename T>
+__device__ __forceinline__ void prof_begin(SC &s, const EnvState<T> &S, int lane) {
   if (lane == 0) {
     s.profon = S.prof != nullptr;
     for (int i = 0; i < 16; i++) s.prof[i] = 0;
@@ -1050,12 +606,13 @@ template <typename T>
 __global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_begin_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
                                                                       const __grid_constant__ StepCfg cfg, const EnvState<T> S, const PipeBuf<T> pb,
                                                                       const float *__restrict__ action, const so101_step_out out) {
+  using SC = Scratch<T, NC_S, NB_S>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Scratch<T> *all = reinterpret_cast<Scratch<T> *>(smem_raw);
+  SC *all = reinterpret_cast<SC *>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int env = blockIdx.x * WARPS_SOLVE + wib;
   if (env >= S.N) return;
-  Scratch<T> &s = all[wib];
+  SC &s = all[wib];
   if (lane == 0) pb.ncon_raw[env] = 0;
   if (S.needs_reset[env]) {  // the step() after a LAST step resets and returns FIRST; no physics this call
     reset_env_scene(cfg, S, out, s, env, lane);
@@ -1067,8 +624,7 @@ __global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_begin_kernel(const __g
   if (lane < NJ) S.ctrl[(size_t)env * 6 + lane] = (T)action[(size_t)env * 6 + lane] + (T)cfg.offsets[lane];  // so100_task.py:266-287
   if (lane == 0) { pb.active[env] = 1; pb.flags[env] = 0; }
   __syncwarp();
-  ArmKin<T> k;
-  scene_kinematics(am, s, k, lane);
+  scene_kinematics(am, s, lane);
   int dropped = 0;
   scene_broadphase(sm, s, pb, env, 0, dropped, lane);
   if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
@@ -1084,16 +640,17 @@ __global__ void __launch_bounds__(WARPS_NARROW * 32) scene_narrow_kernel(const _
   NarrowScratch<T> *all = reinterpret_cast<NarrowScratch<T> *>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   NarrowScratch<T> &s = all[wib];
-  const int nwork = pb.nwork[2 * sub];
+  const int nwork = pb.nwork[4 * sub];
   if (lane == 0) {
     s.profon = S.prof != nullptr; s.dbg = 0;
     for (int i = 0; i < 16; i++) s.prof[i] = 0;
   }
   __syncwarp();
   int dropped = 0;
+#pragma unroll 1
   for (;;) {
     int item = 0;
-    if (lane == 0) item = atomicAdd(pb.nwork + 2 * sub + 1, 1);
+    if (lane == 0) item = atomicAdd(pb.nwork + 4 * sub + 1, 1);
     item = wshfl(item, 0);
     if (item >= nwork) break;
     const uint2 w = pb.work[item];
@@ -1104,9 +661,10 @@ __global__ void __launch_bounds__(WARPS_NARROW * 32) scene_narrow_kernel(const _
       if (lane == 0) s.dbg = (env == cfg.dbg_env && S.step[env] == cfg.dbg_step);
       __syncwarp();
     }
-    Shape<T> A, B;
-    make_shape(sm, xpos, xmat, g1, A);
+    Shape<T> &A = s.shp[0], &B = s.shp[1];
+    make_shape(sm, xpos, xmat, g1, A);  // all lanes write the same values
     make_shape(sm, xpos, xmat, g2, B);
+    __syncwarp();
     int ncon = 0;
     if (A.type == G_PLANE) { PROF_START(s); collide_plane(sm, s, A, B, ncon, dropped, lane); PROF_ACC(s, P_PLANE, lane); }
     else collide_convex(sm, s, A, B, ncon, dropped, lane);
@@ -1130,19 +688,35 @@ __global__ void __launch_bounds__(WARPS_NARROW * 32) scene_narrow_kernel(const _
   prof_flush(s, S, lane);
 }
 
-// gather the env's raw contacts into shared memory in oracle order (pair order, then manifold order)
-template <typename T>
-__device__ void gather_contacts(const PipeBuf<T> &pb, Scratch<T> &s, int env, int &dropped, int lane) {
+// Gather the env's raw contacts into shared memory in oracle order (pair order, then manifold order).  Returns false (and
+// touches nothing) when the env needs more than NC contacts or NB Jacobian blocks: the caller defers it to the large tier.
+template <typename T, typename SC>
+__device__ __noinline__ bool gather_contacts(const SceneModel<T> &sm, const PipeBuf<T> &pb, SC &s, int env, int &dropped, int lane) {
+  auto &R = s.sol;
+  constexpr int NC = sizeof(R.D0) / sizeof(T), NB = sizeof(R.w1[0]) / sizeof(T);
   int nraw = pb.ncon_raw[env];
+  if (nraw > NC && NC < CONBUF) return false;
   if (nraw > CONBUF) { dropped += nraw - CONBUF; nraw = CONBUF; }
   const int *keys = pb.con_key + (size_t)env * CONBUF;
-  constexpr int RSL = (CONBUF + 31) / 32;
+  constexpr int RSL = (NC + 31) / 32;
   int mykey[RSL], rank[RSL];
+  int nblk = 0;
 #pragma unroll
-  for (int k = 0; k < RSL; k++) { const int i = lane + 32 * k; mykey[k] = i < nraw ? keys[i] : 0x7fffffff; rank[k] = 0; }
+  for (int k = 0; k < RSL; k++) {
+    const int i = lane + 32 * k;
+    mykey[k] = i < nraw ? keys[i] : 0x7fffffff; rank[k] = 0;
+    if (i < nraw) {
+      const int s1 = sm.body_slot[sm.geom_body[(mykey[k] >> 8) & 0xff]], s2 = sm.body_slot[sm.geom_body[mykey[k] & 0xff]];
+      const int a1 = s1 < 0 ? 31 : (s1 < NJ ? 0 : s1), a2 = s2 < 0 ? 31 : (s2 < NJ ? 0 : s2);
+      nblk += (a1 != 31) + (a2 != 31 && a2 != a1);
+    }
+  }
+  nblk = warp_sum(nblk);
+  if (nblk > NB && NC < CONBUF) return false;
   // rank = number of contacts with a smaller key (keys are unique: pair index and manifold index)
 #pragma unroll
   for (int kk = 0; kk < RSL; kk++) {
+#pragma unroll 1
     for (int jl = 0; jl < 32; jl++) {
       const int j = 32 * kk + jl;
       if (j >= nraw) break;
@@ -1151,41 +725,33 @@ __device__ void gather_contacts(const PipeBuf<T> &pb, Scratch<T> &s, int env, in
       for (int k = 0; k < RSL; k++) rank[k] += kj < mykey[k];
     }
   }
-  const int n = nraw < NCON ? nraw : NCON;
-  if (nraw > NCON) dropped += nraw - NCON;
 #pragma unroll
   for (int k = 0; k < RSL; k++) {
     const int i = lane + 32 * k;
-    if (i < nraw && rank[k] < NCON) {
+    if (i < nraw) {
       const int c = rank[k];
       const T *src = pb.con + ((size_t)env * CONBUF + i) * 8;
       const T nrm[3] = {src[0], src[1], src[2]};
       T frame[9];
       frame_from_normal(nrm, frame);
 #pragma unroll
-      for (int e = 0; e < 9; e++) s.c_frame[e][c] = frame[e];
-      s.c_pos[0][c] = src[3]; s.c_pos[1][c] = src[4]; s.c_pos[2][c] = src[5];
-      s.c_dist[c] = src[6];
-      s.c_g1[c] = (mykey[k] >> 8) & 0xff; s.c_g2[c] = mykey[k] & 0xff;
+      for (int e = 0; e < 9; e++) R.v.con.frame[e][c] = frame[e];
+      R.v.con.pos[0][c] = src[3]; R.v.con.pos[1][c] = src[4]; R.v.con.pos[2][c] = src[5];
+      R.v.con.dist[c] = src[6];
+      R.v.con.g1[c] = (mykey[k] >> 8) & 0xff; R.v.con.g2[c] = mykey[k] & 0xff;
     }
   }
-  if (lane == 0) { s.ncon = n; pb.ncon_raw[env] = 0; }
+  if (lane == 0) { s.ncon = nraw; pb.ncon_raw[env] = 0; }
   __syncwarp();
+  return true;
 }
 
-// Per substep, warp per env: smooth dynamics, constraint rows from the gathered contacts, Newton, Euler; then either the
-// kinematics + broad phase of the next substep or (last substep) the task layer.
-template <typename T>
-__global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_solve_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
-                                                                      const __grid_constant__ StepCfg cfg, const EnvState<T> S, const PipeBuf<T> pb,
-                                                                      const so101_step_out out, int sub) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Scratch<T> *all = reinterpret_cast<Scratch<T> *>(smem_raw);
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int env = blockIdx.x * WARPS_SOLVE + wib;
-  if (env >= S.N) return;
-  if (!pb.active[env]) return;
-  Scratch<T> &s = all[wib];
+// One substep of one env (warp): smooth dynamics, constraint rows from the gathered contacts, Newton, Euler; then either
+// the kinematics + broad phase of the next substep or (last substep) the task layer.  Returns false if the env must be
+// handled by the large solver tier instead (nothing has been modified in that case).
+template <typename T, typename SC>
+__device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
+                                          const so101_step_out &out, int sub, int env, SC &s, int lane) {
   prof_begin(s, S, lane);
   for (int i = lane; i < NQ; i += 32) s.q[i] = S.qpos[(size_t)env * NQ + i];
   for (int i = lane; i < NV; i += 32) { s.qd[i] = S.qvel[(size_t)env * NV + i]; s.warm[i] = S.warm[(size_t)env * NV + i]; }
@@ -1194,113 +760,104 @@ __global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_solve_kernel(const __g
   __syncwarp();
   int iters = 0, dropped = 0;
   const bool last = sub == cfg.nsub - 1;
+  PROF_START(s);
+  if (!gather_contacts(sm, pb, s, env, dropped, lane)) return false;
+  PROF_CNT(s, P_NCON, s.ncon, lane);
+  scene_kinematics(am, s, lane);
   {
-    PROF_START(s);
+    T qa[NJ], qda[NJ], ca[NJ], M[21], bias[NJ], frc[NJ], qs[NJ];
+#pragma unroll
+    for (int i = 0; i < NJ; i++) { qa[i] = s.q[i]; qda[i] = s.qd[i]; ca[i] = s.ctrl[i]; }
+    arm_crb_rne(am, s.kin, qda, M, bias);
+    arm_actuation(am, qa, qda, ca, frc);
+    T L[21];
+#pragma unroll
+    for (int i = 0; i < 21; i++) L[i] = M[i];
+    chol6(L);
+#pragma unroll
+    for (int i = 0; i < NJ; i++) qs[i] = frc[i] - bias[i];
+    chol6_solve(L, qs);
     ArmRows<T> arows;
-    {
-      ArmKin<T> k;
-      scene_kinematics(am, s, k, lane);
-      T qa[NJ], qda[NJ], ca[NJ], M[21], bias[NJ], frc[NJ], qs[NJ];
+    arm_make_rows(am, qa, qda, qs, arows);
+    if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < NJ; i++) { qa[i] = s.q[i]; qda[i] = s.qd[i]; ca[i] = s.ctrl[i]; }
-      arm_crb_rne(am, k, qda, M, bias);
-      arm_actuation(am, qa, qda, ca, frc);
-      T L[21];
+      for (int i = 0; i < 21; i++) s.Marm[i] = M[i];
 #pragma unroll
-      for (int i = 0; i < 21; i++) L[i] = M[i];
-      chol6(L);
-#pragma unroll
-      for (int i = 0; i < NJ; i++) qs[i] = frc[i] - bias[i];
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 21; i++) s.Marm[i] = M[i];
-#pragma unroll
-        for (int i = 0; i < NJ; i++) s.fsm[i] = qs[i];
-      }
-      chol6_solve(L, qs);
-      arm_make_rows(am, qa, qda, qs, arows);
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NJ; i++) s.qacc_s[i] = qs[i];
-      }
+      for (int i = 0; i < NJ; i++) s.qacc_s[i] = qs[i];
+      s.arows = arows;
     }
-    if (lane < NPROP) {  // one lane per prop
-      T M[21], bias[6], x[6];
-      prop_dynamics(sm, am, s, lane, M, bias);
-#pragma unroll
-      for (int i = 0; i < 21; i++) s.Mprop[lane][i] = M[i];
-#pragma unroll
-      for (int i = 0; i < 6; i++) { x[i] = -bias[i]; s.fsm[NJ + 6 * lane + i] = x[i]; }
-      chol6(M);
-      chol6_solve(M, x);
-#pragma unroll
-      for (int i = 0; i < 6; i++) s.qacc_s[NJ + 6 * lane + i] = x[i];
-    }
-    __syncwarp();
-    PROF_ACC(s, P_DYN, lane);
-    gather_contacts(pb, s, env, dropped, lane);
-    PROF_CNT(s, P_NCON, s.ncon, lane);
-    if (S.dbg_contacts && last) {  // parity probe: contacts of the last substep
-      float *dst = S.dbg_contacts + (size_t)env * (1 + 9 * NCON);
-      if (lane == 0) dst[0] = (float)s.ncon;
-      for (int c = lane; c < s.ncon; c += 32) {
-        float *r = dst + 1 + 9 * c;
-        r[0] = (float)s.c_g1[c]; r[1] = (float)s.c_g2[c]; r[2] = (float)s.c_dist[c];
-        for (int e = 0; e < 3; e++) { r[3 + e] = (float)s.c_pos[e][c]; r[6 + e] = (float)s.c_frame[e][c]; }
-      }
-    }
-    build_rows(sm, am, s, dropped, lane);
-    PROF_ACC(s, P_ROWS, lane);
-    if (lane < NV) s.delta[lane] = s.warm[lane] - s.qacc_s[lane];
-    __syncwarp();
-    iters = scene_solve(sm, am, s, arows, cfg.max_iter, (T)cfg.tol, lane);
-    __syncwarp();
-    PROF_ACC(s, P_SOLVE, lane);
-    PROF_CNT(s, P_NEWTON, iters, lane);
-    PROF_CNT(s, P_NSUB, 1, lane);
-    // [upstream] mj_Euler
-    T qacc = T(0);
-    if (lane < NV) {
-      qacc = s.qacc_s[lane] + s.delta[lane];
-      s.warm[lane] = qacc;
-      s.qd[lane] += sm.timestep * qacc;
-    }
-    const bool badnow = __any_sync(FULL, lane < NV && !(t_abs(qacc) < T(1e10)));
-    if (badnow && lane == 0) pb.flags[env] = 1;
-    __syncwarp();
-    if (lane < NJ) s.q[lane] += sm.timestep * s.qd[lane];
-    if (lane >= 8 && lane < 8 + NPROP) {
-      const int p = lane - 8;
-      T *qp = s.q + NJ + 7 * p;
-      const T *v = s.qd + NJ + 6 * p;
-      for (int c = 0; c < 3; c++) qp[c] += sm.timestep * v[c];
-      const T w[3] = {v[3], v[4], v[5]};
-      const T nw = t_sqrt(dot3(w, w)), ang = nw * sm.timestep;
-      T qn[4] = {qp[3], qp[4], qp[5], qp[6]};
-      if (ang > T(0)) {
-        T sn, cn;
-        t_sincos(T(0.5) * ang, &sn, &cn);
-        const T qr[4] = {cn, w[0] / nw * sn, w[1] / nw * sn, w[2] / nw * sn};
-        quat_mul(qn, qn, qr);
-      }
-      T n = t_sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
-      if (n < T(1e-15)) { qn[0] = T(1); qn[1] = qn[2] = qn[3] = T(0); n = T(1); }
-      for (int c = 0; c < 4; c++) qp[3 + c] = qn[c] / n;
-    }
-    __syncwarp();
-    PROF_ACC(s, P_INTEG, lane);
   }
+  if (lane < NPROP) {  // one lane per prop
+    T M[21], bias[6], x[6];
+    prop_dynamics(sm, am, s, lane, M, bias);
+#pragma unroll
+    for (int i = 0; i < 21; i++) s.Mprop[lane][i] = M[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) x[i] = -bias[i];
+    chol6(M);
+    chol6_solve(M, x);
+#pragma unroll
+    for (int i = 0; i < 6; i++) s.qacc_s[NJ + 6 * lane + i] = x[i];
+  }
+  __syncwarp();
+  PROF_ACC(s, P_DYN, lane);
+  if (S.dbg_contacts && last) {  // parity probe: contacts of the last substep
+    float *dst = S.dbg_contacts + (size_t)env * (1 + 9 * NCON);
+    const int n = s.ncon < NCON ? s.ncon : NCON;
+    if (lane == 0) dst[0] = (float)n;
+    for (int c = lane; c < n; c += 32) {
+      float *r = dst + 1 + 9 * c;
+      r[0] = (float)s.sol.v.con.g1[c]; r[1] = (float)s.sol.v.con.g2[c]; r[2] = (float)s.sol.v.con.dist[c];
+      for (int e = 0; e < 3; e++) { r[3 + e] = (float)s.sol.v.con.pos[e][c]; r[6 + e] = (float)s.sol.v.con.frame[e][c]; }
+    }
+  }
+  build_rows(sm, s, dropped, lane);
+  PROF_ACC(s, P_ROWS, lane);
+  if (lane < NV) s.delta[lane] = s.warm[lane] - s.qacc_s[lane];
+  __syncwarp();
+  iters = scene_solve(am, sm.impratio, s, cfg.max_iter, (T)cfg.tol, lane);
+  __syncwarp();
+  PROF_ACC(s, P_SOLVE, lane);
+  PROF_CNT(s, P_NEWTON, iters, lane);
+  PROF_CNT(s, P_NSUB, 1, lane);
+  // [upstream] mj_Euler
+  T qacc = T(0);
+  if (lane < NV) {
+    qacc = s.qacc_s[lane] + s.delta[lane];
+    s.warm[lane] = qacc;
+    s.qd[lane] += sm.timestep * qacc;
+  }
+  const bool badnow = __any_sync(FULL, lane < NV && !(t_abs(qacc) < T(1e10)));
+  if (badnow && lane == 0) pb.flags[env] = 1;
+  __syncwarp();
+  if (lane < NJ) s.q[lane] += sm.timestep * s.qd[lane];
+  if (lane >= 8 && lane < 8 + NPROP) {
+    const int p = lane - 8;
+    T *qp = s.q + NJ + 7 * p;
+    const T *v = s.qd + NJ + 6 * p;
+    for (int c = 0; c < 3; c++) qp[c] += sm.timestep * v[c];
+    const T w[3] = {v[3], v[4], v[5]};
+    const T nw = t_sqrt(dot3(w, w)), ang = nw * sm.timestep;
+    T qn[4] = {qp[3], qp[4], qp[5], qp[6]};
+    if (ang > T(0)) {
+      T sn, cn;
+      t_sincos(T(0.5) * ang, &sn, &cn);
+      const T qr[4] = {cn, w[0] / nw * sn, w[1] / nw * sn, w[2] / nw * sn};
+      quat_mul(qn, qn, qr);
+    }
+    T n = t_sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+    if (n < T(1e-15)) { qn[0] = T(1); qn[1] = qn[2] = qn[3] = T(0); n = T(1); }
+    for (int c = 0; c < 4; c++) qp[3 + c] = qn[c] / n;
+  }
+  __syncwarp();
+  PROF_ACC(s, P_INTEG, lane);
   for (int i = lane; i < NQ; i += 32) S.qpos[(size_t)env * NQ + i] = s.q[i];
   for (int i = lane; i < NV; i += 32) { S.qvel[(size_t)env * NV + i] = s.qd[i]; S.warm[(size_t)env * NV + i] = s.warm[i]; }
   // poses at the new state: next substep's collision, or (mj_step1 refresh) the task layer
-  {
-    ArmKin<T> k;
-    scene_kinematics(am, s, k, lane);
-  }
+  scene_kinematics(am, s, lane);
   if (!last) {
     scene_broadphase(sm, s, pb, env, sub + 1, dropped, lane);
   } else {
-    PROF_START(s);
     const bool bad = pb.flags[env] != 0;
     const int t = S.step[env] + 1;
     float reward = scene_reward(sm, s), discount = 1.f;
@@ -1316,12 +873,51 @@ __global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_solve_kernel(const __g
   }
   if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
   prof_flush(s, S, lane);
+  return true;
+}
+
+// Small tier: warp per env; envs that need more contact / block storage are queued for the large tier.
+template <typename T>
+__global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_solve_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
+                                                                      const __grid_constant__ StepCfg cfg, const EnvState<T> S, const PipeBuf<T> pb,
+                                                                      const so101_step_out out, int sub) {
+  using SC = Scratch<T, NC_S, NB_S>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SC *all = reinterpret_cast<SC *>(smem_raw);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int env = blockIdx.x * WARPS_SOLVE + wib;
+  if (env >= S.N) return;
+  if (!pb.active[env]) return;
+  if (!solve_env(am, sm, cfg, S, pb, out, sub, env, all[wib], lane)) {
+    if (lane == 0) pb.big[atomicAdd(pb.nwork + 4 * sub + 2, 1)] = env;
+  }
+}
+// Large tier: a few single-warp CTAs walk the queue (usually empty).
+template <typename T>
+__global__ void __launch_bounds__(32) scene_solve_big_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
+                                                            const __grid_constant__ StepCfg cfg, const EnvState<T> S, const PipeBuf<T> pb,
+                                                            const so101_step_out out, int sub) {
+  using SC = Scratch<T, NC_L, NB_L>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SC &s = *reinterpret_cast<SC *>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  const int n = pb.nwork[4 * sub + 2];
+#pragma unroll 1
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(pb.nwork + 4 * sub + 3, 1);
+    item = wshfl(item, 0);
+    if (item >= n) break;
+    solve_env(am, sm, cfg, S, pb, out, sub, pb.big[item], s, lane);
+    __syncwarp();
+  }
 }
 
 template <typename T>
 __global__ void scene_reset_kernel(const __grid_constant__ StepCfg cfg, const EnvState<T> S, const uint8_t *__restrict__ mask, const so101_step_out out) {
+  using SC = Scratch<T, NC_S, NB_S>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Scratch<T> *all = reinterpret_cast<Scratch<T> *>(smem_raw);
+  SC *all = reinterpret_cast<SC *>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int env = blockIdx.x * WARPS_SOLVE + wib;
   if (env >= S.N) return;
@@ -1331,8 +927,8 @@ __global__ void scene_reset_kernel(const __grid_constant__ StepCfg cfg, const En
 
 template <typename T>
 size_t scene_smem_bytes() {
-  const size_t a = sizeof(Scratch<T>) * WARPS_SOLVE, b = sizeof(NarrowScratch<T>) * WARPS_NARROW;
-  return a > b ? a : b;
+  const size_t a = sizeof(Scratch<T, NC_S, NB_S>) * WARPS_SOLVE, b = sizeof(NarrowScratch<T>) * WARPS_NARROW, c = sizeof(Scratch<T, NC_L, NB_L>);
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 template <typename T>
@@ -1346,33 +942,37 @@ int scene_narrow_grid() {
   return (nb > 0 ? nb : 1) * (sms > 0 ? sms : 1);
 }
 
-// Launches of one control step: 1 memset + 1 + 2 * nsub kernels, all on the caller's stream.  Returns the kernel count.
+// Launches of one control step: 1 memset + 1 + 3 * nsub kernels, all on the caller's stream.  Returns the kernel count.
 template <typename T>
 int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
                       const float *action, const so101_step_out &out, cudaStream_t stream) {
   static bool configured = false;
-  const size_t smem_env = sizeof(Scratch<T>) * WARPS_SOLVE, smem_nar = sizeof(NarrowScratch<T>) * WARPS_NARROW;
+  const size_t smem_env = sizeof(Scratch<T, NC_S, NB_S>) * WARPS_SOLVE, smem_nar = sizeof(NarrowScratch<T>) * WARPS_NARROW,
+               smem_big = sizeof(Scratch<T, NC_L, NB_L>);
   if (!configured) {
     cudaFuncSetAttribute(scene_begin_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
     cudaFuncSetAttribute(scene_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
+    cudaFuncSetAttribute(scene_solve_big_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
     cudaFuncSetAttribute(scene_narrow_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nar);
     cudaFuncSetAttribute(scene_reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
     configured = true;
   }
-  cudaMemsetAsync(pb.nwork, 0, sizeof(int) * 2 * (cfg.nsub + 1), stream);
+  cudaMemsetAsync(pb.nwork, 0, sizeof(int) * 4 * (cfg.nsub + 1), stream);
   const int grid_env = (S.N + WARPS_SOLVE - 1) / WARPS_SOLVE;
   scene_begin_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, stream>>>(am, sm, cfg, S, pb, action, out);
   // narrow phase: persistent grid sized to the machine (pairs are pulled with an atomic cursor)
   const int grid_nar = pb.narrow_grid;
+  const int grid_big = S.N < 592 ? S.N : 592;
   for (int sub = 0; sub < cfg.nsub; sub++) {
     scene_narrow_kernel<T><<<grid_nar, WARPS_NARROW * 32, smem_nar, stream>>>(sm, cfg, S, pb, sub);
     scene_solve_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, stream>>>(am, sm, cfg, S, pb, out, sub);
+    scene_solve_big_kernel<T><<<grid_big, 32, smem_big, stream>>>(am, sm, cfg, S, pb, out, sub);
   }
-  return 1 + 2 * cfg.nsub;
+  return 1 + 3 * cfg.nsub;
 }
 template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream) {
-  const size_t smem = sizeof(Scratch<T>) * WARPS_SOLVE;
+  const size_t smem = sizeof(Scratch<T, NC_S, NB_S>) * WARPS_SOLVE;
   cudaFuncSetAttribute(scene_reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   scene_reset_kernel<T><<<(S.N + WARPS_SOLVE - 1) / WARPS_SOLVE, WARPS_SOLVE * 32, smem, stream>>>(cfg, S, mask, out);
 }

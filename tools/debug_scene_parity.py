@@ -11,7 +11,7 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 seed = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 prec = sys.argv[4] if len(sys.argv) > 4 else 'f64'
 env = create_batched_task_env('SO100HandOverBanana', num_envs=N, time_limit=30.0, control_timestep=0.002, precision=prec)
-env.sample_prop_initial_states(seed=seed, clearance=0.002, settle_steps=0)
+env.sample_prop_initial_states(seed=seed, clearance=float(os.environ.get('SO101_DBG_CLEARANCE', '0.002')), settle_steps=0)
 q0, v0 = env.get_state(torch.float64)
 env.debug_contacts()
 sims = []

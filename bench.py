@@ -6,8 +6,9 @@
 
 A "step" is one control step (0.02 s = 10 physics substeps + observations + reward/termination) of ALL lockstep envs.
 Workloads:
-  arm4096      config 2: arm-only, collisions off, 4096 envs per GPU
-  banana16384  config 3: SO100HandOverBanana with contacts, 16384 envs per GPU   (when the contact path is built)
+  banana16384  config 3: SO100HandOverBanana pick-and-place with contacts, 16384 envs per GPU  (DEFAULT: the config the
+               "pick-place env-steps/sec" metric is quoted on; largest single-GPU pick-place config in BASELINE.json)
+  arm4096      config 2: arm-only, collisions off, 4096 envs per GPU (also measured and attached as `other_workloads`)
 value  = env-steps/s with inputs resident in HBM (CUDA events around each step, L2 flushed between steps).
 e2e    = env-steps/s through BatchedEnvironment.step_host(): pinned host action in, reward/discount/step_type/joints_pos out,
          copies and the stream sync inside the timed region.
@@ -53,8 +54,24 @@ def _cpu_worker(args):
   rs = np.random.RandomState(seed)
   lo = np.array([-np.pi, -3.14158, -3.14158, -3.14158, -3.14158, 0.0]); hi = np.array([np.pi, 3.14158, 3.14158, 3.14158, 3.14158, 0.08])
   rng = sim.meta['jnt_range'].reshape(-1, 2)[:6]
-  q = sim.meta['qpos0'].copy(); q[:6] = 0.25 * rs.uniform(rng[:, 0], rng[:, 1])
-  sim.set_state(q, np.zeros(sim.nv))
+  q = sim.meta['qpos0'].copy()
+  if sim.nq == 6:    # config 2: arm qpos ~ U(1/4 joint range)
+    q[:6] = 0.25 * rs.uniform(rng[:, 0], rng[:, 1])
+    sim.set_state(q, np.zeros(sim.nv))
+  else:              # config 3: props at the reference drop height (so100_hand_over.py:37-55), settled 1 s (untimed), arm at qpos 0
+    u = rs.uniform(size=5)
+    while np.hypot(-0.3 + 0.1 * u[3] + 0.1778, -0.1 + 0.2 * u[4] - 0.1656) < 0.151:   # bowl vs static cylinder (see task_suite._bowl_obstacles)
+      u[3:5] = rs.uniform(size=2)
+    yaw = (2 * u[2] - 1) * 0.1 * np.pi
+    q[:6] = 0
+    q[6:13] = [0.2 + 0.1 * u[0], -0.1 + 0.2 * u[1], 0.45, np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)]
+    q[13:20] = [-0.3 + 0.1 * u[3], -0.1 + 0.2 * u[4], 0.45, 1, 0, 0, 0]
+    sim.set_state(q, np.zeros(sim.nv))
+    for _ in range(50):
+      sim.control_step(np.zeros(6))
+    qs, vs = sim.qpos.copy(), sim.qvel.copy()
+    qs[:6] = 0; vs[:6] = 0
+    sim.set_state(qs, vs)
   acts = rs.uniform(lo, hi, size=(256, 6)) * 0.3
   n, t0 = 0, time.perf_counter()
   while time.perf_counter() - t0 < seconds:
@@ -116,14 +133,15 @@ class ClockSampler:
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=200)
-  ap.add_argument('--warmup', type=int, default=20)
+  ap.add_argument('--steps', type=int, default=100)
+  ap.add_argument('--warmup', type=int, default=10)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-  ap.add_argument('--workload', default=os.environ.get('SO101_BENCH_WORKLOAD', 'arm4096'), choices=list(WORKLOADS))
+  ap.add_argument('--workload', default=os.environ.get('SO101_BENCH_WORKLOAD', 'banana16384'), choices=list(WORKLOADS))
   ap.add_argument('--envs', type=int, default=0, help='envs per GPU (default: the workload size)')
   ap.add_argument('--precision', default='f32', choices=['f32', 'f64'])
   ap.add_argument('--cpu-seconds', type=float, default=10.0)
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-secondary', action='store_true', help='skip the attached arm4096 measurement')
   a = ap.parse_args()
   rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
   local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -156,28 +174,60 @@ def main():
 
   import torch
   import torch.distributed as dist
-  from so101_sim_b200.task_suite import create_batched_task_env
   if not torch.cuda.is_available():
     raise SystemExit('bench.py: no CUDA device (this framework has no CPU fallback; use --impl reference for the CPU arm)')
   torch.cuda.set_device(local_rank)
   dev = torch.device('cuda', local_rank)
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
-  env = create_batched_task_env(w['task'], num_envs=envs, time_limit=30.0, seed=rank, device=dev, precision=a.precision)
+  res = run_workload(a.workload, envs, a.steps, a.warmup, a.precision, dev, rank, world, local_rank)
+  if rank == 0:
+    out = dict(metric=METRIC, value=res['value'], unit='env-steps/s', n_gpus=world, steps=a.steps, warmup=a.warmup,
+               ms_per_step=res['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None,
+               dtype=a.precision, data='synthetic', config=config, e2e=res['e2e'], gpu_launches=res['gpu_launches'],
+               clocks=res['clocks'], roofline=res['roofline'], kernels=res['kernels'], wall_s=res['wall_s'],
+               mean_return=res['mean_return'], diverged=res['diverged'], contacts_dropped=res['contacts_dropped'])
+    if world == 1 and not a.no_secondary and a.workload != 'arm4096':
+      # BASELINE config 2 (arm-only) measured beside the headline workload: a short run, kernel-only and e2e
+      r2 = run_workload('arm4096', WORKLOADS['arm4096']['envs'], 50, 5, a.precision, dev, rank, world, local_rank)
+      out['other_workloads'] = {'arm4096': {k: r2[k] for k in ('value', 'ms_per_step', 'e2e', 'gpu_launches', 'roofline')}}
+    if not a.no_cpu_baseline and world == 1:
+      out['cpu_baseline'] = cpu_baseline(a.workload, a.cpu_seconds, os.cpu_count() or 1)
+    print(json.dumps(out))
+  if world > 1:
+    dist.destroy_process_group()
+  return 0
+
+
+def ncu_traffic(workload, envs):
+  """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json), or None."""
+  p = os.path.join(ROOT, 'profiles', 'traffic.json')
+  if not os.path.exists(p):
+    return None, None
+  t = json.load(open(p)).get(f'{workload}:{envs}')
+  return (t['dram_bytes_per_launch'], t['source']) if t else (None, None)
+
+
+def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_rank):
+  import torch
+  import torch.distributed as dist
+  from so101_sim_b200.task_suite import create_batched_task_env
+  w = WORKLOADS[name]
+  env = create_batched_task_env(w['task'], num_envs=envs, time_limit=30.0, seed=rank, device=dev, precision=precision)
   if w['task'] == 'SO100ArmOnly':
     env.sample_arm_initial_states(seed=0 + 1000 * rank)
   else:
     env.sample_prop_initial_states(seed=0 + 1000 * rank, spawn_z=0.45, settle_steps=50)  # reference drop height, settled 1 s
   env.reset()
-  total = a.warmup + a.steps
+  total = warmup + steps
   g = torch.Generator(device=dev); g.manual_seed(1 + 1000 * rank)
   spec = env.action_spec()
   lo, hi = torch.tensor(spec.minimum, device=dev), torch.tensor(spec.maximum, device=dev)
   nact = min(total, 64)
   acts = (lo + torch.rand(nact, envs, 6, generator=g, device=dev) * (hi - lo)) * 0.3
   flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-  ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
-  ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+  ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+  ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
   ret_sum = torch.zeros(envs, device=dev); ep_len = torch.zeros(envs, dtype=torch.int32, device=dev)
 
   def barrier():
@@ -185,28 +235,30 @@ def main():
       dist.barrier()
     torch.cuda.synchronize()
 
-  for i in range(a.warmup):
+  for i in range(warmup):
     env.step(acts[i % nact])
   c0 = env.counters()
+  k0 = env.kernel_times(True)   # per-kernel CUDA events on the launching stream from here on
   barrier()
   with ClockSampler(local_rank) as clocks:
     t_wall0 = time.perf_counter()
-    for i in range(a.steps):
+    for i in range(steps):
       flush.fill_(i & 0xFF)
       ev0[i].record()
-      ts = env.step(acts[(a.warmup + i) % nact])
+      ts = env.step(acts[(warmup + i) % nact])
       ev1[i].record()
       ret_sum += ts.reward; ep_len += 1
     barrier()
     t_wall = time.perf_counter() - t_wall0
   c1 = env.counters()
-  step_ms = [ev0[i].elapsed_time(ev1[i]) for i in range(a.steps)]
+  k1 = env.kernel_times(False)
+  step_ms = [ev0[i].elapsed_time(ev1[i]) for i in range(steps)]
   dev_ms = float(sum(step_ms))
   t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
   dev_ms = float(t.item())
-  value = envs * world * a.steps / (dev_ms * 1e-3)
+  value = envs * world * steps / (dev_ms * 1e-3)
 
   # ---- e2e: host buffers through the public API (H2D + step + D2H + sync per step)
   pin = dict(pin_memory=True)
@@ -217,14 +269,14 @@ def main():
     env.step_host(h_act[i % len(h_act)], h_rew, h_dis, h_st, h_jp)
   barrier()
   e0 = time.perf_counter()
-  for i in range(a.steps):
+  for i in range(steps):
     env.step_host(h_act[i % len(h_act)], h_rew, h_dis, h_st, h_jp)
   barrier()
   e2e_s = time.perf_counter() - e0
   t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  e2e_value = envs * world * a.steps / float(t.item())
+  e2e_value = envs * world * steps / float(t.item())
   h2d, d2h = envs * 6 * 4, envs * (4 + 4 + 1 + 24)
 
   # ---- episode statistics: the ONLY collective on this path (NCCL all_gather of return / length / success)
@@ -236,28 +288,29 @@ def main():
   else:
     mean_return = float(ret_sum.mean())
 
-  if rank == 0:
-    peak, peak_src = measured_peak_gbs()
-    launches = c1['kernel_launches'] - c0['kernel_launches']
-    per_launch_ms = dev_ms / max(1, a.steps)
-    achieved = envs * w['bytes_per_env_step'] / (per_launch_ms * 1e-3) / 1e9
-    out = dict(metric=METRIC, value=value, unit='env-steps/s', n_gpus=world, steps=a.steps, warmup=a.warmup,
-               ms_per_step=dev_ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-               dtype=a.precision, data='synthetic', config=config,
-               e2e=dict(value=e2e_value, unit='env-steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-               gpu_launches=launches, clocks=clocks.summary(),
-               roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=None,
-                             kernel='arm_step_kernel' if not w['collide'] else 'scene_step_kernel',
-                             bytes_per_env_step=w['bytes_per_env_step'], peak_source=peak_src,
-                             note='algorithmic state bytes / CUDA-event step time; the path is FP32-latency bound, see profiles/'),
-               wall_s=t_wall, mean_return=mean_return, diverged=c1['diverged'])
-    if not a.no_cpu_baseline and world == 1:
-      out['cpu_baseline'] = cpu_baseline(a.workload, a.cpu_seconds, 1)
-    print(json.dumps(out))
-  if world > 1:
-    dist.destroy_process_group()
+  # ---- roofline of the dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events inside the C-ABI,
+  # on the launching stream).  One scene-kernel launch advances every env by ONE substep = envs / nsub env-steps.
+  peak, peak_src = measured_peak_gbs()
+  kern = {k: dict(ms=k1[k][0] - k0[k][0], launches=k1[k][1] - k0[k][1]) for k in k1 if k1[k][1] - k0[k][1] > 0}
+  ktot = sum(v['ms'] for v in kern.values()) or 1.0
+  for v in kern.values():
+    v['share_of_kernel_time'] = v['ms'] / ktot; v['us_per_launch'] = 1e3 * v['ms'] / v['launches']
+  dom = max(kern, key=lambda k: kern[k]['ms'])
+  per_launch_steps = envs if dom == 'arm_step_kernel' else envs / env.n_substeps
+  bytes_per_launch = per_launch_steps * w['bytes_per_env_step']
+  achieved = bytes_per_launch / (kern[dom]['us_per_launch'] * 1e-6) / 1e9
+  traffic, traffic_src = ncu_traffic(name, envs)
+  roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=traffic, kernel=dom,
+                  us_per_launch=kern[dom]['us_per_launch'], algorithmic_bytes_per_launch=bytes_per_launch,
+                  bytes_per_env_step=w['bytes_per_env_step'], env_steps_per_launch=per_launch_steps, peak_source=peak_src,
+                  traffic_source=traffic_src,
+                  note='state-only algorithmic bytes (SURVEY.md 8d) over the CUDA-event launch time; the path is latency / '
+                       'instruction-issue bound, not HBM bound: see profiles/ for issue-slot and stall evidence')
+  res = dict(value=value, ms_per_step=dev_ms / steps, e2e=dict(value=e2e_value, unit='env-steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+             gpu_launches=c1['kernel_launches'] - c0['kernel_launches'], clocks=clocks.summary(), roofline=roofline, kernels=kern,
+             wall_s=t_wall, mean_return=mean_return, diverged=c1['diverged'], contacts_dropped=c1['contacts_dropped'])
   env.close()
-  return 0
+  return res
 
 
 if __name__ == '__main__':

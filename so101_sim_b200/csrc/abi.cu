@@ -39,6 +39,7 @@ struct HandleBase {
   virtual void debug_read(const char *field, float *dst, size_t count, cudaStream_t s) = 0;
   virtual void step_host(const float *action, float *reward, float *discount, uint8_t *step_type, float *jpos, cudaStream_t s) = 0;
   virtual uint64_t diverged() = 0;
+  KernelTimer timer;
 };
 
 static void quat2mat(const double *q, double *m) {
@@ -231,8 +232,8 @@ struct Handle : HandleBase {
     launches += 1;
   }
   void step(const float *action, const so101_step_out &out, cudaStream_t s) override {
-    if (scene) launches += launch_scene_step<T>(am, scene->dev, sc, S, pipe, action, out, s);
-    else { launch_arm_step<T>(am, sc, S, action, out, s); launches += 1; }
+    if (scene) launches += launch_scene_step<T>(am, scene->dev, sc, S, pipe, action, out, s, &timer);
+    else { timer.begin(4, s); launch_arm_step<T>(am, sc, S, action, out, s); timer.end(4, s); launches += 1; }
     steps += 1;
   }
   void debug_read(const char *field, float *dst, size_t count, cudaStream_t s) override {
@@ -396,6 +397,16 @@ int so101_step_host(so101_handle h, const float *action_host, float *reward_host
 int so101_counters(so101_handle h, uint64_t out[4]) {
   API_BEGIN(h)
   out[2] = H->diverged(); out[0] = H->launches; out[1] = H->steps; out[3] = H->dropped;
+  API_END()
+}
+int so101_kernel_times(so101_handle h, int enable, double ms_out[5], uint64_t launches_out[5]) {
+  API_BEGIN(h)
+  H->timer.collect();
+  for (int i = 0; i < KernelTimer::NK; i++) {
+    if (ms_out) ms_out[i] = H->timer.ms[i];
+    if (launches_out) launches_out[i] = H->timer.count[i];
+  }
+  H->timer.on = enable != 0;
   API_END()
 }
 int so101_debug_read(so101_handle h, const char *field, float *dst_dev, size_t count, void *stream) {

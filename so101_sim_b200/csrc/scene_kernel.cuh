@@ -1,5 +1,8 @@
 #pragma once
 #include <cuda_runtime.h>
+
+#include <array>
+#include <vector>
 #include "arm_dynamics.cuh"
 #include "arm_solver.cuh"
 #include "env_state.cuh"
@@ -24,9 +27,47 @@ struct PipeBuf {
   int narrow_grid;          // CTAs of the persistent narrow-phase kernel
 };
 
+// Optional per-kernel timing with CUDA events on the launching stream (so101_kernel_times; bench.py's roofline leg).
+// Kernel ids: 0 begin, 1 narrow phase, 2 solve (small tier), 3 solve (large tier), 4 arm-only step.
+struct KernelTimer {
+  static constexpr int NK = 5;
+  bool on = false;
+  std::vector<std::array<cudaEvent_t, 2>> ev[NK];
+  size_t used[NK] = {};
+  double ms[NK] = {};
+  uint64_t count[NK] = {};
+  void begin(int id, cudaStream_t s) {
+    if (!on) return;
+    if (used[id] == ev[id].size()) {
+      std::array<cudaEvent_t, 2> e;
+      cudaEventCreate(&e[0]); cudaEventCreate(&e[1]);
+      ev[id].push_back(e);
+    }
+    cudaEventRecord(ev[id][used[id]][0], s);
+  }
+  void end(int id, cudaStream_t s) {
+    if (!on) return;
+    cudaEventRecord(ev[id][used[id]][1], s);
+    used[id]++;
+  }
+  void collect() {  // host-synchronises on the recorded events
+    for (int id = 0; id < NK; id++) {
+      for (size_t i = 0; i < used[id]; i++) {
+        float t = 0.f;
+        cudaEventSynchronize(ev[id][i][1]);
+        if (cudaEventElapsedTime(&t, ev[id][i][0], ev[id][i][1]) == cudaSuccess) { ms[id] += t; count[id]++; }
+      }
+      used[id] = 0;
+    }
+  }
+  ~KernelTimer() {
+    for (auto &v : ev) for (auto &e : v) { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); }
+  }
+};
+
 template <typename T>
 int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
-                      const float *action, const so101_step_out &out, cudaStream_t stream);
+                      const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt);
 template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream);
 template <typename T>

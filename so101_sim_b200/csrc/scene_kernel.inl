@@ -945,28 +945,40 @@ int scene_narrow_grid() {
 // Launches of one control step: 1 memset + 1 + 3 * nsub kernels, all on the caller's stream.  Returns the kernel count.
 template <typename T>
 int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
-                      const float *action, const so101_step_out &out, cudaStream_t stream) {
-  static bool configured = false;
+                      const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt) {
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
   const size_t smem_env = sizeof(Scratch<T, NC_S, NB_S>) * WARPS_SOLVE, smem_nar = sizeof(NarrowScratch<T>) * WARPS_NARROW,
                smem_big = sizeof(Scratch<T, NC_L, NB_L>);
-  if (!configured) {
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaFuncSetAttribute(scene_begin_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
     cudaFuncSetAttribute(scene_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
     cudaFuncSetAttribute(scene_solve_big_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
     cudaFuncSetAttribute(scene_narrow_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nar);
     cudaFuncSetAttribute(scene_reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
+  KernelTimer none;
+  KernelTimer &t = kt ? *kt : none;
   cudaMemsetAsync(pb.nwork, 0, sizeof(int) * 4 * (cfg.nsub + 1), stream);
   const int grid_env = (S.N + WARPS_SOLVE - 1) / WARPS_SOLVE;
+  t.begin(0, stream);
   scene_begin_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, stream>>>(am, sm, cfg, S, pb, action, out);
+  t.end(0, stream);
   // narrow phase: persistent grid sized to the machine (pairs are pulled with an atomic cursor)
   const int grid_nar = pb.narrow_grid;
   const int grid_big = S.N < 592 ? S.N : 592;
   for (int sub = 0; sub < cfg.nsub; sub++) {
+    t.begin(1, stream);
     scene_narrow_kernel<T><<<grid_nar, WARPS_NARROW * 32, smem_nar, stream>>>(sm, cfg, S, pb, sub);
+    t.end(1, stream);
+    t.begin(2, stream);
     scene_solve_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, stream>>>(am, sm, cfg, S, pb, out, sub);
+    t.end(2, stream);
+    t.begin(3, stream);
     scene_solve_big_kernel<T><<<grid_big, 32, smem_big, stream>>>(am, sm, cfg, S, pb, out, sub);
+    t.end(3, stream);
   }
   return 1 + 3 * cfg.nsub;
 }

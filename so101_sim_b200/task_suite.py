@@ -297,6 +297,15 @@ class BatchedEnvironment:
     self._check(self._lib.so101_counters(self._h, ctypes.byref(c)))
     return dict(kernel_launches=int(c[0]), control_steps=int(c[1]), diverged=int(c[2]), contacts_dropped=int(c[3]))
 
+  KERNEL_NAMES = ('scene_begin_kernel', 'scene_narrow_kernel', 'scene_solve_kernel', 'scene_solve_big_kernel', 'arm_step_kernel')
+
+  def kernel_times(self, enable: bool = True) -> dict:
+    """Accumulated per-kernel device time (CUDA events around each launch, recorded while enabled) -> {name: (ms, launches)};
+    then switches the recording on/off for the following steps."""
+    ms = (ctypes.c_double * 5)(); n = (ctypes.c_uint64 * 5)()
+    self._check(self._lib.so101_kernel_times(self._h, int(enable), ctypes.byref(ms), ctypes.byref(n)))
+    return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNEL_NAMES)}
+
   # ------------------------------------------------------------------ synthetic initial states (BASELINE.md §3)
   def sample_arm_initial_states(self, seed: int = 0, fraction: float = 0.25):
     """BASELINE config 2: arm qpos ~ U(fraction * joint range), qvel = 0 (Philox stream `seed`)."""
@@ -322,7 +331,7 @@ class BatchedEnvironment:
     bv = np.concatenate([verts[a:a + n] for g, (a, n) in enumerate(zip(m['geom_vertadr'], m['geom_vertnum']))
                          if m['geom_body'][g] == bowl_body and m['geom_type'][g] == 5])
     out = []
-    for g in range(int(m['ngeom'])):
+    for g in range(int(np.asarray(m['ngeom']).reshape(-1)[0])):
       b = int(m['geom_body'][g])
       if m['geom_type'][g] != 3 or m['body_weld'][b] != 0 or m['body_parent'][b] != 0:
         continue

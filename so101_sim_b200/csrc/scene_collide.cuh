@@ -29,6 +29,13 @@ struct FPt {
   T x, y, h;
 };
 
+// Height interpolant of a support feature over its (t1, t2) plane: constant (vertex), line (edge) or plane (face).
+template <typename T>
+struct HPlane {
+  int mode;
+  T x0, y0, h0, ex, ey, eh, el, fx, fy, fh, det;
+};
+
 // Per-warp scratch of one narrow-phase pair.  The EPA polytope is dead once epa() has returned (normal, depth and
 // witness points are in registers), so the manifold stage re-uses its storage.
 template <typename T>
@@ -36,15 +43,16 @@ struct CollideScratch {
   union {
     struct {  // EPA polytope
       T Vw[3][EPA_MAXV], Va[3][EPA_MAXV], Vb[3][EPA_MAXV];
-      int Fv[3][EPA_MAXF];
+      unsigned char Fv[3][EPA_MAXF];  // vertex ids < EPA_MAXV
       T Fn[3][EPA_MAXF], Fd[EPA_MAXF];
-      int Falive[EPA_MAXF];
-      int horizon[EPA_MAXF][2];
+      unsigned char Falive[EPA_MAXF];
+      unsigned char horizon[EPA_MAXF][2];
     };
     struct {  // manifold
       T cand[3][MAXCAND];
       FPt<T> P[MAXCAND], Hh[2 * MAXCAND + 2], FA[MAXFEAT], FB[MAXFEAT], R[2 * MAXFEAT + 8], bufA[2 * MAXFEAT + 8], bufB[2 * MAXFEAT + 8];
-      T mdist[2 * MAXFEAT + 8];
+      T mdist[2 * MAXFEAT + 8], mdist2[2 * MAXFEAT + 8];
+      HPlane<T> hp[2];  // height interpolants of the two features
     };
   };
 };
@@ -520,71 +528,98 @@ __device__ __noinline__ int feature(const SceneModel<T> &sm, CollideScratch<T> &
   return nout;
 }
 
-// ---- scalar helpers (lane 0 only) mirroring the oracle
+// ---- manifold helpers mirroring the oracle (same expressions, evaluated once per feature / in parallel over points)
+// Height of feature P at (x, y): the oracle's feature_height() split into a per-feature setup (lane 0) ...
 template <typename T>
-__device__ __noinline__ T feature_height(const FPt<T> *P, int n, T x, T y) {
-  if (n == 1) return P[0].h;
+__device__ __noinline__ void feature_plane(const FPt<T> *P, int n, HPlane<T> &hp) {
+  hp.mode = 0; hp.x0 = P[0].x; hp.y0 = P[0].y; hp.h0 = P[0].h;
+  if (n == 1) return;
   int i1 = 1;
   T best = T(-1);
-  #pragma unroll 1
+#pragma unroll 1
   for (int i = 1; i < n; i++) { const T dx = P[i].x - P[0].x, dy = P[i].y - P[0].y, l = dx * dx + dy * dy; if (l > best) { best = l; i1 = i; } }
   const T ex = P[i1].x - P[0].x, ey = P[i1].y - P[0].y, eh = P[i1].h - P[0].h, el = ex * ex + ey * ey;
-  if (n == 2 || el < T(1e-20)) {
-    if (el < T(1e-20)) return P[0].h;
-    const T t = ((x - P[0].x) * ex + (y - P[0].y) * ey) / el;
-    return P[0].h + t * eh;
-  }
+  hp.ex = ex; hp.ey = ey; hp.eh = eh; hp.el = el;
+  if (el < T(1e-20)) return;
+  hp.mode = 1;
+  if (n == 2) return;
   int i2 = -1;
   best = T(0);
-  #pragma unroll 1
+#pragma unroll 1
   for (int i = 1; i < n; i++) { const T a = t_abs(ex * (P[i].y - P[0].y) - ey * (P[i].x - P[0].x)); if (a > best) { best = a; i2 = i; } }
-  if (i2 < 0 || best < T(1e-12) * el) { const T t = ((x - P[0].x) * ex + (y - P[0].y) * ey) / el; return P[0].h + t * eh; }
-  const T fx = P[i2].x - P[0].x, fy = P[i2].y - P[0].y, fh = P[i2].h - P[0].h, det = ex * fy - ey * fx;
-  const T px = x - P[0].x, py = y - P[0].y, u = (px * fy - py * fx) / det, v = (ex * py - ey * px) / det;
-  return P[0].h + u * eh + v * fh;
+  if (i2 < 0 || best < T(1e-12) * el) return;
+  hp.mode = 2;
+  hp.fx = P[i2].x - P[0].x; hp.fy = P[i2].y - P[0].y; hp.fh = P[i2].h - P[0].h; hp.det = ex * hp.fy - ey * hp.fx;
+}
+// ... and a per-point evaluation (any lane)
+template <typename T>
+__device__ __forceinline__ T plane_height(const HPlane<T> &hp, T x, T y) {
+  if (hp.mode == 0) return hp.h0;
+  const T px = x - hp.x0, py = y - hp.y0;
+  if (hp.mode == 1) { const T t = (px * hp.ex + py * hp.ey) / hp.el; return hp.h0 + t * hp.eh; }
+  const T u = (px * hp.fy - py * hp.fx) / hp.det, v = (hp.ex * py - hp.ey * px) / hp.det;
+  return hp.h0 + u * hp.eh + v * hp.fh;
 }
 
+// Sutherland-Hodgman clip of `subj` (n points; polygon, segment or point) against the convex polygon `clip` (m >= 3), all
+// lanes: one lane per subject vertex, ballot compaction keeps the oracle's output order.  Result in `out`, count returned.
 template <typename T>
-__device__ __noinline__ int clip_poly(CollideScratch<T> &cs, const FPt<T> *subj, int n, const FPt<T> *clip, int m, FPt<T> *out) {
+__device__ __noinline__ int clip_poly(CollideScratch<T> &cs, const FPt<T> *subj, int n, const FPt<T> *clip, int m, FPt<T> *out, int lane) {
+  constexpr int CAP = 2 * MAXFEAT + 8;
   int na = n;
   FPt<T> *in = cs.bufA, *res = cs.bufB;
-  #pragma unroll 1
-  for (int i = 0; i < n; i++) in[i] = subj[i];
-  #pragma unroll 1
+#pragma unroll 1
+  for (int i = lane; i < n; i += 32) in[i] = subj[i];
+  __syncwarp();
+#pragma unroll 1
   for (int e = 0; e < m && na > 0; e++) {
     const T ax = clip[e].x, ay = clip[e].y, bx = clip[(e + 1) % m].x, by = clip[(e + 1) % m].y;
     const T ex = bx - ax, ey = by - ay, tol = T(1e-12);
     int nr = 0;
-    if (na == 2) {
+    if (na == 2) {  // open segment (uniform across lanes; written by lane 0)
       const FPt<T> P = in[0], Q = in[1];
       const T sp = ex * (P.y - ay) - ey * (P.x - ax), sq = ex * (Q.y - ay) - ey * (Q.x - ax);
       const bool pin = sp >= -tol, qin = sq >= -tol;
-      if (pin && qin) { res[nr++] = P; res[nr++] = Q; }
+      FPt<T> r0 = P, r1 = Q;
+      if (pin && qin) nr = 2;
       else if (pin || qin) {
         const T t = sp / (sp - sq);
         const FPt<T> I = {P.x + t * (Q.x - P.x), P.y + t * (Q.y - P.y), P.h + t * (Q.h - P.h)};
-        if (pin) { res[nr++] = P; res[nr++] = I; } else { res[nr++] = I; res[nr++] = Q; }
+        if (pin) r1 = I; else r0 = I;
+        nr = 2;
       }
+      if (lane == 0 && nr) { res[0] = r0; res[1] = r1; }
     } else {
-      #pragma unroll 1
-      for (int i = 0; i < na; i++) {
-        const FPt<T> P = in[i], Q = in[(i + 1) % na];
-        const T sp = ex * (P.y - ay) - ey * (P.x - ax), sq = ex * (Q.y - ay) - ey * (Q.x - ax);
-        const bool pin = sp >= -tol, qin = sq >= -tol;
-        if (pin && nr < 2 * MAXFEAT + 8) res[nr++] = P;
-        if (na > 1 && pin != qin && nr < 2 * MAXFEAT + 8) {
-          const T t = sp / (sp - sq);
-          res[nr++] = FPt<T>{P.x + t * (Q.x - P.x), P.y + t * (Q.y - P.y), P.h + t * (Q.h - P.h)};
+#pragma unroll 1
+      for (int i0 = 0; i0 < na; i0 += 32) {
+        const int i = i0 + lane;
+        bool pin = false, cross = false;
+        FPt<T> P{}, I{};
+        if (i < na && !(na == 1 && i > 0)) {
+          P = in[i];
+          const FPt<T> Q = in[(i + 1) % na];
+          const T sp = ex * (P.y - ay) - ey * (P.x - ax), sq = ex * (Q.y - ay) - ey * (Q.x - ax);
+          const bool qin = sq >= -tol;
+          pin = sp >= -tol;
+          cross = na > 1 && pin != qin;
+          if (cross) { const T t = sp / (sp - sq); I = FPt<T>{P.x + t * (Q.x - P.x), P.y + t * (Q.y - P.y), P.h + t * (Q.h - P.h)}; }
         }
-        if (na == 1) break;
+        const unsigned mp = __ballot_sync(FULL, pin), mx = __ballot_sync(FULL, cross), lt = (1u << lane) - 1;
+        const int o = nr + __popc(mp & lt) + __popc(mx & lt);
+        if (pin && o < CAP) res[o] = P;
+        if (cross && o + (pin ? 1 : 0) < CAP) res[o + (pin ? 1 : 0)] = I;
+        nr += __popc(mp) + __popc(mx);
       }
+      if (nr > CAP) nr = CAP;
     }
+    __syncwarp();
     FPt<T> *tmp = in; in = res; res = tmp;
     na = nr;
     if (na > 2 * MAXFEAT) na = 2 * MAXFEAT;
   }
-  #pragma unroll 1
-  for (int i = 0; i < na; i++) out[i] = in[i];
+#pragma unroll 1
+  for (int i = lane; i < na; i += 32) out[i] = in[i];
+  __syncwarp();
   return na;
 }
 

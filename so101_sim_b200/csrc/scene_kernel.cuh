@@ -13,12 +13,19 @@ namespace so101 {
 // Scene-kernel state layout is array-of-rows ([N][nq] etc.): one warp owns one env and reads its row with one
 // coalesced request (the arm-only kernel, one THREAD per env, uses [k][N] instead).
 
+constexpr int WQ = 128;             // work queues (>= ngeom)
+constexpr int WSTRIDE = WQ + 4;     // counters per substep
+enum { W_CURSOR = WQ, W_NBIG = WQ + 1, W_BIGCURSOR = WQ + 2 };
+
 // Device scratch that crosses the kernels of one substep (written by one kernel, read by the next; L2-resident).
 template <typename T>
 struct PipeBuf {
   T *xpos, *xmat;           // [N][NSLOT*3], [N][NSLOT*9]  world poses of the 8 dynamic bodies
-  uint2 *work;              // [N*PAIRCAP]  narrow-phase work list: (env, g1 | g2 << 8 | pair index << 16)
-  int *nwork;               // [nsub+1][4]  per substep: pairs appended, pair cursor, large-tier envs queued, large-tier cursor
+  uint2 *work;              // [WQ][work_cap]  narrow-phase work queues, one per second geom g2 (so that consecutive items
+                            //   collide the same hull): (env, g1 | g2 << 8 | pair index << 16)
+  int work_cap;             // entries per queue
+  int *nwork;               // [nsub+1][WSTRIDE]  per substep: items per queue [0..WQ), then pair cursor, large-tier envs
+                            //   queued, large-tier cursor
   int *big;                 // [N]  envs deferred to the large solver tier in this substep
   T *con;                   // [N][CONBUF][8]  raw contacts: normal3, pos3, dist
   int *con_key;             // [N][CONBUF]     pair index << 20 | manifold index << 16 | g1 << 8 | g2  (sort key)

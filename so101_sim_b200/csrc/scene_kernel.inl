@@ -178,40 +178,47 @@ __device__ __noinline__ int manifold(const SceneModel<T> &sm, NarrowScratch<T> &
   const int na = feature(sm, cs, A, frame, t1, t2, delta, cs.FA, lane);
   const int nb = feature(sm, cs, B, nn, t1, t2, delta, cs.FB, lane);
   int u = 0;
+  for (int i = lane; i < nb; i += 32) cs.FB[i].h = -cs.FB[i].h;  // heights of B's feature were measured along -n
+  __syncwarp();
+  int nr = 0;
+  {  // subject = the smaller feature when the other one is a polygon
+    const bool a_subj = (na >= 3 && nb >= 3) || (nb >= 3 && na <= 2), b_subj = na >= 3 && (nb == 2 || nb == 1);
+    if (a_subj) nr = clip_poly(cs, cs.FA, na, cs.FB, nb, cs.R, lane);
+    else if (b_subj) nr = clip_poly(cs, cs.FB, nb, cs.FA, na, cs.R, lane);
+  }
+  if (lane == 0) { feature_plane(cs.FA, na, cs.hp[0]); feature_plane(cs.FB, nb, cs.hp[1]); }
+  __syncwarp();
+  // penetrating points only (lane per clipped point, order kept): -> bufA / mdist2
+  int k = 0;
+#pragma unroll 1
+  for (int i0 = 0; i0 < nr; i0 += 32) {
+    const int i = i0 + lane;
+    bool keep = false;
+    FPt<T> P{};
+    T di = T(0);
+    if (i < nr) {
+      P = cs.R[i];
+      const T ha = plane_height(cs.hp[0], P.x, P.y), hb = plane_height(cs.hp[1], P.x, P.y);
+      di = hb - ha;
+      keep = di < T(0);
+      P.h = T(0.5) * (ha + hb);
+    }
+    const unsigned mk = __ballot_sync(FULL, keep);
+    if (keep) { const int o = k + __popc(mk & ((1u << lane) - 1)); cs.bufA[o] = P; cs.mdist2[o] = di; }
+    k += __popc(mk);
+  }
+  __syncwarp();
   if (lane == 0) {
-#ifdef SO101_DEVICE_PRINTF
-    if (s.dbg) {
-      printf("MANIFOLD g=(%d,%d) n=(%.17g,%.17g,%.17g) depth=%.17g na=%d nb=%d\n", A.geom, B.geom, (double)n[0], (double)n[1], (double)n[2], (double)depth, na, nb);
-      for (int i = 0; i < na; i++) printf("  FA[%d]=(%.17g,%.17g,%.17g)\n", i, (double)cs.FA[i].x, (double)cs.FA[i].y, (double)cs.FA[i].h);
-      for (int i = 0; i < nb; i++) printf("  FB[%d]=(%.17g,%.17g,%.17g)\n", i, (double)cs.FB[i].x, (double)cs.FB[i].y, (double)cs.FB[i].h);
-    }
-#endif
-    for (int i = 0; i < nb; i++) cs.FB[i].h = -cs.FB[i].h;
-    int nr = 0;
-    {  // subject = the smaller feature when the other one is a polygon
-      const bool a_subj = (na >= 3 && nb >= 3) || (nb >= 3 && na <= 2), b_subj = na >= 3 && (nb == 2 || nb == 1);
-      if (a_subj) nr = clip_poly(cs, cs.FA, na, cs.FB, nb, cs.R);
-      else if (b_subj) nr = clip_poly(cs, cs.FB, nb, cs.FA, na, cs.R);
-    }
-    int k = 0;
-    for (int i = 0; i < nr; i++) {
-      const T ha = feature_height(cs.FA, na, cs.R[i].x, cs.R[i].y), hb = feature_height(cs.FB, nb, cs.R[i].x, cs.R[i].y);
-      const T di = hb - ha;
-      if (di < T(0)) { cs.R[k] = cs.R[i]; cs.R[k].h = T(0.5) * (ha + hb); cs.mdist[k] = di; k++; }
-    }
     for (int i = 0; i < k; i++) {
       int dup = 0;
       for (int j = 0; j < u; j++)
-        if (t_abs(cs.R[i].x - cs.R[j].x) + t_abs(cs.R[i].y - cs.R[j].y) < T(1e-7)) {
+        if (t_abs(cs.bufA[i].x - cs.R[j].x) + t_abs(cs.bufA[i].y - cs.R[j].y) < T(1e-7)) {
           dup = 1;
-          if (cs.mdist[i] < cs.mdist[j]) { cs.R[j] = cs.R[i]; cs.mdist[j] = cs.mdist[i]; }
+          if (cs.mdist2[i] < cs.mdist[j]) { cs.R[j] = cs.bufA[i]; cs.mdist[j] = cs.mdist2[i]; }
           break;
         }
-      if (!dup) { cs.R[u] = cs.R[i]; cs.mdist[u] = cs.mdist[i]; u++; }
+      if (!dup) { cs.R[u] = cs.bufA[i]; cs.mdist[u] = cs.mdist2[i]; u++; }
     }
-#ifdef SO101_DEVICE_PRINTF
-    if (s.dbg) { printf("  nr=%d k=%d u=%d\n", nr, k, u); for (int i = 0; i < u; i++) printf("  R[%d]=(%.17g,%.17g) d=%.17g\n", i, (double)cs.R[i].x, (double)cs.R[i].y, (double)cs.mdist[i]); }
-#endif
     u = reduce_manifold(cs.R, cs.mdist, u);
     for (int i = 0; i < u; i++) {
       T pos[3];
@@ -444,11 +451,16 @@ __device__ __noinline__ void scene_broadphase(const SceneModel<T> &sm, S &s, con
   }
   if (npq > PAIRCAP) { dropped += npq - PAIRCAP; npq = PAIRCAP; }
   __syncwarp();
-  // append (env, g1 | g2 << 8 | pair index << 16) to the work list of this substep
-  int base = 0;
-  if (lane == 0 && npq > 0) base = atomicAdd(pb.nwork + 4 * sub, npq);
-  base = wshfl(base, 0);
-  for (int i = lane; i < npq; i += 32) pb.work[(size_t)base + i] = make_uint2((unsigned)env, cs.pairq[i]);
+  // append (env, g1 | g2 << 8 | pair index << 16) to the work queue of its second geom
+  int qdrop = 0;
+  for (int i = lane; i < npq; i += 32) {
+    const unsigned pq = cs.pairq[i];
+    const int g2 = (int)((pq >> 8) & 0xff);
+    const int slot = atomicAdd(pb.nwork + WSTRIDE * sub + g2, 1);
+    if (slot < pb.work_cap) pb.work[(size_t)g2 * pb.work_cap + slot] = make_uint2((unsigned)env, pq);
+    else qdrop++;
+  }
+  dropped += warp_sum(qdrop);
   PROF_ACC(s, P_BROAD, lane);
   PROF_CNT(s, P_NPQ, npq, lane);
   __syncwarp();
@@ -640,20 +652,43 @@ __global__ void __launch_bounds__(WARPS_NARROW * 32) scene_narrow_kernel(const _
   NarrowScratch<T> *all = reinterpret_cast<NarrowScratch<T> *>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   NarrowScratch<T> &s = all[wib];
-  const int nwork = pb.nwork[4 * sub];
+  // queue offsets: exclusive prefix sum of the per-geom item counts (each warp builds its own copy: 4 counts per lane)
+  __shared__ int qpref[WARPS_NARROW][WQ + 1];
+  {
+    const int *cnt = pb.nwork + WSTRIDE * sub;
+    int c[4], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { c[k] = min(cnt[4 * lane + k], pb.work_cap); tot += c[k]; }
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+    int run = incl - tot;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { qpref[wib][4 * lane + k] = run; run += c[k]; }
+    if (lane == 31) qpref[wib][WQ] = run;
+  }
   if (lane == 0) {
     s.profon = S.prof != nullptr; s.dbg = 0;
     for (int i = 0; i < 16; i++) s.prof[i] = 0;
   }
   __syncwarp();
+  const int nwork = qpref[wib][WQ];
   int dropped = 0;
+  constexpr int CHUNK = 4;  // consecutive items of one queue per cursor grab: same hull, warm L1
 #pragma unroll 1
   for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(pb.nwork + 4 * sub + 1, 1);
-    item = wshfl(item, 0);
-    if (item >= nwork) break;
-    const uint2 w = pb.work[item];
+    int item0 = 0;
+    if (lane == 0) item0 = atomicAdd(pb.nwork + WSTRIDE * sub + W_CURSOR, CHUNK);
+    item0 = wshfl(item0, 0);
+    if (item0 >= nwork) break;
+#pragma unroll 1
+  for (int item = item0; item < min(item0 + CHUNK, nwork); item++) {
+    // queue of this item: largest q with qpref[q] <= item
+    int q = 0;
+#pragma unroll
+    for (int step = WQ / 2; step > 0; step >>= 1)
+      if (qpref[wib][q + step] <= item) q += step;
+    const uint2 w = pb.work[(size_t)q * pb.work_cap + (item - qpref[wib][q])];
     const int env = (int)w.x, g1 = (int)(w.y & 0xff), g2 = (int)((w.y >> 8) & 0xff), pidx = (int)(w.y >> 16);
     const T(*xpos)[3] = reinterpret_cast<const T(*)[3]>(pb.xpos + (size_t)env * (NSLOT * 3));
     const T(*xmat)[9] = reinterpret_cast<const T(*)[9]>(pb.xmat + (size_t)env * (NSLOT * 9));
@@ -683,6 +718,7 @@ __global__ void __launch_bounds__(WARPS_NARROW * 32) scene_narrow_kernel(const _
       }
       __syncwarp();
     }
+  }
   }
   if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
   prof_flush(s, S, lane);
@@ -889,7 +925,7 @@ __global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_solve_kernel(const __g
   if (env >= S.N) return;
   if (!pb.active[env]) return;
   if (!solve_env(am, sm, cfg, S, pb, out, sub, env, all[wib], lane)) {
-    if (lane == 0) pb.big[atomicAdd(pb.nwork + 4 * sub + 2, 1)] = env;
+    if (lane == 0) pb.big[atomicAdd(pb.nwork + WSTRIDE * sub + W_NBIG, 1)] = env;
   }
 }
 // Large tier: a few single-warp CTAs walk the queue (usually empty).
@@ -901,11 +937,11 @@ __global__ void __launch_bounds__(32) scene_solve_big_kernel(const __grid_consta
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SC &s = *reinterpret_cast<SC *>(smem_raw);
   const int lane = threadIdx.x & 31;
-  const int n = pb.nwork[4 * sub + 2];
+  const int n = pb.nwork[WSTRIDE * sub + W_NBIG];
 #pragma unroll 1
   for (;;) {
     int item = 0;
-    if (lane == 0) item = atomicAdd(pb.nwork + 4 * sub + 3, 1);
+    if (lane == 0) item = atomicAdd(pb.nwork + WSTRIDE * sub + W_BIGCURSOR, 1);
     item = wshfl(item, 0);
     if (item >= n) break;
     solve_env(am, sm, cfg, S, pb, out, sub, pb.big[item], s, lane);
@@ -961,7 +997,7 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
   }
   KernelTimer none;
   KernelTimer &t = kt ? *kt : none;
-  cudaMemsetAsync(pb.nwork, 0, sizeof(int) * 4 * (cfg.nsub + 1), stream);
+  cudaMemsetAsync(pb.nwork, 0, sizeof(int) * WSTRIDE * (cfg.nsub + 1), stream);
   const int grid_env = (S.N + WARPS_SOLVE - 1) / WARPS_SOLVE;
   t.begin(0, stream);
   scene_begin_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, stream>>>(am, sm, cfg, S, pb, action, out);

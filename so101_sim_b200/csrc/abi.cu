@@ -200,6 +200,7 @@ struct Handle : HandleBase {
     if (scene) {  // inter-kernel scratch of the scene pipeline
       pipe.xpos = dalloc<T>(N * NSLOT * 3); pipe.xmat = dalloc<T>(N * NSLOT * 9);
       pipe.work_cap = (int)(4 * N + 64); pipe.work = dalloc<uint2>((size_t)WQ * pipe.work_cap); pipe.nwork = dalloc<int>(WSTRIDE * (c.n_substeps + 1)); pipe.big = dalloc<int>(N);
+      if (b.scalar("ngeom") > GMAX_GEOMS) throw std::runtime_error("model has more geoms than the broad phase can hold");
       if (b.scalar("ngeom") > WQ) throw std::runtime_error("model has more geoms than narrow-phase work queues");
       pipe.con = dalloc<T>(N * CONBUF * 8); pipe.con_key = dalloc<int>(N * CONBUF); pipe.ncon_raw = dalloc<int>(N);
       pipe.active = dalloc<uint8_t>(N); pipe.flags = dalloc<uint8_t>(N);

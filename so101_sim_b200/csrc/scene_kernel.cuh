@@ -13,6 +13,7 @@ namespace so101 {
 // Scene-kernel state layout is array-of-rows ([N][nq] etc.): one warp owns one env and reads its row with one
 // coalesced request (the arm-only kernel, one THREAD per env, uses [k][N] instead).
 
+constexpr int GMAX_GEOMS = 96;       // geoms per model the broad phase holds in shared memory
 constexpr int WQ = 128;             // work queues (>= ngeom)
 constexpr int WSTRIDE = WQ + 4;     // counters per substep
 enum { W_CURSOR = WQ, W_NBIG = WQ + 1, W_BIGCURSOR = WQ + 2 };

@@ -31,10 +31,15 @@ constexpr int NOUT = 8;          // contacts one pair can emit (manifold <= MAXM
 constexpr int NC_S = 32, NB_S = 40;
 constexpr int NC_L = CONBUF, NB_L = CONBUF + 32;
 
+constexpr int GMAX = GMAX_GEOMS;  // geoms the broad phase can hold (model: 83 colliding geoms)
+constexpr int CANDCAP = 256;  // geom pairs that may survive the bounding-sphere test per env
+
 template <typename T>
 struct BroadScratch {
   unsigned pairq[PAIRCAP];
-  T gcenter[3][96];  // world bounding-sphere centres of all geoms
+  unsigned cand[CANDCAP];
+  T gcenter[3][GMAX];                  // world bounding-sphere centres of all geoms
+  T opos[3][GMAX], omat[9][GMAX];      // world oriented boxes (geom AABB in the geom frame) of all geoms
 };
 
 // per-warp scratch of the narrow-phase kernel: one candidate pair at a time
@@ -380,7 +385,8 @@ __device__ __noinline__ void scene_broadphase(const SceneModel<T> &sm, S &s, con
     for (int i = lane; i < NSLOT * 3; i += 32) gx[i] = (&s.xpos[0][0])[i];
     for (int i = lane; i < NSLOT * 9; i += 32) gm[i] = (&s.xmat[0][0])[i];
   }
-  // world bounding-sphere centres of all geoms
+  // world bounding spheres and oriented boxes of all geoms (lane per geom)
+#pragma unroll 1
   for (int g = lane; g < sm.ngeom; g += 32) {
     const int slot = sm.geom_slot[g];
     const T bc[3] = {sm.geom_bcenter[3 * g], sm.geom_bcenter[3 * g + 1], sm.geom_bcenter[3 * g + 2]};
@@ -390,10 +396,18 @@ __device__ __noinline__ void scene_broadphase(const SceneModel<T> &sm, S &s, con
       mulmv(t, s.xmat[slot], bc);
       for (int c = 0; c < 3; c++) cs.gcenter[c][g] = s.xpos[slot][c] + t[c];
     }
+    T pos[3], mat[9], half[3];
+    geom_obb(sm, s, g, pos, mat, half);
+#pragma unroll
+    for (int c = 0; c < 3; c++) cs.opos[c][g] = pos[c];
+#pragma unroll
+    for (int c = 0; c < 9; c++) cs.omat[c][g] = mat[c];
   }
   __syncwarp();
-  int npq = 0;
-  for (int p = 0; p < sm.npair; p++) {  // uniform loop; broad-phase order == oracle order
+  // phase 1: body-pair spheres, then geom-pair spheres -> candidate list (order kept: broad-phase order == oracle order)
+  int ncand = 0;
+#pragma unroll 1
+  for (int p = 0; p < sm.npair; p++) {  // uniform loop
     const int b1 = sm.bodypair[2 * p], b2 = sm.bodypair[2 * p + 1];
     if (b1 != 0) {
       T c1[3], c2[3], t[3];
@@ -411,43 +425,67 @@ __device__ __noinline__ void scene_broadphase(const SceneModel<T> &sm, S &s, con
     }
     const int a1 = sm.body_geomadr[b1], n1 = sm.body_geomnum[b1], a2 = sm.body_geomadr[b2], n2 = sm.body_geomnum[b2];
     const int total = n1 * n2;
+#pragma unroll 1
     for (int base = 0; base < total; base += 32) {
       const int k = base + lane;
       bool keep = false;
       int g1 = 0, g2 = 0;
       if (k < total) {
         g1 = a1 + k / n2; g2 = a2 + k % n2;
-        const int ty1 = sm.geom_type[g1];
-        const T cA[3] = {cs.gcenter[0][g1], cs.gcenter[1][g1], cs.gcenter[2][g1]}, cB[3] = {cs.gcenter[0][g2], cs.gcenter[1][g2], cs.gcenter[2][g2]};
-        const T rA = sm.geom_rbound[g1], rB = sm.geom_rbound[g2];
-        if (ty1 == G_PLANE) {
+        const T cB[3] = {cs.gcenter[0][g2], cs.gcenter[1][g2], cs.gcenter[2][g2]};
+        const T rB = sm.geom_rbound[g2];
+        if (sm.geom_type[g1] == G_PLANE) {
           const T n[3] = {sm.geom_mat[9 * g1 + 2], sm.geom_mat[9 * g1 + 5], sm.geom_mat[9 * g1 + 8]};
           const T pp[3] = {sm.geom_pos[3 * g1], sm.geom_pos[3 * g1 + 1], sm.geom_pos[3 * g1 + 2]};
           keep = !(dot3(n, cB) - dot3(n, pp) - rB > T(0));
-          if (keep) {
-            T pos[3], mat[9], half[3];
-            geom_obb(sm, s, g2, pos, mat, half);
-            const T ext = t_abs(n[0] * mat[0] + n[1] * mat[3] + n[2] * mat[6]) * half[0] + t_abs(n[0] * mat[1] + n[1] * mat[4] + n[2] * mat[7]) * half[1] +
-                          t_abs(n[0] * mat[2] + n[1] * mat[5] + n[2] * mat[8]) * half[2];
-            keep = !(dot3(n, pos) - dot3(n, pp) - ext > T(0));
-          }
         } else {
-          T t[3];
-          sub3(t, cA, cB);
-          const T r = rA + rB;
+          const T t[3] = {cs.gcenter[0][g1] - cB[0], cs.gcenter[1][g1] - cB[1], cs.gcenter[2][g1] - cB[2]};
+          const T r = sm.geom_rbound[g1] + rB;
           keep = !(dot3(t, t) > r * r);
-          if (keep) {
-            T p1[3], m1[9], h1[3], p2[3], m2[9], h2[3];
-            geom_obb(sm, s, g1, p1, m1, h1); geom_obb(sm, s, g2, p2, m2, h2);
-            keep = obb_overlap(p1, m1, h1, p2, m2, h2);
-          }
         }
       }
       const unsigned m = __ballot_sync(FULL, keep);
-      const int idx = npq + __popc(m & ((1u << lane) - 1));
-      if (keep && idx < PAIRCAP) cs.pairq[idx] = (unsigned)g1 | ((unsigned)g2 << 8) | ((unsigned)idx << 16);
-      npq += __popc(m);
+      const int idx = ncand + __popc(m & ((1u << lane) - 1));
+      if (keep && idx < CANDCAP) cs.cand[idx] = (unsigned)g1 | ((unsigned)g2 << 8);
+      ncand += __popc(m);
     }
+  }
+  if (ncand > CANDCAP) { dropped += ncand - CANDCAP; ncand = CANDCAP; }
+  __syncwarp();
+  // phase 2: oriented boxes on the compacted candidates (lane per candidate)
+  int npq = 0;
+#pragma unroll 1
+  for (int base = 0; base < ncand; base += 32) {
+    const int k = base + lane;
+    bool keep = false;
+    int g1 = 0, g2 = 0;
+    if (k < ncand) {
+      const unsigned cd = cs.cand[k];
+      g1 = (int)(cd & 0xff); g2 = (int)(cd >> 8);
+      T p2[3], m2[9], h2[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) { p2[c] = cs.opos[c][g2]; h2[c] = sm.geom_aabb[6 * g2 + 3 + c] + T(1e-4); }
+#pragma unroll
+      for (int c = 0; c < 9; c++) m2[c] = cs.omat[c][g2];
+      if (sm.geom_type[g1] == G_PLANE) {
+        const T n[3] = {sm.geom_mat[9 * g1 + 2], sm.geom_mat[9 * g1 + 5], sm.geom_mat[9 * g1 + 8]};
+        const T pp[3] = {sm.geom_pos[3 * g1], sm.geom_pos[3 * g1 + 1], sm.geom_pos[3 * g1 + 2]};
+        const T ext = t_abs(n[0] * m2[0] + n[1] * m2[3] + n[2] * m2[6]) * h2[0] + t_abs(n[0] * m2[1] + n[1] * m2[4] + n[2] * m2[7]) * h2[1] +
+                      t_abs(n[0] * m2[2] + n[1] * m2[5] + n[2] * m2[8]) * h2[2];
+        keep = !(dot3(n, p2) - dot3(n, pp) - ext > T(0));
+      } else {
+        T p1[3], m1[9], h1[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { p1[c] = cs.opos[c][g1]; h1[c] = sm.geom_aabb[6 * g1 + 3 + c] + T(1e-4); }
+#pragma unroll
+        for (int c = 0; c < 9; c++) m1[c] = cs.omat[c][g1];
+        keep = obb_overlap(p1, m1, h1, p2, m2, h2);
+      }
+    }
+    const unsigned m = __ballot_sync(FULL, keep);
+    const int idx = npq + __popc(m & ((1u << lane) - 1));
+    if (keep && idx < PAIRCAP) cs.pairq[idx] = (unsigned)g1 | ((unsigned)g2 << 8) | ((unsigned)idx << 16);
+    npq += __popc(m);
   }
   if (npq > PAIRCAP) { dropped += npq - PAIRCAP; npq = PAIRCAP; }
   __syncwarp();

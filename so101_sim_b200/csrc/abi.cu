@@ -199,7 +199,7 @@ struct Handle : HandleBase {
     d_steptype = dalloc<uint8_t>(N);
     if (scene) {  // inter-kernel scratch of the scene pipeline
       pipe.xpos = dalloc<T>(N * NSLOT * 3); pipe.xmat = dalloc<T>(N * NSLOT * 9);
-      pipe.work_cap = (int)(4 * N + 64); pipe.work = dalloc<uint2>((size_t)WQ * pipe.work_cap); pipe.nwork = dalloc<int>(WSTRIDE * (c.n_substeps + 1)); pipe.big = dalloc<int>(N);
+      pipe.work_cap = (int)(4 * N + 64); pipe.work = dalloc<uint2>((size_t)WQ * pipe.work_cap); pipe.nwork = dalloc<int>(WSTRIDE * (c.n_substeps + 1)); pipe.big = dalloc<int>(2 * N);
       if (b.scalar("ngeom") > GMAX_GEOMS) throw std::runtime_error("model has more geoms than the broad phase can hold");
       if (b.scalar("ngeom") > WQ) throw std::runtime_error("model has more geoms than narrow-phase work queues");
       pipe.con = dalloc<T>(N * CONBUF * 8); pipe.con_key = dalloc<int>(N * CONBUF); pipe.ncon_raw = dalloc<int>(N);
@@ -249,6 +249,14 @@ struct Handle : HandleBase {
       if (count < (size_t)S.N * nv) throw std::runtime_error("debug_read: buffer too small");
       if (scene) launch_cast_copy<T, float>(S.warm, dst, (size_t)S.N * nv, s); else launch_soa_to_rows<T, float>(S.warm, dst, S.N, nv, s);
       launches += 1;
+    } else if (f == "dropcat") {
+      // 8 drop counters by buffer (see scene_solve.cuh: g_dropcat), since the library was loaded
+      if (count < 8) throw std::runtime_error("debug_read: buffer too small");
+      int h[8]; float hf[8];
+      CUDA_OK(cudaStreamSynchronize(s));
+      scene_dropcat<T>(h);
+      for (int i = 0; i < 8; i++) hf[i] = (float)h[i];
+      CUDA_OK(cudaMemcpy(dst, hf, sizeof hf, cudaMemcpyHostToDevice));
     } else if (f == "prof") {
       // 16 stage-profile accumulators (clock64 sums / counters over all envs since create); needs SO101_PROFILE=1 at create
       if (!S.prof) throw std::runtime_error("debug_read: create the handle with SO101_PROFILE=1 to enable the stage profile");

@@ -10,10 +10,9 @@
 
 namespace so101 {
 
-constexpr int NCON = 64;         // contacts the solver keeps per env (extra ones are dropped and counted)
-constexpr int NBLK = 96;         // 6x6 Jacobian blocks per env: one per dynamic body touched by a contact
+constexpr int NCON = 64;         // contacts per env the parity probe (debug_contacts) can report
 constexpr int PAIRCAP = 64;      // candidate geom pairs per env per substep (after the OBB mid phase)
-constexpr int CONBUF = 96;       // raw contacts per env the narrow phase may write between two kernels
+constexpr int CONBUF = 128;      // raw contacts per env the narrow phase may write between two kernels
 constexpr int EPA_MAXV = 96, EPA_MAXF = 256;
 constexpr int MAXCAND = 64, MAXFEAT = 32, MAXMANI = 4;
 constexpr unsigned FULL = 0xffffffffu;
@@ -138,6 +137,7 @@ __device__ __forceinline__ void support(const SceneModel<T> &sm, const Shape<T> 
       const int oi = __shfl_xor_sync(FULL, bi, o);
       if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
+    if (bi == 0x7fffffff) bi = 0;  // non-finite direction (diverged env): any vertex, but never out of bounds
     const Vec4<T> v = sm.hull_vert[s.vadr + bi];
     p[0] = v.x; p[1] = v.y; p[2] = v.z;
   } else if (s.type == G_BOX) {
@@ -169,7 +169,7 @@ __device__ __noinline__ void msupport(const SceneModel<T> &sm, const Shape<T> &A
 
 // boolean GJK; mirrors gjk_intersect() of the oracle.  Uniform control flow across the warp.
 template <typename T>
-__device__ __noinline__ int gjk_intersect(const SceneModel<T> &sm, const Shape<T> &A, const Shape<T> &B, MPoint<T> *S, int &np, int lane) {
+__device__ __noinline__ int gjk_intersect(const SceneModel<T> &sm, const Shape<T> &A, const Shape<T> &B, MPoint<T> *S, int &np, int &iters, int lane) {
   T d[3];
   sub3(d, B.center, A.center);
   if (dot3(d, d) < T(1e-20)) { d[0] = T(1); d[1] = T(0); d[2] = T(0); }
@@ -177,6 +177,7 @@ __device__ __noinline__ int gjk_intersect(const SceneModel<T> &sm, const Shape<T
   #pragma unroll 1
   for (int it = 0; it < 64; it++) {
     MPoint<T> p;
+    iters = it + 1;
     msupport(sm, A, B, d, p, lane);
     if (dot3(p.w, d) < T(0)) { np = n; return 0; }
     S[n++] = p;
@@ -260,8 +261,9 @@ __device__ __noinline__ int epa_add_face(CollideScratch<T> &cs, int &nf, int a, 
 
 template <typename T>
 __device__ __noinline__ int epa(const SceneModel<T> &sm, CollideScratch<T> &cs, const Shape<T> &A, const Shape<T> &B, const MPoint<T> *S, int n, T *normal,
-                   T &depth, T *pa, T *pb, int lane) {
+                   T &depth, T *pa, T *pb, int &iters, int lane) {
   int nv = 0, nf = 0;
+  iters = 0;
   if (n == 1) return 0;
   #pragma unroll 1
   for (int i = 0; i < n; i++) epa_putv(cs, nv++, S[i], lane);
@@ -318,6 +320,7 @@ __device__ __noinline__ int epa(const SceneModel<T> &sm, CollideScratch<T> &cs, 
     best = find_best();
     if (best < 0) return 0;
     if (nv >= EPA_MAXV) break;
+    iters = it + 1;
     const T bn[3] = {cs.Fn[0][best], cs.Fn[1][best], cs.Fn[2][best]}, bd = cs.Fd[best];
     MPoint<T> p;
     msupport(sm, A, B, bn, p, lane);

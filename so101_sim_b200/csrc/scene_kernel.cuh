@@ -15,8 +15,8 @@ namespace so101 {
 
 constexpr int GMAX_GEOMS = 96;       // geoms per model the broad phase holds in shared memory
 constexpr int WQ = 128;             // work queues (>= ngeom)
-constexpr int WSTRIDE = WQ + 4;     // counters per substep
-enum { W_CURSOR = WQ, W_NBIG = WQ + 1, W_BIGCURSOR = WQ + 2 };
+constexpr int WSTRIDE = WQ + 8;     // counters per substep
+enum { W_CURSOR = WQ, W_NTIER = WQ + 1 /* [2]: envs queued for solver tier 1, 2 */, W_TIERCURSOR = WQ + 3 /* [2] */ };
 
 // Device scratch that crosses the kernels of one substep (written by one kernel, read by the next; L2-resident).
 template <typename T>
@@ -27,7 +27,7 @@ struct PipeBuf {
   int work_cap;             // entries per queue
   int *nwork;               // [nsub+1][WSTRIDE]  per substep: items per queue [0..WQ), then pair cursor, large-tier envs
                             //   queued, large-tier cursor
-  int *big;                 // [N]  envs deferred to the large solver tier in this substep
+  int *big;                 // [2][N]  envs deferred to solver tier 1 / tier 2 in this substep
   T *con;                   // [N][CONBUF][8]  raw contacts: normal3, pos3, dist
   int *con_key;             // [N][CONBUF]     pair index << 20 | manifold index << 16 | g1 << 8 | g2  (sort key)
   int *ncon_raw;            // [N]
@@ -82,4 +82,6 @@ template <typename T>
 size_t scene_smem_bytes();
 template <typename T>
 int scene_narrow_grid();
+template <typename T>
+void scene_dropcat(int out[8]);
 }  // namespace so101

@@ -27,9 +27,12 @@ namespace so101 {
 constexpr int WARPS_SOLVE = 2;   // envs (warps) per CTA in the begin / solve kernels
 constexpr int WARPS_NARROW = 4;  // pairs (warps) in flight per CTA in the narrow-phase kernel
 constexpr int NOUT = 8;          // contacts one pair can emit (manifold <= MAXMANI)
-// solver tiers: almost every env has <= NC_S contacts (mean ~20); the rest is deferred to a second, larger instantiation
-constexpr int NC_S = 32, NB_S = 40;
-constexpr int NC_L = CONBUF, NB_L = CONBUF + 32;
+// Solver tiers by contact capacity: a resting scene has ~20 contacts, an arm pressed into the table or props 40-100.  Each
+// tier is the same code with a larger shared-memory scratch; an env that does not fit tier t is queued for tier t + 1.
+constexpr int NC_S = 32, NB_S = 40;            // tier 0: every env, 2 warps per CTA
+constexpr int NC_M = 64, NB_M = 80;            // tier 1
+constexpr int NC_L = CONBUF, NB_L = CONBUF + 32;  // tier 2 (last: excess contacts are dropped and counted)
+constexpr int WARPS_M = 2, WARPS_L = 1;
 
 constexpr int GMAX = GMAX_GEOMS;  // geoms the broad phase can hold (model: 83 colliding geoms)
 constexpr int CANDCAP = 256;  // geom pairs that may survive the bounding-sphere test per env
@@ -74,6 +77,7 @@ struct Scratch {
 
 // stage profiler: lane 0 accumulates clock64 deltas into Scratch::prof when the handle was created with SO101_PROFILE=1
 enum { P_DYN = 0, P_BROAD, P_PLANE, P_GJK, P_EPA, P_MANI, P_ROWS, P_SOLVE, P_INTEG, P_TASK, P_NPQ, P_NCON, P_NEWTON, P_LINE, P_NEPA, P_NSUB };
+enum { P_GJKIT = P_PLANE, P_EPAIT = P_INTEG, P_BIGENV = P_TASK };  // counters that re-use the (tiny) plane / integrate / task slots
 #define PROF_START(s) long long pt_ = (s).profon ? clock64() : 0
 #define PROF_ACC(s, i, lane) do { if ((s).profon) { const long long n_ = clock64(); if ((lane) == 0) (s).prof[i] += n_ - pt_; pt_ = n_; } } while (0)
 #define PROF_CNT(s, i, v, lane) do { if ((s).profon && (lane) == 0) (s).prof[i] += (v); } while (0)
@@ -166,7 +170,7 @@ __device__ __forceinline__ void prop_dynamics(const SceneModel<T> &sm, const Arm
 template <typename T>
 __device__ __forceinline__ void emit_contact(NarrowScratch<T> &s, int &ncon, int &dropped, int g1, int g2, const T *frame, const T *pos, T dist) {
   // lane 0 only; the pair's contacts are staged in shared memory and flushed to the env's raw contact buffer by the caller
-  if (ncon >= NOUT) { dropped++; return; }
+  if (ncon >= NOUT) { dropped++; DROPCAT(0, 1); return; }
   const int c = ncon++;
   s.c_dist[c] = dist;
   for (int e = 0; e < 3; e++) { s.c_pos[e][c] = pos[e]; s.c_normal[e][c] = frame[e]; }
@@ -242,13 +246,16 @@ __device__ __noinline__ void collide_convex(const SceneModel<T> &sm, NarrowScrat
   MPoint<T> S[4];
   int n = 0;
   PROF_START(s);
-  const int hit = gjk_intersect(sm, A, B, S, n, lane);
+  int git = 0, eit = 0;
+  const int hit = gjk_intersect(sm, A, B, S, n, git, lane);
   PROF_ACC(s, P_GJK, lane);
+  PROF_CNT(s, P_GJKIT, git, lane);
   if (!hit) return;
   T normal[3], depth, pa[3], pb[3];
   PROF_CNT(s, P_NEPA, 1, lane);
-  const int ok = epa(sm, s.col, A, B, S, n, normal, depth, pa, pb, lane);
+  const int ok = epa(sm, s.col, A, B, S, n, normal, depth, pa, pb, eit, lane);
   PROF_ACC(s, P_EPA, lane);
+  PROF_CNT(s, P_EPAIT, eit, lane);
   if (!ok) return;
   if (!(depth > T(0))) return;
   const int nm = manifold(sm, s, A, B, normal, depth, ncon, dropped, lane);
@@ -450,7 +457,7 @@ __device__ __noinline__ void scene_broadphase(const SceneModel<T> &sm, S &s, con
       ncand += __popc(m);
     }
   }
-  if (ncand > CANDCAP) { dropped += ncand - CANDCAP; ncand = CANDCAP; }
+  if (ncand > CANDCAP) { dropped += ncand - CANDCAP; if (lane == 0) DROPCAT(1, ncand - CANDCAP); ncand = CANDCAP; }
   __syncwarp();
   // phase 2: oriented boxes on the compacted candidates (lane per candidate)
   int npq = 0;
@@ -487,7 +494,7 @@ __device__ __noinline__ void scene_broadphase(const SceneModel<T> &sm, S &s, con
     if (keep && idx < PAIRCAP) cs.pairq[idx] = (unsigned)g1 | ((unsigned)g2 << 8) | ((unsigned)idx << 16);
     npq += __popc(m);
   }
-  if (npq > PAIRCAP) { dropped += npq - PAIRCAP; npq = PAIRCAP; }
+  if (npq > PAIRCAP) { dropped += npq - PAIRCAP; if (lane == 0) DROPCAT(2, npq - PAIRCAP); npq = PAIRCAP; }
   __syncwarp();
   // append (env, g1 | g2 << 8 | pair index << 16) to the work queue of its second geom
   int qdrop = 0;
@@ -496,7 +503,7 @@ __device__ __noinline__ void scene_broadphase(const SceneModel<T> &sm, S &s, con
     const int g2 = (int)((pq >> 8) & 0xff);
     const int slot = atomicAdd(pb.nwork + WSTRIDE * sub + g2, 1);
     if (slot < pb.work_cap) pb.work[(size_t)g2 * pb.work_cap + slot] = make_uint2((unsigned)env, pq);
-    else qdrop++;
+    else { qdrop++; DROPCAT(3, 1); }
   }
   dropped += warp_sum(qdrop);
   PROF_ACC(s, P_BROAD, lane);
@@ -683,8 +690,11 @@ __global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_begin_kernel(const __g
 
 // Per substep: one warp per candidate geom pair, pulled from the work list with an atomic cursor (pairs differ 10x in
 // cost: a GJK miss vs GJK + EPA + manifold).  Contacts go to the env's raw buffer tagged with (pair index, manifold index).
+#ifndef NARROW_MINB
+#define NARROW_MINB 1  // minimum resident CTAs the compiler must allow (register cap)
+#endif
 template <typename T>
-__global__ void __launch_bounds__(WARPS_NARROW * 32) scene_narrow_kernel(const __grid_constant__ SceneModel<T> sm, const __grid_constant__ StepCfg cfg,
+__global__ void __launch_bounds__(WARPS_NARROW * 32, NARROW_MINB) scene_narrow_kernel(const __grid_constant__ SceneModel<T> sm, const __grid_constant__ StepCfg cfg,
                                                                         const EnvState<T> S, const PipeBuf<T> pb, int sub) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   NarrowScratch<T> *all = reinterpret_cast<NarrowScratch<T> *>(smem_raw);
@@ -739,7 +749,7 @@ __global__ void __launch_bounds__(WARPS_NARROW * 32) scene_narrow_kernel(const _
     make_shape(sm, xpos, xmat, g2, B);
     __syncwarp();
     int ncon = 0;
-    if (A.type == G_PLANE) { PROF_START(s); collide_plane(sm, s, A, B, ncon, dropped, lane); PROF_ACC(s, P_PLANE, lane); }
+    if (A.type == G_PLANE) collide_plane(sm, s, A, B, ncon, dropped, lane);
     else collide_convex(sm, s, A, B, ncon, dropped, lane);
     if (ncon > 0) {
       int base = 0;
@@ -769,8 +779,8 @@ __device__ __noinline__ bool gather_contacts(const SceneModel<T> &sm, const Pipe
   auto &R = s.sol;
   constexpr int NC = sizeof(R.D0) / sizeof(T), NB = sizeof(R.w1[0]) / sizeof(T);
   int nraw = pb.ncon_raw[env];
-  if (nraw > NC && NC < CONBUF) return false;
-  if (nraw > CONBUF) { dropped += nraw - CONBUF; nraw = CONBUF; }
+  if (nraw > NC && NC < CONBUF) return false;  // (NC == CONBUF marks the last tier)
+  if (nraw > CONBUF) { dropped += nraw - CONBUF; if (lane == 0) DROPCAT(4, nraw - CONBUF); nraw = CONBUF; }
   const int *keys = pb.con_key + (size_t)env * CONBUF;
   constexpr int RSL = (NC + 31) / 32;
   int mykey[RSL], rank[RSL];
@@ -835,102 +845,113 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
   int iters = 0, dropped = 0;
   const bool last = sub == cfg.nsub - 1;
   PROF_START(s);
-  if (!gather_contacts(sm, pb, s, env, dropped, lane)) return false;
-  PROF_CNT(s, P_NCON, s.ncon, lane);
-  scene_kinematics(am, s, lane);
-  {
-    T qa[NJ], qda[NJ], ca[NJ], M[21], bias[NJ], frc[NJ], qs[NJ];
-#pragma unroll
-    for (int i = 0; i < NJ; i++) { qa[i] = s.q[i]; qda[i] = s.qd[i]; ca[i] = s.ctrl[i]; }
-    arm_crb_rne(am, s.kin, qda, M, bias);
-    arm_actuation(am, qa, qda, ca, frc);
-    T L[21];
-#pragma unroll
-    for (int i = 0; i < 21; i++) L[i] = M[i];
-    chol6(L);
-#pragma unroll
-    for (int i = 0; i < NJ; i++) qs[i] = frc[i] - bias[i];
-    chol6_solve(L, qs);
-    ArmRows<T> arows;
-    arm_make_rows(am, qa, qda, qs, arows);
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < 21; i++) s.Marm[i] = M[i];
-#pragma unroll
-      for (int i = 0; i < NJ; i++) s.qacc_s[i] = qs[i];
-      s.arows = arows;
+  const bool frozen = pb.flags[env] != 0;  // diverged earlier in this control step: no more physics, no more collision work
+  if (frozen && lane == 0) pb.ncon_raw[env] = 0;
+  if (!frozen && !gather_contacts(sm, pb, s, env, dropped, lane)) return false;
+  if (frozen && lane == 0) s.ncon = 0;
+  __syncwarp();
+  if (!frozen) {
+    PROF_CNT(s, P_NCON, s.ncon, lane);
+    scene_kinematics(am, s, lane);
+    {
+      T qa[NJ], qda[NJ], ca[NJ], M[21], bias[NJ], frc[NJ], qs[NJ];
+  #pragma unroll
+      for (int i = 0; i < NJ; i++) { qa[i] = s.q[i]; qda[i] = s.qd[i]; ca[i] = s.ctrl[i]; }
+      arm_crb_rne(am, s.kin, qda, M, bias);
+      arm_actuation(am, qa, qda, ca, frc);
+      T L[21];
+  #pragma unroll
+      for (int i = 0; i < 21; i++) L[i] = M[i];
+      chol6(L);
+  #pragma unroll
+      for (int i = 0; i < NJ; i++) qs[i] = frc[i] - bias[i];
+      chol6_solve(L, qs);
+      ArmRows<T> arows;
+      arm_make_rows(am, qa, qda, qs, arows);
+      if (lane == 0) {
+  #pragma unroll
+        for (int i = 0; i < 21; i++) s.Marm[i] = M[i];
+  #pragma unroll
+        for (int i = 0; i < NJ; i++) s.qacc_s[i] = qs[i];
+        s.arows = arows;
+      }
     }
-  }
-  if (lane < NPROP) {  // one lane per prop
-    T M[21], bias[6], x[6];
-    prop_dynamics(sm, am, s, lane, M, bias);
-#pragma unroll
-    for (int i = 0; i < 21; i++) s.Mprop[lane][i] = M[i];
-#pragma unroll
-    for (int i = 0; i < 6; i++) x[i] = -bias[i];
-    chol6(M);
-    chol6_solve(M, x);
-#pragma unroll
-    for (int i = 0; i < 6; i++) s.qacc_s[NJ + 6 * lane + i] = x[i];
-  }
-  __syncwarp();
-  PROF_ACC(s, P_DYN, lane);
-  if (S.dbg_contacts && last) {  // parity probe: contacts of the last substep
-    float *dst = S.dbg_contacts + (size_t)env * (1 + 9 * NCON);
-    const int n = s.ncon < NCON ? s.ncon : NCON;
-    if (lane == 0) dst[0] = (float)n;
-    for (int c = lane; c < n; c += 32) {
-      float *r = dst + 1 + 9 * c;
-      r[0] = (float)s.sol.v.con.g1[c]; r[1] = (float)s.sol.v.con.g2[c]; r[2] = (float)s.sol.v.con.dist[c];
-      for (int e = 0; e < 3; e++) { r[3 + e] = (float)s.sol.v.con.pos[e][c]; r[6 + e] = (float)s.sol.v.con.frame[e][c]; }
+    if (lane < NPROP) {  // one lane per prop
+      T M[21], bias[6], x[6];
+      prop_dynamics(sm, am, s, lane, M, bias);
+  #pragma unroll
+      for (int i = 0; i < 21; i++) s.Mprop[lane][i] = M[i];
+  #pragma unroll
+      for (int i = 0; i < 6; i++) x[i] = -bias[i];
+      chol6(M);
+      chol6_solve(M, x);
+  #pragma unroll
+      for (int i = 0; i < 6; i++) s.qacc_s[NJ + 6 * lane + i] = x[i];
     }
-  }
-  build_rows(sm, s, dropped, lane);
-  PROF_ACC(s, P_ROWS, lane);
-  if (lane < NV) s.delta[lane] = s.warm[lane] - s.qacc_s[lane];
-  __syncwarp();
-  iters = scene_solve(am, sm.impratio, s, cfg.max_iter, (T)cfg.tol, lane);
-  __syncwarp();
-  PROF_ACC(s, P_SOLVE, lane);
-  PROF_CNT(s, P_NEWTON, iters, lane);
-  PROF_CNT(s, P_NSUB, 1, lane);
-  // [upstream] mj_Euler
-  T qacc = T(0);
-  if (lane < NV) {
-    qacc = s.qacc_s[lane] + s.delta[lane];
-    s.warm[lane] = qacc;
-    s.qd[lane] += sm.timestep * qacc;
-  }
-  const bool badnow = __any_sync(FULL, lane < NV && !(t_abs(qacc) < T(1e10)));
-  if (badnow && lane == 0) pb.flags[env] = 1;
-  __syncwarp();
-  if (lane < NJ) s.q[lane] += sm.timestep * s.qd[lane];
-  if (lane >= 8 && lane < 8 + NPROP) {
-    const int p = lane - 8;
-    T *qp = s.q + NJ + 7 * p;
-    const T *v = s.qd + NJ + 6 * p;
-    for (int c = 0; c < 3; c++) qp[c] += sm.timestep * v[c];
-    const T w[3] = {v[3], v[4], v[5]};
-    const T nw = t_sqrt(dot3(w, w)), ang = nw * sm.timestep;
-    T qn[4] = {qp[3], qp[4], qp[5], qp[6]};
-    if (ang > T(0)) {
-      T sn, cn;
-      t_sincos(T(0.5) * ang, &sn, &cn);
-      const T qr[4] = {cn, w[0] / nw * sn, w[1] / nw * sn, w[2] / nw * sn};
-      quat_mul(qn, qn, qr);
+    __syncwarp();
+    PROF_ACC(s, P_DYN, lane);
+    if (S.dbg_contacts && last) {  // parity probe: contacts of the last substep
+      float *dst = S.dbg_contacts + (size_t)env * (1 + 9 * NCON);
+      const int n = s.ncon < NCON ? s.ncon : NCON;
+      if (lane == 0) dst[0] = (float)n;
+      for (int c = lane; c < n; c += 32) {
+        float *r = dst + 1 + 9 * c;
+        r[0] = (float)s.sol.v.con.g1[c]; r[1] = (float)s.sol.v.con.g2[c]; r[2] = (float)s.sol.v.con.dist[c];
+        for (int e = 0; e < 3; e++) { r[3 + e] = (float)s.sol.v.con.pos[e][c]; r[6 + e] = (float)s.sol.v.con.frame[e][c]; }
+      }
     }
-    T n = t_sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
-    if (n < T(1e-15)) { qn[0] = T(1); qn[1] = qn[2] = qn[3] = T(0); n = T(1); }
-    for (int c = 0; c < 4; c++) qp[3 + c] = qn[c] / n;
+    build_rows(sm, s, dropped, lane);
+    PROF_ACC(s, P_ROWS, lane);
+    if (lane < NV) s.delta[lane] = s.warm[lane] - s.qacc_s[lane];
+    __syncwarp();
+    iters = scene_solve(am, sm.impratio, s, cfg.max_iter, (T)cfg.tol, lane);
+    __syncwarp();
+    PROF_ACC(s, P_SOLVE, lane);
+    PROF_CNT(s, P_NEWTON, iters, lane);
+    PROF_CNT(s, P_NSUB, 1, lane);
+    // [upstream] mj_Euler
+    T qacc = T(0);
+    if (lane < NV) qacc = s.qacc_s[lane] + s.delta[lane];
+    // [upstream] mj_checkAcc: a non-finite / huge acceleration ends the episode (task_suite.py:153); the env is frozen for the
+    // rest of this control step (its state stays finite) and resets on the next step() call
+    const bool badnow = __any_sync(FULL, lane < NV && !(t_abs(qacc) < T(1e10)));
+    if (badnow) {
+      if (lane == 0) pb.flags[env] = 1;
+      qacc = T(0);
+      if (lane < NV) s.qd[lane] = T(0);
+    }
+    if (lane < NV) {
+      s.warm[lane] = qacc;
+      s.qd[lane] += sm.timestep * qacc;
+    }
+    __syncwarp();
+    if (lane < NJ) s.q[lane] += sm.timestep * s.qd[lane];
+    if (lane >= 8 && lane < 8 + NPROP) {
+      const int p = lane - 8;
+      T *qp = s.q + NJ + 7 * p;
+      const T *v = s.qd + NJ + 6 * p;
+      for (int c = 0; c < 3; c++) qp[c] += sm.timestep * v[c];
+      const T w[3] = {v[3], v[4], v[5]};
+      const T nw = t_sqrt(dot3(w, w)), ang = nw * sm.timestep;
+      T qn[4] = {qp[3], qp[4], qp[5], qp[6]};
+      if (ang > T(0)) {
+        T sn, cn;
+        t_sincos(T(0.5) * ang, &sn, &cn);
+        const T qr[4] = {cn, w[0] / nw * sn, w[1] / nw * sn, w[2] / nw * sn};
+        quat_mul(qn, qn, qr);
+      }
+      T n = t_sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+      if (n < T(1e-15)) { qn[0] = T(1); qn[1] = qn[2] = qn[3] = T(0); n = T(1); }
+      for (int c = 0; c < 4; c++) qp[3 + c] = qn[c] / n;
+    }
+    __syncwarp();
+    for (int i = lane; i < NQ; i += 32) S.qpos[(size_t)env * NQ + i] = s.q[i];
+    for (int i = lane; i < NV; i += 32) { S.qvel[(size_t)env * NV + i] = s.qd[i]; S.warm[(size_t)env * NV + i] = s.warm[i]; }
   }
-  __syncwarp();
-  PROF_ACC(s, P_INTEG, lane);
-  for (int i = lane; i < NQ; i += 32) S.qpos[(size_t)env * NQ + i] = s.q[i];
-  for (int i = lane; i < NV; i += 32) { S.qvel[(size_t)env * NV + i] = s.qd[i]; S.warm[(size_t)env * NV + i] = s.warm[i]; }
   // poses at the new state: next substep's collision, or (mj_step1 refresh) the task layer
   scene_kinematics(am, s, lane);
   if (!last) {
-    scene_broadphase(sm, s, pb, env, sub + 1, dropped, lane);
+    if (!frozen) scene_broadphase(sm, s, pb, env, sub + 1, dropped, lane);
   } else {
     const bool bad = pb.flags[env] != 0;
     const int t = S.step[env] + 1;
@@ -943,7 +964,6 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
       if (bad) atomicAdd(S.diverged_count, 1);
     }
     write_obs_scene(cfg, S, out, s, env, t, reward, discount, st, lane);
-    PROF_ACC(s, P_TASK, lane);
   }
   if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
   prof_flush(s, S, lane);
@@ -963,26 +983,32 @@ __global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_solve_kernel(const __g
   if (env >= S.N) return;
   if (!pb.active[env]) return;
   if (!solve_env(am, sm, cfg, S, pb, out, sub, env, all[wib], lane)) {
-    if (lane == 0) pb.big[atomicAdd(pb.nwork + WSTRIDE * sub + W_NBIG, 1)] = env;
+    if (lane == 0) pb.big[atomicAdd(pb.nwork + WSTRIDE * sub + W_NTIER, 1)] = env;
   }
 }
-// Large tier: a few single-warp CTAs walk the queue (usually empty).
-template <typename T>
-__global__ void __launch_bounds__(32) scene_solve_big_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
-                                                            const __grid_constant__ StepCfg cfg, const EnvState<T> S, const PipeBuf<T> pb,
-                                                            const so101_step_out out, int sub) {
-  using SC = Scratch<T, NC_L, NB_L>;
+// Tiers 1 and 2: persistent CTAs walk the tier's queue (filled by the previous tier during this substep).
+template <typename T, int NC, int NB, int WARPS, int TIER>
+__global__ void __launch_bounds__(WARPS * 32) scene_solve_tier_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
+                                                                     const __grid_constant__ StepCfg cfg, const EnvState<T> S, const PipeBuf<T> pb,
+                                                                     const so101_step_out out, int sub) {
+  using SC = Scratch<T, NC, NB>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SC &s = *reinterpret_cast<SC *>(smem_raw);
-  const int lane = threadIdx.x & 31;
-  const int n = pb.nwork[WSTRIDE * sub + W_NBIG];
+  SC *all = reinterpret_cast<SC *>(smem_raw);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  SC &s = all[wib];
+  int *cnt = pb.nwork + WSTRIDE * sub;
+  const int n = cnt[W_NTIER + TIER - 1];
+  const int *list = pb.big + (size_t)(TIER - 1) * S.N;
 #pragma unroll 1
   for (;;) {
     int item = 0;
-    if (lane == 0) item = atomicAdd(pb.nwork + WSTRIDE * sub + W_BIGCURSOR, 1);
+    if (lane == 0) item = atomicAdd(cnt + W_TIERCURSOR + TIER - 1, 1);
     item = wshfl(item, 0);
     if (item >= n) break;
-    solve_env(am, sm, cfg, S, pb, out, sub, pb.big[item], s, lane);
+    const int env = list[item];
+    if (!solve_env(am, sm, cfg, S, pb, out, sub, env, s, lane)) {
+      if (TIER == 1 && lane == 0) pb.big[(size_t)S.N + atomicAdd(cnt + W_NTIER + 1, 1)] = env;
+    } else if (S.prof && lane == 0) atomicAdd(S.prof + P_BIGENV, 1ull);
     __syncwarp();
   }
 }
@@ -1001,9 +1027,12 @@ __global__ void scene_reset_kernel(const __grid_constant__ StepCfg cfg, const En
 
 template <typename T>
 size_t scene_smem_bytes() {
-  const size_t a = sizeof(Scratch<T, NC_S, NB_S>) * WARPS_SOLVE, b = sizeof(NarrowScratch<T>) * WARPS_NARROW, c = sizeof(Scratch<T, NC_L, NB_L>);
+  const size_t a = sizeof(Scratch<T, NC_M, NB_M>) * WARPS_M, b = sizeof(NarrowScratch<T>) * WARPS_NARROW, c = sizeof(Scratch<T, NC_L, NB_L>) * WARPS_L;
   return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
+
+template <typename T>
+void scene_dropcat(int out[8]) { cudaMemcpyFromSymbol(out, g_dropcat, sizeof(int) * 8); }
 
 template <typename T>
 int scene_narrow_grid() {
@@ -1016,7 +1045,7 @@ int scene_narrow_grid() {
   return (nb > 0 ? nb : 1) * (sms > 0 ? sms : 1);
 }
 
-// Launches of one control step: 1 memset + 1 + 3 * nsub kernels, all on the caller's stream.  Returns the kernel count.
+// Launches of one control step: 1 memset + 1 + 4 * nsub kernels, all on the caller's stream.  Returns the kernel count.
 template <typename T>
 int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
                       const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt) {
@@ -1024,11 +1053,12 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
   int dev = 0;
   cudaGetDevice(&dev);
   const size_t smem_env = sizeof(Scratch<T, NC_S, NB_S>) * WARPS_SOLVE, smem_nar = sizeof(NarrowScratch<T>) * WARPS_NARROW,
-               smem_big = sizeof(Scratch<T, NC_L, NB_L>);
+               smem_m = sizeof(Scratch<T, NC_M, NB_M>) * WARPS_M, smem_l = sizeof(Scratch<T, NC_L, NB_L>) * WARPS_L;
   if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaFuncSetAttribute(scene_begin_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
     cudaFuncSetAttribute(scene_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
-    cudaFuncSetAttribute(scene_solve_big_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
+    cudaFuncSetAttribute(scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
+    cudaFuncSetAttribute(scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
     cudaFuncSetAttribute(scene_narrow_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nar);
     cudaFuncSetAttribute(scene_reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
     if (dev >= 0 && dev < 64) configured[dev] = true;
@@ -1042,7 +1072,7 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
   t.end(0, stream);
   // narrow phase: persistent grid sized to the machine (pairs are pulled with an atomic cursor)
   const int grid_nar = pb.narrow_grid;
-  const int grid_big = S.N < 592 ? S.N : 592;
+  const int grid_m = S.N < 148 * 4 ? S.N : 148 * 4, grid_l = S.N < 148 * 2 ? S.N : 148 * 2;
   for (int sub = 0; sub < cfg.nsub; sub++) {
     t.begin(1, stream);
     scene_narrow_kernel<T><<<grid_nar, WARPS_NARROW * 32, smem_nar, stream>>>(sm, cfg, S, pb, sub);
@@ -1051,10 +1081,11 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
     scene_solve_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, stream>>>(am, sm, cfg, S, pb, out, sub);
     t.end(2, stream);
     t.begin(3, stream);
-    scene_solve_big_kernel<T><<<grid_big, 32, smem_big, stream>>>(am, sm, cfg, S, pb, out, sub);
+    scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1><<<grid_m, WARPS_M * 32, smem_m, stream>>>(am, sm, cfg, S, pb, out, sub);
+    scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2><<<grid_l, WARPS_L * 32, smem_l, stream>>>(am, sm, cfg, S, pb, out, sub);
     t.end(3, stream);
   }
-  return 1 + 3 * cfg.nsub;
+  return 1 + 4 * cfg.nsub;
 }
 template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream) {

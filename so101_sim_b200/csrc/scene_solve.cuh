@@ -16,6 +16,11 @@
 
 namespace so101 {
 
+// where contacts / candidate pairs were dropped by a full buffer since the library was loaded (diagnostics):
+// 0 NOUT per pair, 1 CANDCAP, 2 PAIRCAP, 3 work-queue capacity, 4 CONBUF raw contacts, 5 Jacobian block pool
+__device__ int g_dropcat[8];
+#define DROPCAT(i, n) atomicAdd(&g_dropcat[i], (int)(n))
+
 constexpr int NH = NV * (NV + 1) / 2;  // 171 packed lower-triangular entries
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
@@ -64,7 +69,11 @@ __device__ __noinline__ void build_rows(const SceneModel<T> &sm, S &s, int &drop
     const int my_blk = blk_base + incl - nb;
     blk_base += wshfl(incl, 31);
     const bool fits = my_blk + nb <= NB;
-    dropped += __popc(__ballot_sync(FULL, valid && !fits));
+    {
+      const int nd = __popc(__ballot_sync(FULL, valid && !fits));
+      dropped += nd;
+      if (nd && lane == 0) DROPCAT(5, nd);
+    }
     int baseA = 31, baseB = 31, bA = -1, bB = -1;
     if (valid) {
       const int b1 = sm.geom_body[g1], b2 = sm.geom_body[g2];

@@ -297,7 +297,7 @@ class BatchedEnvironment:
     self._check(self._lib.so101_counters(self._h, ctypes.byref(c)))
     return dict(kernel_launches=int(c[0]), control_steps=int(c[1]), diverged=int(c[2]), contacts_dropped=int(c[3]))
 
-  KERNEL_NAMES = ('scene_begin_kernel', 'scene_narrow_kernel', 'scene_solve_kernel', 'scene_solve_big_kernel', 'arm_step_kernel')
+  KERNEL_NAMES = ("scene_begin_kernel", "scene_narrow_kernel", "scene_solve_kernel", "scene_solve_tier_kernel(1+2)", "arm_step_kernel")
 
   def kernel_times(self, enable: bool = True) -> dict:
     """Accumulated per-kernel device time (CUDA events around each launch, recorded while enabled) -> {name: (ms, launches)};

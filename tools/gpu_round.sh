@@ -1,12 +1,14 @@
 #!/bin/bash
-# One GPU session: parity tests, bench lines, ncu launch list.  Usage (under gpurun): bash tools/gpu_round.sh <tag>
+# One GPU session: parity tests, smoke, bench line, ncu launch list + full capture of the dominant kernel at the bench config.
+# Usage (under gpurun): bash tools/gpu_round.sh <tag>
 tag=${1:-r01}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.txt 2>&1
-timeout 1200 python -m pytest tests -m gpu -x -q -s > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest_gpu.log
-timeout 300 python bench.py --steps 100 --warmup 10 > gpurun_out/${tag}_bench_arm4096.json 2> gpurun_out/${tag}_bench_arm4096.err; echo "bench arm rc=$?"
-timeout 600 python bench.py --workload banana16384 --envs 2048 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_banana2048.json 2> gpurun_out/${tag}_bench_banana2048.err; echo "bench banana2048 rc=$?"
-timeout 900 python bench.py --workload banana16384 --steps 10 --warmup 3 > gpurun_out/${tag}_bench_banana16384.json 2> gpurun_out/${tag}_bench_banana16384.err; echo "bench banana16384 rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${tag}_launches_arm.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_arm.log 2>&1; echo "ncu arm rc=$?"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${tag}_launches_banana.csv python bench.py --workload banana16384 --envs 2048 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_banana.log 2>&1; echo "ncu banana rc=$?"
-tail -3 gpurun_out/${tag}_pytest_gpu.log; cat gpurun_out/${tag}_bench_*.json
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"
+timeout 1200 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err; echo "bench ref rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1700 -c 70 --csv --log-file gpurun_out/${tag}_launches_banana16384.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/${tag}_ncu_l.log 2>&1; echo "ncu launches rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:scene_narrow -s 560 -c 1 -o gpurun_out/${tag}_narrow16384 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/${tag}_ncu_n.log 2>&1; echo "ncu narrow rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:scene_solve_kernel -s 560 -c 1 -o gpurun_out/${tag}_solve16384 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/${tag}_ncu_s.log 2>&1; echo "ncu solve rc=$?"
+tail -2 gpurun_out/${tag}_pytest_gpu.log; tail -2 gpurun_out/${tag}_smoke.log; cut -c1-400 gpurun_out/${tag}_bench.json; cut -c1-300 gpurun_out/${tag}_bench_reference.json

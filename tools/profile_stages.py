@@ -18,7 +18,7 @@ spec = env.action_spec()
 lo, hi = torch.tensor(spec.minimum, device='cuda:0'), torch.tensor(spec.maximum, device='cuda:0')
 acts = (lo + torch.rand(steps, envs, 6, generator=g, device='cuda:0') * (hi - lo)) * 0.3
 p0 = env.debug_read('prof', 16)[0, :16].double().cpu() if False else None
-names = ['dyn', 'broad', 'plane', 'gjk', 'epa', 'manifold', 'rows', 'solve', 'integrate', 'task', 'npq', 'ncon', 'newton', 'line', 'nepa', 'nsub']
+names = ['dyn', 'broad', 'gjk_iters', 'gjk', 'epa', 'manifold', 'rows', 'solve', 'epa_iters', 'big_envs', 'npq', 'ncon', 'newton', 'line', 'nepa', 'nsub']
 def read():
   out = torch.empty(16, dtype=torch.float32, device='cuda:0')
   import ctypes
@@ -32,14 +32,16 @@ for t in range(steps):
 t1.record(); torch.cuda.synchronize()
 b = read() - a
 nsub = float(b[15])
-cyc = {n: float(b[i]) / nsub for i, n in enumerate(names[:10])}
+cyc = {n: float(b[i]) / nsub for i, n in enumerate(names[:10]) if n not in ('gjk_iters', 'epa_iters', 'big_envs')}
 tot = sum(cyc.values())
 res = dict(envs=envs, steps=steps, precision=prec, ms_per_step=t0.elapsed_time(t1) / steps, cycles_per_substep=tot,
            share={k: round(v / tot, 4) for k, v in cyc.items()}, cycles={k: round(v) for k, v in cyc.items()},
            per_substep=dict(pairs=float(b[10]) / nsub, contacts=float(b[11]) / nsub, newton_iters=float(b[12]) / nsub,
-                            line_evals=float(b[13]) / nsub, epa_calls=float(b[14]) / nsub))
+                            line_evals=float(b[13]) / nsub, epa_calls=float(b[14]) / nsub,
+                            gjk_iters_per_pair=float(b[2]) / max(float(b[10]), 1), epa_iters_per_call=float(b[8]) / max(float(b[14]), 1), big_tier_env_fraction=float(b[9]) / nsub))
 q, v = env.get_state()
 ncon = env.debug_read('ncon').flatten(); it = env.debug_read('solver_iter').flatten()
 res['ncon_last'] = dict(mean=float(ncon.mean()), max=float(ncon.max())); res['iter_last'] = dict(mean=float(it.mean()), max=float(it.max()))
 res['counters'] = env.counters()
+h = torch.histc(ncon.float(), bins=13, min=0, max=104); res['ncon_hist_bins_of_8'] = [int(x) for x in h.tolist()]
 print(json.dumps(res))

@@ -101,10 +101,10 @@ int so101_step_host(so101_handle h, const float *action_host, float *reward_host
 int so101_counters(so101_handle h, uint64_t out[4]);
 
 /* Per-kernel device time, measured with CUDA events recorded on the caller's stream around every launch while enabled.
- * Returns the totals accumulated so far (ms and launch counts; index 0 scene begin, 1 scene narrow phase, 2 scene solve,
- * 3 scene solve large tier, 4 arm-only step), then switches recording on/off for the following calls.  Synchronises the
+ * Returns the totals accumulated so far (ms and launch counts; index 0 scene begin, 1 scene EPA + manifold, 2 scene solve
+ * tier 0, 3 scene solve tiers 1 + 2, 4 arm-only step, 5 scene boolean GJK), then switches recording on/off for the following calls.  Synchronises the
  * host on the recorded events.  No reference counterpart: measurement support for bench.py's roofline leg. */
-int so101_kernel_times(so101_handle h, int enable, double ms_out[5], uint64_t launches_out[5]);
+int so101_kernel_times(so101_handle h, int enable, double ms_out[6], uint64_t launches_out[6]);
 
 /* Debug/parity probe: copy one internal structure-of-arrays field ("qacc", "ncon", "solver_iter", ...) of all envs to a
  * caller-owned device buffer of `count` floats.  Used by the parity tests only. */

@@ -200,6 +200,7 @@ struct Handle : HandleBase {
     if (scene) {  // inter-kernel scratch of the scene pipeline
       pipe.xpos = dalloc<T>(N * NSLOT * 3); pipe.xmat = dalloc<T>(N * NSLOT * 9);
       pipe.work_cap = (int)(4 * N + 64); pipe.work = dalloc<uint2>((size_t)WQ * pipe.work_cap); pipe.nwork = dalloc<int>(WSTRIDE * (c.n_substeps + 1)); pipe.big = dalloc<int>(2 * N);
+      pipe.hit_cap = (int)(N * 32); pipe.hits = dalloc<HitRec<T>>((size_t)pipe.hit_cap);
       if (b.scalar("ngeom") > GMAX_GEOMS) throw std::runtime_error("model has more geoms than the broad phase can hold");
       if (b.scalar("ngeom") > WQ) throw std::runtime_error("model has more geoms than narrow-phase work queues");
       pipe.con = dalloc<T>(N * CONBUF * 8); pipe.con_key = dalloc<int>(N * CONBUF); pipe.ncon_raw = dalloc<int>(N);
@@ -409,7 +410,7 @@ int so101_counters(so101_handle h, uint64_t out[4]) {
   out[2] = H->diverged(); out[0] = H->launches; out[1] = H->steps; out[3] = H->dropped;
   API_END()
 }
-int so101_kernel_times(so101_handle h, int enable, double ms_out[5], uint64_t launches_out[5]) {
+int so101_kernel_times(so101_handle h, int enable, double ms_out[6], uint64_t launches_out[6]) {
   API_BEGIN(h)
   H->timer.collect();
   for (int i = 0; i < KernelTimer::NK; i++) {

@@ -167,8 +167,51 @@ __device__ __noinline__ void msupport(const SceneModel<T> &sm, const Shape<T> &A
   sub3(p.w, p.a, p.b);
 }
 
-// boolean GJK; mirrors gjk_intersect() of the oracle.  Uniform control flow across the warp.
+// ---- one THREAD per pair (boolean-GJK kernel): the thread scans all hull vertices itself.  Lanes of a warp work on the same
+// hull for different envs (queue order), so every vertex load is a warp-wide broadcast.  Same first-maximum tie-break as the
+// warp-cooperative support() above.
 template <typename T>
+__device__ __forceinline__ void support_seq(const SceneModel<T> &sm, const Shape<T> &s, const T *dir, T *out) {
+  T dl[3], p[3];
+  mulmtv(dl, s.mat, dir);
+  if (s.type == G_HULL) {
+    T bv = -INFINITY;
+    int bi = 0x7fffffff;
+    const Vec4<T> *vt = sm.hull_vert + s.vadr;
+#pragma unroll 4
+    for (int i = 0; i < s.vnum; i++) {
+      const Vec4<T> v = vt[i];
+      const T val = v.x * dl[0] + v.y * dl[1] + v.z * dl[2];
+      if (val > bv) { bv = val; bi = i; }
+    }
+    if (bi == 0x7fffffff) bi = 0;
+    const Vec4<T> v = vt[bi];
+    p[0] = v.x; p[1] = v.y; p[2] = v.z;
+  } else if (s.type == G_BOX) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) p[c] = dl[c] >= T(0) ? s.size[c] : -s.size[c];
+  } else if (s.type == G_CYLINDER) {
+    const T n = t_sqrt(dl[0] * dl[0] + dl[1] * dl[1]);
+    p[0] = n > T(1e-15) ? s.size[0] * dl[0] / n : T(0); p[1] = n > T(1e-15) ? s.size[0] * dl[1] / n : T(0);
+    p[2] = dl[2] >= T(0) ? s.size[1] : -s.size[1];
+  } else if (s.type == G_CAPSULE || s.type == G_SPHERE) {
+    const T n = t_sqrt(dot3(dl, dl));
+#pragma unroll
+    for (int c = 0; c < 3; c++) p[c] = n > T(1e-15) ? s.size[0] * dl[c] / n : T(0);
+    if (s.type == G_CAPSULE) p[2] += dl[2] >= T(0) ? s.size[1] : -s.size[1];
+  } else { p[0] = p[1] = p[2] = T(0); }
+  local2world(s, p, out);
+}
+template <typename T>
+__device__ __noinline__ void msupport_seq(const SceneModel<T> &sm, const Shape<T> &A, const Shape<T> &B, const T *d, MPoint<T> &p) {
+  const T nd[3] = {-d[0], -d[1], -d[2]};
+  support_seq(sm, A, d, p.a); support_seq(sm, B, nd, p.b);
+  sub3(p.w, p.a, p.b);
+}
+
+// boolean GJK; mirrors gjk_intersect() of the oracle.  Uniform control flow across the warp.
+// SEQ = true: one thread per pair (msupport_seq); false: one warp per pair (msupport)
+template <typename T, bool SEQ>
 __device__ __noinline__ int gjk_intersect(const SceneModel<T> &sm, const Shape<T> &A, const Shape<T> &B, MPoint<T> *S, int &np, int &iters, int lane) {
   T d[3];
   sub3(d, B.center, A.center);
@@ -178,7 +221,7 @@ __device__ __noinline__ int gjk_intersect(const SceneModel<T> &sm, const Shape<T
   for (int it = 0; it < 64; it++) {
     MPoint<T> p;
     iters = it + 1;
-    msupport(sm, A, B, d, p, lane);
+    if constexpr (SEQ) msupport_seq(sm, A, B, d, p); else msupport(sm, A, B, d, p, lane);
     if (dot3(p.w, d) < T(0)) { np = n; return 0; }
     S[n++] = p;
     if (n == 1) { d[0] = -S[0].w[0]; d[1] = -S[0].w[1]; d[2] = -S[0].w[2]; }

@@ -16,7 +16,16 @@ namespace so101 {
 constexpr int GMAX_GEOMS = 96;       // geoms per model the broad phase holds in shared memory
 constexpr int WQ = 128;             // work queues (>= ngeom)
 constexpr int WSTRIDE = WQ + 8;     // counters per substep
-enum { W_CURSOR = WQ, W_NTIER = WQ + 1 /* [2]: envs queued for solver tier 1, 2 */, W_TIERCURSOR = WQ + 3 /* [2] */ };
+enum { W_CURSOR = WQ, W_NTIER = WQ + 1 /* [2]: envs queued for solver tier 1, 2 */, W_TIERCURSOR = WQ + 3 /* [2] */,
+       W_NHIT = WQ + 5 /* intersecting pairs found by the GJK kernel */, W_HITCURSOR = WQ + 6 };
+
+// An intersecting pair handed from the boolean-GJK kernel (thread per pair) to the EPA / manifold kernel (warp per pair).
+template <typename T>
+struct HitRec {
+  unsigned env, packed;  // packed = g1 | g2 << 8 | pair index << 16
+  int n, pad;            // simplex size (0: plane pair, no simplex)
+  T S[4][9];             // GJK simplex: w, a, b of each vertex (MPoint layout)
+};
 
 // Device scratch that crosses the kernels of one substep (written by one kernel, read by the next; L2-resident).
 template <typename T>
@@ -25,6 +34,8 @@ struct PipeBuf {
   uint2 *work;              // [WQ][work_cap]  narrow-phase work queues, one per second geom g2 (so that consecutive items
                             //   collide the same hull): (env, g1 | g2 << 8 | pair index << 16)
   int work_cap;             // entries per queue
+  HitRec<T> *hits;          // [hit_cap]  intersecting pairs of the current substep (arrival order ~ queue order)
+  int hit_cap;
   int *nwork;               // [nsub+1][WSTRIDE]  per substep: items per queue [0..WQ), then pair cursor, large-tier envs
                             //   queued, large-tier cursor
   int *big;                 // [2][N]  envs deferred to solver tier 1 / tier 2 in this substep
@@ -36,9 +47,9 @@ struct PipeBuf {
 };
 
 // Optional per-kernel timing with CUDA events on the launching stream (so101_kernel_times; bench.py's roofline leg).
-// Kernel ids: 0 begin, 1 narrow phase, 2 solve (small tier), 3 solve (large tier), 4 arm-only step.
+// Kernel ids: 0 begin, 1 EPA + manifold, 2 solve (tier 0), 3 solve (tiers 1 + 2), 4 arm-only step, 5 boolean GJK.
 struct KernelTimer {
-  static constexpr int NK = 5;
+  static constexpr int NK = 6;
   bool on = false;
   std::vector<std::array<cudaEvent_t, 2>> ev[NK];
   size_t used[NK] = {};

@@ -242,15 +242,10 @@ __device__ __noinline__ int manifold(const SceneModel<T> &sm, NarrowScratch<T> &
 }
 
 template <typename T>
-__device__ __noinline__ void collide_convex(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shape<T> &A, const Shape<T> &B, int &ncon, int &dropped, int lane) {
-  MPoint<T> S[4];
-  int n = 0;
+__device__ __noinline__ void collide_convex(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shape<T> &A, const Shape<T> &B, const MPoint<T> *S, int n,
+                                            int &ncon, int &dropped, int lane) {
   PROF_START(s);
-  int git = 0, eit = 0;
-  const int hit = gjk_intersect(sm, A, B, S, n, git, lane);
-  PROF_ACC(s, P_GJK, lane);
-  PROF_CNT(s, P_GJKIT, git, lane);
-  if (!hit) return;
+  int eit = 0;
   T normal[3], depth, pa[3], pb[3];
   PROF_CNT(s, P_NEPA, 1, lane);
   const int ok = epa(sm, s.col, A, B, S, n, normal, depth, pa, pb, eit, lane);
@@ -688,6 +683,88 @@ __global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_begin_kernel(const __g
   prof_flush(s, S, lane);
 }
 
+// queue offsets: exclusive prefix sum of the per-geom item counts (each warp builds its own copy: 4 counts per lane)
+__device__ __forceinline__ void build_qpref(int *qpref, const int *cnt, int cap, int lane) {
+  int c[4], tot = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { c[k] = min(cnt[4 * lane + k], cap); tot += c[k]; }
+  int incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+  int run = incl - tot;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { qpref[4 * lane + k] = run; run += c[k]; }
+  if (lane == 31) qpref[WQ] = run;
+  __syncwarp();
+}
+__device__ __forceinline__ int queue_of(const int *qpref, int item) {  // largest q with qpref[q] <= item
+  int q = 0;
+#pragma unroll
+  for (int step = WQ / 2; step > 0; step >>= 1)
+    if (qpref[q + step] <= item) q += step;
+  return q;
+}
+
+// Per substep, ONE THREAD per candidate pair: boolean GJK.  Consecutive threads take consecutive items of one queue = the same
+// hull for different envs, so the vertex scan is a broadcast stream and the warp runs the simplex logic for 32 pairs at once
+// (the warp-per-pair version spent most of its instructions on scalar simplex code executed redundantly by 32 lanes).
+// Intersecting pairs are appended (warp-aggregated) with their simplex to the hit list for the EPA / manifold kernel.
+constexpr int GJK_THREADS = 128;
+template <typename T>
+__global__ void __launch_bounds__(GJK_THREADS) scene_gjk_kernel(const __grid_constant__ SceneModel<T> sm, const EnvState<T> S, const PipeBuf<T> pb, int sub) {
+  __shared__ int qpref[GJK_THREADS / 32][WQ + 1];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int *cnt = pb.nwork + WSTRIDE * sub;
+  build_qpref(qpref[wib], cnt, pb.work_cap, lane);
+  const int nwork = qpref[wib][WQ];
+  const int stride = gridDim.x * GJK_THREADS;
+  long long git_sum = 0;
+#pragma unroll 1
+  for (int item0 = blockIdx.x * GJK_THREADS + wib * 32; item0 < nwork; item0 += stride) {
+    const int item = item0 + lane;
+    bool hit = false;
+    uint2 w = make_uint2(0u, 0u);
+    MPoint<T> Sx[4];
+    int n = 0;
+    if (item < nwork) {
+      const int q = queue_of(qpref[wib], item);
+      w = pb.work[(size_t)q * pb.work_cap + (item - qpref[wib][q])];
+      const int env = (int)w.x, g1 = (int)(w.y & 0xff), g2 = (int)((w.y >> 8) & 0xff);
+      if (sm.geom_type[g1] == G_PLANE) hit = true;  // plane pairs need no simplex
+      else {
+        const T(*xpos)[3] = reinterpret_cast<const T(*)[3]>(pb.xpos + (size_t)env * (NSLOT * 3));
+        const T(*xmat)[9] = reinterpret_cast<const T(*)[9]>(pb.xmat + (size_t)env * (NSLOT * 9));
+        Shape<T> A, B;
+        make_shape(sm, xpos, xmat, g1, A);
+        make_shape(sm, xpos, xmat, g2, B);
+        int it = 0;
+        hit = gjk_intersect<T, true>(sm, A, B, Sx, n, it, lane) != 0;
+        git_sum += it;
+      }
+    }
+    const unsigned m = __ballot_sync(FULL, hit);
+    if (m) {
+      int base = 0;
+      if (lane == __ffs(m) - 1) base = atomicAdd(cnt + W_NHIT, __popc(m));
+      base = __shfl_sync(FULL, base, __ffs(m) - 1);
+      const int idx = base + __popc(m & ((1u << lane) - 1));
+      if (hit) {
+        if (idx < pb.hit_cap) {
+          HitRec<T> &r = pb.hits[idx];
+          r.env = w.x; r.packed = w.y; r.n = n; r.pad = 0;
+          for (int k = 0; k < n; k++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) { r.S[k][c] = Sx[k].w[c]; r.S[k][3 + c] = Sx[k].a[c]; r.S[k][6 + c] = Sx[k].b[c]; }
+        } else DROPCAT(6, 1);
+      }
+    }
+  }
+  if (S.prof) {
+    git_sum = warp_sum(git_sum);
+    if (lane == 0 && git_sum) atomicAdd(S.prof + P_GJKIT, (unsigned long long)git_sum);
+  }
+}
+
 // Per substep: one warp per candidate geom pair, pulled from the work list with an atomic cursor (pairs differ 10x in
 // cost: a GJK miss vs GJK + EPA + manifold).  Contacts go to the env's raw buffer tagged with (pair index, manifold index).
 #ifndef NARROW_MINB
@@ -700,43 +777,25 @@ __global__ void __launch_bounds__(WARPS_NARROW * 32, NARROW_MINB) scene_narrow_k
   NarrowScratch<T> *all = reinterpret_cast<NarrowScratch<T> *>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   NarrowScratch<T> &s = all[wib];
-  // queue offsets: exclusive prefix sum of the per-geom item counts (each warp builds its own copy: 4 counts per lane)
-  __shared__ int qpref[WARPS_NARROW][WQ + 1];
-  {
-    const int *cnt = pb.nwork + WSTRIDE * sub;
-    int c[4], tot = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) { c[k] = min(cnt[4 * lane + k], pb.work_cap); tot += c[k]; }
-    int incl = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-    int run = incl - tot;
-#pragma unroll
-    for (int k = 0; k < 4; k++) { qpref[wib][4 * lane + k] = run; run += c[k]; }
-    if (lane == 31) qpref[wib][WQ] = run;
-  }
   if (lane == 0) {
     s.profon = S.prof != nullptr; s.dbg = 0;
     for (int i = 0; i < 16; i++) s.prof[i] = 0;
   }
   __syncwarp();
-  const int nwork = qpref[wib][WQ];
+  int *cnt = pb.nwork + WSTRIDE * sub;
+  const int nwork = min(cnt[W_NHIT], pb.hit_cap);
   int dropped = 0;
-  constexpr int CHUNK = 4;  // consecutive items of one queue per cursor grab: same hull, warm L1
+  constexpr int CHUNK = 2;  // consecutive hits per cursor grab (arrival order follows the queues: same hull, warm L1)
 #pragma unroll 1
   for (;;) {
     int item0 = 0;
-    if (lane == 0) item0 = atomicAdd(pb.nwork + WSTRIDE * sub + W_CURSOR, CHUNK);
+    if (lane == 0) item0 = atomicAdd(cnt + W_HITCURSOR, CHUNK);
     item0 = wshfl(item0, 0);
     if (item0 >= nwork) break;
 #pragma unroll 1
   for (int item = item0; item < min(item0 + CHUNK, nwork); item++) {
-    // queue of this item: largest q with qpref[q] <= item
-    int q = 0;
-#pragma unroll
-    for (int step = WQ / 2; step > 0; step >>= 1)
-      if (qpref[wib][q + step] <= item) q += step;
-    const uint2 w = pb.work[(size_t)q * pb.work_cap + (item - qpref[wib][q])];
+    const HitRec<T> &rec = pb.hits[item];
+    const uint2 w = make_uint2(rec.env, rec.packed);
     const int env = (int)w.x, g1 = (int)(w.y & 0xff), g2 = (int)((w.y >> 8) & 0xff), pidx = (int)(w.y >> 16);
     const T(*xpos)[3] = reinterpret_cast<const T(*)[3]>(pb.xpos + (size_t)env * (NSLOT * 3));
     const T(*xmat)[9] = reinterpret_cast<const T(*)[9]>(pb.xmat + (size_t)env * (NSLOT * 9));
@@ -750,7 +809,7 @@ __global__ void __launch_bounds__(WARPS_NARROW * 32, NARROW_MINB) scene_narrow_k
     __syncwarp();
     int ncon = 0;
     if (A.type == G_PLANE) collide_plane(sm, s, A, B, ncon, dropped, lane);
-    else collide_convex(sm, s, A, B, ncon, dropped, lane);
+    else collide_convex(sm, s, A, B, reinterpret_cast<const MPoint<T> *>(&rec.S[0][0]), rec.n, ncon, dropped, lane);
     if (ncon > 0) {
       int base = 0;
       if (lane == 0) base = atomicAdd(pb.ncon_raw + env, ncon);
@@ -1045,7 +1104,7 @@ int scene_narrow_grid() {
   return (nb > 0 ? nb : 1) * (sms > 0 ? sms : 1);
 }
 
-// Launches of one control step: 1 memset + 1 + 4 * nsub kernels, all on the caller's stream.  Returns the kernel count.
+// Launches of one control step: 1 memset + 1 + 5 * nsub kernels, all on the caller's stream.  Returns the kernel count.
 template <typename T>
 int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
                       const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt) {
@@ -1072,8 +1131,12 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
   t.end(0, stream);
   // narrow phase: persistent grid sized to the machine (pairs are pulled with an atomic cursor)
   const int grid_nar = pb.narrow_grid;
+  const int grid_gjk = 148 * 8;  // grid-stride over the work items: 148 SMs x 8 resident CTAs of 128 threads
   const int grid_m = S.N < 148 * 4 ? S.N : 148 * 4, grid_l = S.N < 148 * 2 ? S.N : 148 * 2;
   for (int sub = 0; sub < cfg.nsub; sub++) {
+    t.begin(5, stream);
+    scene_gjk_kernel<T><<<grid_gjk, GJK_THREADS, 0, stream>>>(sm, S, pb, sub);
+    t.end(5, stream);
     t.begin(1, stream);
     scene_narrow_kernel<T><<<grid_nar, WARPS_NARROW * 32, smem_nar, stream>>>(sm, cfg, S, pb, sub);
     t.end(1, stream);
@@ -1085,7 +1148,7 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
     scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2><<<grid_l, WARPS_L * 32, smem_l, stream>>>(am, sm, cfg, S, pb, out, sub);
     t.end(3, stream);
   }
-  return 1 + 4 * cfg.nsub;
+  return 1 + 5 * cfg.nsub;
 }
 template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream) {

@@ -27,8 +27,16 @@ typedef struct {
   double pos[3], mat[9]; /* world pose of the geom frame (hulls: the body frame) */
   double size[3];
   const double *vert; int nvert;
+  const int *nbradr, *nbr;  /* hull vertex adjacency (CSR over this geom's vertices, local neighbour ids) */
+  int *hint;                /* hill-climbing warm start: last support vertex of this shape while its pair is processed */
+  int hint_store;
   double center[3], rbound; /* world bounding sphere */
 } shape;
+
+/* Hull support: exhaustive scan for small hulls, otherwise steepest-ascent hill climbing on the hull's vertex graph,
+   warm-started from the previous support vertex of the same shape ([upstream] MuJoCo's mesh support does the same for
+   meshes with a vertex graph).  On a convex hull a graph-local maximum is the global one. */
+#define HILLCLIMB_MIN 40
 
 static inline double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 static inline void cross3(double *r, const double *a, const double *b) {
@@ -59,6 +67,8 @@ static void make_shape(const so_model *m, const so_data *d, int g, shape *s) {
   }
   memcpy(s->size, m->geom_size + 3 * g, sizeof s->size);
   s->vert = m->hull_vert + 3 * m->geom_vertadr[g]; s->nvert = m->geom_vertnum[g];
+  s->nbradr = m->hull_nbradr + m->geom_vertadr[g]; s->nbr = m->hull_nbr;
+  s->hint_store = 0; s->hint = &s->hint_store;
   mulmv(t, d->xmat[b], m->geom_bcenter + 3 * g);
   for (int c = 0; c < 3; c++) s->center[c] = d->xpos[b][c] + t[c];
   s->rbound = m->geom_rbound[g];
@@ -71,7 +81,24 @@ static void support(const shape *s, const double *dir, double *out) {
   switch (s->type) {
     case SO_GEOM_HULL: {
       int best = 0; double bv = -INFINITY;
-      for (int i = 0; i < s->nvert; i++) { double v = dot3(s->vert + 3 * i, dl); if (v > bv) { bv = v; best = i; } }
+      if (s->nvert < HILLCLIMB_MIN) {
+        for (int i = 0; i < s->nvert; i++) { double v = dot3(s->vert + 3 * i, dl); if (v > bv) { bv = v; best = i; } }
+      } else {
+        int cur = *s->hint;
+        bv = dot3(s->vert + 3 * cur, dl);
+        for (;;) {
+          int nxt = cur;
+          for (int k = s->nbradr[cur]; k < s->nbradr[cur + 1]; k++) {
+            int j = s->nbr[k];
+            double v = dot3(s->vert + 3 * j, dl);
+            if (v > bv) { bv = v; nxt = j; }
+          }
+          if (nxt == cur) break;
+          cur = nxt;
+        }
+        best = cur;
+        *s->hint = cur;
+      }
       memcpy(p, s->vert + 3 * best, sizeof p);
       break;
     }
@@ -615,6 +642,7 @@ void so_collide(const so_model *m, so_data *d) {
       for (int g2 = m->body_geomadr[b2]; g2 < m->body_geomadr[b2] + m->body_geomnum[b2]; g2++) {
         shape B;
         make_shape(m, d, g2, &B);
+        A.hint_store = 0; /* hill-climbing warm starts are per pair */
         if (A.type == SO_GEOM_PLANE) {
           double n[3] = {A.mat[2], A.mat[5], A.mat[8]};
           if (dot3(n, B.center) - dot3(n, A.pos) - B.rbound > 0) continue;

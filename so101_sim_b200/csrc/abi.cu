@@ -205,7 +205,6 @@ struct Handle : HandleBase {
       if (b.scalar("ngeom") > WQ) throw std::runtime_error("model has more geoms than narrow-phase work queues");
       pipe.con = dalloc<T>(N * CONBUF * 8); pipe.con_key = dalloc<int>(N * CONBUF); pipe.ncon_raw = dalloc<int>(N);
       pipe.active = dalloc<uint8_t>(N); pipe.flags = dalloc<uint8_t>(N);
-      pipe.narrow_grid = scene_narrow_grid<T>();
     }
   }
   ~Handle() override {

@@ -1,0 +1,381 @@
+// Convex narrow phase with ONE THREAD per intersecting pair: EPA -> support-feature clipping manifold.
+//
+// Same algorithm, tolerances and tie-breaks as the warp-cooperative routines in scene_collide.cuh (and as
+// oracle/so101_collide.c); only the mapping differs.  The 32 lanes of a warp work on 32 different pairs that share the
+// second geom (the work queues are per geom), so hull vertex loads are warp-wide broadcasts, and the branchy polytope /
+// polygon bookkeeping that used to occupy a whole warp per pair now costs one lane.  Per-thread scratch (polytope or
+// manifold buffers, ~9 KB in float) lives in local memory, which the hardware interleaves by lane: lanes that touch the
+// same array index share cache lines.
+#pragma once
+#include "scene_collide.cuh"
+
+namespace so101 {
+
+// contacts a pair can emit (manifold <= MAXMANI)
+template <typename T>
+struct PairContacts {
+  int n;
+  T pos[MAXMANI][3], normal[3], dist[MAXMANI];
+};
+
+template <typename T>
+__device__ __forceinline__ void epa_putv_seq(CollideScratch<T> &cs, int i, const MPoint<T> &p) {
+#pragma unroll
+  for (int c = 0; c < 3; c++) { cs.Vw[c][i] = p.w[c]; cs.Va[c][i] = p.a[c]; cs.Vb[c][i] = p.b[c]; }
+}
+template <typename T>
+__device__ __noinline__ int epa_add_face_seq(CollideScratch<T> &cs, int &nf, int a, int b, int c, const T *inside) {
+  if (nf >= EPA_MAXF) return -1;
+  T va[3], vb[3], vc[3], ab[3], ac[3], n[3], t[3];
+  epa_getv(cs, a, va); epa_getv(cs, b, vb); epa_getv(cs, c, vc);
+  sub3(ab, vb, va); sub3(ac, vc, va);
+  cross3(n, ab, ac);
+  const T l = t_sqrt(dot3(n, n));
+  if (l < T(1e-30)) return -1;
+  n[0] /= l; n[1] /= l; n[2] /= l;
+  sub3(t, va, inside);
+  int v1 = b, v2 = c;
+  if (dot3(n, t) < T(0)) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; v1 = c; v2 = b; }
+  cs.Fv[0][nf] = a; cs.Fv[1][nf] = v1; cs.Fv[2][nf] = v2;
+  cs.Fn[0][nf] = n[0]; cs.Fn[1][nf] = n[1]; cs.Fn[2][nf] = n[2];
+  cs.Fd[nf] = dot3(n, va);
+  cs.Falive[nf] = 1;
+  return nf++;
+}
+template <typename T>
+__device__ __forceinline__ int epa_best_seq(const CollideScratch<T> &cs, int nf) {
+  T bd = INFINITY;
+  int bi = -1;
+#pragma unroll 1
+  for (int f = 0; f < nf; f++)
+    if (cs.Falive[f] && cs.Fd[f] < bd) { bd = cs.Fd[f]; bi = f; }
+  return bi;
+}
+
+template <typename T>
+__device__ __noinline__ int epa_seq(const SceneModel<T> &sm, CollideScratch<T> &cs, Shape<T> &A, Shape<T> &B, const MPoint<T> *S, int n, T *normal,
+                                    T &depth, T *pa, T *pb, int &iters) {
+  int nv = 0, nf = 0;
+  iters = 0;
+  if (n == 1) return 0;
+#pragma unroll 1
+  for (int i = 0; i < n; i++) epa_putv_seq(cs, nv++, S[i]);
+  if (nv == 2) {
+    T v0[3], v1[3], ab[3], ax[3] = {T(0), T(0), T(0)}, d[3];
+    epa_getv(cs, 0, v0); epa_getv(cs, 1, v1);
+    sub3(ab, v1, v0);
+    const int k = t_abs(ab[0]) < t_abs(ab[1]) ? (t_abs(ab[0]) < t_abs(ab[2]) ? 0 : 2) : (t_abs(ab[1]) < t_abs(ab[2]) ? 1 : 2);
+    ax[k] = T(1); cross3(d, ab, ax);
+    MPoint<T> p;
+    msupport_seq(sm, A, B, d, p);
+    T t[3], cr[3];
+    sub3(t, p.w, v0); cross3(cr, ab, t);
+    if (dot3(cr, cr) < T(1e-24)) { d[0] = -d[0]; d[1] = -d[1]; d[2] = -d[2]; msupport_seq(sm, A, B, d, p); }
+    epa_putv_seq(cs, nv++, p);
+  }
+  if (nv == 3) {
+    T v0[3], v1[3], v2[3], ab[3], ac[3], nn[3], t[3];
+    epa_getv(cs, 0, v0); epa_getv(cs, 1, v1); epa_getv(cs, 2, v2);
+    sub3(ab, v1, v0); sub3(ac, v2, v0); cross3(nn, ab, ac);
+    if (dot3(nn, nn) < T(1e-30)) return 0;
+    MPoint<T> p;
+    msupport_seq(sm, A, B, nn, p);
+    sub3(t, p.w, v0);
+    if (t_abs(dot3(t, nn)) < T(1e-12) * t_sqrt(dot3(nn, nn))) {
+      const T m[3] = {-nn[0], -nn[1], -nn[2]};
+      msupport_seq(sm, A, B, m, p);
+      sub3(t, p.w, v0);
+      if (t_abs(dot3(t, nn)) < T(1e-12) * t_sqrt(dot3(nn, nn))) return 0;
+    }
+    epa_putv_seq(cs, nv++, p);
+  }
+  T inside[3] = {T(0), T(0), T(0)};
+  for (int i = 0; i < 4; i++) { T v[3]; epa_getv(cs, i, v); for (int k = 0; k < 3; k++) inside[k] += T(0.25) * v[k]; }
+  if (epa_add_face_seq(cs, nf, 0, 1, 2, inside) < 0 || epa_add_face_seq(cs, nf, 0, 1, 3, inside) < 0 ||
+      epa_add_face_seq(cs, nf, 0, 2, 3, inside) < 0 || epa_add_face_seq(cs, nf, 1, 2, 3, inside) < 0) return 0;
+  int best = -1;
+#pragma unroll 1
+  for (int it = 0; it < 80; it++) {
+    best = epa_best_seq(cs, nf);
+    if (best < 0) return 0;
+    if (nv >= EPA_MAXV) break;
+    iters = it + 1;
+    const T bn[3] = {cs.Fn[0][best], cs.Fn[1][best], cs.Fn[2][best]}, bd = cs.Fd[best];
+    MPoint<T> p;
+    msupport_seq(sm, A, B, bn, p);
+    const T adv = dot3(p.w, bn) - bd;
+    if (adv < T(sizeof(T) == 8 ? 1e-9 : 1e-6)) break;
+    epa_putv_seq(cs, nv, p);
+    // visibility, then the horizon in face order (same order as the oracle)
+    int nh = 0;
+#pragma unroll 1
+    for (int f = 0; f < nf; f++) {
+      if (!cs.Falive[f]) continue;
+      T v0[3], t[3];
+      const T fn[3] = {cs.Fn[0][f], cs.Fn[1][f], cs.Fn[2][f]};
+      epa_getv(cs, cs.Fv[0][f], v0);
+      sub3(t, p.w, v0);
+      if (!(dot3(fn, t) > T(sizeof(T) == 8 ? 1e-12 : 1e-9))) continue;
+      cs.Falive[f] = 0;
+      for (int e = 0; e < 3; e++) {
+        const int a = cs.Fv[e][f], b = cs.Fv[(e + 1) % 3][f];
+        int found = 0;
+#pragma unroll 1
+        for (int h = 0; h < nh; h++)
+          if (cs.horizon[h][0] == b && cs.horizon[h][1] == a) {
+            cs.horizon[h][0] = cs.horizon[nh - 1][0]; cs.horizon[h][1] = cs.horizon[nh - 1][1]; nh--; found = 1;
+            break;
+          }
+        if (!found && nh < EPA_MAXF) { cs.horizon[nh][0] = a; cs.horizon[nh][1] = b; nh++; }
+      }
+    }
+    if (nh == 0) break;
+    int failed = 0;
+#pragma unroll 1
+    for (int h = 0; h < nh; h++)
+      if (epa_add_face_seq(cs, nf, cs.horizon[h][0], cs.horizon[h][1], nv, inside) < 0) failed = 1;
+    nv++;
+    if (failed) break;
+  }
+  if (best < 0 || !cs.Falive[best]) {
+    best = epa_best_seq(cs, nf);
+    if (best < 0) return 0;
+  }
+  const T fn[3] = {cs.Fn[0][best], cs.Fn[1][best], cs.Fn[2][best]}, fd = cs.Fd[best];
+  normal[0] = fn[0]; normal[1] = fn[1]; normal[2] = fn[2];
+  depth = fd > T(0) ? fd : T(0);
+  const T p[3] = {fn[0] * fd, fn[1] * fd, fn[2] * fd};
+  const int i0 = cs.Fv[0][best], i1 = cs.Fv[1][best], i2 = cs.Fv[2][best];
+  T a[3], b[3], c[3], v0[3], v1[3], v2[3];
+  epa_getv(cs, i0, a); epa_getv(cs, i1, b); epa_getv(cs, i2, c);
+  sub3(v0, b, a); sub3(v1, c, a); sub3(v2, p, a);
+  const T d00 = dot3(v0, v0), d01 = dot3(v0, v1), d11 = dot3(v1, v1), d20 = dot3(v2, v0), d21 = dot3(v2, v1), den = d00 * d11 - d01 * d01;
+  T bv = T(1.0 / 3), bw = T(1.0 / 3);
+  if (t_abs(den) > T(1e-30)) { bv = (d11 * d20 - d01 * d21) / den; bw = (d00 * d21 - d01 * d20) / den; }
+  const T bu = T(1) - bv - bw;
+  for (int k = 0; k < 3; k++) {
+    pa[k] = bu * cs.Va[k][i0] + bv * cs.Va[k][i1] + bw * cs.Va[k][i2];
+    pb[k] = bu * cs.Vb[k][i0] + bv * cs.Vb[k][i1] + bw * cs.Vb[k][i2];
+  }
+  return 1;
+}
+
+// vertices of s within delta of the support plane along dir -> CCW 2-D convex polygon in (t1,t2) with heights
+template <typename T>
+__device__ __noinline__ int feature_seq(const SceneModel<T> &sm, CollideScratch<T> &cs, Shape<T> &s, const T *dir, const T *t1, const T *t2, T delta,
+                                        FPt<T> *out) {
+  T sp[3];
+  support_seq(sm, s, dir, sp);
+  const T hmax = dot3(sp, dir);
+  int nc = 0;
+  T w[3];
+  if (s.type == G_HULL) {
+    T dl[3];
+    mulmtv(dl, s.mat, dir);
+    const T off = dot3(s.pos, dir);
+    const Vec4<T> *vt = sm.hull_vert + s.vadr;
+#pragma unroll 2
+    for (int i = 0; i < s.vnum; i++) {
+      const Vec4<T> v = vt[i];
+      if ((v.x * dl[0] + v.y * dl[1] + v.z * dl[2]) + off >= hmax - delta && nc < MAXCAND) {
+        const T l[3] = {v.x, v.y, v.z};
+        local2world(s, l, w);
+        cs.cand[0][nc] = w[0]; cs.cand[1][nc] = w[1]; cs.cand[2][nc] = w[2]; nc++;
+      }
+    }
+  } else if (s.type == G_BOX) {
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+      const T l[3] = {(i & 1 ? T(1) : T(-1)) * s.size[0], (i & 2 ? T(1) : T(-1)) * s.size[1], (i & 4 ? T(1) : T(-1)) * s.size[2]};
+      local2world(s, l, w);
+      if (dot3(w, dir) >= hmax - delta) { cs.cand[0][nc] = w[0]; cs.cand[1][nc] = w[1]; cs.cand[2][nc] = w[2]; nc++; }
+    }
+  } else if (s.type == G_CYLINDER) {
+#pragma unroll 1
+    for (int cap = -1; cap <= 1; cap += 2)
+#pragma unroll 1
+      for (int i = 0; i < 16; i++) {
+        T sn, cn;
+        t_sincos(T(2 * 3.14159265358979323846 / 16) * T(i), &sn, &cn);
+        const T l[3] = {s.size[0] * cn, s.size[0] * sn, T(cap) * s.size[1]};
+        local2world(s, l, w);
+        if (dot3(w, dir) >= hmax - delta) { cs.cand[0][nc] = w[0]; cs.cand[1][nc] = w[1]; cs.cand[2][nc] = w[2]; nc++; }
+      }
+  } else if (s.type == G_CAPSULE) {
+#pragma unroll 1
+    for (int e = -1; e <= 1; e += 2) {
+      const T l[3] = {T(0), T(0), T(e) * s.size[1]};
+      local2world(s, l, w);
+      for (int c = 0; c < 3; c++) w[c] += s.size[0] * dir[c];
+      if (dot3(w, dir) >= hmax - delta) { cs.cand[0][nc] = w[0]; cs.cand[1][nc] = w[1]; cs.cand[2][nc] = w[2]; nc++; }
+    }
+  }
+  if (nc == 0) { cs.cand[0][0] = sp[0]; cs.cand[1][0] = sp[1]; cs.cand[2][0] = sp[2]; nc = 1; }
+  // project, then stable insertion sort by (x, y) [ties keep candidate order] into bufA
+  FPt<T> *sorted = cs.bufA;  // nc <= MAXCAND <= size of bufA
+#pragma unroll 1
+  for (int i = 0; i < nc; i++) {
+    const T cw[3] = {cs.cand[0][i], cs.cand[1][i], cs.cand[2][i]};
+    const FPt<T> p = {dot3(cw, t1), dot3(cw, t2), dot3(cw, dir)};
+    int j = i;
+    while (j > 0 && (p.x < sorted[j - 1].x || (p.x == sorted[j - 1].x && p.y < sorted[j - 1].y))) { sorted[j] = sorted[j - 1]; j--; }
+    sorted[j] = p;
+  }
+  if (nc <= 2) { for (int i = 0; i < nc; i++) out[i] = sorted[i]; return nc; }
+  FPt<T> *H = cs.Hh;
+  int k = 0;
+#pragma unroll 1
+  for (int i = 0; i < nc; i++) {
+    while (k >= 2 && (H[k - 1].x - H[k - 2].x) * (sorted[i].y - H[k - 2].y) - (H[k - 1].y - H[k - 2].y) * (sorted[i].x - H[k - 2].x) <= T(1e-14)) k--;
+    H[k++] = sorted[i];
+  }
+#pragma unroll 1
+  for (int i = nc - 2, t = k + 1; i >= 0; i--) {
+    while (k >= t && (H[k - 1].x - H[k - 2].x) * (sorted[i].y - H[k - 2].y) - (H[k - 1].y - H[k - 2].y) * (sorted[i].x - H[k - 2].x) <= T(1e-14)) k--;
+    H[k++] = sorted[i];
+  }
+  k--;
+  if (k > MAXFEAT) k = MAXFEAT;
+#pragma unroll 1
+  for (int i = 0; i < k; i++) out[i] = H[i];
+  return k;
+}
+
+template <typename T>
+__device__ __noinline__ int clip_poly_seq(CollideScratch<T> &cs, const FPt<T> *subj, int n, const FPt<T> *clip, int m, FPt<T> *out) {
+  constexpr int CAP = 2 * MAXFEAT + 8;
+  int na = n;
+  FPt<T> *in = cs.bufA, *res = cs.bufB;
+#pragma unroll 1
+  for (int i = 0; i < n; i++) in[i] = subj[i];
+#pragma unroll 1
+  for (int e = 0; e < m && na > 0; e++) {
+    const T ax = clip[e].x, ay = clip[e].y, bx = clip[(e + 1) % m].x, by = clip[(e + 1) % m].y;
+    const T ex = bx - ax, ey = by - ay, tol = T(1e-12);
+    int nr = 0;
+    if (na == 2) {
+      const FPt<T> P = in[0], Q = in[1];
+      const T sp = ex * (P.y - ay) - ey * (P.x - ax), sq = ex * (Q.y - ay) - ey * (Q.x - ax);
+      const bool pin = sp >= -tol, qin = sq >= -tol;
+      if (pin && qin) { res[nr++] = P; res[nr++] = Q; }
+      else if (pin || qin) {
+        const T t = sp / (sp - sq);
+        const FPt<T> I = {P.x + t * (Q.x - P.x), P.y + t * (Q.y - P.y), P.h + t * (Q.h - P.h)};
+        if (pin) { res[nr++] = P; res[nr++] = I; } else { res[nr++] = I; res[nr++] = Q; }
+      }
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < na; i++) {
+        const FPt<T> P = in[i], Q = in[(i + 1) % na];
+        const T sp = ex * (P.y - ay) - ey * (P.x - ax), sq = ex * (Q.y - ay) - ey * (Q.x - ax);
+        const bool pin = sp >= -tol, qin = sq >= -tol;
+        if (pin && nr < CAP) res[nr++] = P;
+        if (na > 1 && pin != qin && nr < CAP) {
+          const T t = sp / (sp - sq);
+          res[nr++] = FPt<T>{P.x + t * (Q.x - P.x), P.y + t * (Q.y - P.y), P.h + t * (Q.h - P.h)};
+        }
+        if (na == 1) break;
+      }
+    }
+    FPt<T> *tmp = in; in = res; res = tmp;
+    na = nr;
+    if (na > 2 * MAXFEAT) na = 2 * MAXFEAT;
+  }
+#pragma unroll 1
+  for (int i = 0; i < na; i++) out[i] = in[i];
+  return na;
+}
+
+template <typename T>
+__device__ __forceinline__ void emit_seq(PairContacts<T> &pc, const T *pos, T dist) {
+  if (pc.n >= MAXMANI) return;  // reduce_manifold keeps <= MAXMANI points
+  const int c = pc.n++;
+  pc.dist[c] = dist;
+  pc.pos[c][0] = pos[0]; pc.pos[c][1] = pos[1]; pc.pos[c][2] = pos[2];
+}
+
+// manifold from the two supporting features along normal n (A -> B).  Returns the number of contacts emitted.
+template <typename T>
+__device__ __noinline__ int manifold_seq(const SceneModel<T> &sm, CollideScratch<T> &cs, Shape<T> &A, Shape<T> &B, const T *n, T depth,
+                                         PairContacts<T> &pc) {
+  T frame[9];
+  frame_from_normal(n, frame);
+  const T *t1 = frame + 3, *t2 = frame + 6;
+  const T nn[3] = {-frame[0], -frame[1], -frame[2]};
+  const T delta = depth + T(1e-7);
+  const int na = feature_seq(sm, cs, A, frame, t1, t2, delta, cs.FA);
+  const int nb = feature_seq(sm, cs, B, nn, t1, t2, delta, cs.FB);
+  for (int i = 0; i < nb; i++) cs.FB[i].h = -cs.FB[i].h;  // heights of B's feature were measured along -n
+  int nr = 0;
+  {  // subject = the smaller feature when the other one is a polygon
+    const bool a_subj = (na >= 3 && nb >= 3) || (nb >= 3 && na <= 2), b_subj = na >= 3 && (nb == 2 || nb == 1);
+    if (a_subj) nr = clip_poly_seq(cs, cs.FA, na, cs.FB, nb, cs.R);
+    else if (b_subj) nr = clip_poly_seq(cs, cs.FB, nb, cs.FA, na, cs.R);
+  }
+  feature_plane(cs.FA, na, cs.hp[0]); feature_plane(cs.FB, nb, cs.hp[1]);
+  int k = 0;
+#pragma unroll 1
+  for (int i = 0; i < nr; i++) {
+    const T ha = plane_height(cs.hp[0], cs.R[i].x, cs.R[i].y), hb = plane_height(cs.hp[1], cs.R[i].x, cs.R[i].y);
+    const T di = hb - ha;
+    if (di < T(0)) { cs.R[k] = cs.R[i]; cs.R[k].h = T(0.5) * (ha + hb); cs.mdist[k] = di; k++; }
+  }
+  int u = 0;
+#pragma unroll 1
+  for (int i = 0; i < k; i++) {
+    int dup = 0;
+    for (int j = 0; j < u; j++)
+      if (t_abs(cs.R[i].x - cs.R[j].x) + t_abs(cs.R[i].y - cs.R[j].y) < T(1e-7)) {
+        dup = 1;
+        if (cs.mdist[i] < cs.mdist[j]) { cs.R[j] = cs.R[i]; cs.mdist[j] = cs.mdist[i]; }
+        break;
+      }
+    if (!dup) { cs.R[u] = cs.R[i]; cs.mdist[u] = cs.mdist[i]; u++; }
+  }
+  u = reduce_manifold(cs.R, cs.mdist, u);
+  pc.normal[0] = frame[0]; pc.normal[1] = frame[1]; pc.normal[2] = frame[2];
+  for (int i = 0; i < u; i++) {
+    T pos[3];
+    for (int c = 0; c < 3; c++) pos[c] = cs.R[i].x * t1[c] + cs.R[i].y * t2[c] + cs.R[i].h * frame[c];
+    emit_seq(pc, pos, cs.mdist[i]);
+  }
+  return u;
+}
+
+template <typename T>
+__device__ __noinline__ void collide_convex_seq(const SceneModel<T> &sm, CollideScratch<T> &cs, Shape<T> &A, Shape<T> &B, const MPoint<T> *S, int n,
+                                                PairContacts<T> &pc, int &eit) {
+  T normal[3], depth, pa[3], pb[3];
+  if (!epa_seq(sm, cs, A, B, S, n, normal, depth, pa, pb, eit)) return;
+  if (!(depth > T(0))) return;
+  if (manifold_seq(sm, cs, A, B, normal, depth, pc) > 0) return;
+  T frame[9], pos[3];
+  frame_from_normal(normal, frame);
+  for (int c = 0; c < 3; c++) pos[c] = T(0.5) * (pa[c] + pb[c]);
+  pc.normal[0] = frame[0]; pc.normal[1] = frame[1]; pc.normal[2] = frame[2];
+  emit_seq(pc, pos, -depth);
+}
+
+template <typename T>
+__device__ __noinline__ void collide_plane_seq(const SceneModel<T> &sm, CollideScratch<T> &cs, const Shape<T> &P, Shape<T> &B, PairContacts<T> &pc) {
+  const T n[3] = {P.mat[2], P.mat[5], P.mat[8]}, nn[3] = {-n[0], -n[1], -n[2]};
+  T sp[3];
+  support_seq(sm, B, nn, sp);
+  const T off = dot3(n, P.pos), depth = off - dot3(sp, n);
+  if (!(depth > T(0))) return;
+  T frame[9];
+  frame_from_normal(n, frame);
+  const T *t1 = frame + 3, *t2 = frame + 6;
+  int nb = feature_seq(sm, cs, B, nn, t1, t2, depth + T(1e-7), cs.FB);
+  for (int i = 0; i < nb; i++) { cs.FB[i].h = -cs.FB[i].h; cs.mdist[i] = cs.FB[i].h - off; }
+  nb = reduce_manifold(cs.FB, cs.mdist, nb);
+  pc.normal[0] = frame[0]; pc.normal[1] = frame[1]; pc.normal[2] = frame[2];
+  for (int i = 0; i < nb; i++) {
+    if (cs.mdist[i] >= T(0)) continue;
+    T pos[3];
+    for (int c = 0; c < 3; c++) pos[c] = cs.FB[i].x * t1[c] + cs.FB[i].y * t2[c] + (cs.FB[i].h - T(0.5) * cs.mdist[i]) * frame[c];
+    emit_seq(pc, pos, cs.mdist[i]);
+  }
+}
+
+}  // namespace so101

@@ -23,7 +23,7 @@ enum { W_CURSOR = WQ, W_NTIER = WQ + 1 /* [2]: envs queued for solver tier 1, 2 
 template <typename T>
 struct HitRec {
   unsigned env, packed;  // packed = g1 | g2 << 8 | pair index << 16
-  int n, pad;            // simplex size (0: plane pair, no simplex)
+  int n, hintA, hintB, pad;  // simplex size (0: plane pair, no simplex); hill-climbing warm starts of the two shapes after GJK
   T S[4][9];             // GJK simplex: w, a, b of each vertex (MPoint layout)
 };
 
@@ -43,7 +43,6 @@ struct PipeBuf {
   int *con_key;             // [N][CONBUF]     pair index << 20 | manifold index << 16 | g1 << 8 | g2  (sort key)
   int *ncon_raw;            // [N]
   uint8_t *active, *flags;  // [N]  env steps this call (not being reset) / env diverged during this control step
-  int narrow_grid;          // CTAs of the persistent narrow-phase kernel
 };
 
 // Optional per-kernel timing with CUDA events on the launching stream (so101_kernel_times; bench.py's roofline leg).
@@ -91,8 +90,6 @@ template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream);
 template <typename T>
 size_t scene_smem_bytes();
-template <typename T>
-int scene_narrow_grid();
 template <typename T>
 void scene_dropcat(int out[8]);
 }  // namespace so101

@@ -19,14 +19,16 @@
 //   Newton solve                  (elliptic cones, lane per contact for row work, lane per entry for the Hessian)
 //   semi-implicit Euler           (quaternion integration for the free joints)
 // Task layer: so100_task.py:266-368, so100_hand_over.py:238-275.
+#include <cstdlib>
+#include <string>
+
 #include "scene_kernel.cuh"
+#include "scene_collide_seq.cuh"
 #include "scene_solve.cuh"
 
 namespace so101 {
 
 constexpr int WARPS_SOLVE = 2;   // envs (warps) per CTA in the begin / solve kernels
-constexpr int WARPS_NARROW = 4;  // pairs (warps) in flight per CTA in the narrow-phase kernel
-constexpr int NOUT = 8;          // contacts one pair can emit (manifold <= MAXMANI)
 // Solver tiers by contact capacity: a resting scene has ~20 contacts, an arm pressed into the table or props 40-100.  Each
 // tier is the same code with a larger shared-memory scratch; an env that does not fit tier t is queued for tier t + 1.
 constexpr int NC_S = 32, NB_S = 40;            // tier 0: every env, 2 warps per CTA
@@ -43,16 +45,6 @@ struct BroadScratch {
   unsigned cand[CANDCAP];
   T gcenter[3][GMAX];                  // world bounding-sphere centres of all geoms
   T opos[3][GMAX], omat[9][GMAX];      // world oriented boxes (geom AABB in the geom frame) of all geoms
-};
-
-// per-warp scratch of the narrow-phase kernel: one candidate pair at a time
-template <typename T>
-struct NarrowScratch {
-  CollideScratch<T> col;
-  Shape<T> shp[2];  // the pair's two shapes (world poses), shared by every stage
-  int ncon, dbg, profon;
-  long long prof[16];
-  T c_pos[3][NOUT], c_normal[3][NOUT], c_dist[NOUT];
 };
 
 // per-env scratch of the begin / solve kernels (NC contacts, NB Jacobian blocks)
@@ -164,130 +156,6 @@ __device__ __forceinline__ void prop_dynamics(const SceneModel<T> &sm, const Arm
   mulmtv(cfl, R, cf);
   bias[0] = f[0]; bias[1] = f[1]; bias[2] = f[2];
   bias[3] = tl[0] + cfl[0]; bias[4] = tl[1] + cfl[1]; bias[5] = tl[2] + cfl[2];
-}
-
-// ------------------------------------------------------------------------------------------------ collision driver
-template <typename T>
-__device__ __forceinline__ void emit_contact(NarrowScratch<T> &s, int &ncon, int &dropped, int g1, int g2, const T *frame, const T *pos, T dist) {
-  // lane 0 only; the pair's contacts are staged in shared memory and flushed to the env's raw contact buffer by the caller
-  if (ncon >= NOUT) { dropped++; DROPCAT(0, 1); return; }
-  const int c = ncon++;
-  s.c_dist[c] = dist;
-  for (int e = 0; e < 3; e++) { s.c_pos[e][c] = pos[e]; s.c_normal[e][c] = frame[e]; }
-}
-
-template <typename T>
-__device__ __noinline__ int manifold(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shape<T> &A, const Shape<T> &B, const T *n, T depth, int &ncon, int &dropped, int lane) {
-  CollideScratch<T> &cs = s.col;
-  T frame[9];
-  frame_from_normal(n, frame);
-  const T *t1 = frame + 3, *t2 = frame + 6;
-  const T nn[3] = {-frame[0], -frame[1], -frame[2]};
-  const T delta = depth + T(1e-7);
-  const int na = feature(sm, cs, A, frame, t1, t2, delta, cs.FA, lane);
-  const int nb = feature(sm, cs, B, nn, t1, t2, delta, cs.FB, lane);
-  int u = 0;
-  for (int i = lane; i < nb; i += 32) cs.FB[i].h = -cs.FB[i].h;  // heights of B's feature were measured along -n
-  __syncwarp();
-  int nr = 0;
-  {  // subject = the smaller feature when the other one is a polygon
-    const bool a_subj = (na >= 3 && nb >= 3) || (nb >= 3 && na <= 2), b_subj = na >= 3 && (nb == 2 || nb == 1);
-    if (a_subj) nr = clip_poly(cs, cs.FA, na, cs.FB, nb, cs.R, lane);
-    else if (b_subj) nr = clip_poly(cs, cs.FB, nb, cs.FA, na, cs.R, lane);
-  }
-  if (lane == 0) { feature_plane(cs.FA, na, cs.hp[0]); feature_plane(cs.FB, nb, cs.hp[1]); }
-  __syncwarp();
-  // penetrating points only (lane per clipped point, order kept): -> bufA / mdist2
-  int k = 0;
-#pragma unroll 1
-  for (int i0 = 0; i0 < nr; i0 += 32) {
-    const int i = i0 + lane;
-    bool keep = false;
-    FPt<T> P{};
-    T di = T(0);
-    if (i < nr) {
-      P = cs.R[i];
-      const T ha = plane_height(cs.hp[0], P.x, P.y), hb = plane_height(cs.hp[1], P.x, P.y);
-      di = hb - ha;
-      keep = di < T(0);
-      P.h = T(0.5) * (ha + hb);
-    }
-    const unsigned mk = __ballot_sync(FULL, keep);
-    if (keep) { const int o = k + __popc(mk & ((1u << lane) - 1)); cs.bufA[o] = P; cs.mdist2[o] = di; }
-    k += __popc(mk);
-  }
-  __syncwarp();
-  if (lane == 0) {
-    for (int i = 0; i < k; i++) {
-      int dup = 0;
-      for (int j = 0; j < u; j++)
-        if (t_abs(cs.bufA[i].x - cs.R[j].x) + t_abs(cs.bufA[i].y - cs.R[j].y) < T(1e-7)) {
-          dup = 1;
-          if (cs.mdist2[i] < cs.mdist[j]) { cs.R[j] = cs.bufA[i]; cs.mdist[j] = cs.mdist2[i]; }
-          break;
-        }
-      if (!dup) { cs.R[u] = cs.bufA[i]; cs.mdist[u] = cs.mdist2[i]; u++; }
-    }
-    u = reduce_manifold(cs.R, cs.mdist, u);
-    for (int i = 0; i < u; i++) {
-      T pos[3];
-      for (int c = 0; c < 3; c++) pos[c] = cs.R[i].x * t1[c] + cs.R[i].y * t2[c] + cs.R[i].h * frame[c];
-      emit_contact(s, ncon, dropped, A.geom, B.geom, frame, pos, cs.mdist[i]);
-    }
-  }
-  u = wshfl(u, 0);
-  ncon = wshfl(ncon, 0); dropped = wshfl(dropped, 0);
-  __syncwarp();
-  return u;
-}
-
-template <typename T>
-__device__ __noinline__ void collide_convex(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shape<T> &A, const Shape<T> &B, const MPoint<T> *S, int n,
-                                            int &ncon, int &dropped, int lane) {
-  PROF_START(s);
-  int eit = 0;
-  T normal[3], depth, pa[3], pb[3];
-  PROF_CNT(s, P_NEPA, 1, lane);
-  const int ok = epa(sm, s.col, A, B, S, n, normal, depth, pa, pb, eit, lane);
-  PROF_ACC(s, P_EPA, lane);
-  PROF_CNT(s, P_EPAIT, eit, lane);
-  if (!ok) return;
-  if (!(depth > T(0))) return;
-  const int nm = manifold(sm, s, A, B, normal, depth, ncon, dropped, lane);
-  PROF_ACC(s, P_MANI, lane);
-  if (nm > 0) return;
-  T frame[9], pos[3];
-  frame_from_normal(normal, frame);
-  for (int c = 0; c < 3; c++) pos[c] = T(0.5) * (pa[c] + pb[c]);
-  if (lane == 0) emit_contact(s, ncon, dropped, A.geom, B.geom, frame, pos, -depth);
-  ncon = wshfl(ncon, 0); dropped = wshfl(dropped, 0);
-  __syncwarp();
-}
-
-template <typename T>
-__device__ __noinline__ void collide_plane(const SceneModel<T> &sm, NarrowScratch<T> &s, const Shape<T> &P, const Shape<T> &B, int &ncon, int &dropped, int lane) {
-  CollideScratch<T> &cs = s.col;
-  const T n[3] = {P.mat[2], P.mat[5], P.mat[8]}, nn[3] = {-n[0], -n[1], -n[2]};
-  T sp[3];
-  support(sm, B, nn, sp, lane);
-  const T off = dot3(n, P.pos), depth = off - dot3(sp, n);
-  if (!(depth > T(0))) return;
-  T frame[9];
-  frame_from_normal(n, frame);
-  const T *t1 = frame + 3, *t2 = frame + 6;
-  int nb = feature(sm, cs, B, nn, t1, t2, depth + T(1e-7), cs.FB, lane);
-  if (lane == 0) {
-    for (int i = 0; i < nb; i++) { cs.FB[i].h = -cs.FB[i].h; cs.mdist[i] = cs.FB[i].h - off; }
-    nb = reduce_manifold(cs.FB, cs.mdist, nb);
-    for (int i = 0; i < nb; i++) {
-      if (cs.mdist[i] >= T(0)) continue;
-      T pos[3];
-      for (int c = 0; c < 3; c++) pos[c] = cs.FB[i].x * t1[c] + cs.FB[i].y * t2[c] + (cs.FB[i].h - T(0.5) * cs.mdist[i]) * frame[c];
-      emit_contact(s, ncon, dropped, P.geom, B.geom, frame, pos, cs.mdist[i]);
-    }
-  }
-  ncon = wshfl(ncon, 0); dropped = wshfl(dropped, 0);
-  __syncwarp();
 }
 
 template <typename T>
@@ -725,7 +593,7 @@ __global__ void __launch_bounds__(GJK_THREADS) scene_gjk_kernel(const __grid_con
     bool hit = false;
     uint2 w = make_uint2(0u, 0u);
     MPoint<T> Sx[4];
-    int n = 0;
+    int n = 0, ha = 0, hb = 0;
     if (item < nwork) {
       const int q = queue_of(qpref[wib], item);
       w = pb.work[(size_t)q * pb.work_cap + (item - qpref[wib][q])];
@@ -738,7 +606,8 @@ __global__ void __launch_bounds__(GJK_THREADS) scene_gjk_kernel(const __grid_con
         make_shape(sm, xpos, xmat, g1, A);
         make_shape(sm, xpos, xmat, g2, B);
         int it = 0;
-        hit = gjk_intersect<T, true>(sm, A, B, Sx, n, it, lane) != 0;
+        hit = gjk_intersect(sm, A, B, Sx, n, it) != 0;
+        ha = A.hint; hb = B.hint;
         git_sum += it;
       }
     }
@@ -751,7 +620,7 @@ __global__ void __launch_bounds__(GJK_THREADS) scene_gjk_kernel(const __grid_con
       if (hit) {
         if (idx < pb.hit_cap) {
           HitRec<T> &r = pb.hits[idx];
-          r.env = w.x; r.packed = w.y; r.n = n; r.pad = 0;
+          r.env = w.x; r.packed = w.y; r.n = n; r.hintA = ha; r.hintB = hb; r.pad = 0;
           for (int k = 0; k < n; k++)
 #pragma unroll
             for (int c = 0; c < 3; c++) { r.S[k][c] = Sx[k].w[c]; r.S[k][3 + c] = Sx[k].a[c]; r.S[k][6 + c] = Sx[k].b[c]; }
@@ -765,70 +634,50 @@ __global__ void __launch_bounds__(GJK_THREADS) scene_gjk_kernel(const __grid_con
   }
 }
 
-// Per substep: one warp per candidate geom pair, pulled from the work list with an atomic cursor (pairs differ 10x in
-// cost: a GJK miss vs GJK + EPA + manifold).  Contacts go to the env's raw buffer tagged with (pair index, manifold index).
-#ifndef NARROW_MINB
-#define NARROW_MINB 1  // minimum resident CTAs the compiler must allow (register cap)
-#endif
+// Per substep, ONE THREAD per intersecting pair: EPA -> manifold (scene_collide_seq.cuh), contacts to the env's raw buffer.
+constexpr int NSEQ_THREADS = 64;
 template <typename T>
-__global__ void __launch_bounds__(WARPS_NARROW * 32, NARROW_MINB) scene_narrow_kernel(const __grid_constant__ SceneModel<T> sm, const __grid_constant__ StepCfg cfg,
-                                                                        const EnvState<T> S, const PipeBuf<T> pb, int sub) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  NarrowScratch<T> *all = reinterpret_cast<NarrowScratch<T> *>(smem_raw);
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  NarrowScratch<T> &s = all[wib];
-  if (lane == 0) {
-    s.profon = S.prof != nullptr; s.dbg = 0;
-    for (int i = 0; i < 16; i++) s.prof[i] = 0;
-  }
-  __syncwarp();
+__global__ void __launch_bounds__(NSEQ_THREADS) scene_narrow_seq_kernel(const __grid_constant__ SceneModel<T> sm, const EnvState<T> S, const PipeBuf<T> pb, int sub) {
+  const int lane = threadIdx.x & 31;
   int *cnt = pb.nwork + WSTRIDE * sub;
-  const int nwork = min(cnt[W_NHIT], pb.hit_cap);
-  int dropped = 0;
-  constexpr int CHUNK = 2;  // consecutive hits per cursor grab (arrival order follows the queues: same hull, warm L1)
+  const int nhit = min(cnt[W_NHIT], pb.hit_cap);
+  const int stride = gridDim.x * NSEQ_THREADS;
+  long long eit_sum = 0, nepa = 0;
 #pragma unroll 1
-  for (;;) {
-    int item0 = 0;
-    if (lane == 0) item0 = atomicAdd(cnt + W_HITCURSOR, CHUNK);
-    item0 = wshfl(item0, 0);
-    if (item0 >= nwork) break;
-#pragma unroll 1
-  for (int item = item0; item < min(item0 + CHUNK, nwork); item++) {
+  for (int item = blockIdx.x * NSEQ_THREADS + threadIdx.x; item < nhit; item += stride) {
     const HitRec<T> &rec = pb.hits[item];
-    const uint2 w = make_uint2(rec.env, rec.packed);
-    const int env = (int)w.x, g1 = (int)(w.y & 0xff), g2 = (int)((w.y >> 8) & 0xff), pidx = (int)(w.y >> 16);
+    const int env = (int)rec.env, g1 = (int)(rec.packed & 0xff), g2 = (int)((rec.packed >> 8) & 0xff), pidx = (int)(rec.packed >> 16);
     const T(*xpos)[3] = reinterpret_cast<const T(*)[3]>(pb.xpos + (size_t)env * (NSLOT * 3));
     const T(*xmat)[9] = reinterpret_cast<const T(*)[9]>(pb.xmat + (size_t)env * (NSLOT * 9));
-    if (cfg.dbg_env >= 0) {
-      if (lane == 0) s.dbg = (env == cfg.dbg_env && S.step[env] == cfg.dbg_step);
-      __syncwarp();
-    }
-    Shape<T> &A = s.shp[0], &B = s.shp[1];
-    make_shape(sm, xpos, xmat, g1, A);  // all lanes write the same values
+    Shape<T> A, B;
+    make_shape(sm, xpos, xmat, g1, A);
     make_shape(sm, xpos, xmat, g2, B);
-    __syncwarp();
-    int ncon = 0;
-    if (A.type == G_PLANE) collide_plane(sm, s, A, B, ncon, dropped, lane);
-    else collide_convex(sm, s, A, B, reinterpret_cast<const MPoint<T> *>(&rec.S[0][0]), rec.n, ncon, dropped, lane);
-    if (ncon > 0) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(pb.ncon_raw + env, ncon);
-      base = wshfl(base, 0);
-      if (lane < ncon) {
-        if (base + lane < CONBUF) {
-          T *dst = pb.con + ((size_t)env * CONBUF + base + lane) * 8;
-          dst[0] = s.c_normal[0][lane]; dst[1] = s.c_normal[1][lane]; dst[2] = s.c_normal[2][lane];
-          dst[3] = s.c_pos[0][lane]; dst[4] = s.c_pos[1][lane]; dst[5] = s.c_pos[2][lane];
-          dst[6] = s.c_dist[lane];
-          pb.con_key[(size_t)env * CONBUF + base + lane] = (pidx << 20) | (lane << 16) | (g1 << 8) | g2;
+    A.hint = rec.hintA; B.hint = rec.hintB;  // continue the hill-climbing warm starts where GJK left them
+    CollideScratch<T> cs;
+    PairContacts<T> pc;
+    pc.n = 0;
+    if (A.type == G_PLANE) collide_plane_seq(sm, cs, A, B, pc);
+    else {
+      int eit = 0;
+      collide_convex_seq(sm, cs, A, B, reinterpret_cast<const MPoint<T> *>(&rec.S[0][0]), rec.n, pc, eit);
+      eit_sum += eit; nepa++;
+    }
+    if (pc.n > 0) {
+      const int base = atomicAdd(pb.ncon_raw + env, pc.n);
+      for (int c = 0; c < pc.n; c++)
+        if (base + c < CONBUF) {
+          T *dst = pb.con + ((size_t)env * CONBUF + base + c) * 8;
+          dst[0] = pc.normal[0]; dst[1] = pc.normal[1]; dst[2] = pc.normal[2];
+          dst[3] = pc.pos[c][0]; dst[4] = pc.pos[c][1]; dst[5] = pc.pos[c][2];
+          dst[6] = pc.dist[c];
+          pb.con_key[(size_t)env * CONBUF + base + c] = (pidx << 20) | (c << 16) | (g1 << 8) | g2;
         }
-      }
-      __syncwarp();
     }
   }
+  if (S.prof) {
+    eit_sum = warp_sum(eit_sum); nepa = warp_sum(nepa);
+    if (lane == 0 && nepa) { atomicAdd(S.prof + P_EPAIT, (unsigned long long)eit_sum); atomicAdd(S.prof + P_NEPA, (unsigned long long)nepa); }
   }
-  if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
-  prof_flush(s, S, lane);
 }
 
 // Gather the env's raw contacts into shared memory in oracle order (pair order, then manifold order).  Returns false (and
@@ -1086,23 +935,12 @@ __global__ void scene_reset_kernel(const __grid_constant__ StepCfg cfg, const En
 
 template <typename T>
 size_t scene_smem_bytes() {
-  const size_t a = sizeof(Scratch<T, NC_M, NB_M>) * WARPS_M, b = sizeof(NarrowScratch<T>) * WARPS_NARROW, c = sizeof(Scratch<T, NC_L, NB_L>) * WARPS_L;
+  const size_t a = sizeof(Scratch<T, NC_M, NB_M>) * WARPS_M, b = sizeof(Scratch<T, NC_S, NB_S>) * WARPS_SOLVE, c = sizeof(Scratch<T, NC_L, NB_L>) * WARPS_L;
   return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 template <typename T>
 void scene_dropcat(int out[8]) { cudaMemcpyFromSymbol(out, g_dropcat, sizeof(int) * 8); }
-
-template <typename T>
-int scene_narrow_grid() {
-  const size_t smem_nar = sizeof(NarrowScratch<T>) * WARPS_NARROW;
-  cudaFuncSetAttribute(scene_narrow_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nar);
-  int nb = 0, dev = 0, sms = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scene_narrow_kernel<T>, WARPS_NARROW * 32, smem_nar);
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return (nb > 0 ? nb : 1) * (sms > 0 ? sms : 1);
-}
 
 // Launches of one control step: 1 memset + 1 + 5 * nsub kernels, all on the caller's stream.  Returns the kernel count.
 template <typename T>
@@ -1111,14 +949,13 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  const size_t smem_env = sizeof(Scratch<T, NC_S, NB_S>) * WARPS_SOLVE, smem_nar = sizeof(NarrowScratch<T>) * WARPS_NARROW,
+  const size_t smem_env = sizeof(Scratch<T, NC_S, NB_S>) * WARPS_SOLVE,
                smem_m = sizeof(Scratch<T, NC_M, NB_M>) * WARPS_M, smem_l = sizeof(Scratch<T, NC_L, NB_L>) * WARPS_L;
   if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaFuncSetAttribute(scene_begin_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
     cudaFuncSetAttribute(scene_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
     cudaFuncSetAttribute(scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
     cudaFuncSetAttribute(scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
-    cudaFuncSetAttribute(scene_narrow_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nar);
     cudaFuncSetAttribute(scene_reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
@@ -1129,16 +966,15 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
   t.begin(0, stream);
   scene_begin_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, stream>>>(am, sm, cfg, S, pb, action, out);
   t.end(0, stream);
-  // narrow phase: persistent grid sized to the machine (pairs are pulled with an atomic cursor)
-  const int grid_nar = pb.narrow_grid;
-  const int grid_gjk = 148 * 8;  // grid-stride over the work items: 148 SMs x 8 resident CTAs of 128 threads
+  const int grid_gjk = 148 * 8;
+  const int grid_seq = 148 * 16;
   const int grid_m = S.N < 148 * 4 ? S.N : 148 * 4, grid_l = S.N < 148 * 2 ? S.N : 148 * 2;
   for (int sub = 0; sub < cfg.nsub; sub++) {
     t.begin(5, stream);
     scene_gjk_kernel<T><<<grid_gjk, GJK_THREADS, 0, stream>>>(sm, S, pb, sub);
     t.end(5, stream);
     t.begin(1, stream);
-    scene_narrow_kernel<T><<<grid_nar, WARPS_NARROW * 32, smem_nar, stream>>>(sm, cfg, S, pb, sub);
+    scene_narrow_seq_kernel<T><<<grid_seq, NSEQ_THREADS, 0, stream>>>(sm, S, pb, sub);
     t.end(1, stream);
     t.begin(2, stream);
     scene_solve_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, stream>>>(am, sm, cfg, S, pb, out, sub);

@@ -4,6 +4,5 @@ namespace so101 {
 template int launch_scene_step<double>(const ArmModelT<double> &, const SceneModel<double> &, const StepCfg &, const EnvState<double> &, const PipeBuf<double> &, const float *, const so101_step_out &, cudaStream_t, KernelTimer *);
 template void launch_scene_reset<double>(const StepCfg &, const EnvState<double> &, const uint8_t *, const so101_step_out &, cudaStream_t);
 template size_t scene_smem_bytes<double>();
-template int scene_narrow_grid<double>();
 template void scene_dropcat<double>(int *);
 }  // namespace so101

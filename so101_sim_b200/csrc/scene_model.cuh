@@ -33,6 +33,7 @@ struct SceneModel {
   const T *geom_aabb;  // [ngeom][6] centre, half sizes of the geom's bounding box in the GEOM frame (mid phase)
   const T *geom_friction, *geom_solref, *geom_solimp, *geom_solmix, *geom_margin, *geom_gap;
   const Vec4<T> *hull_vert;  // body-frame hull vertices, 16/32-byte aligned for vector loads
+  const int *hull_nbradr, *hull_nbr;  // vertex adjacency: CSR offsets per global vertex id, local neighbour ids (hill-climbing support)
   // bodies
   const int *bodypair, *body_slot, *body_geomadr, *body_geomnum;
   const T *body_bcenter, *body_rbound, *body_invweight0;  // static bodies: bcenter in the world frame
@@ -175,7 +176,7 @@ struct SceneModelHost {
     d.geom_bcenter = up(cvt(gbc)); d.geom_rbound = up(cvt(b.F("geom_rbound"))); d.geom_aabb = up(cvt(gaabb));
     d.geom_friction = up(cvt(b.F("geom_friction"))); d.geom_solref = up(cvt(b.F("geom_solref"))); d.geom_solimp = up(cvt(b.F("geom_solimp")));
     d.geom_solmix = up(cvt(b.F("geom_solmix"))); d.geom_margin = up(cvt(b.F("geom_margin"))); d.geom_gap = up(cvt(b.F("geom_gap")));
-    d.hull_vert = up(verts);
+    d.hull_vert = up(verts); d.hull_nbradr = up(b.I("hull_nbradr")); d.hull_nbr = up(b.I("hull_nbr"));
     d.bodypair = up(b.I("bodypair")); d.body_slot = up(slot); d.body_geomadr = up(b.I("body_geomadr")); d.body_geomnum = up(b.I("body_geomnum"));
     d.body_bcenter = up(cvt(bbc)); d.body_rbound = up(cvt(b.F("body_rbound"))); d.body_invweight0 = up(cvt(b.F("body_invweight0")));
     for (int p = 0; p < NPROP; p++) {

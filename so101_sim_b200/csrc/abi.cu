@@ -40,6 +40,7 @@ struct HandleBase {
   virtual void step_host(const float *action, float *reward, float *discount, uint8_t *step_type, float *jpos, cudaStream_t s) = 0;
   virtual uint64_t diverged() = 0;
   KernelTimer timer;
+  TierExec tiers;
 };
 
 static void quat2mat(const double *q, double *m) {
@@ -204,7 +205,8 @@ struct Handle : HandleBase {
       if (b.scalar("ngeom") > GMAX_GEOMS) throw std::runtime_error("model has more geoms than the broad phase can hold");
       if (b.scalar("ngeom") > WQ) throw std::runtime_error("model has more geoms than narrow-phase work queues");
       pipe.con = dalloc<T>(N * CONBUF * 8); pipe.con_key = dalloc<int>(N * CONBUF); pipe.ncon_raw = dalloc<int>(N);
-      pipe.active = dalloc<uint8_t>(N); pipe.flags = dalloc<uint8_t>(N);
+      pipe.active = dalloc<uint8_t>(N); pipe.flags = dalloc<uint8_t>(N); pipe.tier = dalloc<uint8_t>(N);
+      tiers.init();
     }
   }
   ~Handle() override {
@@ -234,7 +236,7 @@ struct Handle : HandleBase {
     launches += 1;
   }
   void step(const float *action, const so101_step_out &out, cudaStream_t s) override {
-    if (scene) launches += launch_scene_step<T>(am, scene->dev, sc, S, pipe, action, out, s, &timer);
+    if (scene) launches += launch_scene_step<T>(am, scene->dev, sc, S, pipe, action, out, s, &timer, &tiers);
     else { timer.begin(4, s); launch_arm_step<T>(am, sc, S, action, out, s); timer.end(4, s); launches += 1; }
     steps += 1;
   }

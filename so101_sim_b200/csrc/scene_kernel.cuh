@@ -43,6 +43,21 @@ struct PipeBuf {
   int *con_key;             // [N][CONBUF]     pair index << 20 | manifold index << 16 | g1 << 8 | g2  (sort key)
   int *ncon_raw;            // [N]
   uint8_t *active, *flags;  // [N]  env steps this call (not being reset) / env diverged during this control step
+  uint8_t *tier;            // [N]  solver tier of the env in this substep (by contact / Jacobian-block count)
+};
+
+// Side streams for the larger solver tiers: they run concurrently with tier 0 (different envs) and join before the next kernel.
+struct TierExec {
+  cudaStream_t sm = nullptr, sl = nullptr;
+  cudaEvent_t fork = nullptr, joinm = nullptr, joinl = nullptr;
+  void init() {
+    cudaStreamCreateWithFlags(&sm, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&sl, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&joinm, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&joinl, cudaEventDisableTiming);
+  }
+  ~TierExec() {
+    if (sm) { cudaStreamDestroy(sm); cudaStreamDestroy(sl); cudaEventDestroy(fork); cudaEventDestroy(joinm); cudaEventDestroy(joinl); }
+  }
 };
 
 // Optional per-kernel timing with CUDA events on the launching stream (so101_kernel_times; bench.py's roofline leg).
@@ -85,7 +100,7 @@ struct KernelTimer {
 
 template <typename T>
 int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
-                      const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt);
+                      const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt, TierExec *tx);
 template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream);
 template <typename T>

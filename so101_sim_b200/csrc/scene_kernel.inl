@@ -687,8 +687,7 @@ __device__ __noinline__ bool gather_contacts(const SceneModel<T> &sm, const Pipe
   auto &R = s.sol;
   constexpr int NC = sizeof(R.D0) / sizeof(T), NB = sizeof(R.w1[0]) / sizeof(T);
   int nraw = pb.ncon_raw[env];
-  if (nraw > NC && NC < CONBUF) return false;  // (NC == CONBUF marks the last tier)
-  if (nraw > CONBUF) { dropped += nraw - CONBUF; if (lane == 0) DROPCAT(4, nraw - CONBUF); nraw = CONBUF; }
+  if (nraw > NC) { dropped += nraw - NC; if (lane == 0) DROPCAT(4, nraw - NC); nraw = NC; }  // (the classifier picked a tier that fits)
   const int *keys = pb.con_key + (size_t)env * CONBUF;
   constexpr int RSL = (NC + 31) / 32;
   int mykey[RSL], rank[RSL];
@@ -703,8 +702,6 @@ __device__ __noinline__ bool gather_contacts(const SceneModel<T> &sm, const Pipe
       nblk += (a1 != 31) + (a2 != 31 && a2 != a1);
     }
   }
-  nblk = warp_sum(nblk);
-  if (nblk > NB && NC < CONBUF) return false;
   // rank = number of contacts with a smaller key (keys are unique: pair index and manifold index)
 #pragma unroll
   for (int kk = 0; kk < RSL; kk++) {
@@ -878,7 +875,28 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
   return true;
 }
 
-// Small tier: warp per env; envs that need more contact / block storage are queued for the large tier.
+// Per substep, thread per env: pick the solver tier whose contact / Jacobian-block capacity fits the env's raw contacts and
+// queue tier-1 / tier-2 envs, so that the three tier kernels can run concurrently on separate streams.
+template <typename T>
+__global__ void scene_classify_kernel(const __grid_constant__ SceneModel<T> sm, const EnvState<T> S, const PipeBuf<T> pb, int sub) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= S.N || !pb.active[env]) return;
+  int n = pb.ncon_raw[env];
+  if (n > CONBUF) n = CONBUF;
+  const int *keys = pb.con_key + (size_t)env * CONBUF;
+  int nblk = 0;
+  for (int i = 0; i < n; i++) {
+    const int k = keys[i];
+    const int s1 = sm.body_slot[sm.geom_body[(k >> 8) & 0xff]], s2 = sm.body_slot[sm.geom_body[k & 0xff]];
+    const int a1 = s1 < 0 ? 31 : (s1 < NJ ? 0 : s1), a2 = s2 < 0 ? 31 : (s2 < NJ ? 0 : s2);
+    nblk += (a1 != 31) + (a2 != 31 && a2 != a1);
+  }
+  const int tier = (n <= NC_S && nblk <= NB_S) ? 0 : ((n <= NC_M && nblk <= NB_M) ? 1 : 2);
+  pb.tier[env] = (uint8_t)tier;
+  if (tier > 0) pb.big[(size_t)(tier - 1) * S.N + atomicAdd(pb.nwork + WSTRIDE * sub + W_NTIER + tier - 1, 1)] = env;
+}
+
+// Tier 0: warp per env (every env whose contacts fit the small scratch).
 template <typename T>
 __global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_solve_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
                                                                       const __grid_constant__ StepCfg cfg, const EnvState<T> S, const PipeBuf<T> pb,
@@ -889,10 +907,8 @@ __global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_solve_kernel(const __g
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int env = blockIdx.x * WARPS_SOLVE + wib;
   if (env >= S.N) return;
-  if (!pb.active[env]) return;
-  if (!solve_env(am, sm, cfg, S, pb, out, sub, env, all[wib], lane)) {
-    if (lane == 0) pb.big[atomicAdd(pb.nwork + WSTRIDE * sub + W_NTIER, 1)] = env;
-  }
+  if (!pb.active[env] || pb.tier[env] != 0) return;
+  solve_env(am, sm, cfg, S, pb, out, sub, env, all[wib], lane);
 }
 // Tiers 1 and 2: persistent CTAs walk the tier's queue (filled by the previous tier during this substep).
 template <typename T, int NC, int NB, int WARPS, int TIER>
@@ -914,9 +930,8 @@ __global__ void __launch_bounds__(WARPS * 32) scene_solve_tier_kernel(const __gr
     item = wshfl(item, 0);
     if (item >= n) break;
     const int env = list[item];
-    if (!solve_env(am, sm, cfg, S, pb, out, sub, env, s, lane)) {
-      if (TIER == 1 && lane == 0) pb.big[(size_t)S.N + atomicAdd(cnt + W_NTIER + 1, 1)] = env;
-    } else if (S.prof && lane == 0) atomicAdd(S.prof + P_BIGENV, 1ull);
+    solve_env(am, sm, cfg, S, pb, out, sub, env, s, lane);
+    if (S.prof && lane == 0) atomicAdd(S.prof + P_BIGENV, 1ull);
     __syncwarp();
   }
 }
@@ -942,10 +957,10 @@ size_t scene_smem_bytes() {
 template <typename T>
 void scene_dropcat(int out[8]) { cudaMemcpyFromSymbol(out, g_dropcat, sizeof(int) * 8); }
 
-// Launches of one control step: 1 memset + 1 + 5 * nsub kernels, all on the caller's stream.  Returns the kernel count.
+// Launches of one control step: 1 memset + 1 + 6 * nsub kernels, all on the caller's stream.  Returns the kernel count.
 template <typename T>
 int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
-                      const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt) {
+                      const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt, TierExec *tx) {
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -976,15 +991,22 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
     t.begin(1, stream);
     scene_narrow_seq_kernel<T><<<grid_seq, NSEQ_THREADS, 0, stream>>>(sm, S, pb, sub);
     t.end(1, stream);
+    scene_classify_kernel<T><<<(S.N + 127) / 128, 128, 0, stream>>>(sm, S, pb, sub);
+    // the three solver tiers work on disjoint envs: tiers 1 and 2 run on side streams beside tier 0 and join before the
+    // next kernel
+    cudaEventRecord(tx->fork, stream);
+    cudaStreamWaitEvent(tx->sm, tx->fork, 0); cudaStreamWaitEvent(tx->sl, tx->fork, 0);
+    t.begin(3, tx->sm);
+    scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1><<<grid_m, WARPS_M * 32, smem_m, tx->sm>>>(am, sm, cfg, S, pb, out, sub);
+    t.end(3, tx->sm);
+    scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2><<<grid_l, WARPS_L * 32, smem_l, tx->sl>>>(am, sm, cfg, S, pb, out, sub);
+    cudaEventRecord(tx->joinm, tx->sm); cudaEventRecord(tx->joinl, tx->sl);
     t.begin(2, stream);
     scene_solve_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, stream>>>(am, sm, cfg, S, pb, out, sub);
     t.end(2, stream);
-    t.begin(3, stream);
-    scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1><<<grid_m, WARPS_M * 32, smem_m, stream>>>(am, sm, cfg, S, pb, out, sub);
-    scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2><<<grid_l, WARPS_L * 32, smem_l, stream>>>(am, sm, cfg, S, pb, out, sub);
-    t.end(3, stream);
+    cudaStreamWaitEvent(stream, tx->joinm, 0); cudaStreamWaitEvent(stream, tx->joinl, 0);
   }
-  return 1 + 5 * cfg.nsub;
+  return 1 + 6 * cfg.nsub;
 }
 template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream) {

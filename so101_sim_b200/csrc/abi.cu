@@ -2,6 +2,7 @@
 // PyTorch owns every tensor that crosses this boundary; the handle owns only its SoA state and scratch.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -30,7 +31,7 @@ struct HandleBase {
   so101_config cfg{};
   int nq = 0, nv = 0, nu = 0, nbody = 0;
   uint64_t launches = 0, steps = 0, dropped = 0;
-  virtual ~HandleBase() {}
+  virtual ~HandleBase() { for (auto &t : tiers) t.destroy(); }
   virtual void set_state(const float *q, const float *v, bool initial, cudaStream_t s) = 0;
   virtual void get_state(float *q, float *v, cudaStream_t s) = 0;
   virtual void get_state_f64(double *q, double *v, cudaStream_t s) = 0;
@@ -40,7 +41,7 @@ struct HandleBase {
   virtual void step_host(const float *action, float *reward, float *discount, uint8_t *step_type, float *jpos, cudaStream_t s) = 0;
   virtual uint64_t diverged() = 0;
   KernelTimer timer;
-  TierExec tiers;
+  std::vector<TierExec> tiers;  // one per pipeline group
 };
 
 static void quat2mat(const double *q, double *m) {
@@ -152,7 +153,8 @@ struct Handle : HandleBase {
   ArmModelT<T> am;
   std::unique_ptr<SceneModelHost<T>> scene;  // non-null: full contact scene (warp per env, row-major state)
   EnvState<T> S{};
-  PipeBuf<T> pipe{};
+  PipeBuf<T> pipe{};                 // per-env scratch shared by all groups
+  std::vector<PipeBuf<T>> groups;    // per-group queues / counters (views of `pipe` with their own work lists)
   StepCfg sc{};
   std::vector<void *> allocs;
   float *d_action = nullptr, *d_reward = nullptr, *d_discount = nullptr, *d_jpos = nullptr;
@@ -199,14 +201,27 @@ struct Handle : HandleBase {
     d_action = dalloc<float>(6 * N); d_reward = dalloc<float>(N); d_discount = dalloc<float>(N); d_jpos = dalloc<float>(6 * N);
     d_steptype = dalloc<uint8_t>(N);
     if (scene) {  // inter-kernel scratch of the scene pipeline
-      pipe.xpos = dalloc<T>(N * NSLOT * 3); pipe.xmat = dalloc<T>(N * NSLOT * 9);
-      pipe.work_cap = (int)(4 * N + 64); pipe.work = dalloc<uint2>((size_t)WQ * pipe.work_cap); pipe.nwork = dalloc<int>(WSTRIDE * (c.n_substeps + 1)); pipe.big = dalloc<int>(2 * N);
-      pipe.hit_cap = (int)(N * 32); pipe.hits = dalloc<HitRec<T>>((size_t)pipe.hit_cap);
       if (b.scalar("ngeom") > GMAX_GEOMS) throw std::runtime_error("model has more geoms than the broad phase can hold");
       if (b.scalar("ngeom") > WQ) throw std::runtime_error("model has more geoms than narrow-phase work queues");
+      pipe.xpos = dalloc<T>(N * NSLOT * 3); pipe.xmat = dalloc<T>(N * NSLOT * 9);
       pipe.con = dalloc<T>(N * CONBUF * 8); pipe.con_key = dalloc<int>(N * CONBUF); pipe.ncon_raw = dalloc<int>(N);
       pipe.active = dalloc<uint8_t>(N); pipe.flags = dalloc<uint8_t>(N); pipe.tier = dalloc<uint8_t>(N);
-      tiers.init();
+      // pipeline groups: independent env ranges whose kernel sequences run on their own streams.  Measured on B200 at 16384
+      // envs (profiles/r01_groups.txt): 1 group 72 ms/step, 2: 78, 4: 99, 8: 135 -- the kernels do not overlap enough to pay
+      // for their shorter, tail-dominated launches, so the default is ONE group; SO101_GROUPS keeps the experiment available.
+      int ng = getenv("SO101_GROUPS") ? atoi(getenv("SO101_GROUPS")) : 1;
+      const int by_size = (int)((N + 2047) / 2048);
+      ng = std::max(1, std::min(std::min(ng, 8), by_size));
+      tiers.resize(ng);
+      for (int g = 0; g < ng; g++) {
+        PipeBuf<T> p = pipe;
+        p.env0 = (int)(N * g / ng); p.nenv = (int)(N * (g + 1) / ng) - p.env0;
+        p.work_cap = 4 * p.nenv + 64; p.work = dalloc<uint2>((size_t)WQ * p.work_cap);
+        p.nwork = dalloc<int>(WSTRIDE * (c.n_substeps + 1)); p.big = dalloc<int>(2 * (size_t)p.nenv);
+        p.hit_cap = p.nenv * 32; p.hits = dalloc<HitRec<T>>((size_t)p.hit_cap);
+        groups.push_back(p);
+        tiers[g].init();
+      }
     }
   }
   ~Handle() override {
@@ -236,7 +251,7 @@ struct Handle : HandleBase {
     launches += 1;
   }
   void step(const float *action, const so101_step_out &out, cudaStream_t s) override {
-    if (scene) launches += launch_scene_step<T>(am, scene->dev, sc, S, pipe, action, out, s, &timer, &tiers);
+    if (scene) launches += launch_scene_step<T>(am, scene->dev, sc, S, groups.data(), tiers.data(), (int)groups.size(), action, out, s, &timer);
     else { timer.begin(4, s); launch_arm_step<T>(am, sc, S, action, out, s); timer.end(4, s); launches += 1; }
     steps += 1;
   }
@@ -251,6 +266,13 @@ struct Handle : HandleBase {
       if (count < (size_t)S.N * nv) throw std::runtime_error("debug_read: buffer too small");
       if (scene) launch_cast_copy<T, float>(S.warm, dst, (size_t)S.N * nv, s); else launch_soa_to_rows<T, float>(S.warm, dst, S.N, nv, s);
       launches += 1;
+    } else if (f == "epahist") {
+      if (count < 8) throw std::runtime_error("debug_read: buffer too small");
+      int h[8]; float hf[8];
+      CUDA_OK(cudaStreamSynchronize(s));
+      scene_epahist<T>(h);
+      for (int i = 0; i < 8; i++) hf[i] = (float)h[i];
+      CUDA_OK(cudaMemcpy(dst, hf, sizeof hf, cudaMemcpyHostToDevice));
     } else if (f == "dropcat") {
       // 8 drop counters by buffer (see scene_solve.cuh: g_dropcat), since the library was loaded
       if (count < 8) throw std::runtime_error("debug_read: buffer too small");

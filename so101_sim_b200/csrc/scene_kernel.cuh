@@ -38,25 +38,34 @@ struct PipeBuf {
   int hit_cap;
   int *nwork;               // [nsub+1][WSTRIDE]  per substep: items per queue [0..WQ), then pair cursor, large-tier envs
                             //   queued, large-tier cursor
-  int *big;                 // [2][N]  envs deferred to solver tier 1 / tier 2 in this substep
+  int *big;                 // [2][nenv]  envs of solver tier 1 / tier 2 in this substep
   T *con;                   // [N][CONBUF][8]  raw contacts: normal3, pos3, dist
   int *con_key;             // [N][CONBUF]     pair index << 20 | manifold index << 16 | g1 << 8 | g2  (sort key)
   int *ncon_raw;            // [N]
   uint8_t *active, *flags;  // [N]  env steps this call (not being reset) / env diverged during this control step
   uint8_t *tier;            // [N]  solver tier of the env in this substep (by contact / Jacobian-block count)
+  int env0, nenv;           // env range of this pipeline group (work queues, hit list, counters and tier queues are per group)
 };
 
-// Side streams for the larger solver tiers: they run concurrently with tier 0 (different envs) and join before the next kernel.
+// Streams of one pipeline group.  The envs of a handle are split into a few groups whose kernel sequences run concurrently
+// (every kernel here is bound by the latency of its slowest warps, so independent groups fill each other's idle issue
+// slots); inside a group the two larger solver tiers run on side streams beside tier 0 and join before the next kernel.
 struct TierExec {
-  cudaStream_t sm = nullptr, sl = nullptr;
-  cudaEvent_t fork = nullptr, joinm = nullptr, joinl = nullptr;
+  cudaStream_t main = nullptr, sm = nullptr, sl = nullptr;
+  cudaEvent_t start = nullptr, fork = nullptr, joinm = nullptr, joinl = nullptr, done = nullptr;
   void init() {
+    cudaStreamCreateWithFlags(&main, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&sm, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&sl, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&joinm, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&joinl, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&joinl, cudaEventDisableTiming); cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&start, cudaEventDisableTiming);
   }
-  ~TierExec() {
-    if (sm) { cudaStreamDestroy(sm); cudaStreamDestroy(sl); cudaEventDestroy(fork); cudaEventDestroy(joinm); cudaEventDestroy(joinl); }
+  void destroy() {
+    if (main) {
+      cudaStreamDestroy(main); cudaStreamDestroy(sm); cudaStreamDestroy(sl);
+      cudaEventDestroy(fork); cudaEventDestroy(joinm); cudaEventDestroy(joinl); cudaEventDestroy(done); cudaEventDestroy(start);
+      main = nullptr;
+    }
   }
 };
 
@@ -98,13 +107,16 @@ struct KernelTimer {
   }
 };
 
+// pb / tx: one entry per pipeline group (ngroups of them)
 template <typename T>
-int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
-                      const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt, TierExec *tx);
+int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> *pb,
+                      TierExec *tx, int ngroups, const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt);
 template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream);
 template <typename T>
 size_t scene_smem_bytes();
 template <typename T>
 void scene_dropcat(int out[8]);
+template <typename T>
+void scene_epahist(int out[8]);
 }  // namespace so101

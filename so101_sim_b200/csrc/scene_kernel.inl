@@ -530,8 +530,8 @@ __global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_begin_kernel(const __g
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SC *all = reinterpret_cast<SC *>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int env = blockIdx.x * WARPS_SOLVE + wib;
-  if (env >= S.N) return;
+  const int env = pb.env0 + blockIdx.x * WARPS_SOLVE + wib;
+  if (env >= pb.env0 + pb.nenv) return;
   SC &s = all[wib];
   if (lane == 0) pb.ncon_raw[env] = 0;
   if (S.needs_reset[env]) {  // the step() after a LAST step resets and returns FIRST; no physics this call
@@ -661,6 +661,7 @@ __global__ void __launch_bounds__(NSEQ_THREADS) scene_narrow_seq_kernel(const __
       int eit = 0;
       collide_convex_seq(sm, cs, A, B, reinterpret_cast<const MPoint<T> *>(&rec.S[0][0]), rec.n, pc, eit);
       eit_sum += eit; nepa++;
+      if (S.prof) atomicAdd(&g_epahist[eit <= 2 ? 0 : eit <= 5 ? 1 : eit <= 10 ? 2 : eit <= 20 ? 3 : eit <= 40 ? 4 : eit <= 79 ? 5 : 6], 1);
     }
     if (pc.n > 0) {
       const int base = atomicAdd(pb.ncon_raw + env, pc.n);
@@ -879,8 +880,8 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
 // queue tier-1 / tier-2 envs, so that the three tier kernels can run concurrently on separate streams.
 template <typename T>
 __global__ void scene_classify_kernel(const __grid_constant__ SceneModel<T> sm, const EnvState<T> S, const PipeBuf<T> pb, int sub) {
-  const int env = blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= S.N || !pb.active[env]) return;
+  const int env = pb.env0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= pb.env0 + pb.nenv || !pb.active[env]) return;
   int n = pb.ncon_raw[env];
   if (n > CONBUF) n = CONBUF;
   const int *keys = pb.con_key + (size_t)env * CONBUF;
@@ -893,7 +894,7 @@ __global__ void scene_classify_kernel(const __grid_constant__ SceneModel<T> sm, 
   }
   const int tier = (n <= NC_S && nblk <= NB_S) ? 0 : ((n <= NC_M && nblk <= NB_M) ? 1 : 2);
   pb.tier[env] = (uint8_t)tier;
-  if (tier > 0) pb.big[(size_t)(tier - 1) * S.N + atomicAdd(pb.nwork + WSTRIDE * sub + W_NTIER + tier - 1, 1)] = env;
+  if (tier > 0) pb.big[(size_t)(tier - 1) * pb.nenv + atomicAdd(pb.nwork + WSTRIDE * sub + W_NTIER + tier - 1, 1)] = env;
 }
 
 // Tier 0: warp per env (every env whose contacts fit the small scratch).
@@ -905,8 +906,8 @@ __global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_solve_kernel(const __g
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SC *all = reinterpret_cast<SC *>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int env = blockIdx.x * WARPS_SOLVE + wib;
-  if (env >= S.N) return;
+  const int env = pb.env0 + blockIdx.x * WARPS_SOLVE + wib;
+  if (env >= pb.env0 + pb.nenv) return;
   if (!pb.active[env] || pb.tier[env] != 0) return;
   solve_env(am, sm, cfg, S, pb, out, sub, env, all[wib], lane);
 }
@@ -922,7 +923,7 @@ __global__ void __launch_bounds__(WARPS * 32) scene_solve_tier_kernel(const __gr
   SC &s = all[wib];
   int *cnt = pb.nwork + WSTRIDE * sub;
   const int n = cnt[W_NTIER + TIER - 1];
-  const int *list = pb.big + (size_t)(TIER - 1) * S.N;
+  const int *list = pb.big + (size_t)(TIER - 1) * pb.nenv;
 #pragma unroll 1
   for (;;) {
     int item = 0;
@@ -956,11 +957,14 @@ size_t scene_smem_bytes() {
 
 template <typename T>
 void scene_dropcat(int out[8]) { cudaMemcpyFromSymbol(out, g_dropcat, sizeof(int) * 8); }
-
-// Launches of one control step: 1 memset + 1 + 6 * nsub kernels, all on the caller's stream.  Returns the kernel count.
 template <typename T>
-int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
-                      const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt, TierExec *tx) {
+void scene_epahist(int out[8]) { cudaMemcpyFromSymbol(out, g_epahist, sizeof(int) * 8); }
+
+// Launches of one control step: per pipeline group 1 memset + 1 + 6 * nsub kernels on the group's streams, forked from and
+// joined back into the caller's stream.  Returns the kernel count.
+template <typename T>
+int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> *pbs,
+                      TierExec *txs, int ngroups, const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt) {
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -976,37 +980,55 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
   }
   KernelTimer none;
   KernelTimer &t = kt ? *kt : none;
-  cudaMemsetAsync(pb.nwork, 0, sizeof(int) * WSTRIDE * (cfg.nsub + 1), stream);
-  const int grid_env = (S.N + WARPS_SOLVE - 1) / WARPS_SOLVE;
-  t.begin(0, stream);
-  scene_begin_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, stream>>>(am, sm, cfg, S, pb, action, out);
-  t.end(0, stream);
-  const int grid_gjk = 148 * 8;
-  const int grid_seq = 148 * 16;
-  const int grid_m = S.N < 148 * 4 ? S.N : 148 * 4, grid_l = S.N < 148 * 2 ? S.N : 148 * 2;
-  for (int sub = 0; sub < cfg.nsub; sub++) {
-    t.begin(5, stream);
-    scene_gjk_kernel<T><<<grid_gjk, GJK_THREADS, 0, stream>>>(sm, S, pb, sub);
-    t.end(5, stream);
-    t.begin(1, stream);
-    scene_narrow_seq_kernel<T><<<grid_seq, NSEQ_THREADS, 0, stream>>>(sm, S, pb, sub);
-    t.end(1, stream);
-    scene_classify_kernel<T><<<(S.N + 127) / 128, 128, 0, stream>>>(sm, S, pb, sub);
-    // the three solver tiers work on disjoint envs: tiers 1 and 2 run on side streams beside tier 0 and join before the
-    // next kernel
-    cudaEventRecord(tx->fork, stream);
-    cudaStreamWaitEvent(tx->sm, tx->fork, 0); cudaStreamWaitEvent(tx->sl, tx->fork, 0);
-    t.begin(3, tx->sm);
-    scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1><<<grid_m, WARPS_M * 32, smem_m, tx->sm>>>(am, sm, cfg, S, pb, out, sub);
-    t.end(3, tx->sm);
-    scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2><<<grid_l, WARPS_L * 32, smem_l, tx->sl>>>(am, sm, cfg, S, pb, out, sub);
-    cudaEventRecord(tx->joinm, tx->sm); cudaEventRecord(tx->joinl, tx->sl);
-    t.begin(2, stream);
-    scene_solve_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, stream>>>(am, sm, cfg, S, pb, out, sub);
-    t.end(2, stream);
-    cudaStreamWaitEvent(stream, tx->joinm, 0); cudaStreamWaitEvent(stream, tx->joinl, 0);
+  cudaEventRecord(txs[0].start, stream);  // every group starts after the work already queued on the caller's stream
+  for (int g = 0; g < ngroups; g++) cudaStreamWaitEvent(txs[g].main, txs[0].start, 0);
+  // interleave the groups' launches substep by substep so that their kernels are in flight together
+  for (int g = 0; g < ngroups; g++) {
+    const PipeBuf<T> &pb = pbs[g];
+    cudaStream_t st = txs[g].main;
+    cudaMemsetAsync(pb.nwork, 0, sizeof(int) * WSTRIDE * (cfg.nsub + 1), st);
+    const int grid_env = (pb.nenv + WARPS_SOLVE - 1) / WARPS_SOLVE;
+    t.begin(0, st);
+    scene_begin_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, st>>>(am, sm, cfg, S, pb, action, out);
+    t.end(0, st);
   }
-  return 1 + 6 * cfg.nsub;
+  const int sms = 148;
+  for (int sub = 0; sub < cfg.nsub; sub++) {
+    for (int g = 0; g < ngroups; g++) {
+      const PipeBuf<T> &pb = pbs[g];
+      TierExec &tx = txs[g];
+      cudaStream_t st = tx.main;
+      const int grid_env = (pb.nenv + WARPS_SOLVE - 1) / WARPS_SOLVE;
+      const int grid_gjk = max(1, min(sms * 8, (pb.nenv * 16 + GJK_THREADS - 1) / GJK_THREADS));
+      const int grid_seq = max(1, min(sms * 16, (pb.nenv * 12 + NSEQ_THREADS - 1) / NSEQ_THREADS));
+      const int grid_m = pb.nenv < sms * 4 ? pb.nenv : sms * 4, grid_l = pb.nenv < sms * 2 ? pb.nenv : sms * 2;
+      t.begin(5, st);
+      scene_gjk_kernel<T><<<grid_gjk, GJK_THREADS, 0, st>>>(sm, S, pb, sub);
+      t.end(5, st);
+      t.begin(1, st);
+      scene_narrow_seq_kernel<T><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub);
+      t.end(1, st);
+      scene_classify_kernel<T><<<(pb.nenv + 127) / 128, 128, 0, st>>>(sm, S, pb, sub);
+      // the three solver tiers work on disjoint envs: tiers 1 and 2 run on side streams beside tier 0 and join before the
+      // next kernel
+      cudaEventRecord(tx.fork, st);
+      cudaStreamWaitEvent(tx.sm, tx.fork, 0); cudaStreamWaitEvent(tx.sl, tx.fork, 0);
+      t.begin(3, tx.sm);
+      scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1><<<grid_m, WARPS_M * 32, smem_m, tx.sm>>>(am, sm, cfg, S, pb, out, sub);
+      t.end(3, tx.sm);
+      scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2><<<grid_l, WARPS_L * 32, smem_l, tx.sl>>>(am, sm, cfg, S, pb, out, sub);
+      cudaEventRecord(tx.joinm, tx.sm); cudaEventRecord(tx.joinl, tx.sl);
+      t.begin(2, st);
+      scene_solve_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, st>>>(am, sm, cfg, S, pb, out, sub);
+      t.end(2, st);
+      cudaStreamWaitEvent(st, tx.joinm, 0); cudaStreamWaitEvent(st, tx.joinl, 0);
+    }
+  }
+  for (int g = 0; g < ngroups; g++) {
+    cudaEventRecord(txs[g].done, txs[g].main);
+    cudaStreamWaitEvent(stream, txs[g].done, 0);
+  }
+  return ngroups * (1 + 6 * cfg.nsub);
 }
 template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream) {

@@ -10,12 +10,15 @@ from so101_sim_b200.task_suite import create_batched_task_env
 envs = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 prec = sys.argv[3] if len(sys.argv) > 3 else 'f32'
+pre = int(sys.argv[4]) if len(sys.argv) > 4 else 0   # random-action control steps before the measured ones
 env = create_batched_task_env('SO100HandOverBanana', num_envs=envs, time_limit=30.0, seed=0, device='cuda:0', precision=prec)
 env.sample_prop_initial_states(seed=0, spawn_z=0.45, settle_steps=50)
 env.reset()
 g = torch.Generator(device='cuda:0'); g.manual_seed(1)
 spec = env.action_spec()
 lo, hi = torch.tensor(spec.minimum, device='cuda:0'), torch.tensor(spec.maximum, device='cuda:0')
+for _ in range(pre):
+  env.step((lo + torch.rand(envs, 6, generator=g, device='cuda:0') * (hi - lo)) * 0.3)
 acts = (lo + torch.rand(steps, envs, 6, generator=g, device='cuda:0') * (hi - lo)) * 0.3
 p0 = env.debug_read('prof', 16)[0, :16].double().cpu() if False else None
 names = ['dyn', 'broad', 'gjk_iters', 'gjk', 'epa', 'manifold', 'rows', 'solve', 'epa_iters', 'big_envs', 'npq', 'ncon', 'newton', 'line', 'nepa', 'nsub']
@@ -43,5 +46,9 @@ q, v = env.get_state()
 ncon = env.debug_read('ncon').flatten(); it = env.debug_read('solver_iter').flatten()
 res['ncon_last'] = dict(mean=float(ncon.mean()), max=float(ncon.max())); res['iter_last'] = dict(mean=float(it.mean()), max=float(it.max()))
 res['counters'] = env.counters()
+eh = torch.empty(8, dtype=torch.float32, device='cuda:0')
+import ctypes as _ct
+env._check(env._lib.so101_debug_read(env._h, b'epahist', _ct.c_void_p(eh.data_ptr()), 8, env._stream()))
+res['epa_iter_hist(<=2,<=5,<=10,<=20,<=40,<=79,cap)'] = [int(x) for x in eh.tolist()[:7]]
 h = torch.histc(ncon.float(), bins=13, min=0, max=104); res['ncon_hist_bins_of_8'] = [int(x) for x in h.tolist()]
 print(json.dumps(res))

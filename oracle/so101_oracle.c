@@ -17,6 +17,10 @@
  */
 #include "so101_oracle.h"
 
+/* [upstream] mjOption.ls_tolerance = 0.01: the 1-D search stops once the slope has dropped to 1 % of its initial value;
+   the outer Newton tolerance decides the accuracy of the solution. */
+#define LS_TOLERANCE 0.01
+
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -607,7 +611,7 @@ static void solve_newton(const so_model *m, so_data *d) {
     double alpha = -df0 / ddf0, lo = 0, hi = -1, dlo = df0;
     for (int ls = 0; ls < 60; ls++) {
       line_eval(m, d, jar, jv, alpha, quadGauss, &f, &df, &ddf);
-      if (fabs(df) <= 1e-13 * fabs(df0)) break;
+      if (fabs(df) <= LS_TOLERANCE * fabs(df0)) break;
       if (df < 0) { lo = alpha; dlo = df; } else hi = alpha;
       double next = alpha - df / ddf;
       if (hi > 0 && (next <= lo || next >= hi)) next = 0.5 * (lo + hi);

@@ -568,7 +568,7 @@ __device__ __noinline__ int scene_solve(const ArmModelT<T> &am, T impratio, S &s
       T df = q1 + alpha * q2, ddf = q2;
       f = q0 + alpha * q1 + T(0.5) * alpha * alpha * q2;
       rows_line(s, al, impratio, alpha, f, df, ddf, lane);
-      if (t_abs(df) <= T(sizeof(T) == 8 ? 1e-13 : 1e-6) * t_abs(df0)) break;
+      if (t_abs(df) <= T(0.01) * t_abs(df0)) break;  // [upstream] mjOption.ls_tolerance = 0.01 (same constant in the oracle)
       if (df < T(0)) lo = alpha; else hi = alpha;
       T next = alpha - df / ddf;
       if (hi > T(0) && (next <= lo || next >= hi)) next = T(0.5) * (lo + hi);

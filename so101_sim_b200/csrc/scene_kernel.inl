@@ -1000,7 +1000,8 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
       cudaStream_t st = tx.main;
       const int grid_env = (pb.nenv + WARPS_SOLVE - 1) / WARPS_SOLVE;
       const int grid_gjk = max(1, min(sms * 8, (pb.nenv * 16 + GJK_THREADS - 1) / GJK_THREADS));
-      const int grid_seq = max(1, min(sms * 16, (pb.nenv * 12 + NSEQ_THREADS - 1) / NSEQ_THREADS));
+      static const int seq_per_sm = getenv("SO101_SEQ_CTAS") ? atoi(getenv("SO101_SEQ_CTAS")) : 16;  // CTAs of 64 threads per SM
+      const int grid_seq = max(1, min(sms * seq_per_sm, (pb.nenv * 12 + NSEQ_THREADS - 1) / NSEQ_THREADS));
       const int grid_m = pb.nenv < sms * 4 ? pb.nenv : sms * 4, grid_l = pb.nenv < sms * 2 ? pb.nenv : sms * 2;
       t.begin(5, st);
       scene_gjk_kernel<T><<<grid_gjk, GJK_THREADS, 0, st>>>(sm, S, pb, sub);

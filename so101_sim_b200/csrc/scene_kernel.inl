@@ -1,22 +1,24 @@
-// Control step of the FULL contact scene (BASELINE config 3: SO100HandOverBanana, nq=20 nv=18) as a pipeline of
-// three kernels per physics substep, all envs in lockstep:
+// Control step of the FULL contact scene (BASELINE config 3: SO100HandOverBanana, nq=20 nv=18) as a pipeline of small
+// kernels per physics substep, all envs in lockstep (DESIGN.md section 4 has the table):
 //
-//   scene_begin_kernel   (once per control step, warp per env)  auto-reset, action -> ctrl, kinematics, broad/mid phase
-//   scene_narrow_kernel  (per substep, warp per candidate geom PAIR drawn from a device-wide work list)
-//                        convex narrow phase: boolean GJK -> EPA -> support-feature clipping (multiccd manifold)
-//   scene_solve_kernel   (per substep, warp per env) smooth dynamics, contact gather, constraint rows, elliptic-cone
-//                        Newton, semi-implicit Euler, then kinematics + broad phase of the NEXT substep, or (last
-//                        substep) the task layer: observation delay rings, SO100HandOver reward, discount, time limit.
+//   scene_begin_kernel       (once per control step, warp per env)  auto-reset, action -> ctrl, kinematics, broad/mid phase
+//   scene_gjk_kernel         (thread per candidate geom pair)        boolean GJK over per-geom work queues -> hit list
+//   scene_narrow_seq_kernel  (thread per intersecting pair)          EPA -> support-feature clipping manifold -> raw contacts
+//   scene_classify_kernel    (thread per env)                        solver tier by contact / Jacobian-block count
+//   scene_solve_kernel + scene_solve_tier_kernel x2 (warp per env, concurrent streams)
+//                            smooth dynamics, contact gather, constraint rows, elliptic-cone Newton, semi-implicit Euler,
+//                            then kinematics + broad phase of the NEXT substep, or (last substep) the task layer:
+//                            observation delay rings, SO100HandOver reward, discount, time limit.
 //
-// Splitting by stage keeps each kernel's code and shared-memory footprint small (more resident warps, no instruction-
-// cache thrash) and turns the narrow phase — whose cost varies 10x between pairs — into a flat, dynamically balanced
-// work list.  What crosses kernels (body poses, pair list, raw contacts; ~1 KB per env) stays L2-resident.
+// Splitting by stage keeps each kernel's code and shared-memory footprint small (more resident warps, less instruction-
+// cache thrash) and turns the narrow phase - whose cost varies 10x between pairs - into flat work lists.  What crosses
+// kernels (body poses, pair queues, hit list, raw contacts; a few KB per env) is written once and read once.
 // Per substep order ([upstream] mj_step; legacy dm_control order is equivalent):
 //   arm FK / CRB / RNE            (all lanes redundantly, registers; arm_dynamics.cuh)
 //   prop kinematics, M, bias      (free joints: linear dofs world frame, angular dofs body frame)
-//   collision                     (scene_collide.cuh: lanes over vertices / faces)
+//   collision                     (scene_collide.cuh, scene_collide_seq.cuh)
 //   constraint rows               (lane per contact: parameter mixing, impedance, Jacobian blocks, aref)
-//   Newton solve                  (elliptic cones, lane per contact for row work, lane per entry for the Hessian)
+//   Newton solve                  (scene_solve.cuh)
 //   semi-implicit Euler           (quaternion integration for the free joints)
 // Task layer: so100_task.py:266-368, so100_hand_over.py:238-275.
 #include <cstdlib>

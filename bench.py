@@ -28,6 +28,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's own banner / debug lines ("NCCL version ...") go to stderr
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 
 WORKLOADS = {
     # name: (task, envs per GPU, blob, collide, algorithmic bytes per env-step [SURVEY.md §8d])

@@ -60,7 +60,7 @@ struct Scratch {
   T Mprop[NPROP][21];
   T Marm[21];
   T H[NH];
-  T qacc_s[NV], delta[NV], grad[NV], search[NV], Md[NV];
+  T qacc_s[NV], delta[NV], grad[NV], search[NV], Md[NV], hscale[NV];
   int ncon, dbg, profon;
   long long prof[16];  // developer probe (SO101_PROFILE=1): per-stage clock64 sums and counters of this env
   union {

@@ -232,16 +232,19 @@ __device__ __forceinline__ int cone_eval(const Cone<T> &k, const T *x, T &cost, 
   const T Dm = k.D[0] / (mu * mu * (T(1) + mu * mu)), NmT = N - mu * Tt;
   cost = T(0.5) * Dm * NmT * NmT;
   force[0] = -Dm * NmT * mu;
-  const T sDm = t_sqrt(Dm), c2 = -Dm * NmT * mu;  // c2 > 0 in the middle zone
-  const T s2 = t_sqrt(c2 / (Tt * Tt * Tt));
+  // c2 > 0 in the middle zone.  Everything is written with the bounded ratios c2 / T and U / T: in float32 the textbook
+  // form sqrt(c2 / T^3) overflows when the tangential slip T is tiny (T^3 underflows), which launched props into orbit.
+  const T sDm = t_sqrt(Dm), c2 = -Dm * NmT * mu;
+  const T ct = c2 / Tt, sct = t_sqrt(ct);
   v1[0] = sDm * mu;  // S0 * g0, g0 = 1
 #pragma unroll
   for (int j = 1; j < 6; j++)
     if (j < dim) {
-      force[j] = -force[0] / Tt * U[j] * k.S[j];
-      v1[j] = sDm * k.S[j] * (-mu * U[j] / Tt);
-      v2[j] = s2 * k.S[j] * U[j];
-      e[j] = c2 / Tt * k.S[j] * k.S[j];
+      const T un = U[j] / Tt;
+      force[j] = -force[0] * un * k.S[j];
+      v1[j] = sDm * k.S[j] * (-mu * un);
+      v2[j] = sct * k.S[j] * un;
+      e[j] = ct * k.S[j] * k.S[j];
     }
   return 2;
 }
@@ -549,9 +552,27 @@ __device__ __noinline__ int scene_solve(const ArmModelT<T> &am, T impratio, S &s
     const T mdl = lane < NV ? s.Md[lane] : T(0);
     const T gn = t_sqrt(warp_sum(gl * gl));
     if (am.solver_scale * gn < tol) break;
+    // float32 only: symmetric diagonal (Jacobi) scaling H' = S H S, S = diag(H_ii^-1/2).  The Hessian mixes translational
+    // and rotational dofs of bodies from 0.04 kg props to the armature-dominated arm with contact stiffness up to 1e5 and
+    // rolling-friction rows 1e-4 of that: its condition number exceeds what a float32 Cholesky resolves unless the scales
+    // are taken out first.  (float64 keeps the unscaled factorisation: bit-compatible with the oracle.)
+    T hs = T(1);
+    if (sizeof(T) == 4) {
+      if (lane < NV) { const T dgn = s.H[tri(lane, lane)]; hs = dgn > T(1e-30) ? T(1) / t_sqrt(dgn) : T(1); s.hscale[lane] = hs; }
+      __syncwarp();
+#pragma unroll 1
+      for (int en = lane; en < NH; en += 32) {
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= en) i++;
+        const int j = en - i * (i + 1) / 2;
+        s.H[en] *= s.hscale[i] * s.hscale[j];
+      }
+      __syncwarp();
+    }
     T sr;
-    if (decoupled) { cholesky_blocks(s.H, lane); sr = chol_solve_blocks(s.H, -gl, lane); }
-    else { cholesky_packed(s.H, lane); sr = chol_solve_packed(s.H, -gl, lane); }
+    if (decoupled) { cholesky_blocks(s.H, lane); sr = chol_solve_blocks(s.H, -gl * hs, lane); }
+    else { cholesky_packed(s.H, lane); sr = chol_solve_packed(s.H, -gl * hs, lane); }
+    sr *= hs;
     if (lane < NV) s.search[lane] = sr;
     __syncwarp();
     contacts_Jx<T>(s, s.search, lane);

@@ -4,13 +4,20 @@ import pytest
 
 from oracle.oracle import OracleSim
 
+import json
+import os
+
 # KAT-1: reference so101_rl.ipynb:219-229 — one env.step from arm qpos = 0 with calibration offsets applied
-# (run from the repo root, calibration/red_arm.json:5-40) and action [0,0,0,0,0,0.5].
-KAT1_OFFSETS = [28, 42, 18, -21, 1009, -158]
-KAT1_ACTION = [0, 0, 0, 0, 0, 0.5]
-KAT1_COMMANDED = [28, 42, 18, -21, 1009, -157.5]
-KAT1_QPOS = np.array([5.85192160e-02, 5.80983147e-02, 6.58658498e-02, -8.00624348e-02, 7.67682376e-02, -7.65953670e-02])
-KAT1_QVEL = np.array([5.32876236, 5.27619008, 5.98870371, -7.27788632, 6.97910317, -6.96330033])
+# (run from the repo root, calibration/red_arm.json:5-40) and action [0,0,0,0,0,0.5].  The fixture is the notebook's
+# printed output, extracted by tools/make_golden.py.
+_G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+KAT1 = json.load(open(os.path.join(_G, 'kat1_so101_rl.json')))
+KAT2 = json.load(open(os.path.join(_G, 'kat2_reset_observation.json')))
+KAT1_OFFSETS = KAT1['calibration_offsets']
+KAT1_ACTION = KAT1['action']
+KAT1_COMMANDED = KAT1['commanded_joints_pos']
+KAT1_QPOS = np.array(KAT1['physics_state'][:6])
+KAT1_QVEL = np.array(KAT1['physics_state'][20:26])
 
 
 @pytest.mark.parametrize('model', ['so100_arm', 'so100_handover_banana'])
@@ -29,3 +36,35 @@ def test_kat1_sensitivity_friction_rows_matter():
   s = OracleSim('so100_arm', collide=False)
   s.control_step(KAT1_ACTION, offsets=[0] * 6)  # unsaturated actuators -> different state
   assert np.abs(s.qpos[:6] - KAT1_QPOS).max() > 1e-3
+
+
+def test_kat1_fixture_is_the_notebook_printout():
+  assert KAT1_COMMANDED == [28, 42, 18, -21, 1009, -157.5] and KAT1['joints_pos'] == [0.0] * 6 and KAT1['joints_vel'] == []
+  assert len(KAT1['physics_state']) == 38 and len(KAT1['delayed_physics_state']) == 38
+  np.testing.assert_allclose(KAT1_QPOS[0], 5.85192160e-02, rtol=1e-9)
+  # state BEFORE the step (delayed_physics_state): arm at qpos 0, props at rest on the table
+  before = np.array(KAT1['delayed_physics_state'])
+  assert np.all(before[:6] == 0) and abs(before[8] - 0.4217) < 1e-3 and abs(before[15] - 0.4226) < 1e-3
+
+
+def test_kat1_props_stay_at_rest_in_the_oracle():
+  """From the notebook's own pre-step state the props must barely move during the step (reference: |dz| < 1e-6)."""
+  s = OracleSim('so100_handover_banana', collide=True)
+  before = np.array(KAT1['delayed_physics_state'])
+  s.set_state(before[:20], before[20:])
+  s.control_step(KAT1_ACTION, offsets=KAT1_OFFSETS)
+  after = np.array(KAT1['physics_state'])
+  np.testing.assert_allclose(s.qpos[:6], after[:6], rtol=2e-9)   # arm: exact pin
+  # props: the stand-in inertia meshes and the unpinned contact pipeline only allow an approximate pin (rest pose within 1 mm)
+  assert np.abs(s.qpos[6:9] - after[6:9]).max() < 1e-3 and np.abs(s.qpos[13:16] - after[13:16]).max() < 1e-3
+
+
+def test_kat2_reset_observation_semantics():
+  """examples/so101_rl_breakdown.ipynb:274-298 — zero offsets: commanded = HOME_CTRL, arm qpos = 0, joints_vel empty."""
+  from so101_sim_b200.task_suite import OBSERVATION_KEYS, SO100_HOME_CTRL
+  np.testing.assert_allclose(KAT2['commanded_joints_pos'], SO100_HOME_CTRL, atol=1e-5)
+  assert KAT2['joints_pos'] == [0.0] * 6 and KAT2['joints_vel'] == [] and KAT2['undelayed_joints_vel'] == []
+  assert KAT2['physics_state'] == KAT2['delayed_physics_state'] and KAT2['physics_state'][:6] == [0.0] * 6
+  assert tuple(k for k in KAT2['observation_keys'] if not k.endswith('_cam')) == OBSERVATION_KEYS
+  # printed action bounds (2 decimals): +-3.14 for the five arm joints, [0, 0.08] for the jaw
+  assert KAT2['action_spec']['minimum'] == [-3.14] * 5 + [0.0] and KAT2['action_spec']['maximum'] == [3.14] * 5 + [0.08]

@@ -202,6 +202,7 @@ struct Handle : HandleBase {
     d_steptype = dalloc<uint8_t>(N);
     if (scene) {  // inter-kernel scratch of the scene pipeline
       if (b.scalar("ngeom") > GMAX_GEOMS) throw std::runtime_error("model has more geoms than the broad phase can hold");
+      if (b.scalar("nbody") > 16) throw std::runtime_error("model has more bodies than the broad phase can hold");
       if (b.scalar("ngeom") > WQ) throw std::runtime_error("model has more geoms than narrow-phase work queues");
       pipe.xpos = dalloc<T>(N * NSLOT * 3); pipe.xmat = dalloc<T>(N * NSLOT * 9);
       pipe.con = dalloc<T>(N * CONBUF * 8); pipe.con_key = dalloc<int>(N * CONBUF); pipe.ncon_raw = dalloc<int>(N);

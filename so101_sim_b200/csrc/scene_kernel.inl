@@ -36,7 +36,7 @@ constexpr int WARPS_SOLVE = 2;   // envs (warps) per CTA in the begin / solve ke
 constexpr int NC_S = 32, NB_S = 40;            // tier 0: every env, 2 warps per CTA
 constexpr int NC_M = 64, NB_M = 80;            // tier 1
 constexpr int NC_L = CONBUF, NB_L = CONBUF + 32;  // tier 2 (last: excess contacts are dropped and counted)
-constexpr int WARPS_M = 2, WARPS_L = 1;
+constexpr int WARPS_M = 1, WARPS_L = 1;  // single-warp CTAs: small enough to co-reside with tier-0 CTAs on an SM
 
 constexpr int GMAX = GMAX_GEOMS;  // geoms the broad phase can hold (model: 83 colliding geoms)
 constexpr int CANDCAP = 256;  // geom pairs that may survive the bounding-sphere test per env
@@ -47,6 +47,7 @@ struct BroadScratch {
   unsigned cand[CANDCAP];
   T gcenter[3][GMAX];                  // world bounding-sphere centres of all geoms
   T opos[3][GMAX], omat[9][GMAX];      // world oriented boxes (geom AABB in the geom frame) of all geoms
+  T bcenter[3][16];                    // world bounding-sphere centres of the bodies
 };
 
 // per-env scratch of the begin / solve kernels (NC contacts, NB Jacobian blocks)
@@ -276,50 +277,61 @@ __device__ __noinline__ void scene_broadphase(const SceneModel<T> &sm, S &s, con
     for (int c = 0; c < 9; c++) cs.omat[c][g] = mat[c];
   }
   __syncwarp();
-  // phase 1: body-pair spheres, then geom-pair spheres -> candidate list (order kept: broad-phase order == oracle order)
+  // phase 1: body-pair spheres (lane per body pair), then geom-pair spheres over the static pair list of the surviving body
+  // pairs -> candidate list (order kept: broad-phase order == oracle order)
+  for (int bdy = lane; bdy < sm.nbody; bdy += 32) {  // world bounding-sphere centres of the bodies
+    const int sl = sm.body_slot[bdy];
+    const T bc[3] = {sm.body_bcenter[3 * bdy], sm.body_bcenter[3 * bdy + 1], sm.body_bcenter[3 * bdy + 2]};
+    T c[3] = {bc[0], bc[1], bc[2]};
+    if (sl >= 0) { T t[3]; mulmv(t, s.xmat[sl], bc); for (int e = 0; e < 3; e++) c[e] = s.xpos[sl][e] + t[e]; }
+    cs.bcenter[0][bdy] = c[0]; cs.bcenter[1][bdy] = c[1]; cs.bcenter[2][bdy] = c[2];
+  }
+  __syncwarp();
   int ncand = 0;
 #pragma unroll 1
-  for (int p = 0; p < sm.npair; p++) {  // uniform loop
-    const int b1 = sm.bodypair[2 * p], b2 = sm.bodypair[2 * p + 1];
-    if (b1 != 0) {
-      T c1[3], c2[3], t[3];
-      const int s1 = sm.body_slot[b1], s2 = sm.body_slot[b2];
-      for (int k = 0; k < 2; k++) {
-        const int b = k ? b2 : b1, sl = k ? s2 : s1;
-        T *c = k ? c2 : c1;
-        const T bc[3] = {sm.body_bcenter[3 * b], sm.body_bcenter[3 * b + 1], sm.body_bcenter[3 * b + 2]};
-        if (sl < 0) { c[0] = bc[0]; c[1] = bc[1]; c[2] = bc[2]; }
-        else { mulmv(t, s.xmat[sl], bc); for (int e = 0; e < 3; e++) c[e] = s.xpos[sl][e] + t[e]; }
+  for (int p0 = 0; p0 < sm.npair; p0 += 32) {
+    const int p = p0 + lane;
+    bool live = false;
+    if (p < sm.npair) {
+      const int b1 = sm.bodypair[2 * p], b2 = sm.bodypair[2 * p + 1];
+      live = true;
+      if (b1 != 0) {  // (the world body holds only the floor plane: always descend)
+        const T t[3] = {cs.bcenter[0][b1] - cs.bcenter[0][b2], cs.bcenter[1][b1] - cs.bcenter[1][b2], cs.bcenter[2][b1] - cs.bcenter[2][b2]};
+        const T r = sm.body_rbound[b1] + sm.body_rbound[b2];
+        live = !(dot3(t, t) > r * r);
       }
-      sub3(t, c1, c2);
-      const T r = sm.body_rbound[b1] + sm.body_rbound[b2];
-      if (dot3(t, t) > r * r) continue;
     }
-    const int a1 = sm.body_geomadr[b1], n1 = sm.body_geomnum[b1], a2 = sm.body_geomadr[b2], n2 = sm.body_geomnum[b2];
-    const int total = n1 * n2;
+    unsigned livemask = __ballot_sync(FULL, live);
 #pragma unroll 1
-    for (int base = 0; base < total; base += 32) {
-      const int k = base + lane;
-      bool keep = false;
-      int g1 = 0, g2 = 0;
-      if (k < total) {
-        g1 = a1 + k / n2; g2 = a2 + k % n2;
-        const T cB[3] = {cs.gcenter[0][g2], cs.gcenter[1][g2], cs.gcenter[2][g2]};
-        const T rB = sm.geom_rbound[g2];
-        if (sm.geom_type[g1] == G_PLANE) {
-          const T n[3] = {sm.geom_mat[9 * g1 + 2], sm.geom_mat[9 * g1 + 5], sm.geom_mat[9 * g1 + 8]};
-          const T pp[3] = {sm.geom_pos[3 * g1], sm.geom_pos[3 * g1 + 1], sm.geom_pos[3 * g1 + 2]};
-          keep = !(dot3(n, cB) - dot3(n, pp) - rB > T(0));
-        } else {
-          const T t[3] = {cs.gcenter[0][g1] - cB[0], cs.gcenter[1][g1] - cB[1], cs.gcenter[2][g1] - cB[2]};
-          const T r = sm.geom_rbound[g1] + rB;
-          keep = !(dot3(t, t) > r * r);
+    while (livemask) {
+      const int pp = p0 + __ffs(livemask) - 1;
+      livemask &= livemask - 1;
+      const int k0 = sm.pair_start[pp], k1 = sm.pair_start[pp + 1];
+#pragma unroll 1
+      for (int base = k0; base < k1; base += 32) {
+        const int k = base + lane;
+        bool keep = false;
+        unsigned gp = 0;
+        if (k < k1) {
+          gp = sm.geompair[k];
+          const int g1 = (int)(gp & 0xff), g2 = (int)(gp >> 8);
+          const T cB[3] = {cs.gcenter[0][g2], cs.gcenter[1][g2], cs.gcenter[2][g2]};
+          const T rB = sm.geom_rbound[g2];
+          if (sm.geom_type[g1] == G_PLANE) {
+            const T n[3] = {sm.geom_mat[9 * g1 + 2], sm.geom_mat[9 * g1 + 5], sm.geom_mat[9 * g1 + 8]};
+            const T pp3[3] = {sm.geom_pos[3 * g1], sm.geom_pos[3 * g1 + 1], sm.geom_pos[3 * g1 + 2]};
+            keep = !(dot3(n, cB) - dot3(n, pp3) - rB > T(0));
+          } else {
+            const T t[3] = {cs.gcenter[0][g1] - cB[0], cs.gcenter[1][g1] - cB[1], cs.gcenter[2][g1] - cB[2]};
+            const T r = sm.geom_rbound[g1] + rB;
+            keep = !(dot3(t, t) > r * r);
+          }
         }
+        const unsigned m = __ballot_sync(FULL, keep);
+        const int idx = ncand + __popc(m & ((1u << lane) - 1));
+        if (keep && idx < CANDCAP) cs.cand[idx] = gp;
+        ncand += __popc(m);
       }
-      const unsigned m = __ballot_sync(FULL, keep);
-      const int idx = ncand + __popc(m & ((1u << lane) - 1));
-      if (keep && idx < CANDCAP) cs.cand[idx] = (unsigned)g1 | ((unsigned)g2 << 8);
-      ncand += __popc(m);
     }
   }
   if (ncand > CANDCAP) { dropped += ncand - CANDCAP; if (lane == 0) DROPCAT(1, ncand - CANDCAP); ncand = CANDCAP; }
@@ -1004,7 +1016,7 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
       const int grid_gjk = max(1, min(sms * 8, (pb.nenv * 16 + GJK_THREADS - 1) / GJK_THREADS));
       static const int seq_per_sm = getenv("SO101_SEQ_CTAS") ? atoi(getenv("SO101_SEQ_CTAS")) : 16;  // CTAs of 64 threads per SM
       const int grid_seq = max(1, min(sms * seq_per_sm, (pb.nenv * 12 + NSEQ_THREADS - 1) / NSEQ_THREADS));
-      const int grid_m = pb.nenv < sms * 4 ? pb.nenv : sms * 4, grid_l = pb.nenv < sms * 2 ? pb.nenv : sms * 2;
+      const int grid_m = pb.nenv < sms * 8 ? pb.nenv : sms * 8, grid_l = pb.nenv < sms * 4 ? pb.nenv : sms * 4;
       t.begin(5, st);
       scene_gjk_kernel<T><<<grid_gjk, GJK_THREADS, 0, st>>>(sm, S, pb, sub);
       t.end(5, st);
@@ -1016,10 +1028,11 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
       // next kernel
       cudaEventRecord(tx.fork, st);
       cudaStreamWaitEvent(tx.sm, tx.fork, 0); cudaStreamWaitEvent(tx.sl, tx.fork, 0);
+      // largest tier first: its few, long envs should not start last
+      scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2><<<grid_l, WARPS_L * 32, smem_l, tx.sl>>>(am, sm, cfg, S, pb, out, sub);
       t.begin(3, tx.sm);
       scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1><<<grid_m, WARPS_M * 32, smem_m, tx.sm>>>(am, sm, cfg, S, pb, out, sub);
       t.end(3, tx.sm);
-      scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2><<<grid_l, WARPS_L * 32, smem_l, tx.sl>>>(am, sm, cfg, S, pb, out, sub);
       cudaEventRecord(tx.joinm, tx.sm); cudaEventRecord(tx.joinl, tx.sl);
       t.begin(2, st);
       scene_solve_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, st>>>(am, sm, cfg, S, pb, out, sub);

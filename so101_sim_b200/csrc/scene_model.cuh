@@ -36,6 +36,8 @@ struct SceneModel {
   const int *hull_nbradr, *hull_nbr;  // vertex adjacency: CSR offsets per global vertex id, local neighbour ids (hill-climbing support)
   // bodies
   const int *bodypair, *body_slot, *body_geomadr, *body_geomnum;
+  const int *pair_start;          // [npair + 1]  range of body pair p in geompair
+  const unsigned *geompair;       // static candidate geom pairs (g1 | g2 << 8) in broad-phase order (pair-major, g1-major)
   const T *body_bcenter, *body_rbound, *body_invweight0;  // static bodies: bcenter in the world frame
   // free props
   T prop_mass[NPROP], prop_ipos[NPROP][3], prop_Icom[NPROP][6], prop_Iorg[NPROP][6];  // inertia about COM / body origin, body axes
@@ -177,6 +179,18 @@ struct SceneModelHost {
     d.geom_friction = up(cvt(b.F("geom_friction"))); d.geom_solref = up(cvt(b.F("geom_solref"))); d.geom_solimp = up(cvt(b.F("geom_solimp")));
     d.geom_solmix = up(cvt(b.F("geom_solmix"))); d.geom_margin = up(cvt(b.F("geom_margin"))); d.geom_gap = up(cvt(b.F("geom_gap")));
     d.hull_vert = up(verts); d.hull_nbradr = up(b.I("hull_nbradr")); d.hull_nbr = up(b.I("hull_nbr"));
+    {
+      std::vector<int> pstart; std::vector<unsigned> gpairs;
+      const auto &bpv = b.I("bodypair"), &ga = b.I("body_geomadr"), &gn = b.I("body_geomnum");
+      for (size_t p = 0; p < bpv.size() / 2; p++) {
+        pstart.push_back((int)gpairs.size());
+        const int b1 = bpv[2 * p], b2 = bpv[2 * p + 1];
+        for (int g1 = ga[b1]; g1 < ga[b1] + gn[b1]; g1++)
+          for (int g2 = ga[b2]; g2 < ga[b2] + gn[b2]; g2++) gpairs.push_back((unsigned)g1 | ((unsigned)g2 << 8));
+      }
+      pstart.push_back((int)gpairs.size());
+      d.pair_start = up(pstart); d.geompair = up(gpairs);
+    }
     d.bodypair = up(b.I("bodypair")); d.body_slot = up(slot); d.body_geomadr = up(b.I("body_geomadr")); d.body_geomnum = up(b.I("body_geomnum"));
     d.body_bcenter = up(cvt(bbc)); d.body_rbound = up(cvt(b.F("body_rbound"))); d.body_invweight0 = up(cvt(b.F("body_invweight0")));
     for (int p = 0; p < NPROP; p++) {

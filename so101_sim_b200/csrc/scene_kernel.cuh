@@ -13,6 +13,7 @@ namespace so101 {
 // Scene-kernel state layout is array-of-rows ([N][nq] etc.): one warp owns one env and reads its row with one
 // coalesced request (the arm-only kernel, one THREAD per env, uses [k][N] instead).
 
+constexpr int KINW = 128;             // floats per env in PipeBuf::kin (ArmKin 90 + anchors 18 + axes 18)
 constexpr int GMAX_GEOMS = 96;       // geoms per model the broad phase holds in shared memory
 constexpr int WQ = 128;             // work queues (>= ngeom)
 constexpr int WSTRIDE = WQ + 8;     // counters per substep
@@ -31,6 +32,8 @@ struct HitRec {
 template <typename T>
 struct PipeBuf {
   T *xpos, *xmat;           // [N][NSLOT*3], [N][NSLOT*9]  world poses of the 8 dynamic bodies
+  T *kin;                   // [N][KINW]  arm kinematic state (ArmKin, joint anchors, axes) at the current qpos: written by the
+                            //   kinematics that follows each integration, re-used by the next substep's dynamics
   uint2 *work;              // [WQ][work_cap]  narrow-phase work queues, one per second geom g2 (so that consecutive items
                             //   collide the same hull): (env, g1 | g2 << 8 | pair index << 16)
   int work_cap;             // entries per queue

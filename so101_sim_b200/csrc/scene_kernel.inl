@@ -120,6 +120,18 @@ __device__ __noinline__ void scene_kinematics(const ArmModelT<T> &am, S &s, int 
   __syncwarp();
 }
 
+// poses and arm kinematic state published by the previous kernel's broad phase (same qpos) -> shared memory
+template <typename T, typename S>
+__device__ __forceinline__ void load_kinematics(const PipeBuf<T> &pb, S &s, int env, int lane) {
+  const T *gx = pb.xpos + (size_t)env * (NSLOT * 3), *gm = pb.xmat + (size_t)env * (NSLOT * 9), *gk = pb.kin + (size_t)env * KINW;
+  for (int i = lane; i < NSLOT * 3; i += 32) (&s.xpos[0][0])[i] = gx[i];
+  for (int i = lane; i < NSLOT * 9; i += 32) (&s.xmat[0][0])[i] = gm[i];
+  T *kk = reinterpret_cast<T *>(&s.kin);
+  for (int i = lane; i < 90; i += 32) kk[i] = gk[i];
+  if (lane < 18) { (&s.arm_p[0][0])[lane] = gk[90 + lane]; (&s.arm_a[0][0])[lane] = gk[108 + lane]; }
+  __syncwarp();
+}
+
 // free-joint mass block (packed lower 6x6) and bias force for prop p (uniform; [upstream] mj_crb / mj_rne for a free body)
 template <typename T, typename S>
 __device__ __forceinline__ void prop_dynamics(const SceneModel<T> &sm, const ArmModelT<T> &am, const S &s, int p, T (&M)[21], T (&bias)[6]) {
@@ -257,6 +269,12 @@ __device__ __noinline__ void scene_broadphase(const SceneModel<T> &sm, S &s, con
     T *gx = pb.xpos + (size_t)env * (NSLOT * 3), *gm = pb.xmat + (size_t)env * (NSLOT * 9);
     for (int i = lane; i < NSLOT * 3; i += 32) gx[i] = (&s.xpos[0][0])[i];
     for (int i = lane; i < NSLOT * 9; i += 32) gm[i] = (&s.xmat[0][0])[i];
+    // ... and the arm's kinematic state for the next substep's dynamics (same qpos: no second forward-kinematics pass)
+    static_assert(sizeof(ArmKin<T>) == 90 * sizeof(T), "ArmKin layout");
+    T *gk = pb.kin + (size_t)env * KINW;
+    const T *kk = reinterpret_cast<const T *>(&s.kin);
+    for (int i = lane; i < 90; i += 32) gk[i] = kk[i];
+    if (lane < 18) { gk[90 + lane] = (&s.arm_p[0][0])[lane]; gk[108 + lane] = (&s.arm_a[0][0])[lane]; }
   }
   // world bounding spheres and oriented boxes of all geoms (lane per geom)
 #pragma unroll 1
@@ -772,7 +790,7 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
   __syncwarp();
   if (!frozen) {
     PROF_CNT(s, P_NCON, s.ncon, lane);
-    scene_kinematics(am, s, lane);
+    load_kinematics(pb, s, env, lane);
     {
       T qa[NJ], qda[NJ], ca[NJ], M[21], bias[NJ], frc[NJ], qs[NJ];
   #pragma unroll

@@ -18,8 +18,8 @@
 #include "so101_oracle.h"
 
 #define MINVAL 1e-15
-#define MAXFEAT 32  /* vertices kept per supporting feature */
-#define MAXCAND 64  /* slab candidates examined per feature (first ones in vertex order) */
+#define MAXFEAT 16  /* vertices kept per supporting feature */
+#define MAXCAND 32  /* slab candidates of a primitive / small hull feature (the exact-hull path) */
 #define MAXMANIFOLD 4
 
 typedef struct {
@@ -313,20 +313,66 @@ static int epa(const shape *A, const shape *B, mpoint *S, int n, double *normal,
 /* ------------------------------------------------------------------------------------------ support features */
 typedef struct { double x, y, h; } fpt; /* tangent-plane coordinates and height along the direction */
 
+/* Large hull features (more than FEAT_EXACT slab vertices: rims and finely tessellated patches) are represented by their
+   extreme points along FEAT_DIRS tangent-plane directions, counter-clockwise from -x (where the monotone chain of the
+   exact path starts as well): an inscribed convex polygon found in the same pass that counts the slab, with no storage,
+   sort or hull construction.  Small features (faces, edges, vertices) keep the exact 2-D hull. */
+#define FEAT_EXACT 16
+#define FEAT_DIRS 16
+static const double FEAT_COS[8] = {1.0, 0.92387953251128674, 0.70710678118654752, 0.38268343236508977, 0.0,
+                                   -0.38268343236508977, -0.70710678118654752, -0.92387953251128674};
+static const double FEAT_SIN[8] = {0.0, 0.38268343236508977, 0.70710678118654752, 0.92387953251128674, 1.0,
+                                   0.92387953251128674, 0.70710678118654752, 0.38268343236508977};
+
 /* vertices of `s` whose height along dir (unit) is within delta of the maximum -> 2-D convex polygon (CCW) with heights */
 static int feature(const shape *s, const double *dir, const double *t1, const double *t2, double delta, fpt *out) {
   double cand[MAXCAND][3];
-  int nc = 0;
+  fpt P[MAXCAND];
+  int nc = 0, projected = 0;
   double sp[3];
   support(s, dir, sp);
   double hmax = dot3(sp, dir);
   double w[3];
   switch (s->type) {
     case SO_GEOM_HULL: {
-      double dl[3]; mulmtv(dl, s->mat, dir);
-      double off = dot3(s->pos, dir);
-      for (int i = 0; i < s->nvert && nc < MAXCAND; i++)
-        if (dot3(s->vert + 3 * i, dl) + off >= hmax - delta) { local2world(s, s->vert + 3 * i, cand[nc]); nc++; }
+      /* tangent-plane coordinates are evaluated in the hull frame: x = v . (R^T t1) + pos . t1 */
+      double dl[3], t1l[3], t2l[3];
+      mulmtv(dl, s->mat, dir); mulmtv(t1l, s->mat, t1); mulmtv(t2l, s->mat, t2);
+      double off = dot3(s->pos, dir), ox = dot3(s->pos, t1), oy = dot3(s->pos, t2);
+      double emax[8], emin[8]; int imax[8], imin[8], nband = 0;
+      for (int k = 0; k < 8; k++) { emax[k] = -INFINITY; emin[k] = INFINITY; imax[k] = imin[k] = 0; }
+      for (int i = 0; i < s->nvert; i++) {
+        const double *v = s->vert + 3 * i;
+        if (!(dot3(v, dl) + off >= hmax - delta)) continue;
+        nband++;
+        double x = dot3(v, t1l) + ox, y = dot3(v, t2l) + oy;
+        for (int k = 0; k < 8; k++) {
+          double val = FEAT_COS[k] * x + FEAT_SIN[k] * y;
+          if (val > emax[k]) { emax[k] = val; imax[k] = i; }
+          if (val < emin[k]) { emin[k] = val; imin[k] = i; }
+        }
+      }
+      if (nband > FEAT_EXACT) {
+        /* direction j (angle pi + j * 2 pi / 16): j < 8 -> minimum along direction j, else maximum along direction j - 8 */
+        int kept[FEAT_DIRS], nk = 0;
+        for (int j = 0; j < FEAT_DIRS; j++) {
+          int idx = j < 8 ? imin[j] : imax[j - 8], dup = 0;
+          for (int q = 0; q < nk; q++) if (kept[q] == idx) dup = 1;
+          if (!dup) kept[nk++] = idx;
+        }
+        for (int q = 0; q < nk; q++) {
+          const double *v = s->vert + 3 * kept[q];
+          out[q].x = dot3(v, t1l) + ox; out[q].y = dot3(v, t2l) + oy; out[q].h = dot3(v, dl) + off;
+        }
+        return nk;
+      }
+      for (int i = 0; i < s->nvert && nc < MAXCAND; i++) {
+        const double *v = s->vert + 3 * i;
+        double h = dot3(v, dl) + off;
+        if (!(h >= hmax - delta)) continue;
+        P[nc].x = dot3(v, t1l) + ox; P[nc].y = dot3(v, t2l) + oy; P[nc].h = h; nc++;
+      }
+      if (nc > 0) projected = 1;
       break;
     }
     case SO_GEOM_BOX:
@@ -357,8 +403,8 @@ static int feature(const shape *s, const double *dir, const double *t1, const do
   }
   if (nc == 0) { memcpy(cand[0], sp, sizeof sp); nc = 1; }
   /* project and take the 2-D convex hull (Andrew's monotone chain) */
-  fpt P[MAXCAND];
-  for (int i = 0; i < nc; i++) { P[i].x = dot3(cand[i], t1); P[i].y = dot3(cand[i], t2); P[i].h = dot3(cand[i], dir); }
+  if (!projected)
+    for (int i = 0; i < nc; i++) { P[i].x = dot3(cand[i], t1); P[i].y = dot3(cand[i], t2); P[i].h = dot3(cand[i], dir); }
   for (int i = 1; i < nc; i++) { /* insertion sort by (x, y) */
     fpt k = P[i]; int j = i - 1;
     while (j >= 0 && (P[j].x > k.x || (P[j].x == k.x && P[j].y > k.y))) { P[j + 1] = P[j]; j--; }

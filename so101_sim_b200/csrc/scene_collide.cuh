@@ -12,7 +12,18 @@ constexpr int NCON = 64;         // contacts per env the parity probe (debug_con
 constexpr int PAIRCAP = 64;      // candidate geom pairs per env per substep (after the OBB mid phase)
 constexpr int CONBUF = 128;      // raw contacts per env the narrow phase may write between two kernels
 constexpr int EPA_MAXV = 96, EPA_MAXF = 256;
-constexpr int MAXCAND = 64, MAXFEAT = 32, MAXMANI = 4;
+constexpr int MAXCAND = 32, MAXFEAT = 16, MAXMANI = 4;
+// Hull slabs with more than FEAT_EXACT vertices are represented by their extreme points along 16 tangent-plane directions
+// (scene_collide_seq.cuh feature_seq; oracle/so101_collide.c feature()); smaller ones keep the exact 2-D hull.
+constexpr int FEAT_EXACT = 16;
+template <typename T> __device__ __forceinline__ constexpr T feat_cos(int k) {
+  return k == 0 ? T(1.0) : k == 1 ? T(0.92387953251128674) : k == 2 ? T(0.70710678118654752) : k == 3 ? T(0.38268343236508977) : k == 4 ? T(0.0)
+       : k == 5 ? T(-0.38268343236508977) : k == 6 ? T(-0.70710678118654752) : T(-0.92387953251128674);
+}
+template <typename T> __device__ __forceinline__ constexpr T feat_sin(int k) {
+  return k == 0 ? T(0.0) : k == 1 ? T(0.38268343236508977) : k == 2 ? T(0.70710678118654752) : k == 3 ? T(0.92387953251128674) : k == 4 ? T(1.0)
+       : k == 5 ? T(0.92387953251128674) : k == 6 ? T(0.70710678118654752) : T(0.38268343236508977);
+}
 constexpr unsigned FULL = 0xffffffffu;
 
 template <typename T>

@@ -169,20 +169,66 @@ __device__ __noinline__ int feature_seq(const SceneModel<T> &sm, CollideScratch<
   const T hmax = dot3(sp, dir);
   int nc = 0;
   T w[3];
+  bool projected = false;
+  FPt<T> *sorted = cs.bufA;  // nc <= MAXCAND <= size of bufA
   if (s.type == G_HULL) {
-    T dl[3];
-    mulmtv(dl, s.mat, dir);
-    const T off = dot3(s.pos, dir);
+    // tangent-plane coordinates are evaluated in the hull frame: x = v . (R^T t1) + pos . t1  (as the oracle does)
+    T dl[3], t1l[3], t2l[3];
+    mulmtv(dl, s.mat, dir); mulmtv(t1l, s.mat, t1); mulmtv(t2l, s.mat, t2);
+    const T off = dot3(s.pos, dir), ox = dot3(s.pos, t1), oy = dot3(s.pos, t2);
     const Vec4<T> *vt = sm.hull_vert + s.vadr;
+    // pass 1: count the slab and track its extreme vertices along 16 tangent-plane directions (8 axes, min and max), all in
+    // registers.  A slab with more than FEAT_EXACT vertices (rims, finely tessellated patches) is represented by those
+    // extremes - an inscribed convex polygon, counter-clockwise from -x - with no candidate storage, sort or hull pass.
+    T emax[8], emin[8];
+    int imax[8], imin[8], nband = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { emax[k] = -INFINITY; emin[k] = INFINITY; imax[k] = imin[k] = 0; }
+    const T thr = hmax - delta;
 #pragma unroll 2
     for (int i = 0; i < s.vnum; i++) {
       const Vec4<T> v = vt[i];
-      if ((v.x * dl[0] + v.y * dl[1] + v.z * dl[2]) + off >= hmax - delta && nc < MAXCAND) {
-        const T l[3] = {v.x, v.y, v.z};
-        local2world(s, l, w);
-        cs.cand[0][nc] = w[0]; cs.cand[1][nc] = w[1]; cs.cand[2][nc] = w[2]; nc++;
+      if (!((v.x * dl[0] + v.y * dl[1] + v.z * dl[2]) + off >= thr)) continue;
+      nband++;
+      const T x = (v.x * t1l[0] + v.y * t1l[1] + v.z * t1l[2]) + ox, y = (v.x * t2l[0] + v.y * t2l[1] + v.z * t2l[2]) + oy;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const T val = feat_cos<T>(k) * x + feat_sin<T>(k) * y;
+        if (val > emax[k]) { emax[k] = val; imax[k] = i; }
+        if (val < emin[k]) { emin[k] = val; imin[k] = i; }
       }
     }
+    if (nband > FEAT_EXACT) {
+      int kept[16], nk = 0;
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int idx = j < 8 ? imin[j] : imax[j - 8];
+        bool dup = false;
+#pragma unroll
+        for (int q = 0; q < j; q++) dup = dup || (q < nk && kept[q] == idx);
+        if (!dup) {
+          // kept[] is indexed statically so that it stays in registers: slot nk is found by unrolled selection
+#pragma unroll
+          for (int q = 0; q < 16; q++) if (q == nk) kept[q] = idx;
+          const Vec4<T> v = vt[idx];
+          out[nk].x = (v.x * t1l[0] + v.y * t1l[1] + v.z * t1l[2]) + ox;
+          out[nk].y = (v.x * t2l[0] + v.y * t2l[1] + v.z * t2l[2]) + oy;
+          out[nk].h = (v.x * dl[0] + v.y * dl[1] + v.z * dl[2]) + off;
+          nk++;
+        }
+      }
+      return nk;
+    }
+    // pass 2 (small slab): the candidates themselves, in vertex order
+#pragma unroll 2
+    for (int i = 0; i < s.vnum && nc < nband; i++) {
+      const Vec4<T> v = vt[i];
+      const T h = (v.x * dl[0] + v.y * dl[1] + v.z * dl[2]) + off;
+      if (!(h >= thr)) continue;
+      const T x = (v.x * t1l[0] + v.y * t1l[1] + v.z * t1l[2]) + ox, y = (v.x * t2l[0] + v.y * t2l[1] + v.z * t2l[2]) + oy;
+      cs.cand[0][nc] = x; cs.cand[1][nc] = y; cs.cand[2][nc] = h; nc++;
+    }
+    projected = nc > 0;
   } else if (s.type == G_BOX) {
 #pragma unroll 1
     for (int i = 0; i < 8; i++) {
@@ -212,11 +258,10 @@ __device__ __noinline__ int feature_seq(const SceneModel<T> &sm, CollideScratch<
   }
   if (nc == 0) { cs.cand[0][0] = sp[0]; cs.cand[1][0] = sp[1]; cs.cand[2][0] = sp[2]; nc = 1; }
   // project, then stable insertion sort by (x, y) [ties keep candidate order] into bufA
-  FPt<T> *sorted = cs.bufA;  // nc <= MAXCAND <= size of bufA
 #pragma unroll 1
   for (int i = 0; i < nc; i++) {
     const T cw[3] = {cs.cand[0][i], cs.cand[1][i], cs.cand[2][i]};
-    const FPt<T> p = {dot3(cw, t1), dot3(cw, t2), dot3(cw, dir)};
+    const FPt<T> p = projected ? FPt<T>{cw[0], cw[1], cw[2]} : FPt<T>{dot3(cw, t1), dot3(cw, t2), dot3(cw, dir)};
     int j = i;
     while (j > 0 && (p.x < sorted[j - 1].x || (p.x == sorted[j - 1].x && p.y < sorted[j - 1].y))) { sorted[j] = sorted[j - 1]; j--; }
     sorted[j] = p;

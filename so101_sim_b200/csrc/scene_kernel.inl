@@ -667,9 +667,9 @@ __global__ void __launch_bounds__(GJK_THREADS) scene_gjk_kernel(const __grid_con
 }
 
 // Per substep, ONE THREAD per intersecting pair: EPA -> manifold (scene_collide_seq.cuh), contacts to the env's raw buffer.
-constexpr int NSEQ_THREADS = 64;
+constexpr int NSEQ_THREADS = 64, NSEQ_MINCTAS = 12;
 template <typename T>
-__global__ void __launch_bounds__(NSEQ_THREADS) scene_narrow_seq_kernel(const __grid_constant__ SceneModel<T> sm, const EnvState<T> S, const PipeBuf<T> pb, int sub) {
+__global__ void __launch_bounds__(NSEQ_THREADS, NSEQ_MINCTAS) scene_narrow_seq_kernel(const __grid_constant__ SceneModel<T> sm, const EnvState<T> S, const PipeBuf<T> pb, int sub) {
   const int lane = threadIdx.x & 31;
   int *cnt = pb.nwork + WSTRIDE * sub;
   const int nhit = min(cnt[W_NHIT], pb.hit_cap);

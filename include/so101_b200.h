@@ -78,6 +78,11 @@ int so101_dims(so101_handle h, int *nq, int *nv, int *nu, int *nbody);
 /* Install per-env initial states (row-major [N,nq], [N,nv] device pointers).  These are the states an env returns to on
  * reset; replaces the pose sampling of initialize_episode (so100_task.py:304-320, so100_hand_over.py:320-323). */
 int so101_set_initial_state(so101_handle h, const float *qpos_dev, const float *qvel_dev, void *stream);
+/* Install a POOL of `rounds` initial states per env (row-major [rounds,N,nq], [rounds,N,nv] device pointers): episode e of an
+ * env (counted from this call) starts from pool entry e % rounds, so consecutive episodes see different sampled-and-settled
+ * prop placements, as the reference re-samples them in every initialize_episode (so100_hand_over.py:208-229,320-323 with
+ * the distributions :37-55).  Replaces the single state of so101_set_initial_state. */
+int so101_set_reset_pool(so101_handle h, const float *qpos_dev, const float *qvel_dev, int rounds, void *stream);
 /* replaces composer.Environment.reset(): envs with mask[i] != 0 (all when mask_dev == NULL) go back to their initial
  * state, ctrl = home + offsets, delay buffers refilled with the initial value, step counter 0.  Writes the FIRST
  * TimeStep blocks of `out` for the reset envs. */

@@ -25,7 +25,7 @@ class Config(ctypes.Structure):
 
 EXPORTS = ('so101_abi_version', 'so101_create', 'so101_destroy', 'so101_last_error', 'so101_dims', 'so101_set_initial_state',
            'so101_reset', 'so101_step', 'so101_get_state', 'so101_set_state', 'so101_get_state_f64', 'so101_step_host',
-           'so101_counters', 'so101_debug_read', 'so101_kernel_times')
+           'so101_counters', 'so101_debug_read', 'so101_kernel_times', 'so101_set_reset_pool')
 
 _lib = None
 
@@ -46,6 +46,7 @@ def load() -> ctypes.CDLL:
   L.so101_dims.restype = ci; L.so101_dims.argtypes = [vp] + [ctypes.POINTER(ci)] * 4
   for f in ('so101_set_initial_state', 'so101_set_state', 'so101_get_state', 'so101_get_state_f64'):
     getattr(L, f).restype = ci; getattr(L, f).argtypes = [vp, vp, vp, vp]
+  L.so101_set_reset_pool.restype = ci; L.so101_set_reset_pool.argtypes = [vp, vp, vp, ci, vp]
   L.so101_reset.restype = ci; L.so101_reset.argtypes = [vp, vp, ctypes.POINTER(StepOut), vp]
   L.so101_step.restype = ci; L.so101_step.argtypes = [vp, vp, ctypes.POINTER(StepOut), vp]
   L.so101_step_host.restype = ci; L.so101_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp]

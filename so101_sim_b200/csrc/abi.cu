@@ -33,6 +33,7 @@ struct HandleBase {
   uint64_t launches = 0, steps = 0, dropped = 0;
   virtual ~HandleBase() { for (auto &t : tiers) t.destroy(); }
   virtual void set_state(const float *q, const float *v, bool initial, cudaStream_t s) = 0;
+  virtual void set_reset_pool(const float *q, const float *v, int rounds, cudaStream_t s) = 0;
   virtual void get_state(float *q, float *v, cudaStream_t s) = 0;
   virtual void get_state_f64(double *q, double *v, cudaStream_t s) = 0;
   virtual void reset(const uint8_t *mask, const so101_step_out &out, cudaStream_t s) = 0;
@@ -157,6 +158,7 @@ struct Handle : HandleBase {
   std::vector<PipeBuf<T>> groups;    // per-group queues / counters (views of `pipe` with their own work lists)
   StepCfg sc{};
   std::vector<void *> allocs;
+  size_t pool_cap = 1;
   float *d_action = nullptr, *d_reward = nullptr, *d_discount = nullptr, *d_jpos = nullptr;
   uint8_t *d_steptype = nullptr;
 
@@ -184,7 +186,7 @@ struct Handle : HandleBase {
     S.N = c.num_envs; S.nq = nq; S.nv = nv;
     S.qpos = dalloc<T>(nq * N); S.qvel = dalloc<T>(nv * N); S.warm = dalloc<T>(nv * N);
     S.init_qpos = dalloc<T>(nq * N); S.init_qvel = dalloc<T>(nv * N); S.ctrl = dalloc<T>(6 * N);
-    S.step = dalloc<int>(N); S.needs_reset = dalloc<uint8_t>(N);
+    S.step = dalloc<int>(N); S.needs_reset = dalloc<uint8_t>(N); S.episode = dalloc<int>(N); S.npool = 1;
     S.ring_joints = dalloc<float>((size_t)(c.joints_delay_steps + 1) * 6 * N);
     S.ring_phys = dalloc<float>((size_t)(c.physics_delay_steps + 1) * (nq + nv) * N);
     S.diverged_count = dalloc<int>(2); S.solver_iter = dalloc<int>(N); S.ncon = dalloc<int>(N);
@@ -234,8 +236,28 @@ struct Handle : HandleBase {
       launches += 1;
     };
     put(q, S.qpos, nq); put(v, S.qvel, nv);
-    if (initial) { put(q, S.init_qpos, nq); put(v, S.init_qvel, nv); }
+    if (initial) { S.npool = 1; put(q, S.init_qpos, nq); put(v, S.init_qvel, nv); }
     CUDA_OK(cudaMemsetAsync(S.warm, 0, sizeof(T) * nv * S.N, s));
+  }
+  // Reset pool: `rounds` initial states per env ([rounds][N][nq] / [rounds][N][nv] rows); episode e of an env starts from
+  // entry e % rounds.  The pool storage grows on demand and replaces the single initial state.
+  void set_reset_pool(const float *q, const float *v, int rounds, cudaStream_t s) override {
+    if (rounds < 1) throw std::runtime_error("reset pool needs at least one round");
+    const size_t N = S.N;
+    if ((size_t)rounds > pool_cap) {
+      CUDA_OK(cudaStreamSynchronize(s));
+      S.init_qpos = dalloc<T>((size_t)rounds * nq * N); S.init_qvel = dalloc<T>((size_t)rounds * nv * N);  // (old pool is freed with the handle)
+      pool_cap = rounds;
+    }
+    for (int r = 0; r < rounds; r++) {
+      const float *qr = q + (size_t)r * N * nq, *vr = v + (size_t)r * N * nv;
+      T *dq = S.init_qpos + (size_t)r * N * nq, *dv = S.init_qvel + (size_t)r * N * nv;
+      if (scene) { launch_cast_copy<float, T>(qr, dq, N * nq, s); launch_cast_copy<float, T>(vr, dv, N * nv, s); }
+      else { launch_rows_to_soa<T>(qr, dq, S.N, nq, s); launch_rows_to_soa<T>(vr, dv, S.N, nv, s); }
+      launches += 2;
+    }
+    S.npool = rounds;
+    CUDA_OK(cudaMemsetAsync(S.episode, 0, sizeof(int) * N, s));
   }
   void get_state(float *q, float *v, cudaStream_t s) override {
     if (scene) { launch_cast_copy<T, float>(S.qpos, q, (size_t)S.N * nq, s); launch_cast_copy<T, float>(S.qvel, v, (size_t)S.N * nv, s); }
@@ -387,6 +409,12 @@ int so101_set_initial_state(so101_handle h, const float *qpos_dev, const float *
   API_BEGIN(h)
   if (!qpos_dev || !qvel_dev) throw std::runtime_error("null state pointer");
   H->set_state(qpos_dev, qvel_dev, true, (cudaStream_t)stream);
+  API_END()
+}
+int so101_set_reset_pool(so101_handle h, const float *qpos_dev, const float *qvel_dev, int rounds, void *stream) {
+  API_BEGIN(h)
+  if (!qpos_dev || !qvel_dev) throw std::runtime_error("null state pointer");
+  H->set_reset_pool(qpos_dev, qvel_dev, rounds, (cudaStream_t)stream);
   API_END()
 }
 int so101_set_state(so101_handle h, const float *qpos_dev, const float *qvel_dev, void *stream) {

@@ -48,9 +48,12 @@ template <typename T>
 __device__ __forceinline__ void reset_env_arm(const StepCfg &cfg, const EnvState<T> &S, const so101_step_out &out, int env) {
   const int N = S.N;
   T q[NJ], qd[NJ], ctrl[NJ];
+  const int ep = S.episode[env];
+  const size_t pool = (size_t)(ep % S.npool) * NJ * N;  // reset pool entry of this episode
+  S.episode[env] = ep + 1;
 #pragma unroll
   for (int i = 0; i < NJ; i++) {
-    q[i] = S.init_qpos[i * N + env]; qd[i] = S.init_qvel[i * N + env];
+    q[i] = S.init_qpos[pool + i * N + env]; qd[i] = S.init_qvel[pool + i * N + env];
     ctrl[i] = (T)cfg.home[i] + (T)cfg.offsets[i];  // so100_task.py:316-317
     S.qpos[i * N + env] = q[i]; S.qvel[i * N + env] = qd[i]; S.warm[i * N + env] = T(0); S.ctrl[i * N + env] = ctrl[i];
   }

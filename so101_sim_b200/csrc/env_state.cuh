@@ -10,7 +10,9 @@ template <typename T>
 struct EnvState {
   int N, nq, nv;
   T *qpos, *qvel, *warm;            // [nq][N], [nv][N], [nv][N]  (warm = qacc_warmstart)
-  T *init_qpos, *init_qvel;         // reset targets
+  T *init_qpos, *init_qvel;         // reset pool [npool][...same layout as qpos / qvel...]: episode e of an env starts from entry e % npool
+  int npool;                        // entries in the reset pool (>= 1)
+  int *episode;                     // [N] resets this env has gone through (selects the pool entry)
   T *ctrl;                          // [6][N]
   int *step;                        // [N] control steps since reset
   uint8_t *needs_reset;             // [N] previous step was LAST (dm_control auto-reset on next step)

@@ -185,17 +185,30 @@ __device__ __noinline__ int feature_seq(const SceneModel<T> &sm, CollideScratch<
 #pragma unroll
     for (int k = 0; k < 8; k++) { emax[k] = -INFINITY; emin[k] = INFINITY; imax[k] = imin[k] = 0; }
     const T thr = hmax - delta;
-#pragma unroll 2
-    for (int i = 0; i < s.vnum; i++) {
-      const Vec4<T> v = vt[i];
-      if (!((v.x * dl[0] + v.y * dl[1] + v.z * dl[2]) + off >= thr)) continue;
-      nband++;
-      const T x = (v.x * t1l[0] + v.y * t1l[1] + v.z * t1l[2]) + ox, y = (v.x * t2l[0] + v.y * t2l[1] + v.z * t2l[2]) + oy;
+    // four heights per trip (independent loads); the few in-slab vertices are then handled one by one in index order.  The
+    // first FEAT_EXACT of them are also stored, so that a small slab needs no second scan.
+#pragma unroll 1
+    for (int i0 = 0; i0 < s.vnum; i0 += 4) {
+      const int rem = s.vnum - i0;
+      const Vec4<T> v0 = vt[i0], v1 = vt[i0 + (rem > 1 ? 1 : 0)], v2 = vt[i0 + (rem > 2 ? 2 : 0)], v3 = vt[i0 + (rem > 3 ? 3 : 0)];
+      unsigned hit = ((v0.x * dl[0] + v0.y * dl[1] + v0.z * dl[2]) + off >= thr ? 1u : 0u) |
+                     (rem > 1 && (v1.x * dl[0] + v1.y * dl[1] + v1.z * dl[2]) + off >= thr ? 2u : 0u) |
+                     (rem > 2 && (v2.x * dl[0] + v2.y * dl[1] + v2.z * dl[2]) + off >= thr ? 4u : 0u) |
+                     (rem > 3 && (v3.x * dl[0] + v3.y * dl[1] + v3.z * dl[2]) + off >= thr ? 8u : 0u);
+#pragma unroll 1
+      while (hit) {
+        const int i = i0 + __ffs(hit) - 1;
+        hit &= hit - 1;
+        const Vec4<T> v = vt[i];
+        const T x = (v.x * t1l[0] + v.y * t1l[1] + v.z * t1l[2]) + ox, y = (v.x * t2l[0] + v.y * t2l[1] + v.z * t2l[2]) + oy;
+        if (nband < FEAT_EXACT) { cs.cand[0][nband] = x; cs.cand[1][nband] = y; cs.cand[2][nband] = (v.x * dl[0] + v.y * dl[1] + v.z * dl[2]) + off; }
+        nband++;
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const T val = feat_cos<T>(k) * x + feat_sin<T>(k) * y;
-        if (val > emax[k]) { emax[k] = val; imax[k] = i; }
-        if (val < emin[k]) { emin[k] = val; imin[k] = i; }
+        for (int k = 0; k < 8; k++) {
+          const T val = feat_cos<T>(k) * x + feat_sin<T>(k) * y;
+          if (val > emax[k]) { emax[k] = val; imax[k] = i; }
+          if (val < emin[k]) { emin[k] = val; imin[k] = i; }
+        }
       }
     }
     if (nband > FEAT_EXACT) {
@@ -219,15 +232,7 @@ __device__ __noinline__ int feature_seq(const SceneModel<T> &sm, CollideScratch<
       }
       return nk;
     }
-    // pass 2 (small slab): the candidates themselves, in vertex order
-#pragma unroll 2
-    for (int i = 0; i < s.vnum && nc < nband; i++) {
-      const Vec4<T> v = vt[i];
-      const T h = (v.x * dl[0] + v.y * dl[1] + v.z * dl[2]) + off;
-      if (!(h >= thr)) continue;
-      const T x = (v.x * t1l[0] + v.y * t1l[1] + v.z * t1l[2]) + ox, y = (v.x * t2l[0] + v.y * t2l[1] + v.z * t2l[2]) + oy;
-      cs.cand[0][nc] = x; cs.cand[1][nc] = y; cs.cand[2][nc] = h; nc++;
-    }
+    nc = nband;  // small slab: the candidates themselves (stored by the scan, in vertex order)
     projected = nc > 0;
   } else if (s.type == G_BOX) {
 #pragma unroll 1

@@ -530,10 +530,15 @@ __device__ void write_obs_scene(const StepCfg &cfg, const EnvState<T> &S, const 
 
 template <typename T, typename SC>
 __device__ void reset_env_scene(const StepCfg &cfg, const EnvState<T> &S, const so101_step_out &out, SC &s, int env, int lane) {
-  for (int i = lane; i < NQ; i += 32) { s.q[i] = S.init_qpos[(size_t)env * NQ + i]; S.qpos[(size_t)env * NQ + i] = s.q[i]; }
-  for (int i = lane; i < NV; i += 32) { s.qd[i] = S.init_qvel[(size_t)env * NV + i]; S.qvel[(size_t)env * NV + i] = s.qd[i]; S.warm[(size_t)env * NV + i] = T(0); }
+  // initialize_episode (so100_hand_over.py:320-323): each episode starts from the next entry of the env's pool of sampled and
+  // settled prop placements
+  const int ep = S.episode[env];
+  const size_t slot = (size_t)(ep % S.npool) * S.N + env;
+  __syncwarp();
+  for (int i = lane; i < NQ; i += 32) { s.q[i] = S.init_qpos[slot * NQ + i]; S.qpos[(size_t)env * NQ + i] = s.q[i]; }
+  for (int i = lane; i < NV; i += 32) { s.qd[i] = S.init_qvel[slot * NV + i]; S.qvel[(size_t)env * NV + i] = s.qd[i]; S.warm[(size_t)env * NV + i] = T(0); }
   if (lane < NJ) { s.ctrl[lane] = (T)cfg.home[lane] + (T)cfg.offsets[lane]; S.ctrl[(size_t)env * 6 + lane] = s.ctrl[lane]; }
-  if (lane == 0) { S.step[env] = 0; S.needs_reset[env] = 0; }
+  if (lane == 0) { S.step[env] = 0; S.needs_reset[env] = 0; S.episode[env] = ep + 1; }
   __syncwarp();
   write_obs_scene(cfg, S, out, s, env, 0, 0.f, 1.f, SO101_STEP_FIRST, lane);
 }

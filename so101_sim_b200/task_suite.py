@@ -388,6 +388,32 @@ class BatchedEnvironment:
     self.reset()
     return q, v
 
+  def set_reset_pool(self, qpos: torch.Tensor, qvel: torch.Tensor):
+    """Install `rounds` initial states per env (qpos [rounds, N, nq], qvel [rounds, N, nv]): episode e of an env starts from
+    entry e % rounds (so101_set_reset_pool).  The episode counters restart at 0."""
+    q = qpos.to(device=self.device, dtype=torch.float32).contiguous(); v = qvel.to(device=self.device, dtype=torch.float32).contiguous()
+    if q.dim() != 3 or q.shape[1:] != (self.num_envs, self.nq) or v.shape != (q.shape[0], self.num_envs, self.nv):
+      raise ValueError(f'expected qpos [R, {self.num_envs}, {self.nq}] and qvel [R, {self.num_envs}, {self.nv}]')
+    self._check(self._lib.so101_set_reset_pool(self._h, ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(v.data_ptr()), int(q.shape[0]),
+                                               self._stream()))
+    self.reset_rounds = int(q.shape[0])
+
+  def randomize_resets(self, rounds: int = 4, seed: int | None = None, **sample_kwargs):
+    """Batched initialize_episode (so100_hand_over.py:320-323): the reference re-samples both prop placements in EVERY reset
+    (PropPlacer with the distributions at so100_hand_over.py:37-55, then a physics settle).  Here `rounds` placements per env
+    are sampled, rejected against the static obstacles and settled on the device up front (sample_prop_initial_states with
+    seeds seed, seed + 1, ...), and every auto-reset / reset() of an env moves on to its next placement: no host work and no
+    settle inside step().  Returns the pool (qpos [rounds, N, nq], qvel [rounds, N, nv])."""
+    seed = self.seed if seed is None else int(seed)
+    qs, vs = [], []
+    for r in range(int(rounds)):
+      q, v = self.sample_prop_initial_states(seed=seed + r, **sample_kwargs)
+      qs.append(q.clone()); vs.append(v.clone())
+    Q, V = torch.stack(qs), torch.stack(vs)
+    self.set_reset_pool(Q, V)
+    self.reset()
+    return Q, V
+
 
 def create_batched_task_env(task_name: str, num_envs: int, time_limit: float, seed: int | None = None,
                             control_timestep: float = DEFAULT_CONTROL_TIMESTEP, cameras: tuple = (), device='cuda:0',

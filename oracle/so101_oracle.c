@@ -132,6 +132,7 @@ so_model *so_model_load(const void *blob, size_t len) {
   m->bodypair = (const int *)blob_find(b, "bodypair", &c, 1); m->npair = (int)c / 2;
   blob_find(b, "hull_vert", &c, 0); m->nvert = (int)c / 3;
   BI(prop_body); BF(reward_obj_box); BF(reward_box_pos); BF(reward_box_half);
+  blob_find(b, "reward_box_pos", &c, 0); m->nreward_box = (int)c / 3;
   if (m->nq > SO_NQMAX || m->nv > SO_NVMAX || m->nbody > SO_NBMAX || m->nu > SO_NUMAX) { so_model_free(m); return NULL; }
   return m;
 }
@@ -745,10 +746,13 @@ double so_reward(const so_model *m, const so_data *d) {
   for (int c = 0; c < 3; c++) p0[c] = t[c] + d->xipos[ob][c];
   /* oobb_utils.py:175-199 — container box into world */
   double q1[4], p1[3], ident[4] = {1, 0, 0, 0};
-  quat_rot(t, m->reward_box_pos, d->xquat[cb]);
-  for (int c = 0; c < 3; c++) p1[c] = t[c] + d->xpos[cb][c];
   quat_mul(q1, d->xquat[cb], ident);
-  return so_overlap_oobb_oobb(p0, q0, m->reward_obj_box + 3, p1, q1, m->reward_box_half) ? 1.0 : 0.0;
+  for (int k = 0; k < m->nreward_box; k++) { /* so100_hand_over.py:263-273: every overlap box must be touched */
+    quat_rot(t, m->reward_box_pos + 3 * k, d->xquat[cb]);
+    for (int c = 0; c < 3; c++) p1[c] = t[c] + d->xpos[cb][c];
+    if (!so_overlap_oobb_oobb(p0, q0, m->reward_obj_box + 3, p1, q1, m->reward_box_half + 3 * k)) return 0.0;
+  }
+  return 1.0;
 }
 
 /* ------------------------------------------------------------------------------------------ ctypes access */

@@ -46,7 +46,8 @@ typedef struct so_model {
   const double *hull_vert;
   const int *hull_face, *hull_nbradr, *hull_nbr;
   const int *bodypair, *prop_body;
-  const double *reward_obj_box, *reward_box_pos, *reward_box_half;
+  const double *reward_obj_box, *reward_box_pos, *reward_box_half;  /* box k: pos + 3k, half + 3k */
+  int nreward_box;
   void *blob_copy;
 } so_model;
 

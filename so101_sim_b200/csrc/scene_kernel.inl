@@ -491,9 +491,12 @@ __device__ float scene_reward(const SceneModel<T> &sm, const S &s) {
   T q1[4] = {qb[0], qb[1], qb[2], qb[3]}, p1[3];
   const T n = t_sqrt(q1[0] * q1[0] + q1[1] * q1[1] + q1[2] * q1[2] + q1[3] * q1[3]);
   for (int i = 0; i < 4; i++) q1[i] /= n;
-  mulmv(t, s.xmat[NJ + 1], sm.reward_box_pos);
-  for (int c = 0; c < 3; c++) p1[c] = t[c] + s.xpos[NJ + 1][c];
-  return overlap_oobb_oobb(p0, q0, sm.reward_obj_box + 3, p1, q1, sm.reward_box_half) ? 1.f : 0.f;
+  for (int k = 0; k < sm.nreward_box; k++) {  // every overlap box must be touched by the object's box (so100_hand_over.py:263-273)
+    mulmv(t, s.xmat[NJ + 1], sm.reward_box_pos[k]);
+    for (int c = 0; c < 3; c++) p1[c] = t[c] + s.xpos[NJ + 1][c];
+    if (!overlap_oobb_oobb(p0, q0, sm.reward_obj_box + 3, p1, q1, sm.reward_box_half[k])) return 0.f;
+  }
+  return 1.f;
 }
 
 // ------------------------------------------------------------------------------------------------ task layer: observations

@@ -15,6 +15,7 @@ namespace so101 {
 
 enum { G_PLANE = 0, G_SPHERE = 1, G_CAPSULE = 2, G_CYLINDER = 3, G_BOX = 4, G_HULL = 5 };
 constexpr int NPROP = 2;
+constexpr int MAXREWARDBOX = 2;  // container overlap boxes (banana / bowl: 1, pen / utensil holder: 2)
 constexpr int NSLOT = NJ + NPROP;   // dynamic bodies whose pose lives in shared memory: 6 arm links + 2 props
 constexpr int NV = NJ + 6 * NPROP;  // 18
 constexpr int NQ = NJ + 7 * NPROP;  // 20
@@ -43,7 +44,9 @@ struct SceneModel {
   T prop_mass[NPROP], prop_ipos[NPROP][3], prop_Icom[NPROP][6], prop_Iorg[NPROP][6];  // inertia about COM / body origin, body axes
   T prop_Riq[NPROP][9];  // body_iquat as a matrix (body <- inertial frame), for the reward's ximat
   // task constants (so100_hand_over.py:87-93, oobb_utils.py:165-172)
-  T reward_obj_box[6], reward_box_pos[3], reward_box_half[3];
+  T reward_obj_box[6];
+  int nreward_box;  // overlap boxes of the container (so100_hand_over.py:87-93,104-116): ALL must be overlapped (:263-273)
+  T reward_box_pos[MAXREWARDBOX][3], reward_box_half[MAXREWARDBOX][3];
   T impratio, timestep;
 };
 
@@ -211,7 +214,11 @@ struct SceneModelHost {
       for (int c = 0; c < 9; c++) d.prop_Riq[p][c] = (T)Ri[c];
     }
     for (int c = 0; c < 6; c++) d.reward_obj_box[c] = (T)b.F("reward_obj_box")[c];
-    for (int c = 0; c < 3; c++) { d.reward_box_pos[c] = (T)b.F("reward_box_pos")[c]; d.reward_box_half[c] = (T)b.F("reward_box_half")[c]; }
+    d.nreward_box = (int)b.F("reward_box_pos").size() / 3;
+    if (d.nreward_box < 1 || d.nreward_box > MAXREWARDBOX || b.F("reward_box_half").size() != b.F("reward_box_pos").size())
+      throw std::runtime_error("model blob: unsupported number of reward overlap boxes");
+    for (int k = 0; k < d.nreward_box; k++)
+      for (int c = 0; c < 3; c++) { d.reward_box_pos[k][c] = (T)b.F("reward_box_pos")[3 * k + c]; d.reward_box_half[k][c] = (T)b.F("reward_box_half")[3 * k + c]; }
     d.impratio = (T)b.F("opt")[4]; d.timestep = (T)b.F("opt")[0];
   }
 };

@@ -86,20 +86,23 @@ class SO100Task:
 
 
 class SO100HandOver(SO100Task):
-  """so100_hand_over.py:121-326 (banana config, overlap reward)."""
-  model_name = 'so100_handover_banana'
+  """so100_hand_over.py:121-326 (overlap reward): banana -> bowl (:81-96) and pen -> utensil holder (:97-117).  The object /
+  container models, the container mesh scale and the overlap boxes are compiled into the model blob (tools/compile_model.py)."""
   collide = True
+  # object -> (model blob, instruction, (object z, container z) just above rest on the table top or None = spawn height)
+  CONFIGS = {
+      'banana': ('so100_handover_banana', 'pick up the banana and put it in the bowl using the SO100 arm', (0.4217, 0.4226)),
+      'pen': ('so100_handover_pen', 'pick up the pen and put it in the container using the SO100 arm', None),
+  }
 
   def __init__(self, object_name, reward_based_on_overlap=True, **kwargs):
     super().__init__(**kwargs)
-    configs = {'banana': 'pick up the banana and put it in the bowl using the SO100 arm', 'pen': None}
-    if object_name not in configs:
-      raise ValueError(f'Invalid object name: {object_name}, must be one of {configs.keys()}')  # so100_hand_over.py:146-150
-    if object_name != 'banana':
-      raise NotImplementedError('SO100HandOverPen: model blob not compiled yet (SURVEY.md §8f row 3)')
+    if object_name not in self.CONFIGS:
+      raise ValueError(f'Invalid object name: {object_name}, must be one of {self.CONFIGS.keys()}')  # so100_hand_over.py:146-150
     if not reward_based_on_overlap:
       raise NotImplementedError('contact/distance reward fallback (so100_hand_over.py:277-318) is a "next" row')
-    self.instruction = configs[object_name]
+    self.object_name = object_name
+    self.model_name, self.instruction, self.rest_heights = self.CONFIGS[object_name]
 
 
 class SO100ArmOnly(SO100Task):
@@ -353,11 +356,14 @@ class BatchedEnvironment:
     `spawn_z` (the reference uses 0.45 for both props, so100_hand_over.py:37-55) overrides the rest-height start: the props
     then drop ~3 cm and need ~50 settle steps.  Installs the result as the per-env reset state."""
     if self.nq != 20:
-      raise RuntimeError('sample_prop_initial_states needs the SO100HandOverBanana model')
+      raise RuntimeError('sample_prop_initial_states needs a SO100HandOver model')
     N, dev = self.num_envs, self.device
     g = torch.Generator(device='cpu'); g.manual_seed(int(seed))
     u = torch.rand(N, 5, generator=g)
-    zo, zb = (0.4217 + clearance, 0.4226 + clearance) if spawn_z is None else (float(spawn_z), float(spawn_z))
+    rest = getattr(self.task, 'rest_heights', None)
+    if spawn_z is None and rest is None:  # no known rest pose (pen / holder): drop from the reference's spawn height
+      spawn_z, settle_steps = 0.45, max(settle_steps, 60) if settle_steps > 0 else 0
+    zo, zb = (rest[0] + clearance, rest[1] + clearance) if spawn_z is None else (float(spawn_z), float(spawn_z))
     obstacles = self._bowl_obstacles(zb)
     for _ in range(max_attempts - 1):
       bx, by = -0.3 + 0.1 * u[:, 3], -0.1 + 0.2 * u[:, 4]

@@ -81,3 +81,23 @@ def test_props_come_to_rest_near_the_reference_rest_heights():
     s.control_step(np.zeros(6))
   assert abs(s.qpos[8] - 0.4217) < 1e-3 and abs(s.qpos[15] - 0.4226) < 1e-3
   assert np.abs(s.qvel[6:9]).max() < 5e-3 and np.abs(s.qvel[12:15]).max() < 5e-3
+
+
+def test_pen_in_the_utensil_holder_triggers_the_two_box_reward():
+  """SO100HandOverPen (so100_hand_over.py:97-117): the reward needs the pen's box to overlap BOTH container boxes (inside the
+  holder and above it, :104-116,263-273) with both props at rest; a pen lying on the table overlaps neither."""
+  m = read_blob('so100_handover_pen')
+  assert m['reward_box_pos'].size == 6 and m['reward_box_half'].size == 6 and int(m['prop_mass_standin'][0]) == 0
+  np.testing.assert_allclose(m['reward_box_pos'].reshape(2, 3), np.array([[0, 0, 0.02666], [0, 0, 0.25]]) * 0.6)
+  q = m['qpos0'].copy()
+  q[:6] = 0
+  q[13:20] = [-0.25, 0.05, 0.4503, 1, 0, 0, 0]
+  s = OracleSim('so100_handover_pen', collide=True)
+  q[6:13] = [-0.25, 0.05, 0.4503 + 0.105, np.cos(np.pi / 4), np.sin(np.pi / 4), 0, 0]  # long axis (body y) up, inside the holder
+  s.set_state(q, np.zeros(18))
+  rewards = [s.control_step(np.zeros(6)) for _ in range(12)]
+  assert rewards[0] == 0.0 and max(rewards) == 1.0  # moving at first, then at rest inside both boxes
+  s = OracleSim('so100_handover_pen', collide=True)
+  q[6:13] = [0.25, 0.0, 0.4283, 1, 0, 0, 0]
+  s.set_state(q, np.zeros(18))
+  assert max(s.control_step(np.zeros(6)) for _ in range(12)) == 0.0

@@ -187,3 +187,65 @@ def test_kernel_times_and_launch_counts(built):
   env.kernel_times(True); env.step(zero)
   assert env.kernel_times(False)['scene_begin_kernel'][1] == 4   # totals accumulate
   env.close()
+
+
+# ------------------------------------------------------------------------------------------------ SO100HandOverPen (so100_hand_over.py:97-117)
+def _pen_in_holder_state(env_or_meta, n):
+  """Row 0: the pen standing inside the utensil holder (rotated so that its long axis, body y, points up); row 1..: pen lying on
+  the table away from the holder."""
+  q = torch.tensor(env_or_meta['qpos0'], dtype=torch.float32).repeat(n, 1)
+  q[:, :6] = 0
+  q[:, 13:16] = torch.tensor([-0.25, 0.05, 0.4503]); q[:, 16] = 1; q[:, 17:20] = 0
+  q[:, 6:9] = torch.tensor([0.25, 0.0, 0.4283]); q[:, 9] = 1; q[:, 10:13] = 0
+  q[0, 6:9] = torch.tensor([-0.25, 0.05, 0.4503 + 0.105])
+  q[0, 9] = float(np.cos(np.pi / 4)); q[0, 10] = float(np.sin(np.pi / 4)); q[0, 11:13] = 0  # +90 degrees about x: y -> z
+  return q
+
+
+def test_pen_scene_matches_oracle_and_rewards(built):
+  """SO100HandOverPen: same kernels, second model blob (pen x(1.5,1,1.5) + utensil holder x0.6, 52 hulls) and TWO overlap boxes
+  that must both be touched (so100_hand_over.py:104-116,263-273).  float64 state parity over contact-rich steps, and the
+  reward / discount / step_type flags equal the oracle's at every step."""
+  env = _env(built, task_name='SO100HandOverPen', num_envs=3, precision='f64')
+  assert env.task.get_instruction() == 'pick up the pen and put it in the container using the SO100 arm'
+  q = _pen_in_holder_state(env.model, 3)
+  q[2, 6:9] = torch.tensor([0.22, 0.03, 0.45])  # dropped from the reference's spawn height
+  v = torch.zeros(3, 18)
+  env.set_initial_state(q, v)
+  env.reset()
+  sims = []
+  for e in range(3):
+    o = OracleSim('so100_handover_pen', collide=True)
+    o.set_state(q[e].double().numpy(), np.zeros(18))
+    sims.append(o)
+  acts = _actions(env, 30, seed=3, scale=0.1)
+  seen_success = False
+  for t in range(30):
+    ts = env.step(acts[t])
+    qg, vg = env.get_state(torch.float64)
+    for e, o in enumerate(sims):
+      if o is None:
+        continue
+      r = o.control_step(acts[t, e].double().cpu().numpy())
+      assert float(ts.reward[e]) == r, (t, e)
+      assert np.abs(o.qpos - qg[e].cpu().numpy()).max() < 1e-5, (t, e, np.abs(o.qpos - qg[e].cpu().numpy()).max())
+      if r >= 1.0:
+        assert e == 0 and float(ts.discount[e]) == 0.0 and int(ts.step_type[e]) == 2
+        seen_success = True
+        sims[e] = None  # the env auto-resets on the next step
+  assert seen_success, 'the pen standing in the holder must trigger the two-box overlap reward once it is at rest'
+  env.close()
+
+
+def test_pen_f32_rollout_and_reset_pool(built):
+  env = _env(built, task_name='SO100HandOverPen', num_envs=16)
+  Q, V = env.randomize_resets(rounds=2, seed=3, settle_steps=60)
+  assert torch.isfinite(Q).all() and float(V[..., 6:].abs().max()) < 0.1
+  # both rest on the table top (z 0.42): the pen's body origin ends ~2 mm below it (the mesh is off-centre), the holder's base
+  # sits at its origin; the rejection sampling keeps the holder off the static cylinder obstacle (scene_pbr.xml:144-146)
+  assert float((Q[..., 8] - 0.4180).abs().max()) < 5e-3 and float((Q[..., 15] - 0.4204).abs().max()) < 2e-3
+  acts = _actions(env, 20, seed=5)
+  for t in range(20):
+    ts = env.step(acts[t])
+  assert torch.isfinite(ts.observation['physics_state']).all() and env.counters()['diverged'] == 0
+  env.close()

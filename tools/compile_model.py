@@ -199,7 +199,8 @@ def parse_mjcf(model: Model, path, prefix='', attach_free=False, mesh_scale=1.0)
   root = ET.parse(path).getroot()
   base = os.path.dirname(path)
   comp = root.find('compiler')
-  meshdir = os.path.join(base, comp.get('meshdir', '') if comp is not None else '')
+  # (assetdir is the fallback of meshdir: edr/pen and the gso models use it)
+  meshdir = os.path.join(base, (comp.get('meshdir') or comp.get('assetdir') or '') if comp is not None else '')
   opt = root.find('option')
   if opt is not None and not attach_free:
     if opt.get('impratio'): model.opt['impratio'] = float(opt.get('impratio'))
@@ -410,6 +411,20 @@ def finalize(model: Model, standin_meshes):
         e['mframe'] = (p, R, np.zeros(3), half)
       G.append(e)
   ng = len(G)
+  # non-colliding mesh geoms whose file is present (visual / mass meshes): only their AABB matters, for the body's BVH root box
+  vis = {}
+  for bi, b in enumerate(model.bodies):
+    for g in b.get('massgeoms', []):
+      if any(g is c for c in b['geoms']) or g['type'] != 'mesh' or g['mesh'][0] is None:
+        continue
+      v, f = g['mesh']
+      v = v@q2m(g['quat']).T+g['pos']
+      vol, com, I = mesh_mass_props(v, f)
+      w, V = np.linalg.eigh(I*np.sign(vol)); order = np.argsort(-w); V = V[:, order]
+      if np.linalg.det(V) < 0: V[:, 2] = -V[:, 2]
+      loc = (v-com)@V
+      vis.setdefault(bi, []).append((com, V, 0.5*(loc.min(0)+loc.max(0)), 0.5*(loc.max(0)-loc.min(0))))
+  A['_vis'] = vis
   # body geom ranges (colliding geoms are contiguous per body by construction)
   body_geomadr = np.zeros(nb, dtype=np.int32); body_geomnum = np.zeros(nb, dtype=np.int32)
   k = 0
@@ -571,9 +586,8 @@ def body_root_box(A, body):
   frame -> (centre3, half3).  Read by oobb_utils.get_oobb (oobb_utils.py:165-172)."""
   Ri = q2m(A['body_iquat'][body]); pi = A['body_ipos'][body]
   lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
-  for g in A['_G']:
-    if g['body'] != body: continue
-    com, V, c, h = g['mframe']
+  frames = [g['mframe'] for g in A['_G'] if g['body'] == body]+A['_vis'].get(body, [])
+  for com, V, c, h in frames:
     for sx in (-1, 1):
       for sy in (-1, 1):
         for sz in (-1, 1):
@@ -610,18 +624,30 @@ def write_blob(path, A):
     f.write(payload)
 
 
-def build(ref_root, with_props=True):
+# so100_hand_over.py:80-118 — object / container models, container mesh scale and the overlap boxes in the container frame
+HANDOVER = {
+    'banana': dict(object=('011_banana/', 'ycb/011_banana/google_64k'), container=('024_bowl/', 'ycb/024_bowl/google_64k'), scale=1.5,
+                   boxes=[(np.array([-0.017, -0.045, 0.035])*1.5, np.array([0.02, 0.02, 0.01])*1.5)]),
+    'pen': dict(object=('pen/', 'edr/pen'), container=('utensil_holder/', 'gso/BIA_Cordon_Bleu_White_Porcelain_Utensil_Holder_900028'),
+                scale=0.6, boxes=[(np.array([0.0, 0.0, 0.02666])*0.6, np.array([0.04666, 0.04666, 0.025])*0.6),
+                                  (np.array([0.0, 0.0, 0.25])*0.6, np.array([0.1, 0.1, 0.01666])*0.6)]),
+}
+
+
+def build(ref_root, task=None):
   assets = os.path.join(ref_root, 'so101_sim', 'assets')
   m = Model()
   parse_mjcf(m, os.path.join(assets, 'so100', 'scene_pbr.xml'))
   standin = {}
+  with_props = task is not None
   if with_props:
-    # so100_hand_over.py:159-199 — object first, then container scaled by 1.5
-    for nm, rel, sc in (('011_banana/', 'ycb/011_banana/google_64k', 1.0), ('024_bowl/', 'ycb/024_bowl/google_64k', 1.5)):
+    cfg = HANDOVER[task]
+    # so100_hand_over.py:159-199 — object first, then the container with its meshes scaled
+    for (nm, rel), sc in ((cfg['object'], 1.0), (cfg['container'], cfg['scale'])):
       nb0 = len(m.bodies)
       parse_mjcf(m, os.path.join(assets, rel, 'model.xml'), prefix=nm, attach_free=True, mesh_scale=sc)
       v, f = load_obj(os.path.join(assets, rel, 'meshes', 'coacd_merged.obj'))
-      standin[m.bodies[nb0]['name']] = (v*sc, f)
+      standin[m.bodies[nb0]['name']] = (v*sc, f)  # used only when the mass-defining visual mesh is missing from the checkout
       # dm_control names: attachment frame '011_banana/' with the inner (unnamed) body; we keep one body (identity offset)
   A = finalize(m, standin)
   A['nprop'] = 2 if with_props else 0
@@ -629,13 +655,13 @@ def build(ref_root, with_props=True):
     nb = A['nbody']
     A['prop_body'] = np.array([nb-2, nb-1], dtype=np.int32)
     A['reward_obj_box'] = body_root_box(A, nb-2)
-    # so100_hand_over.py:87-93
-    A['reward_box_pos'] = np.array([-0.017, -0.045, 0.035])*1.5
-    A['reward_box_half'] = np.array([0.02, 0.02, 0.01])*1.5
+    A['reward_box_pos'] = np.concatenate([b[0] for b in cfg['boxes']])
+    A['reward_box_half'] = np.concatenate([b[1] for b in cfg['boxes']])
+    A['prop_mass_standin'] = int(any(g.get('missing') for bd in m.bodies[-2:] for g in bd.get('massgeoms', [])))
   else:
     A['prop_body'] = np.zeros(0, dtype=np.int32)
     A['reward_obj_box'] = np.zeros(6); A['reward_box_pos'] = np.zeros(3); A['reward_box_half'] = np.zeros(3)
-  A['prop_mass_standin'] = 1 if with_props else 0
+    A['prop_mass_standin'] = 0
   return A
 
 
@@ -645,7 +671,7 @@ def main():
   ap.add_argument('--out', default=os.path.join(os.path.dirname(__file__), '..', 'so101_sim_b200', 'data'))
   a = ap.parse_args()
   os.makedirs(a.out, exist_ok=True)
-  for name, props in (('so100_arm', False), ('so100_handover_banana', True)):
+  for name, props in (('so100_arm', None), ('so100_handover_banana', 'banana'), ('so100_handover_pen', 'pen')):
     A = build(a.ref, props)
     p = os.path.join(a.out, name+'.blob')
     write_blob(p, A)
@@ -657,7 +683,7 @@ def main():
     print('   dof_invweight0', A['dof_invweight0'])
     print('   meaninertia', A['opt'][8])
     if props:
-      print('   reward_obj_box', A['reward_obj_box'])
+      print('   reward_obj_box', A['reward_obj_box'], 'mass stand-in:', A['prop_mass_standin'])
 
 
 if __name__ == '__main__':

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SO101_ABI_VERSION 1
+#define SO101_ABI_VERSION 2
 
 /* dm_env.StepType values (reference TimeStep.step_type) */
 #define SO101_STEP_FIRST 0
@@ -107,9 +107,10 @@ int so101_counters(so101_handle h, uint64_t out[4]);
 
 /* Per-kernel device time, measured with CUDA events recorded on the caller's stream around every launch while enabled.
  * Returns the totals accumulated so far (ms and launch counts; index 0 scene begin, 1 scene EPA + manifold, 2 scene solve
- * tier 0, 3 scene solve tiers 1 + 2, 4 arm-only step, 5 scene boolean GJK), then switches recording on/off for the following calls.  Synchronises the
- * host on the recorded events.  No reference counterpart: measurement support for bench.py's roofline leg. */
-int so101_kernel_times(so101_handle h, int enable, double ms_out[6], uint64_t launches_out[6]);
+ * tier 0, 3 scene solve tiers 1 + 2, 4 arm-only step, 5 scene boolean GJK, 6 scene kinematics + smooth dynamics, 7 scene broad
+ * phase / task layer), then switches recording on/off for the following calls.  Synchronises the host on the recorded events.
+ * No reference counterpart: measurement support for bench.py's roofline leg. */
+int so101_kernel_times(so101_handle h, int enable, double ms_out[8], uint64_t launches_out[8]);
 
 /* Debug/parity probe: copy one internal structure-of-arrays field ("qacc", "ncon", "solver_iter", ...) of all envs to a
  * caller-owned device buffer of `count` floats.  Used by the parity tests only. */

@@ -206,7 +206,7 @@ struct Handle : HandleBase {
       if (b.scalar("ngeom") > GMAX_GEOMS) throw std::runtime_error("model has more geoms than the broad phase can hold");
       if (b.scalar("nbody") > 16) throw std::runtime_error("model has more bodies than the broad phase can hold");
       if (b.scalar("ngeom") > WQ) throw std::runtime_error("model has more geoms than narrow-phase work queues");
-      pipe.xpos = dalloc<T>(N * NSLOT * 3); pipe.xmat = dalloc<T>(N * NSLOT * 9); pipe.kin = dalloc<T>(N * KINW);
+      pipe.xpos = dalloc<T>(N * NSLOT * 3); pipe.xmat = dalloc<T>(N * NSLOT * 9); pipe.dyn = dalloc<T>(N * DYNW);
       pipe.con = dalloc<T>(N * CONBUF * 8); pipe.con_key = dalloc<int>(N * CONBUF); pipe.ncon_raw = dalloc<int>(N);
       pipe.active = dalloc<uint8_t>(N); pipe.flags = dalloc<uint8_t>(N); pipe.tier = dalloc<uint8_t>(N);
       // pipeline groups: independent env ranges whose kernel sequences run on their own streams.  Measured on B200 at 16384
@@ -462,7 +462,7 @@ int so101_counters(so101_handle h, uint64_t out[4]) {
   out[2] = H->diverged(); out[0] = H->launches; out[1] = H->steps; out[3] = H->dropped;
   API_END()
 }
-int so101_kernel_times(so101_handle h, int enable, double ms_out[6], uint64_t launches_out[6]) {
+int so101_kernel_times(so101_handle h, int enable, double ms_out[8], uint64_t launches_out[8]) {
   API_BEGIN(h)
   H->timer.collect();
   for (int i = 0; i < KernelTimer::NK; i++) {

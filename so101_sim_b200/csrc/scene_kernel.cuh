@@ -13,7 +13,9 @@ namespace so101 {
 // Scene-kernel state layout is array-of-rows ([N][nq] etc.): one warp owns one env and reads its row with one
 // coalesced request (the arm-only kernel, one THREAD per env, uses [k][N] instead).
 
-constexpr int KINW = 128;             // floats per env in PipeBuf::kin (ArmKin 90 + anchors 18 + axes 18)
+// Per-env record written by the thread-per-env kinematics + smooth-dynamics kernel and read by the solve kernels:
+// joint anchors 18, joint axes 18, arm mass matrix 21, prop mass blocks 2 x 21, qacc_smooth 18, arm rows 24
+constexpr int DYN_P = 0, DYN_A = 18, DYN_MARM = 36, DYN_MPROP = 57, DYN_QACC = 99, DYN_ROWS = 117, DYNW = 144;
 constexpr int GMAX_GEOMS = 96;       // geoms per model the broad phase holds in shared memory
 constexpr int WQ = 128;             // work queues (>= ngeom)
 constexpr int WSTRIDE = WQ + 8;     // counters per substep
@@ -32,8 +34,8 @@ struct HitRec {
 template <typename T>
 struct PipeBuf {
   T *xpos, *xmat;           // [N][NSLOT*3], [N][NSLOT*9]  world poses of the 8 dynamic bodies
-  T *kin;                   // [N][KINW]  arm kinematic state (ArmKin, joint anchors, axes) at the current qpos: written by the
-                            //   kinematics that follows each integration, re-used by the next substep's dynamics
+  T *dyn;                   // [N][DYNW]  joint anchors / axes, mass matrices, qacc_smooth and the arm's friction / limit rows at the
+                            //   current state (scene_kindyn_kernel -> solve kernels)
   uint2 *work;              // [WQ][work_cap]  narrow-phase work queues, one per second geom g2 (so that consecutive items
                             //   collide the same hull): (env, g1 | g2 << 8 | pair index << 16)
   int work_cap;             // entries per queue
@@ -73,9 +75,10 @@ struct TierExec {
 };
 
 // Optional per-kernel timing with CUDA events on the launching stream (so101_kernel_times; bench.py's roofline leg).
-// Kernel ids: 0 begin, 1 EPA + manifold, 2 solve (tier 0), 3 solve (tiers 1 + 2), 4 arm-only step, 5 boolean GJK.
+// Kernel ids: 0 begin, 1 EPA + manifold, 2 solve (tier 0), 3 solve (tiers 1 + 2), 4 arm-only step, 5 boolean GJK,
+// 6 kinematics + smooth dynamics (thread per env), 7 broad phase / task layer.
 struct KernelTimer {
-  static constexpr int NK = 6;
+  static constexpr int NK = 8;
   bool on = false;
   std::vector<std::array<cudaEvent_t, 2>> ev[NK];
   size_t used[NK] = {};

@@ -1,15 +1,20 @@
 // Control step of the FULL contact scene (BASELINE config 3: SO100HandOverBanana, nq=20 nv=18) as a pipeline of small
 // kernels per physics substep, all envs in lockstep (DESIGN.md section 4 has the table):
 //
-//   scene_begin_kernel       (once per control step, warp per env)  auto-reset, action -> ctrl, kinematics, broad/mid phase
-//   scene_gjk_kernel         (thread per candidate geom pair)        boolean GJK over per-geom work queues -> hit list
+//   scene_begin_kernel       (once per control step, thread per env) auto-reset, action -> ctrl
+//   scene_kindyn_kernel      (thread per env)                        arm forward kinematics, CRB mass matrix, RNE bias, actuation,
+//                                                                    prop mass blocks, qacc_smooth, friction / limit rows -> dyn record
+//   scene_broad_kernel       (warp per env)                          broad + mid phase -> per-geom work queues; after the last
+//                                                                    substep instead: the task layer (delay rings, reward, flags)
+//   scene_gjk_kernel         (thread per candidate geom pair)        boolean GJK over the work queues -> hit list
 //   scene_narrow_seq_kernel  (thread per intersecting pair)          EPA -> support-feature clipping manifold -> raw contacts
 //   scene_classify_kernel    (thread per env)                        solver tier by contact / Jacobian-block count
 //   scene_solve_kernel + scene_solve_tier_kernel x2 (warp per env, concurrent streams)
-//                            smooth dynamics, contact gather, constraint rows, elliptic-cone Newton, semi-implicit Euler,
-//                            then kinematics + broad phase of the NEXT substep, or (last substep) the task layer:
-//                            observation delay rings, SO100HandOver reward, discount, time limit.
+//                            contact gather, constraint rows, elliptic-cone Newton, semi-implicit Euler
 //
+// The arm's kinematics and smooth dynamics are long straight-line scalar code: one THREAD per env runs them once per 32 envs
+// instead of 32 lanes of a warp running them redundantly, and the warp-per-env solve kernel is left with loop-structured
+// code that is a third of its former size (it was bound by instruction fetch: profiles/r01u_ncu_scene_solve_kernel.txt).
 // Splitting by stage keeps each kernel's code and shared-memory footprint small (more resident warps, less instruction-
 // cache thrash) and turns the narrow phase - whose cost varies 10x between pairs - into flat work lists.  What crosses
 // kernels (body poses, pair queues, hit list, raw contacts; a few KB per env) is written once and read once.
@@ -55,7 +60,6 @@ template <typename T, int NC, int NB>
 struct Scratch {
   T xpos[NSLOT][3], xmat[NSLOT][9];
   T arm_p[NJ][3], arm_a[NJ][3];
-  ArmKin<T> kin;
   ArmRows<T> arows;
   T q[NQ], qd[NV], warm[NV], ctrl[NJ];
   T Mprop[NPROP][21];
@@ -64,10 +68,17 @@ struct Scratch {
   T qacc_s[NV], delta[NV], grad[NV], search[NV], Md[NV], hscale[NV];
   int ncon, dbg, profon;
   long long prof[16];  // developer probe (SO101_PROFILE=1): per-stage clock64 sums and counters of this env
-  union {
-    BroadScratch<T> broad;
-    SolveScratch<T, NC, NB> sol;
-  };
+  SolveScratch<T, NC, NB> sol;
+};
+
+// per-env scratch of the broad-phase / task-layer kernel
+template <typename T>
+struct BroadEnv {
+  T xpos[NSLOT][3], xmat[NSLOT][9];
+  T q[NQ], qd[NV], ctrl[NJ];
+  int profon;
+  long long prof[16];
+  BroadScratch<T> broad;
 };
 
 // stage profiler: lane 0 accumulates clock64 deltas into Scratch::prof when the handle was created with SO101_PROFILE=1
@@ -88,54 +99,26 @@ __device__ __forceinline__ void prop_rotation(const T *quat, T *R) {
   R[5] = T(2) * (y * z - w * x); R[6] = T(2) * (x * z - w * y); R[7] = T(2) * (y * z + w * x);
 }
 
-// positions: arm FK (registers) -> shared poses; prop poses.  Returns the arm kinematic state for the CRB/RNE sweep.
+// poses (and, for the solve kernels, the dyn record) published by scene_kindyn_kernel for the current state -> shared memory
 template <typename T, typename S>
-__device__ __noinline__ void scene_kinematics(const ArmModelT<T> &am, S &s, int lane) {
-  ArmKin<T> k;
-  T qa[NJ];
-#pragma unroll
-  for (int i = 0; i < NJ; i++) qa[i] = s.q[i];
-  T R[NJ][9];
-  arm_fk<T>(am, qa, k, R);
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < NJ; i++) {
-      s.xpos[i][0] = k.p[i].x; s.xpos[i][1] = k.p[i].y; s.xpos[i][2] = k.p[i].z;
-      s.arm_p[i][0] = k.p[i].x; s.arm_p[i][1] = k.p[i].y; s.arm_p[i][2] = k.p[i].z;
-      s.arm_a[i][0] = k.a[i].x; s.arm_a[i][1] = k.a[i].y; s.arm_a[i][2] = k.a[i].z;
-#pragma unroll
-      for (int e = 0; e < 9; e++) s.xmat[i][e] = R[i][e];
-    }
-  }
-  if (lane < NPROP) {
-    const T *qp = s.q + NJ + 7 * lane;
-    T Rp[9];
-    prop_rotation(qp + 3, Rp);
-#pragma unroll
-    for (int c = 0; c < 3; c++) s.xpos[NJ + lane][c] = qp[c];
-#pragma unroll
-    for (int e = 0; e < 9; e++) s.xmat[NJ + lane][e] = Rp[e];
-  }
-  if (lane == 0) s.kin = k;
-  __syncwarp();
-}
-
-// poses and arm kinematic state published by the previous kernel's broad phase (same qpos) -> shared memory
-template <typename T, typename S>
-__device__ __forceinline__ void load_kinematics(const PipeBuf<T> &pb, S &s, int env, int lane) {
-  const T *gx = pb.xpos + (size_t)env * (NSLOT * 3), *gm = pb.xmat + (size_t)env * (NSLOT * 9), *gk = pb.kin + (size_t)env * KINW;
+__device__ __forceinline__ void load_poses(const PipeBuf<T> &pb, S &s, int env, int lane) {
+  const T *gx = pb.xpos + (size_t)env * (NSLOT * 3), *gm = pb.xmat + (size_t)env * (NSLOT * 9);
   for (int i = lane; i < NSLOT * 3; i += 32) (&s.xpos[0][0])[i] = gx[i];
   for (int i = lane; i < NSLOT * 9; i += 32) (&s.xmat[0][0])[i] = gm[i];
-  T *kk = reinterpret_cast<T *>(&s.kin);
-  for (int i = lane; i < 90; i += 32) kk[i] = gk[i];
-  if (lane < 18) { (&s.arm_p[0][0])[lane] = gk[90 + lane]; (&s.arm_a[0][0])[lane] = gk[108 + lane]; }
-  __syncwarp();
+}
+template <typename T, typename S>
+__device__ __forceinline__ void load_dyn(const PipeBuf<T> &pb, S &s, int env, int lane) {
+  const T *gd = pb.dyn + (size_t)env * DYNW;
+  static_assert(sizeof(ArmRows<T>) == 24 * sizeof(T), "ArmRows layout");
+  if (lane < 18) { (&s.arm_p[0][0])[lane] = gd[DYN_P + lane]; (&s.arm_a[0][0])[lane] = gd[DYN_A + lane]; s.qacc_s[lane] = gd[DYN_QACC + lane]; }
+  if (lane < 21) s.Marm[lane] = gd[DYN_MARM + lane];
+  for (int i = lane; i < 42; i += 32) (&s.Mprop[0][0])[i] = gd[DYN_MPROP + i];
+  if (lane < 24) reinterpret_cast<T *>(&s.arows)[lane] = gd[DYN_ROWS + lane];
 }
 
 // free-joint mass block (packed lower 6x6) and bias force for prop p (uniform; [upstream] mj_crb / mj_rne for a free body)
-template <typename T, typename S>
-__device__ __forceinline__ void prop_dynamics(const SceneModel<T> &sm, const ArmModelT<T> &am, const S &s, int p, T (&M)[21], T (&bias)[6]) {
-  const T *R = s.xmat[NJ + p];
+template <typename T>
+__device__ __forceinline__ void prop_dynamics(const SceneModel<T> &sm, const ArmModelT<T> &am, const T *R, const T *qd, int p, T (&M)[21], T (&bias)[6]) {
   const T m = sm.prop_mass[p];
   const T ip[3] = {sm.prop_ipos[p][0], sm.prop_ipos[p][1], sm.prop_ipos[p][2]};
   // M_tt = m I ; M_rt = (-m R [ipos]x)^T ; M_rr = I_origin (body axes, constant)
@@ -156,7 +139,6 @@ __device__ __forceinline__ void prop_dynamics(const SceneModel<T> &sm, const Arm
   const T *Io = sm.prop_Iorg[p];
   M[tri(3, 3)] = Io[0]; M[tri(4, 4)] = Io[1]; M[tri(5, 5)] = Io[2]; M[tri(4, 3)] = Io[3]; M[tri(5, 3)] = Io[4]; M[tri(5, 4)] = Io[5];
   // bias: f = m (w x (w x c) - g), tau_com = w x (Ic w)  (world); generalized: [f ; R^T (tau + c x f)]
-  const T *qd = s.qd + NJ + 6 * p;
   const T wl[3] = {qd[3], qd[4], qd[5]};
   T w[3], c[3], t1[3], t2[3], f[3];
   mulmv(w, R, wl); mulmv(c, R, ip);
@@ -264,18 +246,6 @@ template <typename T, typename S>
 __device__ __noinline__ void scene_broadphase(const SceneModel<T> &sm, S &s, const PipeBuf<T> &pb, int env, int sub, int &dropped, int lane) {
   BroadScratch<T> &cs = s.broad;
   PROF_START(s);
-  // publish the body poses for the narrow-phase kernel
-  {
-    T *gx = pb.xpos + (size_t)env * (NSLOT * 3), *gm = pb.xmat + (size_t)env * (NSLOT * 9);
-    for (int i = lane; i < NSLOT * 3; i += 32) gx[i] = (&s.xpos[0][0])[i];
-    for (int i = lane; i < NSLOT * 9; i += 32) gm[i] = (&s.xmat[0][0])[i];
-    // ... and the arm's kinematic state for the next substep's dynamics (same qpos: no second forward-kinematics pass)
-    static_assert(sizeof(ArmKin<T>) == 90 * sizeof(T), "ArmKin layout");
-    T *gk = pb.kin + (size_t)env * KINW;
-    const T *kk = reinterpret_cast<const T *>(&s.kin);
-    for (int i = lane; i < 90; i += 32) gk[i] = kk[i];
-    if (lane < 18) { gk[90 + lane] = (&s.arm_p[0][0])[lane]; gk[108 + lane] = (&s.arm_a[0][0])[lane]; }
-  }
   // world bounding spheres and oriented boxes of all geoms (lane per geom)
 #pragma unroll 1
   for (int g = lane; g < sm.ngeom; g += 32) {
@@ -561,33 +531,138 @@ __device__ __forceinline__ void prof_flush(SC &s, const EnvState<T> &S, int lane
       if (s.prof[i]) atomicAdd(S.prof + i, (unsigned long long)s.prof[i]);
 }
 
-// Once per control step: dm_control auto-reset, action -> ctrl, kinematics and broad phase of substep 0.
+// envs (warps) per CTA in the begin / broad-phase / task-layer kernels (static shared memory: 48 KB per CTA)
+template <typename T> struct BroadCfg { static constexpr int WARPS = sizeof(T) == 8 ? 2 : 4; };
+#define WARPS_BROAD (BroadCfg<T>::WARPS)
+constexpr int KD_THREADS = 64;   // envs (threads) per CTA in the kinematics + smooth-dynamics kernel
+
+// Once per control step: dm_control auto-reset (writes the FIRST TimeStep), action + calibration -> ctrl.
 template <typename T>
-__global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_begin_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
-                                                                      const __grid_constant__ StepCfg cfg, const EnvState<T> S, const PipeBuf<T> pb,
+__global__ void __launch_bounds__(WARPS_BROAD * 32) scene_begin_kernel(const __grid_constant__ StepCfg cfg, const EnvState<T> S, const PipeBuf<T> pb,
                                                                       const float *__restrict__ action, const so101_step_out out) {
-  using SC = Scratch<T, NC_S, NB_S>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SC *all = reinterpret_cast<SC *>(smem_raw);
+  __shared__ BroadEnv<T> all[WARPS_BROAD];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int env = pb.env0 + blockIdx.x * WARPS_SOLVE + wib;
+  const int env = pb.env0 + blockIdx.x * WARPS_BROAD + wib;
   if (env >= pb.env0 + pb.nenv) return;
-  SC &s = all[wib];
   if (lane == 0) pb.ncon_raw[env] = 0;
   if (S.needs_reset[env]) {  // the step() after a LAST step resets and returns FIRST; no physics this call
-    reset_env_scene(cfg, S, out, s, env, lane);
+    reset_env_scene(cfg, S, out, all[wib], env, lane);
     if (lane == 0) pb.active[env] = 0;
     return;
   }
-  prof_begin(s, S, lane);
-  for (int i = lane; i < NQ; i += 32) s.q[i] = S.qpos[(size_t)env * NQ + i];
   if (lane < NJ) S.ctrl[(size_t)env * 6 + lane] = (T)action[(size_t)env * 6 + lane] + (T)cfg.offsets[lane];  // so100_task.py:266-287
   if (lane == 0) { pb.active[env] = 1; pb.flags[env] = 0; }
+}
+
+// ONE THREAD per env: forward kinematics of the arm and the props at the current qpos (poses for the collision kernels and
+// the constraint Jacobians) and - unless this is the refresh after the last substep - the smooth dynamics the solve kernels
+// start from ([upstream] mj_kinematics, mj_comPos, mj_crb, mj_factorM, mj_rne, mj_fwdActuation, mj_fwdAcceleration and the
+// friction-loss / limit rows of mj_makeConstraint).  All of it is straight-line scalar code on registers, the same functions
+// the arm-only kernel uses (arm_dynamics.cuh, arm_solver.cuh).
+template <typename T>
+__global__ void __launch_bounds__(KD_THREADS) scene_kindyn_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
+                                                                 const EnvState<T> S, const PipeBuf<T> pb, int need_dyn) {
+  const int env = pb.env0 + blockIdx.x * KD_THREADS + threadIdx.x;
+  if (env >= pb.env0 + pb.nenv || !pb.active[env]) return;
+  const T *gq = S.qpos + (size_t)env * NQ, *gv = S.qvel + (size_t)env * NV;
+  T *gx = pb.xpos + (size_t)env * (NSLOT * 3), *gm = pb.xmat + (size_t)env * (NSLOT * 9), *gd = pb.dyn + (size_t)env * DYNW;
+  T qa[NJ], qda[NJ], ca[NJ];
+#pragma unroll
+  for (int i = 0; i < NJ; i++) { qa[i] = gq[i]; qda[i] = gv[i]; ca[i] = S.ctrl[(size_t)env * 6 + i]; }
+  ArmKin<T> k;
+  {
+    T R[NJ][9];
+    arm_fk<T>(am, qa, k, R);
+#pragma unroll
+    for (int i = 0; i < NJ; i++) {
+      gx[3 * i] = k.p[i].x; gx[3 * i + 1] = k.p[i].y; gx[3 * i + 2] = k.p[i].z;
+      gd[DYN_P + 3 * i] = k.p[i].x; gd[DYN_P + 3 * i + 1] = k.p[i].y; gd[DYN_P + 3 * i + 2] = k.p[i].z;
+      gd[DYN_A + 3 * i] = k.a[i].x; gd[DYN_A + 3 * i + 1] = k.a[i].y; gd[DYN_A + 3 * i + 2] = k.a[i].z;
+#pragma unroll
+      for (int e = 0; e < 9; e++) gm[9 * i + e] = R[i][e];
+    }
+  }
+  const bool dyn = need_dyn && !pb.flags[env];  // (a diverged env is frozen for the rest of the control step)
+#pragma unroll 1
+  for (int p = 0; p < NPROP; p++) {
+    const T *qp = gq + NJ + 7 * p;
+    const T quat[4] = {qp[3], qp[4], qp[5], qp[6]};
+    T Rp[9];
+    prop_rotation(quat, Rp);
+#pragma unroll
+    for (int c = 0; c < 3; c++) gx[3 * (NJ + p) + c] = qp[c];
+#pragma unroll
+    for (int e = 0; e < 9; e++) gm[9 * (NJ + p) + e] = Rp[e];
+    if (dyn) {
+      T qdp[6], M[21], bias[6], x[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) qdp[i] = gv[NJ + 6 * p + i];
+      prop_dynamics(sm, am, Rp, qdp, p, M, bias);
+#pragma unroll
+      for (int i = 0; i < 21; i++) gd[DYN_MPROP + 21 * p + i] = M[i];
+#pragma unroll
+      for (int i = 0; i < 6; i++) x[i] = -bias[i];
+      chol6(M);
+      chol6_solve(M, x);
+#pragma unroll
+      for (int i = 0; i < 6; i++) gd[DYN_QACC + NJ + 6 * p + i] = x[i];
+    }
+  }
+  if (!dyn) return;
+  T M[21], bias[NJ], frc[NJ], qs[NJ], L[21];
+  arm_crb_rne(am, k, qda, M, bias);
+  arm_actuation(am, qa, qda, ca, frc);
+#pragma unroll
+  for (int i = 0; i < 21; i++) { L[i] = M[i]; gd[DYN_MARM + i] = M[i]; }
+  chol6(L);
+#pragma unroll
+  for (int i = 0; i < NJ; i++) qs[i] = frc[i] - bias[i];
+  chol6_solve(L, qs);
+  ArmRows<T> arows;
+  arm_make_rows(am, qa, qda, qs, arows);
+#pragma unroll
+  for (int i = 0; i < NJ; i++) {
+    gd[DYN_QACC + i] = qs[i];
+    gd[DYN_ROWS + i] = arows.jar0_f[i]; gd[DYN_ROWS + 6 + i] = arows.jar0_l[i]; gd[DYN_ROWS + 12 + i] = arows.D_l[i]; gd[DYN_ROWS + 18 + i] = arows.js[i];
+  }
+}
+
+// Warp per env, after every kinematics refresh: the broad + mid phase that fills the work queues of substep `sub`, or - after
+// the last substep (`last`) - the task layer on the refreshed poses ([upstream] mj_step1 refresh before the observables
+// and the reward are read): observation delay rings, SO100HandOver reward, discount, time limit, outputs.
+template <typename T>
+__global__ void __launch_bounds__(WARPS_BROAD * 32) scene_broad_kernel(const __grid_constant__ SceneModel<T> sm, const __grid_constant__ StepCfg cfg,
+                                                                      const EnvState<T> S, const PipeBuf<T> pb, const so101_step_out out, int sub, int last) {
+  __shared__ BroadEnv<T> all[WARPS_BROAD];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int env = pb.env0 + blockIdx.x * WARPS_BROAD + wib;
+  if (env >= pb.env0 + pb.nenv || !pb.active[env]) return;
+  BroadEnv<T> &s = all[wib];
+  prof_begin(s, S, lane);
+  load_poses(pb, s, env, lane);
   __syncwarp();
-  scene_kinematics(am, s, lane);
-  int dropped = 0;
-  scene_broadphase(sm, s, pb, env, 0, dropped, lane);
-  if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
+  const bool bad = pb.flags[env] != 0;
+  if (!last) {
+    int dropped = 0;
+    if (!bad) scene_broadphase(sm, s, pb, env, sub, dropped, lane);
+    if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
+  } else {
+    for (int i = lane; i < NQ; i += 32) s.q[i] = S.qpos[(size_t)env * NQ + i];
+    for (int i = lane; i < NV; i += 32) s.qd[i] = S.qvel[(size_t)env * NV + i];
+    if (lane < NJ) s.ctrl[lane] = S.ctrl[(size_t)env * 6 + lane];
+    __syncwarp();
+    const int t = S.step[env] + 1;
+    float reward = scene_reward(sm, s), discount = 1.f;
+    uint8_t st = (cfg.last_step > 0 && t >= cfg.last_step) ? SO101_STEP_LAST : SO101_STEP_MID;
+    if (cfg.terminate_on_success && reward >= 1.f) { discount = 0.f; st = SO101_STEP_LAST; }  // so100_task.py:292-302
+    if (bad) { reward = 0.f; discount = 0.f; st = SO101_STEP_LAST; }                         // task_suite.py:153
+    __syncwarp();
+    if (lane == 0) {
+      S.step[env] = t; S.needs_reset[env] = st == SO101_STEP_LAST;
+      if (bad) atomicAdd(S.diverged_count, 1);
+    }
+    write_obs_scene(cfg, S, out, s, env, t, reward, discount, st, lane);
+  }
   prof_flush(s, S, lane);
 }
 
@@ -776,8 +851,7 @@ __device__ __noinline__ bool gather_contacts(const SceneModel<T> &sm, const Pipe
   return true;
 }
 
-// One substep of one env (warp): smooth dynamics, constraint rows from the gathered contacts, Newton, Euler; then either
-// the kinematics + broad phase of the next substep or (last substep) the task layer.  Returns false if the env must be
+// One substep of one env (warp): constraint rows from the gathered contacts and the dyn record, Newton, semi-implicit Euler.  Returns false if the env must be
 // handled by the large solver tier instead (nothing has been modified in that case).
 template <typename T, typename SC>
 __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
@@ -785,7 +859,6 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
   prof_begin(s, S, lane);
   for (int i = lane; i < NQ; i += 32) s.q[i] = S.qpos[(size_t)env * NQ + i];
   for (int i = lane; i < NV; i += 32) { s.qd[i] = S.qvel[(size_t)env * NV + i]; s.warm[i] = S.warm[(size_t)env * NV + i]; }
-  if (lane < NJ) s.ctrl[lane] = S.ctrl[(size_t)env * 6 + lane];
   if (lane == 0) s.dbg = 0;
   __syncwarp();
   int iters = 0, dropped = 0;
@@ -798,42 +871,8 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
   __syncwarp();
   if (!frozen) {
     PROF_CNT(s, P_NCON, s.ncon, lane);
-    load_kinematics(pb, s, env, lane);
-    {
-      T qa[NJ], qda[NJ], ca[NJ], M[21], bias[NJ], frc[NJ], qs[NJ];
-  #pragma unroll
-      for (int i = 0; i < NJ; i++) { qa[i] = s.q[i]; qda[i] = s.qd[i]; ca[i] = s.ctrl[i]; }
-      arm_crb_rne(am, s.kin, qda, M, bias);
-      arm_actuation(am, qa, qda, ca, frc);
-      T L[21];
-  #pragma unroll
-      for (int i = 0; i < 21; i++) L[i] = M[i];
-      chol6(L);
-  #pragma unroll
-      for (int i = 0; i < NJ; i++) qs[i] = frc[i] - bias[i];
-      chol6_solve(L, qs);
-      ArmRows<T> arows;
-      arm_make_rows(am, qa, qda, qs, arows);
-      if (lane == 0) {
-  #pragma unroll
-        for (int i = 0; i < 21; i++) s.Marm[i] = M[i];
-  #pragma unroll
-        for (int i = 0; i < NJ; i++) s.qacc_s[i] = qs[i];
-        s.arows = arows;
-      }
-    }
-    if (lane < NPROP) {  // one lane per prop
-      T M[21], bias[6], x[6];
-      prop_dynamics(sm, am, s, lane, M, bias);
-  #pragma unroll
-      for (int i = 0; i < 21; i++) s.Mprop[lane][i] = M[i];
-  #pragma unroll
-      for (int i = 0; i < 6; i++) x[i] = -bias[i];
-      chol6(M);
-      chol6_solve(M, x);
-  #pragma unroll
-      for (int i = 0; i < 6; i++) s.qacc_s[NJ + 6 * lane + i] = x[i];
-    }
+    load_poses(pb, s, env, lane);
+    load_dyn(pb, s, env, lane);
     __syncwarp();
     PROF_ACC(s, P_DYN, lane);
     if (S.dbg_contacts && last) {  // parity probe: contacts of the last substep
@@ -894,23 +933,7 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
     for (int i = lane; i < NQ; i += 32) S.qpos[(size_t)env * NQ + i] = s.q[i];
     for (int i = lane; i < NV; i += 32) { S.qvel[(size_t)env * NV + i] = s.qd[i]; S.warm[(size_t)env * NV + i] = s.warm[i]; }
   }
-  // poses at the new state: next substep's collision, or (mj_step1 refresh) the task layer
-  scene_kinematics(am, s, lane);
-  if (!last) {
-    if (!frozen) scene_broadphase(sm, s, pb, env, sub + 1, dropped, lane);
-  } else {
-    const bool bad = pb.flags[env] != 0;
-    const int t = S.step[env] + 1;
-    float reward = scene_reward(sm, s), discount = 1.f;
-    uint8_t st = (cfg.last_step > 0 && t >= cfg.last_step) ? SO101_STEP_LAST : SO101_STEP_MID;
-    if (cfg.terminate_on_success && reward >= 1.f) { discount = 0.f; st = SO101_STEP_LAST; }  // so100_task.py:292-302
-    if (bad) { reward = 0.f; discount = 0.f; st = SO101_STEP_LAST; }                         // task_suite.py:153
-    if (lane == 0) {
-      S.step[env] = t; S.needs_reset[env] = st == SO101_STEP_LAST; S.solver_iter[env] = iters; S.ncon[env] = s.ncon;
-      if (bad) atomicAdd(S.diverged_count, 1);
-    }
-    write_obs_scene(cfg, S, out, s, env, t, reward, discount, st, lane);
-  }
+  if (last && lane == 0) { S.solver_iter[env] = iters; S.ncon[env] = s.ncon; }
   if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
   prof_flush(s, S, lane);
   return true;
@@ -979,11 +1002,9 @@ __global__ void __launch_bounds__(WARPS * 32) scene_solve_tier_kernel(const __gr
 
 template <typename T>
 __global__ void scene_reset_kernel(const __grid_constant__ StepCfg cfg, const EnvState<T> S, const uint8_t *__restrict__ mask, const so101_step_out out) {
-  using SC = Scratch<T, NC_S, NB_S>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SC *all = reinterpret_cast<SC *>(smem_raw);
+  __shared__ BroadEnv<T> all[WARPS_BROAD];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int env = blockIdx.x * WARPS_SOLVE + wib;
+  const int env = blockIdx.x * WARPS_BROAD + wib;
   if (env >= S.N) return;
   if (mask && !mask[env]) return;
   reset_env_scene(cfg, S, out, all[wib], env, lane);
@@ -1000,7 +1021,7 @@ void scene_dropcat(int out[8]) { cudaMemcpyFromSymbol(out, g_dropcat, sizeof(int
 template <typename T>
 void scene_epahist(int out[8]) { cudaMemcpyFromSymbol(out, g_epahist, sizeof(int) * 8); }
 
-// Launches of one control step: per pipeline group 1 memset + 1 + 6 * nsub kernels on the group's streams, forked from and
+// Launches of one control step: per pipeline group 1 memset + 3 + 8 * nsub kernels on the group's streams, forked from and
 // joined back into the caller's stream.  Returns the kernel count.
 template <typename T>
 int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> *pbs,
@@ -1011,26 +1032,33 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
   const size_t smem_env = sizeof(Scratch<T, NC_S, NB_S>) * WARPS_SOLVE,
                smem_m = sizeof(Scratch<T, NC_M, NB_M>) * WARPS_M, smem_l = sizeof(Scratch<T, NC_L, NB_L>) * WARPS_L;
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaFuncSetAttribute(scene_begin_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
     cudaFuncSetAttribute(scene_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
     cudaFuncSetAttribute(scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
     cudaFuncSetAttribute(scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
-    cudaFuncSetAttribute(scene_reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   KernelTimer none;
   KernelTimer &t = kt ? *kt : none;
   cudaEventRecord(txs[0].start, stream);  // every group starts after the work already queued on the caller's stream
   for (int g = 0; g < ngroups; g++) cudaStreamWaitEvent(txs[g].main, txs[0].start, 0);
+  // kinematics (+ smooth dynamics) at the current state, then the broad phase for substep `sub` or the task layer
+  auto refresh = [&](const PipeBuf<T> &pb, cudaStream_t st, int sub, bool last) {
+    t.begin(6, st);
+    scene_kindyn_kernel<T><<<(pb.nenv + KD_THREADS - 1) / KD_THREADS, KD_THREADS, 0, st>>>(am, sm, S, pb, last ? 0 : 1);
+    t.end(6, st);
+    t.begin(7, st);
+    scene_broad_kernel<T><<<(pb.nenv + WARPS_BROAD - 1) / WARPS_BROAD, WARPS_BROAD * 32, 0, st>>>(sm, cfg, S, pb, out, sub, last ? 1 : 0);
+    t.end(7, st);
+  };
   // interleave the groups' launches substep by substep so that their kernels are in flight together
   for (int g = 0; g < ngroups; g++) {
     const PipeBuf<T> &pb = pbs[g];
     cudaStream_t st = txs[g].main;
     cudaMemsetAsync(pb.nwork, 0, sizeof(int) * WSTRIDE * (cfg.nsub + 1), st);
-    const int grid_env = (pb.nenv + WARPS_SOLVE - 1) / WARPS_SOLVE;
     t.begin(0, st);
-    scene_begin_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, st>>>(am, sm, cfg, S, pb, action, out);
+    scene_begin_kernel<T><<<(pb.nenv + WARPS_BROAD - 1) / WARPS_BROAD, WARPS_BROAD * 32, 0, st>>>(cfg, S, pb, action, out);
     t.end(0, st);
+    refresh(pb, st, 0, false);
   }
   const int sms = 148;
   for (int sub = 0; sub < cfg.nsub; sub++) {
@@ -1064,19 +1092,18 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
       scene_solve_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, st>>>(am, sm, cfg, S, pb, out, sub);
       t.end(2, st);
       cudaStreamWaitEvent(st, tx.joinm, 0); cudaStreamWaitEvent(st, tx.joinl, 0);
+      refresh(pb, st, sub + 1, sub == cfg.nsub - 1);
     }
   }
   for (int g = 0; g < ngroups; g++) {
     cudaEventRecord(txs[g].done, txs[g].main);
     cudaStreamWaitEvent(stream, txs[g].done, 0);
   }
-  return ngroups * (1 + 6 * cfg.nsub);
+  return ngroups * (3 + 8 * cfg.nsub);
 }
 template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream) {
-  const size_t smem = sizeof(Scratch<T, NC_S, NB_S>) * WARPS_SOLVE;
-  cudaFuncSetAttribute(scene_reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  scene_reset_kernel<T><<<(S.N + WARPS_SOLVE - 1) / WARPS_SOLVE, WARPS_SOLVE * 32, smem, stream>>>(cfg, S, mask, out);
+  scene_reset_kernel<T><<<(S.N + WARPS_BROAD - 1) / WARPS_BROAD, WARPS_BROAD * 32, 0, stream>>>(cfg, S, mask, out);
 }
 
 }  // namespace so101

@@ -300,12 +300,13 @@ class BatchedEnvironment:
     self._check(self._lib.so101_counters(self._h, ctypes.byref(c)))
     return dict(kernel_launches=int(c[0]), control_steps=int(c[1]), diverged=int(c[2]), contacts_dropped=int(c[3]))
 
-  KERNEL_NAMES = ("scene_begin_kernel", "scene_narrow_kernel", "scene_solve_kernel", "scene_solve_tier_kernel(1+2)", "arm_step_kernel", "scene_gjk_kernel")
+  KERNEL_NAMES = ("scene_begin_kernel", "scene_narrow_kernel", "scene_solve_kernel", "scene_solve_tier_kernel(1+2)", "arm_step_kernel", "scene_gjk_kernel",
+                  "scene_kindyn_kernel", "scene_broad_kernel")
 
   def kernel_times(self, enable: bool = True) -> dict:
     """Accumulated per-kernel device time (CUDA events around each launch, recorded while enabled) -> {name: (ms, launches)};
     then switches the recording on/off for the following steps."""
-    ms = (ctypes.c_double * 6)(); n = (ctypes.c_uint64 * 6)()
+    ms = (ctypes.c_double * 8)(); n = (ctypes.c_uint64 * 8)()
     self._check(self._lib.so101_kernel_times(self._h, int(enable), ctypes.byref(ms), ctypes.byref(n)))
     return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNEL_NAMES)}
 

@@ -170,7 +170,9 @@ def test_f64_contact_rich_rollout_matches_oracle(built):
 
 
 def test_kernel_times_and_launch_counts(built):
-  """so101_kernel_times: CUDA-event time per kernel while enabled; one control step = 1 + 6 x 10 launches per group."""
+  """so101_kernel_times: CUDA-event time per kernel while enabled; one control step = 3 + 8 x 10 launches per group
+  (begin, kinematics + dynamics, broad phase; then per substep GJK, EPA / manifold, classify, three solver tiers, kinematics + dynamics,
+  broad phase or task layer)."""
   env = _env(built, num_envs=8)
   env.sample_prop_initial_states(seed=2, settle_steps=0)
   c0 = env.counters()
@@ -180,7 +182,8 @@ def test_kernel_times_and_launch_counts(built):
     env.step(zero)
   kt = env.kernel_times(False)
   c1 = env.counters()
-  assert c1['kernel_launches'] - c0['kernel_launches'] == 3 * 61
+  assert c1['kernel_launches'] - c0['kernel_launches'] == 3 * 83
+  assert kt['scene_kindyn_kernel'][1] == 33 and kt['scene_broad_kernel'][1] == 33
   assert kt['scene_begin_kernel'][1] == 3 and kt['scene_gjk_kernel'][1] == 30 and kt['scene_narrow_kernel'][1] == 30
   assert kt['scene_solve_kernel'][1] == 30 and all(ms >= 0 for ms, _ in kt.values())
   assert kt['scene_solve_kernel'][0] > 0 and kt['arm_step_kernel'][1] == 0

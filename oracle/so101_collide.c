@@ -270,8 +270,7 @@ static int epa(const shape *A, const shape *B, mpoint *S, int n, double *normal,
     V[nv] = p;
     for (int f = 0; f < nf; f++) {
       if (!F[f].alive) continue;
-      double t[3]; sub3(t, p.w, V[F[f].v[0]].w);
-      if (dot3(F[f].n, t) > 1e-12) {
+      if (dot3(F[f].n, p.w) - F[f].d > 1e-12) { /* p above the face plane (n . v0 = d) */
         F[f].alive = 0;
         for (int e = 0; e < 3; e++) {
           int a = F[f].v[e], b = F[f].v[(e + 1) % 3], found = 0;

@@ -296,6 +296,16 @@ struct Handle : HandleBase {
       scene_epahist<T>(h);
       for (int i = 0; i < 8; i++) hf[i] = (float)h[i];
       CUDA_OK(cudaMemcpy(dst, hf, sizeof hf, cudaMemcpyHostToDevice));
+    } else if (f == "nprof") {
+      // narrow-phase warp timing probe (scene_narrow_seq_kernel, SO101_PROFILE=1): 16 counters as floats
+      if (count < 16) throw std::runtime_error("debug_read: buffer too small");
+      unsigned long long h[16]; float hf[16];
+      CUDA_OK(cudaStreamSynchronize(s));
+      scene_nprof<T>(h);
+      h[3] = (h[3] >> 8) * 256 + (h[3] & 0xff);  // (max warp cycles, geom id) stay packed; floats carry them approximately
+      for (int i = 0; i < 16; i++) hf[i] = (float)h[i];
+      hf[6] = (float)(h[3] & 0xff); hf[3] = (float)(h[3] >> 8);
+      CUDA_OK(cudaMemcpy(dst, hf, sizeof hf, cudaMemcpyHostToDevice));
     } else if (f == "dropcat") {
       // 8 drop counters by buffer (see scene_solve.cuh: g_dropcat), since the library was loaded
       if (count < 8) throw std::runtime_error("debug_read: buffer too small");

@@ -165,12 +165,11 @@ __device__ __forceinline__ void support_seq(const SceneModel<T> &sm, Shape<T> &s
       for (int guard = 0; guard < s.vnum; guard++) {  // (a non-finite direction cannot climb: the loop ends at once)
         int nxt = cur;
         const int k1 = adr[cur + 1];
-#pragma unroll 2
+#pragma unroll 4
         for (int k = adr[cur]; k < k1; k++) {
-          const int j = sm.hull_nbr[k];
-          v = vt[j];
-          const T val = v.x * dl[0] + v.y * dl[1] + v.z * dl[2];
-          if (val > bv) { bv = val; nxt = j; }
+          const Vec4<T> nb = sm.hull_nbrv[k];  // neighbour coordinates stored with the adjacency entry: one load, no index chase
+          const T val = nb.x * dl[0] + nb.y * dl[1] + nb.z * dl[2];
+          if (val > bv) { bv = val; nxt = (int)nb.w; }
         }
         if (nxt == cur) break;
         cur = nxt;

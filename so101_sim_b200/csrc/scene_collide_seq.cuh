@@ -42,13 +42,22 @@ __device__ __noinline__ int epa_add_face_seq(CollideScratch<T> &cs, int &nf, int
   cs.Falive[nf] = 1;
   return nf++;
 }
+// closest face to the origin (first minimum).  Dead faces carry Fd = +inf, so the scan needs one load per face; four faces
+// per trip keep four independent loads in flight (the polytope lives in local memory: a serial chain of ~100-cycle loads
+// otherwise).
 template <typename T>
 __device__ __forceinline__ int epa_best_seq(const CollideScratch<T> &cs, int nf) {
   T bd = INFINITY;
   int bi = -1;
 #pragma unroll 1
-  for (int f = 0; f < nf; f++)
-    if (cs.Falive[f] && cs.Fd[f] < bd) { bd = cs.Fd[f]; bi = f; }
+  for (int f0 = 0; f0 < nf; f0 += 4) {
+    const T d0 = cs.Fd[f0], d1 = f0 + 1 < nf ? cs.Fd[f0 + 1] : T(INFINITY), d2 = f0 + 2 < nf ? cs.Fd[f0 + 2] : T(INFINITY),
+            d3 = f0 + 3 < nf ? cs.Fd[f0 + 3] : T(INFINITY);
+    if (d0 < bd) { bd = d0; bi = f0; }
+    if (d1 < bd) { bd = d1; bi = f0 + 1; }
+    if (d2 < bd) { bd = d2; bi = f0 + 2; }
+    if (d3 < bd) { bd = d3; bi = f0 + 3; }
+  }
   return bi;
 }
 
@@ -106,27 +115,35 @@ __device__ __noinline__ int epa_seq(const SceneModel<T> &sm, CollideScratch<T> &
     const T adv = dot3(p.w, bn) - bd;
     if (adv < T(sizeof(T) == 8 ? 1e-9 : 1e-6)) break;
     epa_putv_seq(cs, nv, p);
-    // visibility, then the horizon in face order (same order as the oracle)
+    // visibility (p above the face plane: n . p - d > eps; dead faces have d = +inf), four faces per trip, then the horizon
+    // edits of the visible ones in face order (same order as the oracle)
     int nh = 0;
+    const T veps = T(sizeof(T) == 8 ? 1e-12 : 1e-9);
 #pragma unroll 1
-    for (int f = 0; f < nf; f++) {
-      if (!cs.Falive[f]) continue;
-      T v0[3], t[3];
-      const T fn[3] = {cs.Fn[0][f], cs.Fn[1][f], cs.Fn[2][f]};
-      epa_getv(cs, cs.Fv[0][f], v0);
-      sub3(t, p.w, v0);
-      if (!(dot3(fn, t) > T(sizeof(T) == 8 ? 1e-12 : 1e-9))) continue;
-      cs.Falive[f] = 0;
-      for (int e = 0; e < 3; e++) {
-        const int a = cs.Fv[e][f], b = cs.Fv[(e + 1) % 3][f];
-        int found = 0;
+    for (int f0 = 0; f0 < nf; f0 += 4) {
+      unsigned vis = 0;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int f = f0 + u < nf ? f0 + u : f0;
+        const T sdist = (cs.Fn[0][f] * p.w[0] + cs.Fn[1][f] * p.w[1] + cs.Fn[2][f] * p.w[2]) - cs.Fd[f];
+        if (f0 + u < nf && sdist > veps) vis |= 1u << u;
+      }
 #pragma unroll 1
-        for (int h = 0; h < nh; h++)
-          if (cs.horizon[h][0] == b && cs.horizon[h][1] == a) {
-            cs.horizon[h][0] = cs.horizon[nh - 1][0]; cs.horizon[h][1] = cs.horizon[nh - 1][1]; nh--; found = 1;
-            break;
-          }
-        if (!found && nh < EPA_MAXF) { cs.horizon[nh][0] = a; cs.horizon[nh][1] = b; nh++; }
+      while (vis) {
+        const int f = f0 + __ffs(vis) - 1;
+        vis &= vis - 1;
+        cs.Falive[f] = 0; cs.Fd[f] = INFINITY;
+        for (int e = 0; e < 3; e++) {
+          const int a = cs.Fv[e][f], b = cs.Fv[(e + 1) % 3][f];
+          int found = 0;
+#pragma unroll 1
+          for (int h = 0; h < nh; h++)
+            if (cs.horizon[h][0] == b && cs.horizon[h][1] == a) {
+              cs.horizon[h][0] = cs.horizon[nh - 1][0]; cs.horizon[h][1] = cs.horizon[nh - 1][1]; nh--; found = 1;
+              break;
+            }
+          if (!found && nh < EPA_MAXF) { cs.horizon[nh][0] = a; cs.horizon[nh][1] = b; nh++; }
+        }
       }
     }
     if (nh == 0) break;
@@ -185,8 +202,22 @@ __device__ __noinline__ int feature_seq(const SceneModel<T> &sm, CollideScratch<
 #pragma unroll
     for (int k = 0; k < 8; k++) { emax[k] = -INFINITY; emin[k] = INFINITY; imax[k] = imin[k] = 0; }
     const T thr = hmax - delta;
-    // four heights per trip (independent loads); the few in-slab vertices are then handled one by one in index order.  The
-    // first FEAT_EXACT of them are also stored, so that a small slab needs no second scan.
+    // one in-slab vertex: count it, keep the first FEAT_EXACT (a small slab then needs no second pass), update the extremes
+    auto take = [&](int i, const Vec4<T> &v) {
+      const T x = (v.x * t1l[0] + v.y * t1l[1] + v.z * t1l[2]) + ox, y = (v.x * t2l[0] + v.y * t2l[1] + v.z * t2l[2]) + oy;
+      if (nband < FEAT_EXACT) { cs.cand[0][nband] = x; cs.cand[1][nband] = y; cs.cand[2][nband] = (v.x * dl[0] + v.y * dl[1] + v.z * dl[2]) + off; }
+      nband++;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const T val = feat_cos<T>(k) * x + feat_sin<T>(k) * y;
+        if (val > emax[k]) { emax[k] = val; imax[k] = i; }
+        if (val < emin[k]) { emin[k] = val; imin[k] = i; }
+      }
+    };
+    // Full scan, four heights per trip (independent loads); the few in-slab vertices are then handled one by one in index order.
+    // (A flood fill of the slab over the vertex graph from the support vertex touches far fewer vertices of the banana's 1000-
+    // vertex hulls but measured 1.6x SLOWER for the kernel: its visited-bit updates and frontier are a serial chain of local-
+    // memory round trips, while this scan streams with all lanes busy.)
 #pragma unroll 1
     for (int i0 = 0; i0 < s.vnum; i0 += 4) {
       const int rem = s.vnum - i0;
@@ -199,16 +230,7 @@ __device__ __noinline__ int feature_seq(const SceneModel<T> &sm, CollideScratch<
       while (hit) {
         const int i = i0 + __ffs(hit) - 1;
         hit &= hit - 1;
-        const Vec4<T> v = vt[i];
-        const T x = (v.x * t1l[0] + v.y * t1l[1] + v.z * t1l[2]) + ox, y = (v.x * t2l[0] + v.y * t2l[1] + v.z * t2l[2]) + oy;
-        if (nband < FEAT_EXACT) { cs.cand[0][nband] = x; cs.cand[1][nband] = y; cs.cand[2][nband] = (v.x * dl[0] + v.y * dl[1] + v.z * dl[2]) + off; }
-        nband++;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const T val = feat_cos<T>(k) * x + feat_sin<T>(k) * y;
-          if (val > emax[k]) { emax[k] = val; imax[k] = i; }
-          if (val < emin[k]) { emin[k] = val; imin[k] = i; }
-        }
+        take(i, vt[i]);
       }
     }
     if (nband > FEAT_EXACT) {
@@ -394,9 +416,11 @@ __device__ __noinline__ int manifold_seq(const SceneModel<T> &sm, CollideScratch
 
 template <typename T>
 __device__ __noinline__ void collide_convex_seq(const SceneModel<T> &sm, CollideScratch<T> &cs, Shape<T> &A, Shape<T> &B, const MPoint<T> *S, int n,
-                                                PairContacts<T> &pc, int &eit) {
+                                                PairContacts<T> &pc, int &eit, long long &t_epa) {
   T normal[3], depth, pa[3], pb[3];
-  if (!epa_seq(sm, cs, A, B, S, n, normal, depth, pa, pb, eit)) return;
+  const int ok = epa_seq(sm, cs, A, B, S, n, normal, depth, pa, pb, eit);
+  t_epa = clock64();  // (stage probe: when this lane left EPA)
+  if (!ok) return;
   if (!(depth > T(0))) return;
   if (manifold_seq(sm, cs, A, B, normal, depth, pc) > 0) return;
   T frame[9], pos[3];

@@ -125,4 +125,6 @@ template <typename T>
 void scene_dropcat(int out[8]);
 template <typename T>
 void scene_epahist(int out[8]);
+template <typename T>
+void scene_nprof(unsigned long long out[16]);
 }  // namespace so101

@@ -760,6 +760,7 @@ __global__ void __launch_bounds__(NSEQ_THREADS, NSEQ_MINCTAS) scene_narrow_seq_k
   long long eit_sum = 0, nepa = 0;
 #pragma unroll 1
   for (int item = blockIdx.x * NSEQ_THREADS + threadIdx.x; item < nhit; item += stride) {
+    const long long t0 = clock64();
     const HitRec<T> &rec = pb.hits[item];
     const int env = (int)rec.env, g1 = (int)(rec.packed & 0xff), g2 = (int)((rec.packed >> 8) & 0xff), pidx = (int)(rec.packed >> 16);
     const T(*xpos)[3] = reinterpret_cast<const T(*)[3]>(pb.xpos + (size_t)env * (NSLOT * 3));
@@ -771,10 +772,11 @@ __global__ void __launch_bounds__(NSEQ_THREADS, NSEQ_MINCTAS) scene_narrow_seq_k
     CollideScratch<T> cs;
     PairContacts<T> pc;
     pc.n = 0;
+    long long t_epa = t0;
     if (A.type == G_PLANE) collide_plane_seq(sm, cs, A, B, pc);
     else {
       int eit = 0;
-      collide_convex_seq(sm, cs, A, B, reinterpret_cast<const MPoint<T> *>(&rec.S[0][0]), rec.n, pc, eit);
+      collide_convex_seq(sm, cs, A, B, reinterpret_cast<const MPoint<T> *>(&rec.S[0][0]), rec.n, pc, eit, t_epa);
       eit_sum += eit; nepa++;
       if (S.prof) atomicAdd(&g_epahist[eit <= 2 ? 0 : eit <= 5 ? 1 : eit <= 10 ? 2 : eit <= 20 ? 3 : eit <= 40 ? 4 : eit <= 79 ? 5 : 6], 1);
     }
@@ -788,6 +790,20 @@ __global__ void __launch_bounds__(NSEQ_THREADS, NSEQ_MINCTAS) scene_narrow_seq_k
           dst[6] = pc.dist[c];
           pb.con_key[(size_t)env * CONBUF + base + c] = (pidx << 20) | (c << 16) | (g1 << 8) | g2;
         }
+    }
+    if (S.prof) {  // stage probe: how long the lanes that were active in this trip spent in EPA and in the manifold stage
+      const long long t1 = clock64();
+      long long e = t_epa - t0, m = t1 - t_epa;
+      const unsigned act = __activemask();
+      for (int o = 16; o > 0; o >>= 1) { e = max(e, __shfl_xor_sync(act, e, o)); m = max(m, __shfl_xor_sync(act, m, o)); }
+      if (lane == __ffs(act) - 1) {
+        const long long tot = e + m;
+        atomicAdd(&g_nprof[0], (unsigned long long)e); atomicAdd(&g_nprof[1], (unsigned long long)m); atomicAdd(&g_nprof[2], 1ull);
+        atomicMax(&g_nprof[3], ((unsigned long long)tot << 8) | (unsigned)g2);
+        atomicMax(&g_nprof[4], (unsigned long long)e); atomicMax(&g_nprof[5], (unsigned long long)m);
+        const int bin = tot < 100000 ? 0 : tot < 200000 ? 1 : tot < 400000 ? 2 : tot < 800000 ? 3 : tot < 1600000 ? 4 : tot < 3200000 ? 5 : 6;
+        atomicAdd(&g_nprof[8 + bin], 1ull);
+      }
     }
   }
   if (S.prof) {
@@ -1020,6 +1036,8 @@ template <typename T>
 void scene_dropcat(int out[8]) { cudaMemcpyFromSymbol(out, g_dropcat, sizeof(int) * 8); }
 template <typename T>
 void scene_epahist(int out[8]) { cudaMemcpyFromSymbol(out, g_epahist, sizeof(int) * 8); }
+template <typename T>
+void scene_nprof(unsigned long long out[16]) { cudaMemcpyFromSymbol(out, g_nprof, sizeof(unsigned long long) * 16); }
 
 // Launches of one control step: per pipeline group 1 memset + 3 + 8 * nsub kernels on the group's streams, forked from and
 // joined back into the caller's stream.  Returns the kernel count.

@@ -6,4 +6,5 @@ template void launch_scene_reset<float>(const StepCfg &, const EnvState<float> &
 template size_t scene_smem_bytes<float>();
 template void scene_dropcat<float>(int *);
 template void scene_epahist<float>(int *);
+template void scene_nprof<float>(unsigned long long *);
 }  // namespace so101

@@ -6,4 +6,5 @@ template void launch_scene_reset<double>(const StepCfg &, const EnvState<double>
 template size_t scene_smem_bytes<double>();
 template void scene_dropcat<double>(int *);
 template void scene_epahist<double>(int *);
+template void scene_nprof<double>(unsigned long long *);
 }  // namespace so101

@@ -35,6 +35,7 @@ struct SceneModel {
   const T *geom_friction, *geom_solref, *geom_solimp, *geom_solmix, *geom_margin, *geom_gap;
   const Vec4<T> *hull_vert;  // body-frame hull vertices, 16/32-byte aligned for vector loads
   const int *hull_nbradr, *hull_nbr;  // vertex adjacency: CSR offsets per global vertex id, local neighbour ids (hill-climbing support)
+  const Vec4<T> *hull_nbrv;           // per adjacency entry: the neighbour's coordinates, w = its local id (one load per neighbour)
   // bodies
   const int *bodypair, *body_slot, *body_geomadr, *body_geomnum;
   const int *pair_start;          // [npair + 1]  range of body pair p in geompair
@@ -182,6 +183,17 @@ struct SceneModelHost {
     d.geom_friction = up(cvt(b.F("geom_friction"))); d.geom_solref = up(cvt(b.F("geom_solref"))); d.geom_solimp = up(cvt(b.F("geom_solimp")));
     d.geom_solmix = up(cvt(b.F("geom_solmix"))); d.geom_margin = up(cvt(b.F("geom_margin"))); d.geom_gap = up(cvt(b.F("geom_gap")));
     d.hull_vert = up(verts); d.hull_nbradr = up(b.I("hull_nbradr")); d.hull_nbr = up(b.I("hull_nbr"));
+    {
+      const auto &nadr = b.I("hull_nbradr"), &nbr = b.I("hull_nbr");
+      std::vector<Vec4<T>> nv(nbr.size());
+      for (int g = 0; g < ngeom; g++) {
+        if (b.I("geom_type")[g] != G_HULL) continue;
+        const int adr = b.I("geom_vertadr")[g], num = b.I("geom_vertnum")[g];
+        for (int v = adr; v < adr + num; v++)
+          for (int k = nadr[v]; k < nadr[v + 1]; k++) { nv[k] = verts[adr + nbr[k]]; nv[k].w = (T)nbr[k]; }
+      }
+      d.hull_nbrv = up(nv);
+    }
     {
       std::vector<int> pstart; std::vector<unsigned> gpairs;
       const auto &bpv = b.I("bodypair"), &ga = b.I("body_geomadr"), &gn = b.I("body_geomnum");

@@ -19,6 +19,7 @@ namespace so101 {
 // where contacts / candidate pairs were dropped by a full buffer since the library was loaded (diagnostics):
 // 0 NOUT per pair, 1 CANDCAP, 2 PAIRCAP, 3 work-queue capacity, 4 CONBUF raw contacts, 5 Jacobian block pool
 __device__ int g_dropcat[8];
+__device__ unsigned long long g_nprof[16];  // narrow-phase warp timing probe (SO101_PROFILE=1): see scene_narrow_seq_kernel
 __device__ int g_epahist[8];  // EPA iterations per call: <=2, <=5, <=10, <=20, <=40, <=79, cap, (unused)
 #define DROPCAT(i, n) atomicAdd(&g_dropcat[i], (int)(n))
 

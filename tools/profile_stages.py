@@ -50,5 +50,9 @@ eh = torch.empty(8, dtype=torch.float32, device='cuda:0')
 import ctypes as _ct
 env._check(env._lib.so101_debug_read(env._h, b'epahist', _ct.c_void_p(eh.data_ptr()), 8, env._stream()))
 res['epa_iter_hist(<=2,<=5,<=10,<=20,<=40,<=79,cap)'] = [int(x) for x in eh.tolist()[:7]]
+npf = torch.empty(16, dtype=torch.float32, device='cuda:0')
+env._check(env._lib.so101_debug_read(env._h, b'nprof', _ct.c_void_p(npf.data_ptr()), 16, env._stream()))
+npf = npf.tolist()
+res['narrow_warp_probe'] = dict(trips=int(npf[2]), mean_epa_cycles=npf[0] / max(npf[2], 1), mean_manifold_cycles=npf[1] / max(npf[2], 1), max_trip_cycles=npf[3], max_trip_geom2=int(npf[6]), max_epa_cycles=npf[4], max_manifold_cycles=npf[5], trip_cycles_hist_100k_200k_400k_800k_1600k_3200k=[int(x) for x in npf[8:15]])
 h = torch.histc(ncon.float(), bins=13, min=0, max=104); res['ncon_hist_bins_of_8'] = [int(x) for x in h.tolist()]
 print(json.dumps(res))

@@ -178,6 +178,7 @@ __device__ __noinline__ int epa_seq(const SceneModel<T> &sm, CollideScratch<T> &
 }
 
 // vertices of s within delta of the support plane along dir -> CCW 2-D convex polygon in (t1,t2) with heights
+constexpr int SCANW = 8;  // hull vertices examined per trip of the slab scan
 template <typename T>
 __device__ __noinline__ int feature_seq(const SceneModel<T> &sm, CollideScratch<T> &cs, Shape<T> &s, const T *dir, const T *t1, const T *t2, T delta,
                                         FPt<T> *out) {
@@ -214,18 +215,23 @@ __device__ __noinline__ int feature_seq(const SceneModel<T> &sm, CollideScratch<
         if (val < emin[k]) { emin[k] = val; imin[k] = i; }
       }
     };
-    // Full scan, four heights per trip (independent loads); the few in-slab vertices are then handled one by one in index order.
+    // Full scan, SCANW heights per trip (independent loads: the vertex loads come from L2 while the L1 is busy with the per-thread
+    // scratch, so the number of round trips is what counts); the few in-slab vertices are then handled one by one in index order.
     // (A flood fill of the slab over the vertex graph from the support vertex touches far fewer vertices of the banana's 1000-
     // vertex hulls but measured 1.6x SLOWER for the kernel: its visited-bit updates and frontier are a serial chain of local-
     // memory round trips, while this scan streams with all lanes busy.)
 #pragma unroll 1
-    for (int i0 = 0; i0 < s.vnum; i0 += 4) {
+    for (int i0 = 0; i0 < s.vnum; i0 += SCANW) {
       const int rem = s.vnum - i0;
-      const Vec4<T> v0 = vt[i0], v1 = vt[i0 + (rem > 1 ? 1 : 0)], v2 = vt[i0 + (rem > 2 ? 2 : 0)], v3 = vt[i0 + (rem > 3 ? 3 : 0)];
-      unsigned hit = ((v0.x * dl[0] + v0.y * dl[1] + v0.z * dl[2]) + off >= thr ? 1u : 0u) |
-                     (rem > 1 && (v1.x * dl[0] + v1.y * dl[1] + v1.z * dl[2]) + off >= thr ? 2u : 0u) |
-                     (rem > 2 && (v2.x * dl[0] + v2.y * dl[1] + v2.z * dl[2]) + off >= thr ? 4u : 0u) |
-                     (rem > 3 && (v3.x * dl[0] + v3.y * dl[1] + v3.z * dl[2]) + off >= thr ? 8u : 0u);
+      T hgt[SCANW];
+#pragma unroll
+      for (int u = 0; u < SCANW; u++) {  // (out-of-range slots re-read the chunk's first vertex and are masked below)
+        const Vec4<T> v = vt[i0 + (u < rem ? u : 0)];
+        hgt[u] = (v.x * dl[0] + v.y * dl[1] + v.z * dl[2]) + off;
+      }
+      unsigned hit = 0;
+#pragma unroll
+      for (int u = 0; u < SCANW; u++) hit |= (u < rem && hgt[u] >= thr) ? (1u << u) : 0u;
 #pragma unroll 1
       while (hit) {
         const int i = i0 + __ffs(hit) - 1;

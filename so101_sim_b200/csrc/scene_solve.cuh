@@ -26,6 +26,13 @@ __device__ int g_epahist[8];  // EPA iterations per call: <=2, <=5, <=10, <=20, 
 constexpr int NH = NV * (NV + 1) / 2;  // 171 packed lower-triangular entries
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
+// row of packed entry en (the inverse of tri): closed form instead of a search loop
+__device__ __forceinline__ int tri_row(int en) {
+  int i = (int)((sqrtf(8.f * (float)en + 1.f) - 1.f) * 0.5f);
+  if ((i + 1) * (i + 2) / 2 <= en) i++;   // guard the float rounding at the row boundaries
+  if (i * (i + 1) / 2 > en) i--;
+  return i;
+}
 
 template <typename T, int NC, int NB>
 struct SolveScratch {
@@ -434,9 +441,7 @@ __device__ __noinline__ void assemble(S &s, T f_arm, T hdiag_arm, int lane) {
   auto &R = s.sol;
   constexpr int NCH = sizeof(R.bmask[0]) / sizeof(unsigned);
   // unpack the lane's entry of a packed 6x6 lower triangle
-  int ti = 0;
-  while ((ti + 1) * (ti + 2) / 2 <= lane) ti++;
-  const int tj = lane - ti * (ti + 1) / 2;
+  const int ti = tri_row(lane), tj = lane - ti * (ti + 1) / 2;
   const int gk = lane - 21;  // gradient entry owned by lanes 21..26
 #pragma unroll 1
   for (int b = 0; b < 3; b++) {
@@ -563,9 +568,7 @@ __device__ __noinline__ int scene_solve(const ArmModelT<T> &am, T impratio, S &s
       __syncwarp();
 #pragma unroll 1
       for (int en = lane; en < NH; en += 32) {
-        int i = 0;
-        while ((i + 1) * (i + 2) / 2 <= en) i++;
-        const int j = en - i * (i + 1) / 2;
+        const int i = tri_row(en), j = en - i * (i + 1) / 2;
         s.H[en] *= s.hscale[i] * s.hscale[j];
       }
       __syncwarp();

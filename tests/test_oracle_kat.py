@@ -68,3 +68,27 @@ def test_kat2_reset_observation_semantics():
   assert tuple(k for k in KAT2['observation_keys'] if not k.endswith('_cam')) == OBSERVATION_KEYS
   # printed action bounds (2 decimals): +-3.14 for the five arm joints, [0, 0.08] for the jaw
   assert KAT2['action_spec']['minimum'] == [-3.14] * 5 + [0.0] and KAT2['action_spec']['maximum'] == [3.14] * 5 + [0.08]
+
+
+def test_overlap_matches_the_reference_oobb_utils_golden():
+  """tests/golden/oobb_overlap.json was produced by executing the reference's own so101_sim/utils/oobb_utils.py
+  (transform_oobb + overlap_oobb_oobb, the 6-axis SAT with strict comparisons) on 240 seeded box pairs built around the
+  task's overlap boxes (tools/make_golden_oobb.py).  The oracle's restatement must return the same booleans, and its
+  quaternion transform must reproduce the reference's world-space container boxes."""
+  import json
+  from oracle.oracle import overlap_oobb_oobb
+  g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'oobb_overlap.json')))
+  assert len(g['cases']) == 240
+  n_true = 0
+  for c in g['cases']:
+    got = overlap_oobb_oobb(c['obj_pos'], c['obj_quat'], c['obj_half'], c['ws_pos'], c['ws_quat'], c['container_half'])
+    assert got == c['overlap'], c
+    n_true += got
+    # transform_oobb (oobb_utils.py:175-199): position = body_pos + R(body_quat) container_pos, rotation = body_quat (x identity)
+    w, x, y, z = c['body_quat']
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                  [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                  [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    np.testing.assert_allclose(np.asarray(c['body_pos']) + R @ np.asarray(c['container_pos']), c['ws_pos'], atol=1e-12)
+    np.testing.assert_allclose(c['ws_quat'], c['body_quat'], atol=1e-15)
+  assert 60 < n_true < 180  # both outcomes are well represented

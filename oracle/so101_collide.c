@@ -198,6 +198,7 @@ static int gjk_intersect(const shape *A, const shape *B, mpoint *S, int *np, lon
 typedef struct { int v[3]; double n[3], d; int alive; } eface;
 #define EPA_MAXV 96
 #define EPA_MAXF 256
+#define EPA_MAXIT 50 /* [upstream] mjOption.ccd_iterations default */
 
 static int epa_add_face(eface *F, int *nf, const mpoint *V, int a, int b, int c, const double *inside) {
   if (*nf >= EPA_MAXF) return -1;
@@ -254,7 +255,7 @@ static int epa(const shape *A, const shape *B, mpoint *S, int n, double *normal,
   if (epa_add_face(F, &nf, V, 0, 1, 2, inside) < 0 || epa_add_face(F, &nf, V, 0, 1, 3, inside) < 0 ||
       epa_add_face(F, &nf, V, 0, 2, 3, inside) < 0 || epa_add_face(F, &nf, V, 1, 2, 3, inside) < 0) return 0;
   int best = -1;
-  for (int it = 0; it < 80; it++) {
+  for (int it = 0; it < EPA_MAXIT; it++) {
     (*iters)++;
     best = -1;
     double bd = INFINITY;

@@ -12,6 +12,7 @@ constexpr int NCON = 64;         // contacts per env the parity probe (debug_con
 constexpr int PAIRCAP = 64;      // candidate geom pairs per env per substep (after the OBB mid phase)
 constexpr int CONBUF = 128;      // raw contacts per env the narrow phase may write between two kernels
 constexpr int EPA_MAXV = 96, EPA_MAXF = 256;
+constexpr int EPA_MAXIT = 50;  // [upstream] mjOption.ccd_iterations default (same constant in the oracle)
 constexpr int MAXCAND = 32, MAXFEAT = 16, MAXMANI = 4;
 // Hull slabs with more than FEAT_EXACT vertices are represented by their extreme points along 16 tangent-plane directions
 // (scene_collide_seq.cuh feature_seq; oracle/so101_collide.c feature()); smaller ones keep the exact 2-D hull.

@@ -104,7 +104,7 @@ __device__ __noinline__ int epa_seq(const SceneModel<T> &sm, CollideScratch<T> &
       epa_add_face_seq(cs, nf, 0, 2, 3, inside) < 0 || epa_add_face_seq(cs, nf, 1, 2, 3, inside) < 0) return 0;
   int best = -1;
 #pragma unroll 1
-  for (int it = 0; it < 80; it++) {
+  for (int it = 0; it < EPA_MAXIT; it++) {
     best = epa_best_seq(cs, nf);
     if (best < 0) return 0;
     if (nv >= EPA_MAXV) break;
@@ -178,6 +178,9 @@ __device__ __noinline__ int epa_seq(const SceneModel<T> &sm, CollideScratch<T> &
 }
 
 // vertices of s within delta of the support plane along dir -> CCW 2-D convex polygon in (t1,t2) with heights
+#ifndef EPA_ITCAP
+#define EPA_ITCAP 80
+#endif
 constexpr int SCANW = 8;  // hull vertices examined per trip of the slab scan
 template <typename T>
 __device__ __noinline__ int feature_seq(const SceneModel<T> &sm, CollideScratch<T> &cs, Shape<T> &s, const T *dir, const T *t1, const T *t2, T delta,

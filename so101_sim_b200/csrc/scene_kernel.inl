@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(NSEQ_THREADS, NSEQ_MINCTAS) scene_narrow_seq_k
       int eit = 0;
       collide_convex_seq(sm, cs, A, B, reinterpret_cast<const MPoint<T> *>(&rec.S[0][0]), rec.n, pc, eit, t_epa);
       eit_sum += eit; nepa++;
-      if (S.prof) atomicAdd(&g_epahist[eit <= 2 ? 0 : eit <= 5 ? 1 : eit <= 10 ? 2 : eit <= 20 ? 3 : eit <= 40 ? 4 : eit <= 79 ? 5 : 6], 1);
+      if (S.prof) atomicAdd(&g_epahist[eit <= 2 ? 0 : eit <= 5 ? 1 : eit <= 10 ? 2 : eit <= 20 ? 3 : eit <= 40 ? 4 : eit < EPA_MAXIT ? 5 : 6], 1);
     }
     if (pc.n > 0) {
       const int base = atomicAdd(pb.ncon_raw + env, pc.n);

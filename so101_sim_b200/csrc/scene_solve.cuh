@@ -20,7 +20,7 @@ namespace so101 {
 // 0 NOUT per pair, 1 CANDCAP, 2 PAIRCAP, 3 work-queue capacity, 4 CONBUF raw contacts, 5 Jacobian block pool
 __device__ int g_dropcat[8];
 __device__ unsigned long long g_nprof[16];  // narrow-phase warp timing probe (SO101_PROFILE=1): see scene_narrow_seq_kernel
-__device__ int g_epahist[8];  // EPA iterations per call: <=2, <=5, <=10, <=20, <=40, <=79, cap, (unused)
+__device__ int g_epahist[8];  // EPA iterations per call: <=2, <=5, <=10, <=20, <=40, < cap, cap, (unused)
 #define DROPCAT(i, n) atomicAdd(&g_dropcat[i], (int)(n))
 
 constexpr int NH = NV * (NV + 1) / 2;  // 171 packed lower-triangular entries

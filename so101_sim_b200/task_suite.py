@@ -100,7 +100,11 @@ class SO100HandOver(SO100Task):
     if object_name not in self.CONFIGS:
       raise ValueError(f'Invalid object name: {object_name}, must be one of {self.CONFIGS.keys()}')  # so100_hand_over.py:146-150
     if not reward_based_on_overlap:
-      raise NotImplementedError('contact/distance reward fallback (so100_hand_over.py:277-318) is a "next" row')
+      # The reference's fallback (so100_hand_over.py:277-318) looks up the body 'so100/hand_link' (:284-288), which does not
+      # exist in the scene it loads (scene_pbr.xml: Base ... Moving_Jaw): mjcf `find` returns None and the first get_reward()
+      # raises AttributeError inside env.step().  There is no working behaviour to reproduce, so this fails at construction.
+      raise NotImplementedError("reward_based_on_overlap=False is not usable in the reference either: its get_reward() raises "
+                                "AttributeError on the missing body 'so100/hand_link' (so100_hand_over.py:284-288)")
     self.object_name = object_name
     self.model_name, self.instruction, self.rest_heights = self.CONFIGS[object_name]
 

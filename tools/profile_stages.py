@@ -49,7 +49,7 @@ res['counters'] = env.counters()
 eh = torch.empty(8, dtype=torch.float32, device='cuda:0')
 import ctypes as _ct
 env._check(env._lib.so101_debug_read(env._h, b'epahist', _ct.c_void_p(eh.data_ptr()), 8, env._stream()))
-res['epa_iter_hist(<=2,<=5,<=10,<=20,<=40,<=79,cap)'] = [int(x) for x in eh.tolist()[:7]]
+res['epa_iter_hist(<=2,<=5,<=10,<=20,<=40,<cap,cap)'] = [int(x) for x in eh.tolist()[:7]]
 npf = torch.empty(16, dtype=torch.float32, device='cuda:0')
 env._check(env._lib.so101_debug_read(env._h, b'nprof', _ct.c_void_p(npf.data_ptr()), 16, env._stream()))
 npf = npf.tolist()

@@ -30,6 +30,7 @@ constexpr unsigned FULL = 0xffffffffu;
 template <typename T>
 struct Shape {
   int type, geom, vadr, vnum;
+  int nbase;  // first adjacency entry of this hull (hull_nbradr[vadr])
   int hint;  // hill-climbing warm start: last support vertex of this shape while its pair is processed
   T pos[3], mat[9], size[3], center[3], rbound;
 };
@@ -97,6 +98,7 @@ template <typename T> __device__ __forceinline__ void local2world(const Shape<T>
 template <typename T>
 __device__ __noinline__ void make_shape(const SceneModel<T> &sm, const T (*xpos)[3], const T (*xmat)[9], int g, Shape<T> &s) {
   s.type = sm.geom_type[g]; s.geom = g; s.vadr = sm.geom_vertadr[g]; s.vnum = sm.geom_vertnum[g];
+  s.nbase = s.type == G_HULL ? sm.hull_nbradr[s.vadr] : 0;
   s.hint = 0;
   s.rbound = sm.geom_rbound[g];
   const int slot = sm.geom_slot[g];
@@ -162,18 +164,22 @@ __device__ __forceinline__ void support_seq(const SceneModel<T> &sm, Shape<T> &s
       int cur = s.hint;
       Vec4<T> v = vt[cur];
       T bv = v.x * dl[0] + v.y * dl[1] + v.z * dl[2];
+      int k0 = adr[cur], k1 = adr[cur + 1];
 #pragma unroll 1
       for (int guard = 0; guard < s.vnum; guard++) {  // (a non-finite direction cannot climb: the loop ends at once)
-        int nxt = cur;
-        const int k1 = adr[cur + 1];
+        unsigned best = 0xffffffffu;
 #pragma unroll 4
-        for (int k = adr[cur]; k < k1; k++) {
-          const Vec4<T> nb = sm.hull_nbrv[k];  // neighbour coordinates stored with the adjacency entry: one load, no index chase
+        for (int k = k0; k < k1; k++) {
+          // neighbour coordinates stored with the adjacency entry, together with where ITS neighbours are: one load per
+          // neighbour and no index chase between steps
+          const Vec4<T> nb = sm.hull_nbrv[k];
           const T val = nb.x * dl[0] + nb.y * dl[1] + nb.z * dl[2];
-          if (val > bv) { bv = val; nxt = (int)nb.w; }
+          if (val > bv) { bv = val; best = nbr_bits(nb.w); }
         }
-        if (nxt == cur) break;
-        cur = nxt;
+        if (best == 0xffffffffu) break;
+        cur = (int)(best & ((1u << NBR_ID_BITS) - 1));
+        k0 = s.nbase + (int)(best >> (NBR_ID_BITS + NBR_DEG_BITS));
+        k1 = k0 + (int)((best >> NBR_ID_BITS) & ((1u << NBR_DEG_BITS) - 1));
       }
       bi = cur;
       s.hint = cur;

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <vector>
 
 #include "arm_dynamics.cuh"
@@ -25,6 +26,21 @@ struct alignas(16) Vec4 {
   T x, y, z, w;
 };
 
+// w of a hull_nbrv entry: local vertex id (11 bits) | degree (7 bits) << 11 | adjacency offset within the hull (14 bits) << 18.
+// float: the bit pattern (never used in arithmetic); double: the integer value.
+constexpr unsigned NBR_ID_BITS = 11, NBR_DEG_BITS = 7, NBR_ADR_BITS = 14;
+template <typename T> __host__ __device__ inline T nbr_pack(unsigned v);
+template <> __host__ __device__ inline float nbr_pack<float>(unsigned v) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(v);
+#else
+  float f; std::memcpy(&f, &v, 4); return f;
+#endif
+}
+template <> __host__ __device__ inline double nbr_pack<double>(unsigned v) { return (double)v; }
+__device__ __forceinline__ unsigned nbr_bits(float w) { return __float_as_uint(w); }
+__device__ __forceinline__ unsigned nbr_bits(double w) { return (unsigned)w; }
+
 template <typename T>
 struct SceneModel {
   int ngeom, npair, nbody;
@@ -35,7 +51,8 @@ struct SceneModel {
   const T *geom_friction, *geom_solref, *geom_solimp, *geom_solmix, *geom_margin, *geom_gap;
   const Vec4<T> *hull_vert;  // body-frame hull vertices, 16/32-byte aligned for vector loads
   const int *hull_nbradr, *hull_nbr;  // vertex adjacency: CSR offsets per global vertex id, local neighbour ids (hill-climbing support)
-  const Vec4<T> *hull_nbrv;           // per adjacency entry: the neighbour's coordinates, w = its local id (one load per neighbour)
+  const Vec4<T> *hull_nbrv;           // per adjacency entry: the neighbour's coordinates; w packs its local id, degree and the offset
+                                      //   of ITS adjacency list inside the hull's (nbr_pack): a hill-climb step costs one round trip
   // bodies
   const int *bodypair, *body_slot, *body_geomadr, *body_geomnum;
   const int *pair_start;          // [npair + 1]  range of body pair p in geompair
@@ -190,7 +207,13 @@ struct SceneModelHost {
         if (b.I("geom_type")[g] != G_HULL) continue;
         const int adr = b.I("geom_vertadr")[g], num = b.I("geom_vertnum")[g];
         for (int v = adr; v < adr + num; v++)
-          for (int k = nadr[v]; k < nadr[v + 1]; k++) { nv[k] = verts[adr + nbr[k]]; nv[k].w = (T)nbr[k]; }
+          for (int k = nadr[v]; k < nadr[v + 1]; k++) {
+            const int j = nbr[k], deg = nadr[adr + j + 1] - nadr[adr + j], off = nadr[adr + j] - nadr[adr];
+            if (j >= (1 << NBR_ID_BITS) || deg >= (1 << NBR_DEG_BITS) || off >= (1 << NBR_ADR_BITS))
+              throw std::runtime_error("hull adjacency does not fit the packed neighbour record");
+            nv[k] = verts[adr + j];
+            nv[k].w = nbr_pack<T>((unsigned)j | ((unsigned)deg << NBR_ID_BITS) | ((unsigned)off << (NBR_ID_BITS + NBR_DEG_BITS)));
+          }
       }
       d.hull_nbrv = up(nv);
     }

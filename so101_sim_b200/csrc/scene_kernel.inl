@@ -58,13 +58,16 @@ struct BroadScratch {
 // per-env scratch of the begin / solve kernels (NC contacts, NB Jacobian blocks)
 template <typename T, int NC, int NB>
 struct Scratch {
-  T xpos[NSLOT][3], xmat[NSLOT][9];
-  T arm_p[NJ][3], arm_a[NJ][3];
+  // the poses are only read while the constraint rows are built, the Hessian only exists afterwards: they share storage
+  // (552 bytes less per env let 8 instead of 7 two-env CTAs of the tier-0 kernel fit the 228 KB of an SM)
+  union {
+    struct { T xpos[NSLOT][3], xmat[NSLOT][9], arm_p[NJ][3], arm_a[NJ][3]; };
+    T H[NH];
+  };
   ArmRows<T> arows;
-  T q[NQ], qd[NV], warm[NV], ctrl[NJ];
+  T q[NQ], qd[NV], warm[NV];
   T Mprop[NPROP][21];
   T Marm[21];
-  T H[NH];
   T qacc_s[NV], delta[NV], grad[NV], search[NV], Md[NV], hscale[NV];
   int ncon, dbg, profon;
   long long prof[16];  // developer probe (SO101_PROFILE=1): per-stage clock64 sums and counters of this env

@@ -252,3 +252,27 @@ def test_pen_f32_rollout_and_reset_pool(built):
     ts = env.step(acts[t])
   assert torch.isfinite(ts.observation['physics_state']).all() and env.counters()['diverged'] == 0
   env.close()
+
+
+def test_specs_match_the_reference_printouts(built):
+  """action_spec bounds and observation keys / shapes as printed by the reference (examples/so101_rl_breakdown.ipynb:65,
+  120-121,355-363 -> tests/golden/kat2_reset_observation.json): min/max = actuator ctrlrange with [0] -> +-pi and the gripper
+  -> [0, 0.08] (so100_task.py:232-251); state dim 38; joints_vel empty."""
+  import json, os
+  kat2 = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'kat2_reset_observation.json')))
+  env = _env(built, num_envs=2)
+  spec = env.action_spec()
+  assert spec.shape == (6,) and spec.dtype == np.float32
+  assert np.round(spec.minimum.astype(np.float64), 2).tolist() == kat2['action_spec']['minimum']
+  assert np.round(spec.maximum.astype(np.float64), 2).tolist() == kat2['action_spec']['maximum']
+  assert abs(float(spec.maximum[0]) - np.pi) < 1e-6 and abs(float(spec.maximum[1]) - 3.14158) < 1e-6
+  ts = env.reset()
+  keys = [k for k in kat2['observation_keys'] if not k.endswith('_cam')]
+  assert list(ts.observation.keys()) == keys == list(env.observation_spec().keys())
+  for k, shp in env.observation_spec().items():
+    assert tuple(ts.observation[k].shape[1:]) == tuple(shp), k
+  assert env.observation_spec()['physics_state'] == (38,) and env.observation_spec()['joints_vel'] == (0,)
+  # reset observation (KAT-2): commanded = HOME_CTRL (zero calibration), arm qpos = 0
+  np.testing.assert_allclose(ts.observation['commanded_joints_pos'][0].cpu().numpy(), kat2['commanded_joints_pos'], atol=1e-5)
+  assert float(ts.observation['joints_pos'].abs().max()) == 0.0
+  env.close()

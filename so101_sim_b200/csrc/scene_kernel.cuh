@@ -18,9 +18,10 @@ namespace so101 {
 constexpr int DYN_P = 0, DYN_A = 18, DYN_MARM = 36, DYN_MPROP = 57, DYN_QACC = 99, DYN_ROWS = 117, DYNW = 144;
 constexpr int GMAX_GEOMS = 96;       // geoms per model the broad phase holds in shared memory
 constexpr int WQ = 128;             // work queues (>= ngeom)
-constexpr int WSTRIDE = WQ + 8;     // counters per substep
+constexpr int WSTRIDE = 2 * WQ + 8; // counters per substep
 enum { W_CURSOR = WQ, W_NTIER = WQ + 1 /* [2]: envs queued for solver tier 1, 2 */, W_TIERCURSOR = WQ + 3 /* [2] */,
-       W_NHIT = WQ + 5 /* intersecting pairs found by the GJK kernel */, W_HITCURSOR = WQ + 6 };
+       W_NHIT = WQ + 5 /* intersecting pairs found by the GJK kernel */, W_HITCURSOR = WQ + 6,
+       W_QHIT = WQ + 8 /* [WQ]: intersecting pairs per work queue */ };
 
 // An intersecting pair handed from the boolean-GJK kernel (thread per pair) to the EPA / manifold kernel (warp per pair).
 template <typename T>
@@ -39,7 +40,9 @@ struct PipeBuf {
   uint2 *work;              // [WQ][work_cap]  narrow-phase work queues, one per second geom g2 (so that consecutive items
                             //   collide the same hull): (env, g1 | g2 << 8 | pair index << 16)
   int work_cap;             // entries per queue
-  HitRec<T> *hits;          // [hit_cap]  intersecting pairs of the current substep (arrival order ~ queue order)
+  HitRec<T> *hits;          // [hit_cap]  intersecting pairs of the current substep: the hits of work queue q occupy the first slots of
+                            //   the queue's own item range, so that the narrow phase sees them grouped by second geom whatever
+                            //   order the GJK warps finished in
   int hit_cap;
   int *nwork;               // [nsub+1][WSTRIDE]  per substep: items per queue [0..WQ), then pair cursor, large-tier envs
                             //   queued, large-tier cursor

@@ -694,7 +694,7 @@ __device__ __forceinline__ int queue_of(const int *qpref, int item) {  // larges
 // Per substep, ONE THREAD per candidate pair: boolean GJK.  Consecutive threads take consecutive items of one queue = the same
 // hull for different envs, so the vertex scan is a broadcast stream and the warp runs the simplex logic for 32 pairs at once
 // (the warp-per-pair version spent most of its instructions on scalar simplex code executed redundantly by 32 lanes).
-// Intersecting pairs are appended (warp-aggregated) with their simplex to the hit list for the EPA / manifold kernel.
+// Intersecting pairs go, with their simplex, to the hit slots of their work queue for the EPA / manifold kernel.
 constexpr int GJK_THREADS = 128;
 template <typename T>
 __global__ void __launch_bounds__(GJK_THREADS) scene_gjk_kernel(const __grid_constant__ SceneModel<T> sm, const EnvState<T> S, const PipeBuf<T> pb, int sub) {
@@ -729,21 +729,17 @@ __global__ void __launch_bounds__(GJK_THREADS) scene_gjk_kernel(const __grid_con
         git_sum += it;
       }
     }
-    const unsigned m = __ballot_sync(FULL, hit);
-    if (m) {
-      int base = 0;
-      if (lane == __ffs(m) - 1) base = atomicAdd(cnt + W_NHIT, __popc(m));
-      base = __shfl_sync(FULL, base, __ffs(m) - 1);
-      const int idx = base + __popc(m & ((1u << lane) - 1));
-      if (hit) {
-        if (idx < pb.hit_cap) {
-          HitRec<T> &r = pb.hits[idx];
-          r.env = w.x; r.packed = w.y; r.n = n; r.hintA = ha; r.hintB = hb; r.pad = 0;
-          for (int k = 0; k < n; k++)
+    if (hit) {
+      // slot inside the queue's own item range (hits <= items of the queue)
+      const int q = queue_of(qpref[wib], item);
+      const int idx = qpref[wib][q] + atomicAdd(cnt + W_QHIT + q, 1);
+      if (idx < pb.hit_cap) {
+        HitRec<T> &r = pb.hits[idx];
+        r.env = w.x; r.packed = w.y; r.n = n; r.hintA = ha; r.hintB = hb; r.pad = 0;
+        for (int k = 0; k < n; k++)
 #pragma unroll
-            for (int c = 0; c < 3; c++) { r.S[k][c] = Sx[k].w[c]; r.S[k][3 + c] = Sx[k].a[c]; r.S[k][6 + c] = Sx[k].b[c]; }
-        } else DROPCAT(6, 1);
-      }
+          for (int c = 0; c < 3; c++) { r.S[k][c] = Sx[k].w[c]; r.S[k][3 + c] = Sx[k].a[c]; r.S[k][6 + c] = Sx[k].b[c]; }
+      } else DROPCAT(6, 1);
     }
   }
   if (S.prof) {
@@ -756,15 +752,20 @@ __global__ void __launch_bounds__(GJK_THREADS) scene_gjk_kernel(const __grid_con
 constexpr int NSEQ_THREADS = 64, NSEQ_MINCTAS = 12;
 template <typename T>
 __global__ void __launch_bounds__(NSEQ_THREADS, NSEQ_MINCTAS) scene_narrow_seq_kernel(const __grid_constant__ SceneModel<T> sm, const EnvState<T> S, const PipeBuf<T> pb, int sub) {
-  const int lane = threadIdx.x & 31;
+  __shared__ int qpref[NSEQ_THREADS / 32][WQ + 1], hpref[NSEQ_THREADS / 32][WQ + 1];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   int *cnt = pb.nwork + WSTRIDE * sub;
-  const int nhit = min(cnt[W_NHIT], pb.hit_cap);
+  build_qpref(qpref[wib], cnt, pb.work_cap, lane);            // where each queue's slots start
+  build_qpref(hpref[wib], cnt + W_QHIT, pb.work_cap, lane);   // hits per queue -> item numbering of this kernel
+  const int nhit = hpref[wib][WQ];
   const int stride = gridDim.x * NSEQ_THREADS;
   long long eit_sum = 0, nepa = 0;
 #pragma unroll 1
   for (int item = blockIdx.x * NSEQ_THREADS + threadIdx.x; item < nhit; item += stride) {
     const long long t0 = clock64();
-    const HitRec<T> &rec = pb.hits[item];
+    const int hq = queue_of(hpref[wib], item), hslot = qpref[wib][hq] + (item - hpref[wib][hq]);
+    if (hslot >= pb.hit_cap) continue;
+    const HitRec<T> &rec = pb.hits[hslot];
     const int env = (int)rec.env, g1 = (int)(rec.packed & 0xff), g2 = (int)((rec.packed >> 8) & 0xff), pidx = (int)(rec.packed >> 16);
     const T(*xpos)[3] = reinterpret_cast<const T(*)[3]>(pb.xpos + (size_t)env * (NSLOT * 3));
     const T(*xmat)[9] = reinterpret_cast<const T(*)[9]>(pb.xmat + (size_t)env * (NSLOT * 9));
@@ -1088,7 +1089,7 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
       TierExec &tx = txs[g];
       cudaStream_t st = tx.main;
       const int grid_env = (pb.nenv + WARPS_SOLVE - 1) / WARPS_SOLVE;
-      const int grid_gjk = max(1, min(sms * 8, (pb.nenv * 16 + GJK_THREADS - 1) / GJK_THREADS));
+      const int grid_gjk = max(1, min(sms * 16, (pb.nenv * 16 + GJK_THREADS - 1) / GJK_THREADS));
       static const int seq_per_sm = getenv("SO101_SEQ_CTAS") ? atoi(getenv("SO101_SEQ_CTAS")) : 16;  // CTAs of 64 threads per SM
       const int grid_seq = max(1, min(sms * seq_per_sm, (pb.nenv * 12 + NSEQ_THREADS - 1) / NSEQ_THREADS));
       const int grid_m = pb.nenv < sms * 8 ? pb.nenv : sms * 8, grid_l = pb.nenv < sms * 4 ? pb.nenv : sms * 4;

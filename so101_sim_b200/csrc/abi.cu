@@ -219,7 +219,10 @@ struct Handle : HandleBase {
       for (int g = 0; g < ng; g++) {
         PipeBuf<T> p = pipe;
         p.env0 = (int)(N * g / ng); p.nenv = (int)(N * (g + 1) / ng) - p.env0;
-        p.work_cap = 4 * p.nenv + 64; p.work = dalloc<uint2>((size_t)WQ * p.work_cap);
+        // A queue holds the candidate pairs of ALL envs that share its key geom.  The static table is the partner of every arm
+        // geom that comes down on it (17 of them), so the per-queue capacity must cover many pairs per env (only the used
+        // entries are ever touched): 4 per env overflowed in long random-action rollouts and silently lost arm-table contacts.
+        p.work_cap = 16 * p.nenv + 64; p.work = dalloc<uint2>((size_t)WQ * p.work_cap);
         p.nwork = dalloc<int>(WSTRIDE * (c.n_substeps + 1)); p.big = dalloc<int>(2 * (size_t)p.nenv);
         p.hit_cap = p.nenv * 32; p.hits = dalloc<HitRec<T>>((size_t)p.hit_cap);
         groups.push_back(p);

@@ -364,13 +364,15 @@ __device__ __noinline__ void scene_broadphase(const SceneModel<T> &sm, S &s, con
   }
   if (npq > PAIRCAP) { dropped += npq - PAIRCAP; if (lane == 0) DROPCAT(2, npq - PAIRCAP); npq = PAIRCAP; }
   __syncwarp();
-  // append (env, g1 | g2 << 8 | pair index << 16) to the work queue of its second geom
+  // append (env, g1 | g2 << 8 | pair index << 16) to the work queue of its second geom - or of its first one when only that
+  // one is a hull (arm link vs table): the queue key is the geom whose vertex data the pair's threads will stream
   int qdrop = 0;
   for (int i = lane; i < npq; i += 32) {
     const unsigned pq = cs.pairq[i];
-    const int g2 = (int)((pq >> 8) & 0xff);
-    const int slot = atomicAdd(pb.nwork + WSTRIDE * sub + g2, 1);
-    if (slot < pb.work_cap) pb.work[(size_t)g2 * pb.work_cap + slot] = make_uint2((unsigned)env, pq);
+    const int g1 = (int)(pq & 0xff), g2 = (int)((pq >> 8) & 0xff);
+    const int q = (sm.geom_type[g2] != G_HULL && sm.geom_type[g1] == G_HULL) ? g1 : g2;
+    const int slot = atomicAdd(pb.nwork + WSTRIDE * sub + q, 1);
+    if (slot < pb.work_cap) pb.work[(size_t)q * pb.work_cap + slot] = make_uint2((unsigned)env, pq);
     else { qdrop++; DROPCAT(3, 1); }
   }
   dropped += warp_sum(qdrop);

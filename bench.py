@@ -301,7 +301,9 @@ def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_r
   for v in kern.values():
     v['share_of_kernel_time'] = v['ms'] / ktot; v['us_per_launch'] = 1e3 * v['ms'] / v['launches']
   dom = max(kern, key=lambda k: kern[k]['ms'])
-  per_launch_steps = envs if dom == 'arm_step_kernel' else envs / env.n_substeps
+  # one launch of a scene kernel advances the envs of ONE pipeline group by one substep: env-steps per launch follow from the
+  # launch count (steps x substeps x groups for the scene kernels, steps for the arm-only kernel)
+  per_launch_steps = envs * steps / kern[dom]['launches']
   bytes_per_launch = per_launch_steps * w['bytes_per_env_step']
   achieved = bytes_per_launch / (kern[dom]['us_per_launch'] * 1e-6) / 1e9
   traffic, traffic_src = ncu_traffic(name, envs)

@@ -209,10 +209,12 @@ struct Handle : HandleBase {
       pipe.xpos = dalloc<T>(N * NSLOT * 3); pipe.xmat = dalloc<T>(N * NSLOT * 9); pipe.dyn = dalloc<T>(N * DYNW);
       pipe.con = dalloc<T>(N * CONBUF * 8); pipe.con_key = dalloc<int>(N * CONBUF); pipe.ncon_raw = dalloc<int>(N);
       pipe.active = dalloc<uint8_t>(N); pipe.flags = dalloc<uint8_t>(N); pipe.tier = dalloc<uint8_t>(N);
-      // pipeline groups: independent env ranges whose kernel sequences run on their own streams.  Measured on B200 at 16384
-      // envs (profiles/r01_groups.txt): 1 group 72 ms/step, 2: 78, 4: 99, 8: 135 -- the kernels do not overlap enough to pay
-      // for their shorter, tail-dominated launches, so the default is ONE group; SO101_GROUPS keeps the experiment available.
-      int ng = getenv("SO101_GROUPS") ? atoi(getenv("SO101_GROUPS")) : 1;
+      // pipeline groups: independent env ranges whose kernel sequences run on their own streams, so that one group's short
+      // kernels (kinematics, broad phase, classify) and kernel tails overlap the other's long ones.  Measured on B200 at 16384
+      // envs (bench.py, random actions): 1 group 41.7 ms/step, 2 groups 40.7, 3: ~same, 4: 15 % slower (every kernel is bound
+      // by the latency of its slowest warps, which shorter launches do not shorten).  With the round-1 kernels 2 groups were
+      // slower (profiles/r01_groups.txt).  SO101_GROUPS overrides.
+      int ng = getenv("SO101_GROUPS") ? atoi(getenv("SO101_GROUPS")) : 2;
       const int by_size = (int)((N + 2047) / 2048);
       ng = std::max(1, std::min(std::min(ng, 8), by_size));
       tiers.resize(ng);

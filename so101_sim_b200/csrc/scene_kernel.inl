@@ -1,12 +1,12 @@
 // Control step of the FULL contact scene (BASELINE config 3: SO100HandOverBanana, nq=20 nv=18) as a pipeline of small
 // kernels per physics substep, all envs in lockstep (DESIGN.md section 4 has the table):
 //
-//   scene_begin_kernel       (once per control step, thread per env) auto-reset, action -> ctrl
+//   scene_begin_kernel       (once per control step, warp per env)   auto-reset from the reset pool, action -> ctrl
 //   scene_kindyn_kernel      (thread per env)                        arm forward kinematics, CRB mass matrix, RNE bias, actuation,
 //                                                                    prop mass blocks, qacc_smooth, friction / limit rows -> dyn record
 //   scene_broad_kernel       (warp per env)                          broad + mid phase -> per-geom work queues; after the last
 //                                                                    substep instead: the task layer (delay rings, reward, flags)
-//   scene_gjk_kernel         (thread per candidate geom pair)        boolean GJK over the work queues -> hit list
+//   scene_gjk_kernel         (thread per candidate geom pair)        boolean GJK over the work queues -> hit slots per queue
 //   scene_narrow_seq_kernel  (thread per intersecting pair)          EPA -> support-feature clipping manifold -> raw contacts
 //   scene_classify_kernel    (thread per env)                        solver tier by contact / Jacobian-block count
 //   scene_solve_kernel + scene_solve_tier_kernel x2 (warp per env, concurrent streams)
@@ -14,12 +14,13 @@
 //
 // The arm's kinematics and smooth dynamics are long straight-line scalar code: one THREAD per env runs them once per 32 envs
 // instead of 32 lanes of a warp running them redundantly, and the warp-per-env solve kernel is left with loop-structured
-// code that is a third of its former size (it was bound by instruction fetch: profiles/r01u_ncu_scene_solve_kernel.txt).
+// code that is a third of its former size (it was bound by instruction fetch: profiles/r01u_ncu_scene_solve_kernel.txt).  The envs of a handle are processed as two
+// pipeline groups on separate streams (abi.cu), so the launches below exist once per group.
 // Splitting by stage keeps each kernel's code and shared-memory footprint small (more resident warps, less instruction-
 // cache thrash) and turns the narrow phase - whose cost varies 10x between pairs - into flat work lists.  What crosses
 // kernels (body poses, pair queues, hit list, raw contacts; a few KB per env) is written once and read once.
 // Per substep order ([upstream] mj_step; legacy dm_control order is equivalent):
-//   arm FK / CRB / RNE            (all lanes redundantly, registers; arm_dynamics.cuh)
+//   arm FK / CRB / RNE            (one thread per env, registers; arm_dynamics.cuh)
 //   prop kinematics, M, bias      (free joints: linear dofs world frame, angular dofs body frame)
 //   collision                     (scene_collide.cuh, scene_collide_seq.cuh)
 //   constraint rows               (lane per contact: parameter mixing, impedance, Jacobian blocks, aref)
@@ -35,7 +36,7 @@
 
 namespace so101 {
 
-constexpr int WARPS_SOLVE = 2;   // envs (warps) per CTA in the begin / solve kernels
+constexpr int WARPS_SOLVE = 2;   // envs (warps) per CTA in the tier-0 solve kernel
 // Solver tiers by contact capacity: a resting scene has ~20 contacts, an arm pressed into the table or props 40-100.  Each
 // tier is the same code with a larger shared-memory scratch; an env that does not fit tier t is queued for tier t + 1.
 constexpr int NC_S = 32, NB_S = 40;            // tier 0: every env, 2 warps per CTA

@@ -202,7 +202,7 @@ __device__ __forceinline__ void support_seq(const SceneModel<T> &sm, Shape<T> &s
   local2world(s, p, out);
 }
 template <typename T>
-__device__ __noinline__ void msupport_seq(const SceneModel<T> &sm, Shape<T> &A, Shape<T> &B, const T *d, MPoint<T> &p) {
+__device__ __forceinline__ void msupport_seq(const SceneModel<T> &sm, Shape<T> &A, Shape<T> &B, const T *d, MPoint<T> &p) {
   const T nd[3] = {-d[0], -d[1], -d[2]};
   support_seq(sm, A, d, p.a); support_seq(sm, B, nd, p.b);
   sub3(p.w, p.a, p.b);
@@ -210,7 +210,7 @@ __device__ __noinline__ void msupport_seq(const SceneModel<T> &sm, Shape<T> &A, 
 
 // boolean GJK; mirrors gjk_intersect() of the oracle.  Uniform control flow across the warp.
 template <typename T>
-__device__ __noinline__ int gjk_intersect(const SceneModel<T> &sm, Shape<T> &A, Shape<T> &B, MPoint<T> *S, int &np, int &iters) {
+__device__ __forceinline__ int gjk_intersect(const SceneModel<T> &sm, Shape<T> &A, Shape<T> &B, MPoint<T> *S, int &np, int &iters) {
   T d[3];
   sub3(d, B.center, A.center);
   if (dot3(d, d) < T(1e-20)) { d[0] = T(1); d[1] = T(0); d[2] = T(0); }

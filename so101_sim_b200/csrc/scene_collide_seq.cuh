@@ -24,7 +24,7 @@ __device__ __forceinline__ void epa_putv_seq(CollideScratch<T> &cs, int i, const
   for (int c = 0; c < 3; c++) { cs.Vw[c][i] = p.w[c]; cs.Va[c][i] = p.a[c]; cs.Vb[c][i] = p.b[c]; }
 }
 template <typename T>
-__device__ __noinline__ int epa_add_face_seq(CollideScratch<T> &cs, int &nf, int a, int b, int c, const T *inside) {
+__device__ __forceinline__ int epa_add_face_seq(CollideScratch<T> &cs, int &nf, int a, int b, int c, const T *inside) {
   if (nf >= EPA_MAXF) return -1;
   T va[3], vb[3], vc[3], ab[3], ac[3], n[3], t[3];
   epa_getv(cs, a, va); epa_getv(cs, b, vb); epa_getv(cs, c, vc);

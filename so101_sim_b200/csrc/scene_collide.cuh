@@ -96,7 +96,7 @@ template <typename T> __device__ __forceinline__ void local2world(const Shape<T>
 
 // world pose of geom g.  xpos/xmat: the env's dynamic body poses (shared memory).
 template <typename T>
-__device__ __noinline__ void make_shape(const SceneModel<T> &sm, const T (*xpos)[3], const T (*xmat)[9], int g, Shape<T> &s) {
+__device__ __forceinline__ void make_shape(const SceneModel<T> &sm, const T (*xpos)[3], const T (*xmat)[9], int g, Shape<T> &s) {
   s.type = sm.geom_type[g]; s.geom = g; s.vadr = sm.geom_vertadr[g]; s.vnum = sm.geom_vertnum[g];
   s.nbase = s.type == G_HULL ? sm.hull_nbradr[s.vadr] : 0;
   s.hint = 0;

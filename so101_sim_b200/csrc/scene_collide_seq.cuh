@@ -323,7 +323,7 @@ __device__ __noinline__ int feature_seq(const SceneModel<T> &sm, CollideScratch<
 }
 
 template <typename T>
-__device__ __noinline__ int clip_poly_seq(CollideScratch<T> &cs, const FPt<T> *subj, int n, const FPt<T> *clip, int m, FPt<T> *out) {
+__device__ __forceinline__ int clip_poly_seq(CollideScratch<T> &cs, const FPt<T> *subj, int n, const FPt<T> *clip, int m, FPt<T> *out) {
   constexpr int CAP = 2 * MAXFEAT + 8;
   int na = n;
   FPt<T> *in = cs.bufA, *res = cs.bufB;

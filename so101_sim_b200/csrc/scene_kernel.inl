@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(NSEQ_THREADS, NSEQ_MINCTAS) scene_narrow_seq_k
 // Gather the env's raw contacts into shared memory in oracle order (pair order, then manifold order).  Returns false (and
 // touches nothing) when the env needs more than NC contacts or NB Jacobian blocks: the caller defers it to the large tier.
 template <typename T, typename SC>
-__device__ __noinline__ bool gather_contacts(const SceneModel<T> &sm, const PipeBuf<T> &pb, SC &s, int env, int &dropped, int lane) {
+__device__ __forceinline__ bool gather_contacts(const SceneModel<T> &sm, const PipeBuf<T> &pb, SC &s, int env, int &dropped, int lane) {
   auto &R = s.sol;
   constexpr int NC = sizeof(R.D0) / sizeof(T), NB = sizeof(R.w1[0]) / sizeof(T);
   int nraw = pb.ncon_raw[env];

@@ -55,7 +55,7 @@ struct SolveScratch {
 // ------------------------------------------------------------------------------------------------ constraint rows (lane per contact)
 // S must provide: sol (SolveScratch), ncon, xpos, xmat, arm_p, arm_a, qd.
 template <typename T, typename S>
-__device__ __noinline__ void build_rows(const SceneModel<T> &sm, S &s, int &dropped, int lane) {
+__device__ __forceinline__ void build_rows(const SceneModel<T> &sm, S &s, int &dropped, int lane) {
   auto &R = s.sol;
   constexpr int NC = sizeof(R.D0) / sizeof(T), NB = sizeof(R.w1[0]) / sizeof(T);
   const int ncon = s.ncon;
@@ -274,7 +274,7 @@ __device__ __forceinline__ T blockdiag_mv(const S &s, const T *x, int i) {  // (
 
 // v[r][c] = sum_col J[r][col] x[base + col] over the contact's (<= 2) blocks, for the lane's contacts
 template <typename T, typename S>
-__device__ __noinline__ void contacts_Jx(S &s, const T *x, int lane) {  // -> R.v.ls.jv
+__device__ __forceinline__ void contacts_Jx(S &s, const T *x, int lane) {  // -> R.v.ls.jv
   auto &R = s.sol;
 #pragma unroll 1
   for (int c = lane; c < s.ncon; c += 32) {
@@ -338,7 +338,7 @@ __device__ __noinline__ void rows_line(S &s, const ArmLane<T> &al, T impratio, T
 }
 
 template <typename T>
-__device__ __noinline__ void cholesky_packed(T *H, int lane) {  // in-place lower Cholesky of the packed NV x NV matrix, lanes = rows
+__device__ __forceinline__ void cholesky_packed(T *H, int lane) {  // in-place lower Cholesky of the packed NV x NV matrix, lanes = rows
 #pragma unroll 1
   for (int j = 0; j < NV; j++) {
     T sacc = T(0);
@@ -353,7 +353,7 @@ __device__ __noinline__ void cholesky_packed(T *H, int lane) {  // in-place lowe
   }
 }
 template <typename T>
-__device__ __noinline__ T chol_solve_packed(const T *L, T b, int lane) {  // lane i holds b_i; returns x_i
+__device__ __forceinline__ T chol_solve_packed(const T *L, T b, int lane) {  // lane i holds b_i; returns x_i
 #pragma unroll 1
   for (int k = 0; k < NV; k++) {
     const T yk = wshfl(b, k) / L[tri(k, k)];
@@ -372,7 +372,7 @@ __device__ __noinline__ T chol_solve_packed(const T *L, T b, int lane) {  // lan
 // Block-diagonal case (no contact couples two bodies: the usual resting scene): the three 6x6 blocks factor independently, 6
 // columns instead of 18.  Bitwise identical to the full routines on such a matrix (the skipped products are all 0 * x).
 template <typename T>
-__device__ __noinline__ void cholesky_blocks(T *H, int lane) {
+__device__ __forceinline__ void cholesky_blocks(T *H, int lane) {
   const int b = lane / 6, r = lane - 6 * b, base = 6 * b;
   const bool act = lane < NV;
 #pragma unroll 1
@@ -389,7 +389,7 @@ __device__ __noinline__ void cholesky_blocks(T *H, int lane) {
   }
 }
 template <typename T>
-__device__ __noinline__ T chol_solve_blocks(const T *L, T bv, int lane) {
+__device__ __forceinline__ T chol_solve_blocks(const T *L, T bv, int lane) {
   const int b = lane / 6, r = lane - 6 * b, base = 6 * b;
   const bool act = lane < NV;
 #pragma unroll 1
@@ -407,7 +407,7 @@ __device__ __noinline__ T chol_solve_blocks(const T *L, T bv, int lane) {
 
 // One Newton pass over the contacts: cone forces, factored cone Hessians (e, w1 = J^T v1, w2 = J^T v2).  Lane per contact.
 template <typename T, typename S>
-__device__ __noinline__ void contacts_eval(S &s, T impratio, int lane) {
+__device__ __forceinline__ void contacts_eval(S &s, T impratio, int lane) {
   auto &R = s.sol;
 #pragma unroll 1
   for (int ci = lane; ci < s.ncon; ci += 32) {
@@ -437,7 +437,7 @@ __device__ __noinline__ void contacts_eval(S &s, T impratio, int lane) {
 
 // Hessian H = M + J^T Hc J (+ arm row curvature) and gradient Md - J^T f - f_arm, assembled per body block.
 template <typename T, typename S>
-__device__ __noinline__ void assemble(S &s, T f_arm, T hdiag_arm, int lane) {
+__device__ __forceinline__ void assemble(S &s, T f_arm, T hdiag_arm, int lane) {
   auto &R = s.sol;
   constexpr int NCH = sizeof(R.bmask[0]) / sizeof(unsigned);
   // unpack the lane's entry of a packed 6x6 lower triangle

@@ -10,8 +10,9 @@ Workloads:
                "pick-place env-steps/sec" metric is quoted on; largest single-GPU pick-place config in BASELINE.json)
   arm4096      config 2: arm-only, collisions off, 4096 envs per GPU (also measured and attached as `other_workloads`)
 value  = env-steps/s with inputs resident in HBM (CUDA events around each step, L2 flushed between steps).
-e2e    = env-steps/s through BatchedEnvironment.step_host(): pinned host action in, reward/discount/step_type/joints_pos out,
-         copies and the stream sync inside the timed region.
+e2e    = env-steps/s through BatchedEnvironment.step_host(): pinned host action in, the WHOLE TimeStep (observation dict, reward,
+         discount, step_type) out to pinned host tensors, copies and the stream sync inside the timed region.
+steady_state = the same workload with episodes cycling through auto-reset (short episodes, staggered phases, reset pool).
 """
 from __future__ import annotations
 
@@ -39,6 +40,9 @@ WORKLOADS = {
                         desc='BASELINE config 3: SO100HandOverBanana with contacts, 16384 lockstep envs per GPU'),
 }
 METRIC = 'SO101 pick-place env-steps/sec at 1/2/4/8 B200 vs MuJoCo CPU on host cores'
+# the float32 product path keeps the integration state, the actuator model and the Euler update in float64
+# (so101_sim_b200/csrc/env_state.cuh); dynamics, collision and the constraint solver run in float32
+PRECISION_NOTE = {'f32': 'f32 dynamics / collision / solver, f64 integration state + actuator model + Euler update', 'f64': 'f64'}
 
 
 def measured_peak_gbs():
@@ -144,12 +148,15 @@ def main():
   ap.add_argument('--cpu-seconds', type=float, default=10.0)
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-secondary', action='store_true', help='skip the attached arm4096 measurement')
+  ap.add_argument('--no-steady', action='store_true', help='skip the attached steady-state (cycling episodes) measurement')
+  ap.add_argument('--steady-steps', type=int, default=200)
+  ap.add_argument('--steady-warmup', type=int, default=50)
   a = ap.parse_args()
   rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
   local_rank = int(os.environ.get('LOCAL_RANK', 0))
   w = WORKLOADS[a.workload]
   envs = a.envs or w['envs']
-  config = dict(workload=a.workload, description=w['desc'], envs_per_gpu=envs, substeps_per_step=10, precision=a.precision,
+  config = dict(workload=a.workload, description=w['desc'], envs_per_gpu=envs, substeps_per_step=10, precision=PRECISION_NOTE[a.precision],
                 parallelism=f'env-sharded x{world} (no per-step collective)',
                 l2='256 MiB memset between timed steps, excluded from the timing by per-step CUDA events')
 
@@ -187,12 +194,14 @@ def main():
     out = dict(metric=METRIC, value=res['value'], unit='env-steps/s', n_gpus=world, steps=a.steps, warmup=a.warmup,
                ms_per_step=res['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None,
                dtype=a.precision, data='synthetic', config=config, e2e=res['e2e'], gpu_launches=res['gpu_launches'],
-               clocks=res['clocks'], roofline=res['roofline'], kernels=res['kernels'], wall_s=res['wall_s'],
+               graph_launches=res['graph_launches'], launches_per_step=res['launches_per_step'], clocks=res['clocks'], roofline=res['roofline'], kernels=res['kernels'], wall_s=res['wall_s'],
                mean_return=res['mean_return'], diverged=res['diverged'], contacts_dropped=res['contacts_dropped'])
     if world == 1 and not a.no_secondary and a.workload != 'arm4096':
       # BASELINE config 2 (arm-only) measured beside the headline workload: a short run, kernel-only and e2e
       r2 = run_workload('arm4096', WORKLOADS['arm4096']['envs'], 50, 5, a.precision, dev, rank, world, local_rank)
       out['other_workloads'] = {'arm4096': {k: r2[k] for k in ('value', 'ms_per_step', 'e2e', 'gpu_launches', 'roofline')}}
+    if world == 1 and not a.no_steady and WORKLOADS[a.workload]['collide']:
+      out['steady_state'] = run_steady_state(a.workload, envs, a.steady_steps, a.steady_warmup, a.precision, dev, rank)
     if not a.no_cpu_baseline and world == 1:
       out['cpu_baseline'] = cpu_baseline(a.workload, a.cpu_seconds, os.cpu_count() or 1)
     print(json.dumps(out))
@@ -210,37 +219,52 @@ def ncu_traffic(workload, envs):
   return (t['dram_bytes_per_launch'], t['source']) if t else (None, None)
 
 
+def _actions(env, n, envs, dev, seed):
+  import torch
+  g = torch.Generator(device=dev); g.manual_seed(seed)
+  spec = env.action_spec()
+  lo, hi = torch.tensor(spec.minimum, device=dev), torch.tensor(spec.maximum, device=dev)
+  return (lo + torch.rand(n, envs, 6, generator=g, device=dev) * (hi - lo)) * 0.3
+
+
 def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_rank):
   import torch
   import torch.distributed as dist
+  from so101_sim_b200.sharding import EpisodeStats, gather_episode_stats, rank_seed
   from so101_sim_b200.task_suite import create_batched_task_env
   w = WORKLOADS[name]
-  env = create_batched_task_env(w['task'], num_envs=envs, time_limit=30.0, seed=rank, device=dev, precision=precision)
+  env = create_batched_task_env(w['task'], num_envs=envs, time_limit=30.0, seed=rank, device=dev, precision=precision, reset_rounds=0)
   if w['task'] == 'SO100ArmOnly':
-    env.sample_arm_initial_states(seed=0 + 1000 * rank)
+    env.sample_arm_initial_states(seed=rank_seed(0, rank))
   else:
-    env.sample_prop_initial_states(seed=0 + 1000 * rank, spawn_z=0.45, settle_steps=50)  # reference drop height, settled 1 s
+    env.sample_prop_initial_states(seed=rank_seed(0, rank), spawn_z=0.45, settle_steps=50)  # reference drop height, settled 1 s
   env.reset()
   total = warmup + steps
-  g = torch.Generator(device=dev); g.manual_seed(1 + 1000 * rank)
-  spec = env.action_spec()
-  lo, hi = torch.tensor(spec.minimum, device=dev), torch.tensor(spec.maximum, device=dev)
   nact = min(total, 64)
-  acts = (lo + torch.rand(nact, envs, 6, generator=g, device=dev) * (hi - lo)) * 0.3
+  acts = _actions(env, nact, envs, dev, rank_seed(1, rank))
   flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
   ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
   ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-  ret_sum = torch.zeros(envs, device=dev); ep_len = torch.zeros(envs, dtype=torch.int32, device=dev)
+  stats = EpisodeStats(envs, dev)
+  ret_sum = torch.zeros(envs, device=dev)
 
   def barrier():
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize()
 
+  def max_over_ranks(x):
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+  # ---- value: inputs resident in HBM, one step = one so101_step call (a CUDA-graph replay of the step's kernels); the
+  # per-kernel event timers are OFF here (they need eager launches and ~330 event records per step)
+  env.kernel_times(False)
   for i in range(warmup):
     env.step(acts[i % nact])
   c0 = env.counters()
-  k0 = env.kernel_times(True)   # per-kernel CUDA events on the launching stream from here on
   barrier()
   with ClockSampler(local_rank) as clocks:
     t_wall0 = time.perf_counter()
@@ -249,75 +273,111 @@ def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_r
       ev0[i].record()
       ts = env.step(acts[(warmup + i) % nact])
       ev1[i].record()
-      ret_sum += ts.reward; ep_len += 1
+      stats.update(ts.step_type, ts.reward); ret_sum += ts.reward
     barrier()
     t_wall = time.perf_counter() - t_wall0
   c1 = env.counters()
-  k1 = env.kernel_times(False)
-  step_ms = [ev0[i].elapsed_time(ev1[i]) for i in range(steps)]
-  dev_ms = float(sum(step_ms))
-  t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-  if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  dev_ms = float(t.item())
+  dev_ms = max_over_ranks(float(sum(ev0[i].elapsed_time(ev1[i]) for i in range(steps))))
   value = envs * world * steps / (dev_ms * 1e-3)
 
-  # ---- e2e: host buffers through the public API (H2D + step + D2H + sync per step).  The envs go back to the same initial
-  # state and replay the same action sequence (warm-up included), so both legs time the same stretch of the rollout: the
-  # contact load grows while the random actions flail the arm, and a leg timed later would see a heavier regime.
-  pin = dict(pin_memory=True)
-  h_act = [torch.empty(envs, 6, dtype=torch.float32, **pin).copy_(acts[i].cpu()) for i in range(nact)]
-  h_rew = torch.empty(envs, dtype=torch.float32, **pin); h_dis = torch.empty(envs, dtype=torch.float32, **pin)
-  h_st = torch.empty(envs, dtype=torch.uint8, **pin); h_jp = torch.empty(envs, 6, dtype=torch.float32, **pin)
+  # ---- per-kernel pass (separate from the timed region above): the rollout simply continues for a few steps with CUDA events
+  # around every launch on its launching stream (eager launches)
+  ksteps = max(2, min(steps, 10))
+  k0 = env.kernel_times(True)
+  for i in range(ksteps):
+    env.step(acts[(total + i) % nact])
+  torch.cuda.synchronize()
+  k1 = env.kernel_times(False)
+
+  # ---- e2e: host buffers through the public API (H2D of the action + step + D2H of the WHOLE TimeStep - observation dict,
+  # reward, discount, step_type - + sync, per step).  The envs go back to the same initial state and replay the same action
+  # sequence (warm-up included), so both legs time the same stretch of the rollout.
+  h_act = [torch.empty(envs, 6, dtype=torch.float32, pin_memory=True).copy_(acts[i].cpu()) for i in range(nact)]
+  h_out = env.make_host_timestep()
   env.reset()
   for i in range(warmup):
-    env.step_host(h_act[i % nact], h_rew, h_dis, h_st, h_jp)
+    env.step_host(h_act[i % nact], h_out)
   barrier()
   e0 = time.perf_counter()
   for i in range(steps):
-    env.step_host(h_act[(warmup + i) % nact], h_rew, h_dis, h_st, h_jp)
+    d2h = env.step_host(h_act[(warmup + i) % nact], h_out)
   barrier()
-  e2e_s = time.perf_counter() - e0
-  t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-  if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  e2e_value = envs * world * steps / float(t.item())
-  h2d, d2h = envs * 6 * 4, envs * (4 + 4 + 1 + 24)
+  e2e_value = envs * world * steps / max_over_ranks(time.perf_counter() - e0)
+  h2d = envs * 6 * 4
 
   # ---- episode statistics: the ONLY collective on this path (NCCL all_gather of return / length / success)
-  if world > 1:
-    stats = torch.stack([ret_sum, ep_len.float(), (ret_sum > 0).float()], dim=1).contiguous()
-    gathered = torch.empty(world * envs, 3, device=dev)
-    dist.all_gather_into_tensor(gathered, stats)
-    mean_return = float(gathered[:, 0].mean())
-  else:
-    mean_return = float(ret_sum.mean())
+  gathered = gather_episode_stats(torch.cat([stats.local(), ret_sum[:, None]], dim=1))
+  mean_return = float(gathered[:, 4].mean())
 
   # ---- roofline of the dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events inside the C-ABI,
-  # on the launching stream).  One scene-kernel launch advances every env by ONE substep = envs / nsub env-steps.
+  # on the launching stream).  One scene-kernel launch advances the envs of ONE pipeline group by one substep.
   peak, peak_src = measured_peak_gbs()
   kern = {k: dict(ms=k1[k][0] - k0[k][0], launches=k1[k][1] - k0[k][1]) for k in k1 if k1[k][1] - k0[k][1] > 0}
   ktot = sum(v['ms'] for v in kern.values()) or 1.0
   for v in kern.values():
     v['share_of_kernel_time'] = v['ms'] / ktot; v['us_per_launch'] = 1e3 * v['ms'] / v['launches']
   dom = max(kern, key=lambda k: kern[k]['ms'])
-  # one launch of a scene kernel advances the envs of ONE pipeline group by one substep: env-steps per launch follow from the
-  # launch count (steps x substeps x groups for the scene kernels, steps for the arm-only kernel)
-  per_launch_steps = envs * steps / kern[dom]['launches']
+  per_launch_steps = envs * ksteps / kern[dom]['launches']
   bytes_per_launch = per_launch_steps * w['bytes_per_env_step']
   achieved = bytes_per_launch / (kern[dom]['us_per_launch'] * 1e-6) / 1e9
   traffic, traffic_src = ncu_traffic(name, envs)
   roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=traffic, kernel=dom,
                   us_per_launch=kern[dom]['us_per_launch'], algorithmic_bytes_per_launch=bytes_per_launch,
                   bytes_per_env_step=w['bytes_per_env_step'], env_steps_per_launch=per_launch_steps, peak_source=peak_src,
-                  traffic_source=traffic_src,
+                  traffic_source=traffic_src, whole_step_frac=value / world * w['bytes_per_env_step'] / 1e9 / peak,
+                  timed_over=f'{ksteps} control steps continuing the rollout right after the timed region (eager launches, events on each launching stream)',
                   note='state-only algorithmic bytes (SURVEY.md 8d) over the CUDA-event launch time; the path is latency / '
                        'instruction-issue bound, not HBM bound: see profiles/ for issue-slot and stall evidence')
+  nsteps = c1['control_steps'] - c0['control_steps']
   res = dict(value=value, ms_per_step=dev_ms / steps, e2e=dict(value=e2e_value, unit='env-steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-             gpu_launches=c1['kernel_launches'] - c0['kernel_launches'], clocks=clocks.summary(), roofline=roofline, kernels=kern,
-             wall_s=t_wall, mean_return=mean_return, diverged=c1['diverged'], contacts_dropped=c1['contacts_dropped'])
+             gpu_launches=c1['kernel_launches'] - c0['kernel_launches'], graph_launches=c1['graph_launches'] - c0['graph_launches'],
+             launches_per_step=(c1['kernel_launches'] - c0['kernel_launches']) / max(1, nsteps), clocks=clocks.summary(), roofline=roofline,
+             kernels=kern, wall_s=t_wall, mean_return=mean_return, diverged=c1['diverged'], contacts_dropped=c1['contacts_dropped'])
   env.close()
   return res
+
+
+def run_steady_state(name, envs, steps, warmup, precision, dev, rank, episode_s=6.0, rounds=4):
+  """Steady-state regime (>= 200 steps after >= 50 warm-up) with episodes CYCLING through auto-reset: short
+  episodes (time_limit `episode_s`), a pool of `rounds` sampled-and-settled placements per env, and the envs' episode phases
+  staggered uniformly by masked resets during the warm-up, so that at any timed step the batch holds envs of every age and
+  ~1/episode_steps of them are finishing or restarting."""
+  import torch
+  from so101_sim_b200.task_suite import create_batched_task_env
+  w = WORKLOADS[name]
+  env = create_batched_task_env(w['task'], num_envs=envs, time_limit=episode_s, seed=rank, device=dev, precision=precision, reset_rounds=0)
+  env.randomize_resets(rounds=rounds, seed=1000 * rank, spawn_z=0.45, settle_steps=50)
+  ep_steps = env.last_step
+  nact = 64
+  acts = _actions(env, nact, envs, dev, 1 + 1000 * rank)
+  warmup = max(warmup, ep_steps)
+  ids = torch.arange(envs, device=dev)
+  for i in range(warmup):
+    if i < ep_steps:
+      env.reset((ids % ep_steps) == i)
+    env.step(acts[i % nact])
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+  ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+  ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+  c0 = env.counters()
+  nlast = torch.zeros((), dtype=torch.int64, device=dev); nfirst = torch.zeros((), dtype=torch.int64, device=dev)
+  torch.cuda.synchronize()
+  for i in range(steps):
+    flush.fill_(i & 0xFF)
+    ev0[i].record()
+    ts = env.step(acts[(warmup + i) % nact])
+    ev1[i].record()
+    nlast += (ts.step_type == 2).sum(); nfirst += (ts.step_type == 0).sum()
+  torch.cuda.synchronize()
+  c1 = env.counters()
+  ms = float(sum(ev0[i].elapsed_time(ev1[i]) for i in range(steps)))
+  out = dict(value=envs * steps / (ms * 1e-3), unit='env-steps/s', ms_per_step=ms / steps, steps=steps, warmup=warmup, episode_steps=ep_steps,
+             reset_pool_rounds=rounds, last_steps=int(nlast), first_steps=int(nfirst), diverged=c1['diverged'] - c0['diverged'],
+             contacts_dropped=c1['contacts_dropped'] - c0['contacts_dropped'],
+             note=f'time_limit {episode_s} s episodes ({ep_steps} control steps), phases staggered uniformly by masked resets, random actions; '
+                  'a step() that lands on an env whose previous step was LAST resets it (FIRST) instead of stepping, as dm_control does')
+  env.close()
+  return out
 
 
 if __name__ == '__main__':

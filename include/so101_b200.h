@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SO101_ABI_VERSION 2
+#define SO101_ABI_VERSION 3
 
 /* dm_env.StepType values (reference TimeStep.step_type) */
 #define SO101_STEP_FIRST 0
@@ -93,17 +93,21 @@ int so101_step(so101_handle h, const float *action_dev, const so101_step_out *ou
 /* physics.get_state() / set_state() equivalents (so100_task.py:366-368): row-major [N,nq], [N,nv] device pointers */
 int so101_get_state(so101_handle h, float *qpos_dev, float *qvel_dev, void *stream);
 int so101_set_state(so101_handle h, const float *qpos_dev, const float *qvel_dev, void *stream);
-/* same as so101_get_state but without rounding the internal state to float32 (precision = 64 parity tests) */
+/* The integration state is float64 in both precisions (the float32 path evaluates dynamics and contacts in float32 but
+ * accumulates the Euler update in float64): these two move it without rounding to float32.  initial != 0 also installs the
+ * state as the reset state (like so101_set_initial_state). */
 int so101_get_state_f64(so101_handle h, double *qpos_dev, double *qvel_dev, void *stream);
+int so101_set_state_f64(so101_handle h, const double *qpos_dev, const double *qvel_dev, int initial, void *stream);
 
-/* End-to-end variant with HOST buffers (pinned or pageable): copies action_host [N,6] to the device, steps, copies
- * reward/discount/step_type and joints_pos back, and synchronises the stream before returning.  Any output may be NULL. */
-int so101_step_host(so101_handle h, const float *action_host, float *reward_host, float *discount_host, uint8_t *step_type_host,
-                    float *joints_pos_host, void *stream);
+/* End-to-end variant with HOST buffers (pinned or pageable): copies action_host [N,6] to the device, steps, copies every
+ * block of the TimeStep whose pointer in *out_host is non-NULL (HOST pointers, same shapes as so101_step_out) back, and
+ * synchronises the stream before returning.  This is composer.Environment.step(action) -> TimeStep as a host caller sees it. */
+int so101_step_host(so101_handle h, const float *action_host, const so101_step_out *out_host, void *stream);
 
-/* counters since create: [0] kernels launched by this library, [1] control steps taken, [2] envs that diverged,
- * [3] contacts dropped by a full per-env contact buffer */
-int so101_counters(so101_handle h, uint64_t out[4]);
+/* counters since create: [0] kernels launched by this library (kernels replayed from a captured step graph included),
+ * [1] control steps taken, [2] envs that diverged, [3] contacts dropped by a full per-env contact buffer, [4] step-graph
+ * launches (one cudaGraphLaunch replays all kernels of a control step of the contact scene), [5] reserved */
+int so101_counters(so101_handle h, uint64_t out[6]);
 
 /* Per-kernel device time, measured with CUDA events recorded on the caller's stream around every launch while enabled.
  * Returns the totals accumulated so far (ms and launch counts; index 0 scene begin, 1 scene EPA + manifold, 2 scene solve
@@ -115,6 +119,11 @@ int so101_kernel_times(so101_handle h, int enable, double ms_out[8], uint64_t la
 /* Debug/parity probe: copy one internal structure-of-arrays field ("qacc", "ncon", "solver_iter", ...) of all envs to a
  * caller-owned device buffer of `count` floats.  Used by the parity tests only. */
 int so101_debug_read(so101_handle h, const char *field, float *dst_dev, size_t count, void *stream);
+
+/* Parity probe without a handle: the device's 6-axis box overlap test (the reward geometry, so101_sim/utils/oobb_utils.py:202-273)
+ * on n box pairs, rows of 20 doubles (pos 3, quat 4 wxyz, half 3 of box A, then of box B), evaluated in float32 or float64
+ * (precision = 32 / 64) -> out[i] in {0, 1}.  Used by the golden-vector test of the reward geometry only. */
+int so101_debug_overlap(int precision, int device, const double *cases_dev, int n, uint8_t *out_dev, void *stream);
 
 #ifdef __cplusplus
 }

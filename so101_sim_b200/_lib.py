@@ -25,7 +25,7 @@ class Config(ctypes.Structure):
 
 EXPORTS = ('so101_abi_version', 'so101_create', 'so101_destroy', 'so101_last_error', 'so101_dims', 'so101_set_initial_state',
            'so101_reset', 'so101_step', 'so101_get_state', 'so101_set_state', 'so101_get_state_f64', 'so101_step_host',
-           'so101_counters', 'so101_debug_read', 'so101_kernel_times', 'so101_set_reset_pool')
+           'so101_counters', 'so101_debug_read', 'so101_kernel_times', 'so101_set_reset_pool', 'so101_set_state_f64', 'so101_debug_overlap')
 
 _lib = None
 
@@ -46,14 +46,16 @@ def load() -> ctypes.CDLL:
   L.so101_dims.restype = ci; L.so101_dims.argtypes = [vp] + [ctypes.POINTER(ci)] * 4
   for f in ('so101_set_initial_state', 'so101_set_state', 'so101_get_state', 'so101_get_state_f64'):
     getattr(L, f).restype = ci; getattr(L, f).argtypes = [vp, vp, vp, vp]
+  L.so101_set_state_f64.restype = ci; L.so101_set_state_f64.argtypes = [vp, vp, vp, ci, vp]
+  L.so101_debug_overlap.restype = ci; L.so101_debug_overlap.argtypes = [ci, ci, vp, ci, vp, vp]
   L.so101_set_reset_pool.restype = ci; L.so101_set_reset_pool.argtypes = [vp, vp, vp, ci, vp]
   L.so101_reset.restype = ci; L.so101_reset.argtypes = [vp, vp, ctypes.POINTER(StepOut), vp]
   L.so101_step.restype = ci; L.so101_step.argtypes = [vp, vp, ctypes.POINTER(StepOut), vp]
-  L.so101_step_host.restype = ci; L.so101_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp]
-  L.so101_counters.restype = ci; L.so101_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64 * 4)]
+  L.so101_step_host.restype = ci; L.so101_step_host.argtypes = [vp, vp, ctypes.POINTER(StepOut), vp]
+  L.so101_counters.restype = ci; L.so101_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64 * 6)]
   L.so101_kernel_times.restype = ci; L.so101_kernel_times.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double * 8), ctypes.POINTER(ctypes.c_uint64 * 8)]
   L.so101_debug_read.restype = ci; L.so101_debug_read.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t, vp]
-  if L.so101_abi_version() != 2:
+  if L.so101_abi_version() != 3:
     raise RuntimeError('libso101_b200.so: ABI version mismatch')
   _lib = L
   return L

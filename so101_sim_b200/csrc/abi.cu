@@ -26,20 +26,35 @@ static thread_local std::string g_create_error;
     if (e_ != cudaSuccess) throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+// Every entry point runs with the handle's device current and restores the caller's device on exit (two handles on
+// different GPUs in one process, or a caller that changed torch's current device, must not launch on the wrong device).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 struct HandleBase {
   std::string err;
   so101_config cfg{};
   int nq = 0, nv = 0, nu = 0, nbody = 0;
-  uint64_t launches = 0, steps = 0, dropped = 0;
+  uint64_t launches = 0, steps = 0, dropped = 0, graph_launches = 0;
   virtual ~HandleBase() { for (auto &t : tiers) t.destroy(); }
   virtual void set_state(const float *q, const float *v, bool initial, cudaStream_t s) = 0;
+  virtual void set_state_f64(const double *q, const double *v, bool initial, cudaStream_t s) = 0;
   virtual void set_reset_pool(const float *q, const float *v, int rounds, cudaStream_t s) = 0;
   virtual void get_state(float *q, float *v, cudaStream_t s) = 0;
   virtual void get_state_f64(double *q, double *v, cudaStream_t s) = 0;
   virtual void reset(const uint8_t *mask, const so101_step_out &out, cudaStream_t s) = 0;
   virtual void step(const float *action, const so101_step_out &out, cudaStream_t s) = 0;
   virtual void debug_read(const char *field, float *dst, size_t count, cudaStream_t s) = 0;
-  virtual void step_host(const float *action, float *reward, float *discount, uint8_t *step_type, float *jpos, cudaStream_t s) = 0;
+  virtual void step_host(const float *action, const so101_step_out &host_out, cudaStream_t s) = 0;
   virtual uint64_t diverged() = 0;
   KernelTimer timer;
   std::vector<TierExec> tiers;  // one per pipeline group
@@ -139,10 +154,14 @@ static void build_arm_model(const Blob &b, ArmModelT<T> &am) {
   for (int a = 0; a < NJ; a++) {
     if (b.I("act_jnt")[a] != a) throw std::runtime_error("actuator a must drive joint a");
     if (b.F("act_gear")[a] != 1.0) throw std::runtime_error("actuator gear must be 1");
-    am.gain[a] = (T)b.F("act_gain")[a];
-    for (int c = 0; c < 3; c++) am.bias[a][c] = (T)b.F("act_bias")[3 * a + c];
-    for (int c = 0; c < 2; c++) { am.ctrlrange[a][c] = (T)b.F("act_ctrlrange")[2 * a + c]; am.forcerange[a][c] = (T)b.F("act_forcerange")[2 * a + c]; }
+    am.gain[a] = (T)b.F("act_gain")[a]; am.gain_d[a] = b.F("act_gain")[a];
+    for (int c = 0; c < 3; c++) { am.bias[a][c] = (T)b.F("act_bias")[3 * a + c]; am.bias_d[a][c] = b.F("act_bias")[3 * a + c]; }
+    for (int c = 0; c < 2; c++) {
+      am.ctrlrange[a][c] = (T)b.F("act_ctrlrange")[2 * a + c]; am.forcerange[a][c] = (T)b.F("act_forcerange")[2 * a + c];
+      am.ctrlrange_d[a][c] = b.F("act_ctrlrange")[2 * a + c]; am.forcerange_d[a][c] = b.F("act_forcerange")[2 * a + c];
+    }
   }
+  am.dt_d = dt;
   for (int c = 0; c < 3; c++) am.gravity[c] = (T)opt[1 + c];
   am.dt = (T)dt;
   const int nv = b.scalar("nv");
@@ -152,6 +171,7 @@ static void build_arm_model(const Blob &b, ArmModelT<T> &am) {
 template <typename T>
 struct Handle : HandleBase {
   ArmModelT<T> am;
+  ArmModelT<double> am64;  // float64 arm model for the float64 parts of the float32 path
   std::unique_ptr<SceneModelHost<T>> scene;  // non-null: full contact scene (warp per env, row-major state)
   EnvState<T> S{};
   PipeBuf<T> pipe{};                 // per-env scratch shared by all groups
@@ -159,8 +179,15 @@ struct Handle : HandleBase {
   StepCfg sc{};
   std::vector<void *> allocs;
   size_t pool_cap = 1;
-  float *d_action = nullptr, *d_reward = nullptr, *d_discount = nullptr, *d_jpos = nullptr;
-  uint8_t *d_steptype = nullptr;
+  float *d_action = nullptr;   // staging copy of the caller's action: the captured step graph reads it from a fixed address
+  so101_step_out d_out{};      // device staging of the whole TimeStep for the host-buffer entry point (so101_step_host)
+  // One control step of the contact scene is 166 launches + event fork/joins on 6 streams.  It is captured once per distinct
+  // set of output pointers into a CUDA graph and replayed with a single cudaGraphLaunch (SO101_GRAPH=0 disables; the
+  // per-kernel event timers need eager launches and bypass it).
+  struct StepGraph { so101_step_out key; cudaGraphExec_t exec; };
+  std::vector<StepGraph> graphs;
+  cudaStream_t cap_stream = nullptr;
+  bool use_graph = true;
 
   template <typename U>
   U *dalloc(size_t n) {
@@ -173,9 +200,9 @@ struct Handle : HandleBase {
 
   Handle(const Blob &b, const so101_config &c) {
     cfg = c;
-    CUDA_OK(cudaSetDevice(c.device));
     nq = b.scalar("nq"); nv = b.scalar("nv"); nu = b.scalar("nu"); nbody = b.scalar("nbody");
     build_arm_model<T>(b, am);
+    build_arm_model<double>(b, am64);
     if (nq != NJ || c.collide) {
       if (!c.collide) throw std::runtime_error("models with free props need collide=1");
       scene.reset(new SceneModelHost<T>());
@@ -184,8 +211,8 @@ struct Handle : HandleBase {
     }
     const size_t N = c.num_envs;
     S.N = c.num_envs; S.nq = nq; S.nv = nv;
-    S.qpos = dalloc<T>(nq * N); S.qvel = dalloc<T>(nv * N); S.warm = dalloc<T>(nv * N);
-    S.init_qpos = dalloc<T>(nq * N); S.init_qvel = dalloc<T>(nv * N); S.ctrl = dalloc<T>(6 * N);
+    S.qpos = dalloc<TS>(nq * N); S.qvel = dalloc<TS>(nv * N); S.warm = dalloc<T>(nv * N);
+    S.init_qpos = dalloc<TS>(nq * N); S.init_qvel = dalloc<TS>(nv * N); S.ctrl = dalloc<T>(6 * N);
     S.step = dalloc<int>(N); S.needs_reset = dalloc<uint8_t>(N); S.episode = dalloc<int>(N); S.npool = 1;
     S.ring_joints = dalloc<float>((size_t)(c.joints_delay_steps + 1) * 6 * N);
     S.ring_phys = dalloc<float>((size_t)(c.physics_delay_steps + 1) * (nq + nv) * N);
@@ -194,14 +221,15 @@ struct Handle : HandleBase {
     if (getenv("SO101_PROFILE") && atoi(getenv("SO101_PROFILE"))) S.prof = dalloc<unsigned long long>(16);
     sc.dbg_env = getenv("SO101_DBG_ENV") ? atoi(getenv("SO101_DBG_ENV")) : -1;
     sc.dbg_step = getenv("SO101_DBG_STEP") ? atoi(getenv("SO101_DBG_STEP")) : -1;
+    sc.arm_mode = getenv("SO101_ARM_MODE") ? atoi(getenv("SO101_ARM_MODE")) : 2;
     sc.terminate_on_success = c.terminate_on_success; sc.max_iter = c.solver_iterations; sc.tol = c.solver_tolerance;
     for (int i = 0; i < 6; i++) { sc.offsets[i] = c.calibration_offsets[i]; sc.home[i] = c.home_ctrl[i]; }
     // default initial state: qpos0, zero velocity
-    std::vector<T> q0(nq * N);
-    for (int k = 0; k < nq; k++) for (size_t e = 0; e < N; e++) q0[scene ? e * nq + k : k * N + e] = (T)b.F("qpos0")[k];
-    CUDA_OK(cudaMemcpy(S.init_qpos, q0.data(), q0.size() * sizeof(T), cudaMemcpyHostToDevice));
-    d_action = dalloc<float>(6 * N); d_reward = dalloc<float>(N); d_discount = dalloc<float>(N); d_jpos = dalloc<float>(6 * N);
-    d_steptype = dalloc<uint8_t>(N);
+    std::vector<TS> q0(nq * N);
+    for (int k = 0; k < nq; k++) for (size_t e = 0; e < N; e++) q0[scene ? e * nq + k : k * N + e] = (TS)b.F("qpos0")[k];
+    CUDA_OK(cudaMemcpy(S.init_qpos, q0.data(), q0.size() * sizeof(TS), cudaMemcpyHostToDevice));
+    d_action = dalloc<float>(6 * N);
+    use_graph = !(getenv("SO101_GRAPH") && atoi(getenv("SO101_GRAPH")) == 0);
     if (scene) {  // inter-kernel scratch of the scene pipeline
       if (b.scalar("ngeom") > GMAX_GEOMS) throw std::runtime_error("model has more geoms than the broad phase can hold");
       if (b.scalar("nbody") > 16) throw std::runtime_error("model has more bodies than the broad phase can hold");
@@ -226,52 +254,66 @@ struct Handle : HandleBase {
         // entries are ever touched): 4 per env overflowed in long random-action rollouts and silently lost arm-table contacts.
         p.work_cap = 16 * p.nenv + 64; p.work = dalloc<uint2>((size_t)WQ * p.work_cap);
         p.nwork = dalloc<int>(WSTRIDE * (c.n_substeps + 1)); p.big = dalloc<int>(2 * (size_t)p.nenv);
-        p.hit_cap = p.nenv * 32; p.hits = dalloc<HitRec<T>>((size_t)p.hit_cap);
+        // a hit's slot is its queue's item offset + the queue's hit count: any offset below the group's total item count can
+        // occur, and an env contributes at most PAIRCAP items
+        p.hit_cap = p.nenv * PAIRCAP; p.hits = dalloc<HitRec<T>>((size_t)p.hit_cap);
         groups.push_back(p);
         tiers[g].init();
       }
     }
   }
+  // captured graphs hold EnvState / StepCfg BY VALUE in their kernel parameters: anything that changes them (reset pool size or
+  // storage, debug probes) must drop the graphs
+  void invalidate_graphs() {
+    for (auto &g : graphs) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
   ~Handle() override {
+    for (auto &g : graphs) cudaGraphExecDestroy(g.exec);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
     for (void *p : allocs) cudaFree(p);
   }
-  void set_state(const float *q, const float *v, bool initial, cudaStream_t s) override {
-    auto put = [&](const float *rows, T *dst, int k) {
-      if (scene) launch_cast_copy<float, T>(rows, dst, (size_t)S.N * k, s); else launch_rows_to_soa<T>(rows, dst, S.N, k, s);
+  template <typename A>
+  void set_state_any(const A *q, const A *v, bool initial, cudaStream_t s) {
+    auto put = [&](const A *rows, TS *dst, int k) {
+      if (scene) launch_cast_copy<A, TS>(rows, dst, (size_t)S.N * k, s); else launch_rows_to_soa<A, TS>(rows, dst, S.N, k, s);
       launches += 1;
     };
     put(q, S.qpos, nq); put(v, S.qvel, nv);
-    if (initial) { S.npool = 1; put(q, S.init_qpos, nq); put(v, S.init_qvel, nv); }
+    if (initial) { if (S.npool != 1) invalidate_graphs(); S.npool = 1; put(q, S.init_qpos, nq); put(v, S.init_qvel, nv); }
     CUDA_OK(cudaMemsetAsync(S.warm, 0, sizeof(T) * nv * S.N, s));
   }
+  void set_state(const float *q, const float *v, bool initial, cudaStream_t s) override { set_state_any(q, v, initial, s); }
+  void set_state_f64(const double *q, const double *v, bool initial, cudaStream_t s) override { set_state_any(q, v, initial, s); }
   // Reset pool: `rounds` initial states per env ([rounds][N][nq] / [rounds][N][nv] rows); episode e of an env starts from
   // entry e % rounds.  The pool storage grows on demand and replaces the single initial state.
   void set_reset_pool(const float *q, const float *v, int rounds, cudaStream_t s) override {
     if (rounds < 1) throw std::runtime_error("reset pool needs at least one round");
+    invalidate_graphs();
     const size_t N = S.N;
     if ((size_t)rounds > pool_cap) {
       CUDA_OK(cudaStreamSynchronize(s));
-      S.init_qpos = dalloc<T>((size_t)rounds * nq * N); S.init_qvel = dalloc<T>((size_t)rounds * nv * N);  // (old pool is freed with the handle)
+      S.init_qpos = dalloc<TS>((size_t)rounds * nq * N); S.init_qvel = dalloc<TS>((size_t)rounds * nv * N);  // (old pool is freed with the handle)
       pool_cap = rounds;
     }
     for (int r = 0; r < rounds; r++) {
       const float *qr = q + (size_t)r * N * nq, *vr = v + (size_t)r * N * nv;
-      T *dq = S.init_qpos + (size_t)r * N * nq, *dv = S.init_qvel + (size_t)r * N * nv;
-      if (scene) { launch_cast_copy<float, T>(qr, dq, N * nq, s); launch_cast_copy<float, T>(vr, dv, N * nv, s); }
-      else { launch_rows_to_soa<T>(qr, dq, S.N, nq, s); launch_rows_to_soa<T>(vr, dv, S.N, nv, s); }
+      TS *dq = S.init_qpos + (size_t)r * N * nq, *dv = S.init_qvel + (size_t)r * N * nv;
+      if (scene) { launch_cast_copy<float, TS>(qr, dq, N * nq, s); launch_cast_copy<float, TS>(vr, dv, N * nv, s); }
+      else { launch_rows_to_soa<float, TS>(qr, dq, S.N, nq, s); launch_rows_to_soa<float, TS>(vr, dv, S.N, nv, s); }
       launches += 2;
     }
     S.npool = rounds;
     CUDA_OK(cudaMemsetAsync(S.episode, 0, sizeof(int) * N, s));
   }
   void get_state(float *q, float *v, cudaStream_t s) override {
-    if (scene) { launch_cast_copy<T, float>(S.qpos, q, (size_t)S.N * nq, s); launch_cast_copy<T, float>(S.qvel, v, (size_t)S.N * nv, s); }
-    else { launch_soa_to_rows<T, float>(S.qpos, q, S.N, nq, s); launch_soa_to_rows<T, float>(S.qvel, v, S.N, nv, s); }
+    if (scene) { launch_cast_copy<TS, float>(S.qpos, q, (size_t)S.N * nq, s); launch_cast_copy<TS, float>(S.qvel, v, (size_t)S.N * nv, s); }
+    else { launch_soa_to_rows<TS, float>(S.qpos, q, S.N, nq, s); launch_soa_to_rows<TS, float>(S.qvel, v, S.N, nv, s); }
     launches += 2;
   }
   void get_state_f64(double *q, double *v, cudaStream_t s) override {
-    if (scene) { launch_cast_copy<T, double>(S.qpos, q, (size_t)S.N * nq, s); launch_cast_copy<T, double>(S.qvel, v, (size_t)S.N * nv, s); }
-    else { launch_soa_to_rows<T, double>(S.qpos, q, S.N, nq, s); launch_soa_to_rows<T, double>(S.qvel, v, S.N, nv, s); }
+    if (scene) { launch_cast_copy<TS, double>(S.qpos, q, (size_t)S.N * nq, s); launch_cast_copy<TS, double>(S.qvel, v, (size_t)S.N * nv, s); }
+    else { launch_soa_to_rows<TS, double>(S.qpos, q, S.N, nq, s); launch_soa_to_rows<TS, double>(S.qvel, v, S.N, nv, s); }
     launches += 2;
   }
   void reset(const uint8_t *mask, const so101_step_out &out, cudaStream_t s) override {
@@ -279,9 +321,32 @@ struct Handle : HandleBase {
     launches += 1;
   }
   void step(const float *action, const so101_step_out &out, cudaStream_t s) override {
-    if (scene) launches += launch_scene_step<T>(am, scene->dev, sc, S, groups.data(), tiers.data(), (int)groups.size(), action, out, s, &timer);
-    else { timer.begin(4, s); launch_arm_step<T>(am, sc, S, action, out, s); timer.end(4, s); launches += 1; }
-    steps += 1;
+    if (!scene) { timer.begin(4, s); launch_arm_step<T>(am, am64, sc, S, action, out, s); timer.end(4, s); launches += 1; steps += 1; return; }
+    const int nk = (int)groups.size() * (3 + 8 * sc.nsub);
+    if (!use_graph || timer.on) {
+      launches += launch_scene_step<T>(am, scene->dev, sc, S, groups.data(), tiers.data(), (int)groups.size(), action, out, s, &timer);
+      steps += 1;
+      return;
+    }
+    // graph replay: the action goes through a fixed staging buffer so that the graph does not depend on the caller's pointer
+    if (action != d_action) CUDA_OK(cudaMemcpyAsync(d_action, action, sizeof(float) * 6 * S.N, cudaMemcpyDeviceToDevice, s));
+    cudaGraphExec_t exec = nullptr;
+    for (auto &g : graphs) if (std::memcmp(&g.key, &out, sizeof out) == 0) exec = g.exec;
+    if (!exec) {
+      if (graphs.size() >= 8) { cudaGraphExecDestroy(graphs.front().exec); graphs.erase(graphs.begin()); }
+      if (!cap_stream) CUDA_OK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+      cudaGraph_t graph = nullptr;
+      CUDA_OK(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+      launch_scene_step<T>(am, scene->dev, sc, S, groups.data(), tiers.data(), (int)groups.size(), d_action, out, cap_stream, nullptr);
+      cudaError_t e = cudaStreamEndCapture(cap_stream, &graph);
+      if (e != cudaSuccess || !graph) { cudaGetLastError(); throw std::runtime_error(std::string("step graph capture failed: ") + cudaGetErrorString(e)); }
+      e = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+      graphs.push_back({out, exec});
+    }
+    CUDA_OK(cudaGraphLaunch(exec, s));
+    launches += nk; graph_launches += 1; steps += 1;
   }
   void debug_read(const char *field, float *dst, size_t count, cudaStream_t s) override {
     const std::string f(field);
@@ -334,21 +399,30 @@ struct Handle : HandleBase {
       // enables the probe (the buffer is filled by subsequent steps).
       const size_t need = (size_t)S.N * (1 + 9 * NCON);
       if (count < need) throw std::runtime_error("debug_read: buffer too small");
-      if (!S.dbg_contacts) S.dbg_contacts = dalloc<float>(need);
+      if (!S.dbg_contacts) { S.dbg_contacts = dalloc<float>(need); invalidate_graphs(); }
       CUDA_OK(cudaMemcpyAsync(dst, S.dbg_contacts, need * sizeof(float), cudaMemcpyDeviceToDevice, s));
     } else throw std::runtime_error("debug_read: unknown field " + f);
   }
-  // e2e path: host buffers in, host buffers out, host<->device copies on the caller's stream, one sync at the end
-  void step_host(const float *action, float *reward, float *discount, uint8_t *step_type, float *jpos, cudaStream_t s) override {
-    const size_t N = S.N;
+  // e2e path: host buffers in, the WHOLE TimeStep (every block of so101_step_out that is non-null in host_out) out to host
+  // buffers; host<->device copies on the caller's stream, one sync at the end
+  void step_host(const float *action, const so101_step_out &host_out, cudaStream_t s) override {
+    const size_t N = S.N, sd = (size_t)nq + nv;
+    if (!d_out.reward) {
+      d_out.commanded_joints_pos = dalloc<float>(6 * N); d_out.joints_pos = dalloc<float>(6 * N); d_out.undelayed_joints_pos = dalloc<float>(6 * N);
+      d_out.physics_state = dalloc<float>(sd * N); d_out.delayed_physics_state = dalloc<float>(sd * N);
+      d_out.reward = dalloc<float>(N); d_out.discount = dalloc<float>(N); d_out.step_type = dalloc<uint8_t>(N);
+    }
     CUDA_OK(cudaMemcpyAsync(d_action, action, 6 * N * sizeof(float), cudaMemcpyHostToDevice, s));
-    so101_step_out o{};
-    o.reward = d_reward; o.discount = d_discount; o.step_type = d_steptype; o.joints_pos = d_jpos;
-    step(d_action, o, s);
-    if (reward) CUDA_OK(cudaMemcpyAsync(reward, d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (discount) CUDA_OK(cudaMemcpyAsync(discount, d_discount, N * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (step_type) CUDA_OK(cudaMemcpyAsync(step_type, d_steptype, N, cudaMemcpyDeviceToHost, s));
-    if (jpos) CUDA_OK(cudaMemcpyAsync(jpos, d_jpos, 6 * N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    step(d_action, d_out, s);
+    auto back = [&](void *dst, const void *src, size_t bytes) { if (dst) CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)); };
+    back(host_out.commanded_joints_pos, d_out.commanded_joints_pos, 6 * N * sizeof(float));
+    back(host_out.joints_pos, d_out.joints_pos, 6 * N * sizeof(float));
+    back(host_out.undelayed_joints_pos, d_out.undelayed_joints_pos, 6 * N * sizeof(float));
+    back(host_out.physics_state, d_out.physics_state, sd * N * sizeof(float));
+    back(host_out.delayed_physics_state, d_out.delayed_physics_state, sd * N * sizeof(float));
+    back(host_out.reward, d_out.reward, N * sizeof(float));
+    back(host_out.discount, d_out.discount, N * sizeof(float));
+    back(host_out.step_type, d_out.step_type, N);
     CUDA_OK(cudaStreamSynchronize(s));
   }
   uint64_t diverged() override {
@@ -366,6 +440,7 @@ using namespace so101;
 #define API_BEGIN(h)                                   \
   if (!(h)) return -1;                                 \
   HandleBase *H = reinterpret_cast<HandleBase *>(h);   \
+  DeviceGuard guard_(H->cfg.device);                   \
   try {
 #define API_END()                                                                        \
     cudaError_t e_ = cudaPeekAtLastError();                                              \
@@ -387,6 +462,7 @@ int so101_create(const void *model_blob, size_t blob_len, const so101_config *cf
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw std::runtime_error("no CUDA device: this library has no CPU fallback");
     if (cfg->device < 0 || cfg->device >= ndev) throw std::runtime_error("invalid device ordinal");
     Blob b(model_blob, blob_len);
+    DeviceGuard guard(cfg->device);
     HandleBase *H = nullptr;
     if (cfg->precision == 64) H = new Handle<double>(b, *cfg);
     else if (cfg->precision == 32) H = new Handle<float>(b, *cfg);
@@ -402,7 +478,9 @@ int so101_create(const void *model_blob, size_t blob_len, const so101_config *cf
 
 int so101_destroy(so101_handle h) {
   if (!h) return -1;
-  delete reinterpret_cast<HandleBase *>(h);
+  HandleBase *H = reinterpret_cast<HandleBase *>(h);
+  DeviceGuard guard(H->cfg.device);
+  delete H;
   return 0;
 }
 
@@ -438,6 +516,12 @@ int so101_set_state(so101_handle h, const float *qpos_dev, const float *qvel_dev
   H->set_state(qpos_dev, qvel_dev, false, (cudaStream_t)stream);
   API_END()
 }
+int so101_set_state_f64(so101_handle h, const double *qpos_dev, const double *qvel_dev, int initial, void *stream) {
+  API_BEGIN(h)
+  if (!qpos_dev || !qvel_dev) throw std::runtime_error("null state pointer");
+  H->set_state_f64(qpos_dev, qvel_dev, initial != 0, (cudaStream_t)stream);
+  API_END()
+}
 int so101_get_state(so101_handle h, float *qpos_dev, float *qvel_dev, void *stream) {
   API_BEGIN(h)
   if (!qpos_dev || !qvel_dev) throw std::runtime_error("null state pointer");
@@ -465,16 +549,17 @@ int so101_step(so101_handle h, const float *action_dev, const so101_step_out *ou
   H->step(action_dev, o, (cudaStream_t)stream);
   API_END()
 }
-int so101_step_host(so101_handle h, const float *action_host, float *reward_host, float *discount_host, uint8_t *step_type_host,
-                    float *joints_pos_host, void *stream) {
+int so101_step_host(so101_handle h, const float *action_host, const so101_step_out *out_host, void *stream) {
   API_BEGIN(h)
   if (!action_host) throw std::runtime_error("null action pointer");
-  H->step_host(action_host, reward_host, discount_host, step_type_host, joints_pos_host, (cudaStream_t)stream);
+  so101_step_out o{};
+  if (out_host) o = *out_host;
+  H->step_host(action_host, o, (cudaStream_t)stream);
   API_END()
 }
-int so101_counters(so101_handle h, uint64_t out[4]) {
+int so101_counters(so101_handle h, uint64_t out[6]) {
   API_BEGIN(h)
-  out[2] = H->diverged(); out[0] = H->launches; out[1] = H->steps; out[3] = H->dropped;
+  out[2] = H->diverged(); out[0] = H->launches; out[1] = H->steps; out[3] = H->dropped; out[4] = H->graph_launches; out[5] = 0;
   API_END()
 }
 int so101_kernel_times(so101_handle h, int enable, double ms_out[8], uint64_t launches_out[8]) {
@@ -486,6 +571,13 @@ int so101_kernel_times(so101_handle h, int enable, double ms_out[8], uint64_t la
   }
   H->timer.on = enable != 0;
   API_END()
+}
+int so101_debug_overlap(int precision, int device, const double *cases_dev, int n, uint8_t *out_dev, void *stream) {
+  if (!cases_dev || !out_dev || n < 0 || (precision != 32 && precision != 64)) return -1;
+  DeviceGuard guard(device);
+  if (precision == 32) launch_debug_overlap<float>(cases_dev, n, out_dev, (cudaStream_t)stream);
+  else launch_debug_overlap<double>(cases_dev, n, out_dev, (cudaStream_t)stream);
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
 int so101_debug_read(so101_handle h, const char *field, float *dst_dev, size_t count, void *stream) {
   API_BEGIN(h)

@@ -33,6 +33,8 @@ struct ArmModelT {
   // actuators
   T gain[NJ], bias[NJ][3], ctrlrange[NJ][2], forcerange[NJ][2];
   T gravity[3], dt, solver_scale;  // solver_scale = 1 / (meaninertia * max(1, nv))
+  // float64 copies of what the float64 parts of the float32 path read (actuation and the Euler update, env_state.cuh)
+  double gain_d[NJ], bias_d[NJ][3], ctrlrange_d[NJ][2], forcerange_d[NJ][2], dt_d;
 };
 
 template <typename T> __device__ __forceinline__ T t_sqrt(T x);
@@ -190,6 +192,19 @@ __device__ __forceinline__ void arm_actuation(const ArmModelT<T> &am, const T (&
     const T c = t_clamp(ctrl[i], am.ctrlrange[i][0], am.ctrlrange[i][1]);
     const T f = am.gain[i] * c + am.bias[i][0] + am.bias[i][1] * q[i] + am.bias[i][2] * qd[i];
     frc[i] = t_clamp(f, am.forcerange[i][0], am.forcerange[i][1]);
+  }
+}
+
+// The same actuator model evaluated in float64 on the float64 integration state (the -50 q position feedback would otherwise
+// see the state rounded to float32: 50 * 3e-8 / armature 0.1 = 1.5e-5 rad/s^2 of noise per substep).
+template <typename T>
+__device__ __forceinline__ void arm_actuation_d(const ArmModelT<T> &am, const double (&q)[NJ], const double (&qd)[NJ], const T (&ctrl)[NJ],
+                                                double (&frc)[NJ]) {
+#pragma unroll
+  for (int i = 0; i < NJ; i++) {
+    const double c = t_clamp((double)ctrl[i], am.ctrlrange_d[i][0], am.ctrlrange_d[i][1]);
+    const double f = am.gain_d[i] * c + am.bias_d[i][0] + am.bias_d[i][1] * q[i] + am.bias_d[i][2] * qd[i];
+    frc[i] = t_clamp(f, am.forcerange_d[i][0], am.forcerange_d[i][1]);
   }
 }
 

@@ -7,11 +7,13 @@
 // per control step (coalesced SoA); nothing else touches HBM.
 #include "arm_kernel.cuh"
 
+#include <type_traits>
+
 namespace so101 {
 
 template <typename T>
 __device__ __forceinline__ void write_obs_arm(const StepCfg &cfg, const EnvState<T> &S, const so101_step_out &out, int env, int t,
-                                              const T (&q)[NJ], const T (&qd)[NJ], const T (&ctrl)[NJ], float reward, float discount,
+                                              const TS (&q)[NJ], const TS (&qd)[NJ], const T (&ctrl)[NJ], float reward, float discount,
                                               uint8_t step_type) {
   const int N = S.N;
   // delay rings: slot t % (D+1) holds the value after control step t; read max(t-D, 0)  (INITIAL_VALUE padding,
@@ -47,7 +49,8 @@ __device__ __forceinline__ void write_obs_arm(const StepCfg &cfg, const EnvState
 template <typename T>
 __device__ __forceinline__ void reset_env_arm(const StepCfg &cfg, const EnvState<T> &S, const so101_step_out &out, int env) {
   const int N = S.N;
-  T q[NJ], qd[NJ], ctrl[NJ];
+  TS q[NJ], qd[NJ];
+  T ctrl[NJ];
   const int ep = S.episode[env];
   const size_t pool = (size_t)(ep % S.npool) * NJ * N;  // reset pool entry of this episode
   S.episode[env] = ep + 1;
@@ -63,9 +66,14 @@ __device__ __forceinline__ void reset_env_arm(const StepCfg &cfg, const EnvState
   write_obs_arm(cfg, S, out, env, 0, q, qd, ctrl, 0.f, 1.f, SO101_STEP_FIRST);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(128) arm_step_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ StepCfg cfg,
-                                                      const EnvState<T> S, const float *__restrict__ action, const so101_step_out out) {
+// T = arithmetic of the constraint solver (and of everything else unless stated); TD = arithmetic of the smooth dynamics
+// (FK, CRB, RNE); ACT64 / SOLVE64: actuator model / the M^-1 solve for qacc_smooth in float64; ROUND32: round the state to
+// float32 after every substep (the round-1 behaviour, kept for the error-budget experiment only).  The integration state and
+// the Euler update are float64 in every mode (env_state.cuh).  For T = double all modes are the same code.
+template <typename T, typename TD, bool ACT64, bool SOLVE64, bool ROUND32>
+__global__ void __launch_bounds__(128) arm_step_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ ArmModelT<TD> amd,
+                                                      const __grid_constant__ StepCfg cfg, const EnvState<T> S, const float *__restrict__ action,
+                                                      const so101_step_out out) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   const int N = S.N;
   if (env >= N) return;
@@ -73,7 +81,8 @@ __global__ void __launch_bounds__(128) arm_step_kernel(const __grid_constant__ A
     reset_env_arm(cfg, S, out, env);
     return;
   }
-  T q[NJ], qd[NJ], warm[NJ], ctrl[NJ];
+  TS q[NJ], qd[NJ];
+  T warm[NJ], ctrl[NJ];
 #pragma unroll
   for (int i = 0; i < NJ; i++) {
     q[i] = S.qpos[i * N + env]; qd[i] = S.qvel[i * N + env]; warm[i] = S.warm[i * N + env];
@@ -82,31 +91,53 @@ __global__ void __launch_bounds__(128) arm_step_kernel(const __grid_constant__ A
   int iters = 0;
   bool bad = false;
   for (int sub = 0; sub < cfg.nsub; sub++) {
-    ArmKin<T> k;
-    arm_fk<T>(am, q, k, nullptr);
-    T M[21], bias[NJ], frc[NJ], qacc_s[NJ];
-    arm_crb_rne(am, k, qd, M, bias);
-    arm_actuation(am, q, qd, ctrl, frc);
-    T L[21];
+    TD qf[NJ], qdf[NJ];
 #pragma unroll
-    for (int i = 0; i < 21; i++) L[i] = M[i];
+    for (int i = 0; i < NJ; i++) { qf[i] = (TD)q[i]; qdf[i] = (TD)qd[i]; }
+    ArmKin<TD> k;
+    arm_fk<TD>(amd, qf, k, nullptr);
+    TD Md[21], biasd[NJ];
+    arm_crb_rne(amd, k, qdf, Md, biasd);
+    T M[21], qacc_s[NJ];
+#pragma unroll
+    for (int i = 0; i < 21; i++) M[i] = (T)Md[i];
+    using TA = typename std::conditional<ACT64, double, T>::type;   // actuator force
+    using TQ = typename std::conditional<SOLVE64, double, T>::type;  // qacc_smooth solve
+    TA frc[NJ];
+    if constexpr (ACT64) arm_actuation_d(am, q, qd, ctrl, frc);
+    else {
+      T qt[NJ], qdt[NJ];
+#pragma unroll
+      for (int i = 0; i < NJ; i++) { qt[i] = (T)q[i]; qdt[i] = (T)qd[i]; }
+      arm_actuation(am, qt, qdt, ctrl, frc);
+    }
+    TQ L[21], rhs[NJ];
+#pragma unroll
+    for (int i = 0; i < 21; i++) L[i] = (TQ)Md[i];
     chol6(L);
 #pragma unroll
-    for (int i = 0; i < NJ; i++) qacc_s[i] = frc[i] - bias[i];
-    chol6_solve(L, qacc_s);
+    for (int i = 0; i < NJ; i++) rhs[i] = (TQ)((TA)frc[i] - (TA)biasd[i]);
+    chol6_solve(L, rhs);
+    TS qacc_sd[NJ];
+#pragma unroll
+    for (int i = 0; i < NJ; i++) { qacc_sd[i] = (TS)rhs[i]; qacc_s[i] = (T)rhs[i]; }
+    T qt[NJ], qdt[NJ];
+#pragma unroll
+    for (int i = 0; i < NJ; i++) { qt[i] = (T)q[i]; qdt[i] = (T)qd[i]; }
     ArmRows<T> rows;
-    arm_make_rows(am, q, qd, qacc_s, rows);
+    arm_make_rows(am, qt, qdt, qacc_s, rows);
     T delta[NJ];
 #pragma unroll
     for (int i = 0; i < NJ; i++) delta[i] = warm[i] - qacc_s[i];
     iters = arm_solve(am, M, rows, delta, cfg.max_iter, (T)cfg.tol);
 #pragma unroll
     for (int i = 0; i < NJ; i++) {
-      const T qacc = qacc_s[i] + delta[i];
-      warm[i] = qacc;
-      bad |= !(t_abs(qacc) < T(1e10));  // [upstream] mj_checkAcc (also catches NaN)
-      qd[i] += am.dt * qacc;            // [upstream] mj_Euler: velocity first, then position with the new velocity
-      q[i] += am.dt * qd[i];
+      const TS qacc = qacc_sd[i] + (TS)delta[i];
+      warm[i] = (T)qacc;
+      bad |= !(t_abs(qacc) < TS(1e10));  // [upstream] mj_checkAcc (also catches NaN)
+      qd[i] += am.dt_d * qacc;           // [upstream] mj_Euler: velocity first, then position with the new velocity
+      q[i] += am.dt_d * qd[i];
+      if constexpr (ROUND32) { qd[i] = (TS)(float)qd[i]; q[i] = (TS)(float)q[i]; }
     }
   }
   const int t = S.step[env] + 1;
@@ -135,11 +166,21 @@ __global__ void arm_reset_kernel(const __grid_constant__ StepCfg cfg, const EnvS
 }
 
 template <typename T>
-void launch_arm_step(const ArmModelT<T> &am, const StepCfg &cfg, const EnvState<T> &S, const float *action, const so101_step_out &out,
-                     cudaStream_t stream) {
+void launch_arm_step(const ArmModelT<T> &am, const ArmModelT<double> &am64, const StepCfg &cfg, const EnvState<T> &S, const float *action,
+                     const so101_step_out &out, cudaStream_t stream) {
   // one env per thread; small batches use 32-thread CTAs so that every one of the 148 SMs gets work
   const int threads = S.N <= 148 * 32 * 4 ? 32 : (S.N <= 148 * 64 * 4 ? 64 : 128);
-  arm_step_kernel<T><<<(S.N + threads - 1) / threads, threads, 0, stream>>>(am, cfg, S, action, out);
+  const int grid = (S.N + threads - 1) / threads;
+  if constexpr (sizeof(T) == 8) arm_step_kernel<T, T, false, false, false><<<grid, threads, 0, stream>>>(am, am, cfg, S, action, out);
+  else {
+    switch (cfg.arm_mode) {
+      case 0: arm_step_kernel<T, T, false, false, true><<<grid, threads, 0, stream>>>(am, am, cfg, S, action, out); break;
+      case 1: arm_step_kernel<T, T, false, false, false><<<grid, threads, 0, stream>>>(am, am, cfg, S, action, out); break;
+      case 3: arm_step_kernel<T, T, true, true, false><<<grid, threads, 0, stream>>>(am, am, cfg, S, action, out); break;
+      case 4: arm_step_kernel<T, double, true, true, false><<<grid, threads, 0, stream>>>(am, am64, cfg, S, action, out); break;
+      default: arm_step_kernel<T, T, true, false, false><<<grid, threads, 0, stream>>>(am, am, cfg, S, action, out); break;
+    }
+  }
 }
 template <typename T>
 void launch_arm_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream) {
@@ -147,8 +188,8 @@ void launch_arm_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *m
   arm_reset_kernel<T><<<(S.N + threads - 1) / threads, threads, 0, stream>>>(cfg, S, mask, out);
 }
 
-template void launch_arm_step<float>(const ArmModelT<float> &, const StepCfg &, const EnvState<float> &, const float *, const so101_step_out &, cudaStream_t);
-template void launch_arm_step<double>(const ArmModelT<double> &, const StepCfg &, const EnvState<double> &, const float *, const so101_step_out &, cudaStream_t);
+template void launch_arm_step<float>(const ArmModelT<float> &, const ArmModelT<double> &, const StepCfg &, const EnvState<float> &, const float *, const so101_step_out &, cudaStream_t);
+template void launch_arm_step<double>(const ArmModelT<double> &, const ArmModelT<double> &, const StepCfg &, const EnvState<double> &, const float *, const so101_step_out &, cudaStream_t);
 template void launch_arm_reset<float>(const StepCfg &, const EnvState<float> &, const uint8_t *, const so101_step_out &, cudaStream_t);
 template void launch_arm_reset<double>(const StepCfg &, const EnvState<double> &, const uint8_t *, const so101_step_out &, cudaStream_t);
 

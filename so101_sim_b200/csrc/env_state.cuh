@@ -6,11 +6,19 @@
 
 namespace so101 {
 
+// The integration state (qpos, qvel and the reset pool) is float64 in BOTH precisions: the float32 product path evaluates the
+// dynamics and the contact pipeline in float32 from the rounded state, but accumulates the semi-implicit Euler update (and
+// evaluates the position-feedback actuators, gain 50 on q) in float64.  Rounding the state itself to float32 every substep
+// (|qvel| ~ 5 rad/s: 2e-7 per substep) is what the anti-damped actuators (bias +1 * qvel, scene_pbr.xml:11) amplify ~300x over
+// 100 control steps; the dynamics' own float32 round-off is three orders of magnitude below that.
+using TS = double;
+
 template <typename T>
 struct EnvState {
   int N, nq, nv;
-  T *qpos, *qvel, *warm;            // [nq][N], [nv][N], [nv][N]  (warm = qacc_warmstart)
-  T *init_qpos, *init_qvel;         // reset pool [npool][...same layout as qpos / qvel...]: episode e of an env starts from entry e % npool
+  TS *qpos, *qvel;                  // [nq][N], [nv][N]
+  T *warm;                          // [nv][N]  (qacc_warmstart)
+  TS *init_qpos, *init_qvel;        // reset pool [npool][...same layout as qpos / qvel...]: episode e of an env starts from entry e % npool
   int npool;                        // entries in the reset pool (>= 1)
   int *episode;                     // [N] resets this env has gone through (selects the pool entry)
   T *ctrl;                          // [6][N]
@@ -27,6 +35,7 @@ struct EnvState {
 
 struct StepCfg {
   int nsub, last_step, dj, dp, terminate_on_success, max_iter;
+  int arm_mode;  // developer switch (SO101_ARM_MODE): which parts of the float32 arm path run in float64, see arm_kernel.cu
   float tol;
   int dbg_env, dbg_step;  // developer probe: device printf of one env's manifold inputs (SO101_DBG_ENV / SO101_DBG_STEP)
   float offsets[6], home[6];

@@ -4,8 +4,8 @@
 
 namespace so101 {
 
-template <typename T>
-__global__ void rows_to_soa_kernel(const float *__restrict__ rows, T *__restrict__ soa, int N, int k) {
+template <typename A, typename T>
+__global__ void rows_to_soa_kernel(const A *__restrict__ rows, T *__restrict__ soa, int N, int k) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // index into the SoA array: coalesced stores
   if (i >= N * k) return;
   const int c = i / N, e = i % N;
@@ -31,10 +31,10 @@ template <typename A, typename B>
 inline void launch_cast_copy(const A *src, B *dst, size_t n, cudaStream_t s) {
   cast_copy_kernel<A, B><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, n);
 }
-template <typename T>
-inline void launch_rows_to_soa(const float *rows, T *soa, int N, int k, cudaStream_t s) {
+template <typename A, typename T>
+inline void launch_rows_to_soa(const A *rows, T *soa, int N, int k, cudaStream_t s) {
   const int n = N * k;
-  rows_to_soa_kernel<T><<<(n + 255) / 256, 256, 0, s>>>(rows, soa, N, k);
+  rows_to_soa_kernel<A, T><<<(n + 255) / 256, 256, 0, s>>>(rows, soa, N, k);
 }
 template <typename T, typename U>
 inline void launch_soa_to_rows(const T *soa, U *rows, int N, int k, cudaStream_t s) {

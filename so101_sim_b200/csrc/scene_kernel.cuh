@@ -125,6 +125,8 @@ void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t 
 template <typename T>
 size_t scene_smem_bytes();
 template <typename T>
+void launch_debug_overlap(const double *cases, int n, uint8_t *out, cudaStream_t stream);
+template <typename T>
 void scene_dropcat(int out[8]);
 template <typename T>
 void scene_epahist(int out[8]);

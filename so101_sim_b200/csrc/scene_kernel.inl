@@ -514,8 +514,8 @@ __device__ void reset_env_scene(const StepCfg &cfg, const EnvState<T> &S, const 
   const int ep = S.episode[env];
   const size_t slot = (size_t)(ep % S.npool) * S.N + env;
   __syncwarp();
-  for (int i = lane; i < NQ; i += 32) { s.q[i] = S.init_qpos[slot * NQ + i]; S.qpos[(size_t)env * NQ + i] = s.q[i]; }
-  for (int i = lane; i < NV; i += 32) { s.qd[i] = S.init_qvel[slot * NV + i]; S.qvel[(size_t)env * NV + i] = s.qd[i]; S.warm[(size_t)env * NV + i] = T(0); }
+  for (int i = lane; i < NQ; i += 32) { const TS v = S.init_qpos[slot * NQ + i]; s.q[i] = (T)v; S.qpos[(size_t)env * NQ + i] = v; }
+  for (int i = lane; i < NV; i += 32) { const TS v = S.init_qvel[slot * NV + i]; s.qd[i] = (T)v; S.qvel[(size_t)env * NV + i] = v; S.warm[(size_t)env * NV + i] = T(0); }
   if (lane < NJ) { s.ctrl[lane] = (T)cfg.home[lane] + (T)cfg.offsets[lane]; S.ctrl[(size_t)env * 6 + lane] = s.ctrl[lane]; }
   if (lane == 0) { S.step[env] = 0; S.needs_reset[env] = 0; S.episode[env] = ep + 1; }
   __syncwarp();
@@ -570,11 +570,11 @@ __global__ void __launch_bounds__(KD_THREADS) scene_kindyn_kernel(const __grid_c
                                                                  const EnvState<T> S, const PipeBuf<T> pb, int need_dyn) {
   const int env = pb.env0 + blockIdx.x * KD_THREADS + threadIdx.x;
   if (env >= pb.env0 + pb.nenv || !pb.active[env]) return;
-  const T *gq = S.qpos + (size_t)env * NQ, *gv = S.qvel + (size_t)env * NV;
+  const TS *gq = S.qpos + (size_t)env * NQ, *gv = S.qvel + (size_t)env * NV;
   T *gx = pb.xpos + (size_t)env * (NSLOT * 3), *gm = pb.xmat + (size_t)env * (NSLOT * 9), *gd = pb.dyn + (size_t)env * DYNW;
   T qa[NJ], qda[NJ], ca[NJ];
 #pragma unroll
-  for (int i = 0; i < NJ; i++) { qa[i] = gq[i]; qda[i] = gv[i]; ca[i] = S.ctrl[(size_t)env * 6 + i]; }
+  for (int i = 0; i < NJ; i++) { qa[i] = (T)gq[i]; qda[i] = (T)gv[i]; ca[i] = S.ctrl[(size_t)env * 6 + i]; }
   ArmKin<T> k;
   {
     T R[NJ][9];
@@ -591,18 +591,18 @@ __global__ void __launch_bounds__(KD_THREADS) scene_kindyn_kernel(const __grid_c
   const bool dyn = need_dyn && !pb.flags[env];  // (a diverged env is frozen for the rest of the control step)
 #pragma unroll 1
   for (int p = 0; p < NPROP; p++) {
-    const T *qp = gq + NJ + 7 * p;
-    const T quat[4] = {qp[3], qp[4], qp[5], qp[6]};
+    const TS *qp = gq + NJ + 7 * p;
+    const T quat[4] = {(T)qp[3], (T)qp[4], (T)qp[5], (T)qp[6]};
     T Rp[9];
     prop_rotation(quat, Rp);
 #pragma unroll
-    for (int c = 0; c < 3; c++) gx[3 * (NJ + p) + c] = qp[c];
+    for (int c = 0; c < 3; c++) gx[3 * (NJ + p) + c] = (T)qp[c];
 #pragma unroll
     for (int e = 0; e < 9; e++) gm[9 * (NJ + p) + e] = Rp[e];
     if (dyn) {
       T qdp[6], M[21], bias[6], x[6];
 #pragma unroll
-      for (int i = 0; i < 6; i++) qdp[i] = gv[NJ + 6 * p + i];
+      for (int i = 0; i < 6; i++) qdp[i] = (T)gv[NJ + 6 * p + i];
       prop_dynamics(sm, am, Rp, qdp, p, M, bias);
 #pragma unroll
       for (int i = 0; i < 21; i++) gd[DYN_MPROP + 21 * p + i] = M[i];
@@ -615,14 +615,20 @@ __global__ void __launch_bounds__(KD_THREADS) scene_kindyn_kernel(const __grid_c
     }
   }
   if (!dyn) return;
-  T M[21], bias[NJ], frc[NJ], qs[NJ], L[21];
+  T M[21], bias[NJ], qs[NJ], L[21];
   arm_crb_rne(am, k, qda, M, bias);
-  arm_actuation(am, qa, qda, ca, frc);
+  double frc[NJ];  // actuators on the float64 state (arm_actuation_d; identical to arm_actuation when T = double)
+  {
+    double q64[NJ], qd64[NJ];
+#pragma unroll
+    for (int i = 0; i < NJ; i++) { q64[i] = gq[i]; qd64[i] = gv[i]; }
+    arm_actuation_d(am, q64, qd64, ca, frc);
+  }
 #pragma unroll
   for (int i = 0; i < 21; i++) { L[i] = M[i]; gd[DYN_MARM + i] = M[i]; }
   chol6(L);
 #pragma unroll
-  for (int i = 0; i < NJ; i++) qs[i] = frc[i] - bias[i];
+  for (int i = 0; i < NJ; i++) qs[i] = (T)(frc[i] - (double)bias[i]);
   chol6_solve(L, qs);
   ArmRows<T> arows;
   arm_make_rows(am, qa, qda, qs, arows);
@@ -653,8 +659,8 @@ __global__ void __launch_bounds__(WARPS_BROAD * 32) scene_broad_kernel(const __g
     if (!bad) scene_broadphase(sm, s, pb, env, sub, dropped, lane);
     if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
   } else {
-    for (int i = lane; i < NQ; i += 32) s.q[i] = S.qpos[(size_t)env * NQ + i];
-    for (int i = lane; i < NV; i += 32) s.qd[i] = S.qvel[(size_t)env * NV + i];
+    for (int i = lane; i < NQ; i += 32) s.q[i] = (T)S.qpos[(size_t)env * NQ + i];
+    for (int i = lane; i < NV; i += 32) s.qd[i] = (T)S.qvel[(size_t)env * NV + i];
     if (lane < NJ) s.ctrl[lane] = S.ctrl[(size_t)env * 6 + lane];
     __syncwarp();
     const int t = S.step[env] + 1;
@@ -880,8 +886,8 @@ template <typename T, typename SC>
 __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
                                           const so101_step_out &out, int sub, int env, SC &s, int lane) {
   prof_begin(s, S, lane);
-  for (int i = lane; i < NQ; i += 32) s.q[i] = S.qpos[(size_t)env * NQ + i];
-  for (int i = lane; i < NV; i += 32) { s.qd[i] = S.qvel[(size_t)env * NV + i]; s.warm[i] = S.warm[(size_t)env * NV + i]; }
+  for (int i = lane; i < NQ; i += 32) s.q[i] = (T)S.qpos[(size_t)env * NQ + i];
+  for (int i = lane; i < NV; i += 32) { s.qd[i] = (T)S.qvel[(size_t)env * NV + i]; s.warm[i] = S.warm[(size_t)env * NV + i]; }
   if (lane == 0) s.dbg = 0;
   __syncwarp();
   int iters = 0, dropped = 0;
@@ -926,35 +932,39 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
     if (badnow) {
       if (lane == 0) pb.flags[env] = 1;
       qacc = T(0);
-      if (lane < NV) s.qd[lane] = T(0);
     }
+    // The update itself runs in float64 on the float64 state (env_state.cuh): velocity first, then positions with the new
+    // velocity; free-joint quaternions are advanced by the body-frame angular velocity and renormalised.
+    const TS h = am.dt_d;
+    TS qd_new = TS(0);
     if (lane < NV) {
-      s.warm[lane] = qacc;
-      s.qd[lane] += sm.timestep * qacc;
+      qd_new = badnow ? TS(0) : S.qvel[(size_t)env * NV + lane] + h * (TS)qacc;
+      S.qvel[(size_t)env * NV + lane] = qd_new;
+      S.warm[(size_t)env * NV + lane] = qacc;
     }
-    __syncwarp();
-    if (lane < NJ) s.q[lane] += sm.timestep * s.qd[lane];
+    TS pv[6];  // the six velocities of prop (lane - 8), gathered from the dof lanes
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      const TS a0 = __shfl_sync(FULL, qd_new, NJ + c), a1 = __shfl_sync(FULL, qd_new, NJ + 6 + c);
+      pv[c] = lane == 9 ? a1 : a0;
+    }
+    if (lane < NJ) S.qpos[(size_t)env * NQ + lane] += h * qd_new;
     if (lane >= 8 && lane < 8 + NPROP) {
-      const int p = lane - 8;
-      T *qp = s.q + NJ + 7 * p;
-      const T *v = s.qd + NJ + 6 * p;
-      for (int c = 0; c < 3; c++) qp[c] += sm.timestep * v[c];
-      const T w[3] = {v[3], v[4], v[5]};
-      const T nw = t_sqrt(dot3(w, w)), ang = nw * sm.timestep;
-      T qn[4] = {qp[3], qp[4], qp[5], qp[6]};
-      if (ang > T(0)) {
-        T sn, cn;
-        t_sincos(T(0.5) * ang, &sn, &cn);
-        const T qr[4] = {cn, w[0] / nw * sn, w[1] / nw * sn, w[2] / nw * sn};
+      TS *qp = S.qpos + (size_t)env * NQ + NJ + 7 * (lane - 8);
+      for (int c = 0; c < 3; c++) qp[c] += h * pv[c];
+      const TS w[3] = {pv[3], pv[4], pv[5]};
+      const TS nw = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]), ang = nw * h;
+      TS qn[4] = {qp[3], qp[4], qp[5], qp[6]};
+      if (ang > TS(0)) {
+        TS sn, cn;
+        sincos(TS(0.5) * ang, &sn, &cn);
+        const TS qr[4] = {cn, w[0] / nw * sn, w[1] / nw * sn, w[2] / nw * sn};
         quat_mul(qn, qn, qr);
       }
-      T n = t_sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
-      if (n < T(1e-15)) { qn[0] = T(1); qn[1] = qn[2] = qn[3] = T(0); n = T(1); }
+      TS n = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+      if (n < TS(1e-15)) { qn[0] = TS(1); qn[1] = qn[2] = qn[3] = TS(0); n = TS(1); }
       for (int c = 0; c < 4; c++) qp[3 + c] = qn[c] / n;
     }
-    __syncwarp();
-    for (int i = lane; i < NQ; i += 32) S.qpos[(size_t)env * NQ + i] = s.q[i];
-    for (int i = lane; i < NV; i += 32) { S.qvel[(size_t)env * NV + i] = s.qd[i]; S.warm[(size_t)env * NV + i] = s.warm[i]; }
   }
   if (last && lane == 0) { S.solver_iter[env] = iters; S.ncon[env] = s.ncon; }
   if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
@@ -1033,6 +1043,23 @@ __global__ void scene_reset_kernel(const __grid_constant__ StepCfg cfg, const En
   reset_env_scene(cfg, S, out, all[wib], env, lane);
 }
 
+// Parity probe for the reward geometry: the device 6-axis SAT on n caller-supplied box pairs, rows of 20 doubles
+// (p0 3, q0 4, half0 3, p1 3, q1 4, half1 3), evaluated in T.  tests/test_scene_gpu.py runs the 240 cases produced by the
+// reference's own oobb_utils.py (tests/golden/oobb_overlap.json) through it.
+template <typename T>
+__global__ void debug_overlap_kernel(const double *__restrict__ cases, int n, uint8_t *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double *c = cases + (size_t)i * 20;
+  T v[20];
+  for (int k = 0; k < 20; k++) v[k] = (T)c[k];
+  out[i] = overlap_oobb_oobb<T>(v, v + 3, v + 7, v + 10, v + 13, v + 17) ? 1 : 0;
+}
+template <typename T>
+void launch_debug_overlap(const double *cases, int n, uint8_t *out, cudaStream_t stream) {
+  debug_overlap_kernel<T><<<(n + 63) / 64, 64, 0, stream>>>(cases, n, out);
+}
+
 template <typename T>
 size_t scene_smem_bytes() {
   const size_t a = sizeof(Scratch<T, NC_M, NB_M>) * WARPS_M, b = sizeof(Scratch<T, NC_S, NB_S>) * WARPS_SOLVE, c = sizeof(Scratch<T, NC_L, NB_L>) * WARPS_L;
@@ -1085,7 +1112,9 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
     t.end(0, st);
     refresh(pb, st, 0, false);
   }
-  const int sms = 148;
+  static int sm_count[64] = {};  // SMs of the device the handle lives on (148 on B200): grids are sized in multiples of it
+  if (dev >= 0 && dev < 64 && sm_count[dev] == 0) { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); sm_count[dev] = v > 0 ? v : 148; }
+  const int sms = (dev >= 0 && dev < 64) ? sm_count[dev] : 148;
   for (int sub = 0; sub < cfg.nsub; sub++) {
     for (int g = 0; g < ngroups; g++) {
       const PipeBuf<T> &pb = pbs[g];

@@ -49,7 +49,7 @@ class BatchedSO101LeRobotWrapper:
   """N lockstep copies of SO101LeRobotWrapper (scripts/so101_lerobot_wrapper.py:15-188)."""
 
   def __init__(self, task_name: str = 'SO100HandOverBanana', num_envs: int = 1, cameras: tuple = (), camera_resolution: tuple = (480, 640),
-               time_limit: float = 30.0, device: str = 'cuda:0', seed: int | None = None, reset_rounds: int = 0, **env_kwargs):
+               time_limit: float = 30.0, device: str = 'cuda:0', seed: int | None = None, reset_rounds: int = 1, **env_kwargs):
     if cameras:
       raise NotImplementedError('camera rendering is out of scope of the B200 path: pass cameras=()')
     self.device = device
@@ -60,9 +60,7 @@ class BatchedSO101LeRobotWrapper:
     # (so101_lerobot_wrapper.py:43-49, task_suite.py:134-138)
     self.env = task_suite.create_batched_task_env(task_name=task_name, num_envs=num_envs, time_limit=time_limit, seed=seed, cameras=cameras,
                                                   camera_resolution=camera_resolution, image_observation_enabled=True, device=device,
-                                                  **env_kwargs)
-    if reset_rounds > 0 and self.env.nq == 20:
-      self.env.randomize_resets(rounds=reset_rounds, seed=seed)
+                                                  reset_rounds=reset_rounds, **env_kwargs)
     self.num_envs = self.env.num_envs
     self.episode_index = 0
     self.frame_index = 0

@@ -125,19 +125,24 @@ TASK_FACTORIES = {
 
 def time_limit_to_last_step(time_limit: float, control_timestep: float, physics_timestep: float = PHYSICS_TIMESTEP) -> int:
   """Control-step index whose TimeStep is LAST: dm_control tests `physics.time() >= time_limit` after each control step and
-  MuJoCo accumulates `time += timestep` in float64 (30 s -> step 1501, not 1500)."""
+  MuJoCo accumulates `time += timestep` in float64 (30 s -> step 1501, not 1500).  The float64 running sum is
+  reproduced exactly (np.add.accumulate adds sequentially) in chunks, so large limits cost milliseconds, not a Python loop."""
   if not np.isfinite(time_limit):
     return 0
   nsub = int(round(control_timestep / physics_timestep))
-  t, step = 0.0, 0
+  if time_limit <= 0:
+    return 1
+  if time_limit / physics_timestep > 2e9:
+    raise ValueError('time_limit too large')
+  chunk = nsub * 100_000
+  t, done = 0.0, 0
   while True:
-    for _ in range(nsub):
-      t += physics_timestep
-    step += 1
-    if t >= time_limit:
-      return step
-    if step > 100_000_000:
-      raise ValueError('time_limit too large')
+    acc = np.add.accumulate(np.concatenate(([t], np.full(chunk, physics_timestep))))[1:]
+    ends = acc[nsub - 1::nsub]            # time after each control step of this chunk
+    hit = np.nonzero(ends >= time_limit)[0]
+    if len(hit):
+      return done + int(hit[0]) + 1
+    t, done = float(acc[-1]), done + len(ends)
 
 
 class BatchedEnvironment:
@@ -248,12 +253,22 @@ class BatchedEnvironment:
     self._check(self._lib.so101_step(self._h, ctypes.c_void_p(action.data_ptr()), ctypes.byref(self._out), self._stream()))
     return self._timestep()
 
-  def step_host(self, action_host: torch.Tensor, reward_host, discount_host, step_type_host, joints_pos_host=None):
-    """End-to-end step with (pinned) HOST tensors: H2D of the action, the step, D2H of reward/discount/step_type
-    (+ joints_pos) and a stream sync all happen inside the call (so101_step_host)."""
-    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
-    self._check(self._lib.so101_step_host(self._h, p(action_host), p(reward_host), p(discount_host), p(step_type_host),
-                                          p(joints_pos_host), self._stream()))
+  def make_host_timestep(self) -> dict:
+    """Pinned host tensors for every block of the TimeStep (the observation dict, reward, discount, step_type): the
+    destination of step_host()."""
+    N, sd = self.num_envs, self.nq + self.nv
+    pin = dict(pin_memory=True)
+    return dict(commanded_joints_pos=torch.zeros(N, 6, **pin), joints_pos=torch.zeros(N, 6, **pin), undelayed_joints_pos=torch.zeros(N, 6, **pin),
+                physics_state=torch.zeros(N, sd, **pin), delayed_physics_state=torch.zeros(N, sd, **pin), reward=torch.zeros(N, **pin),
+                discount=torch.zeros(N, **pin), step_type=torch.zeros(N, dtype=torch.uint8, **pin))
+
+  def step_host(self, action_host: torch.Tensor, host_out: dict) -> int:
+    """End-to-end step with (pinned) HOST tensors: H2D of the action, the step, D2H of every TimeStep block present in
+    `host_out` (see make_host_timestep) and a stream sync, all inside the call (so101_step_host).  Returns the bytes copied
+    back."""
+    out = _lib.StepOut(**{k: v.data_ptr() for k, v in host_out.items()})
+    self._check(self._lib.so101_step_host(self._h, ctypes.c_void_p(action_host.data_ptr()), ctypes.byref(out), self._stream()))
+    return sum(v.numel() * v.element_size() for v in host_out.values())
 
   def close(self):
     if not self._closed and getattr(self, '_h', None):
@@ -267,15 +282,25 @@ class BatchedEnvironment:
       pass
 
   # ------------------------------------------------------------------ state access (physics.get_state / set_state)
-  def set_initial_state(self, qpos: torch.Tensor, qvel: torch.Tensor):
-    q = qpos.to(device=self.device, dtype=torch.float32).contiguous(); v = qvel.to(device=self.device, dtype=torch.float32).contiguous()
+  def _put_state(self, qpos, qvel, initial: bool):
+    """float64 tensors go in unrounded (the integration state is float64 in both precisions); anything else as float32."""
+    f64 = qpos.dtype == torch.float64 or qvel.dtype == torch.float64
+    dt = torch.float64 if f64 else torch.float32
+    q = qpos.to(device=self.device, dtype=dt).contiguous(); v = qvel.to(device=self.device, dtype=dt).contiguous()
     assert q.shape == (self.num_envs, self.nq) and v.shape == (self.num_envs, self.nv)
-    self._check(self._lib.so101_set_initial_state(self._h, ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(v.data_ptr()), self._stream()))
+    qp, vp = ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(v.data_ptr())
+    if f64:
+      self._check(self._lib.so101_set_state_f64(self._h, qp, vp, int(initial), self._stream()))
+    elif initial:
+      self._check(self._lib.so101_set_initial_state(self._h, qp, vp, self._stream()))
+    else:
+      self._check(self._lib.so101_set_state(self._h, qp, vp, self._stream()))
+
+  def set_initial_state(self, qpos: torch.Tensor, qvel: torch.Tensor):
+    self._put_state(qpos, qvel, True)
 
   def set_state(self, qpos: torch.Tensor, qvel: torch.Tensor):
-    q = qpos.to(device=self.device, dtype=torch.float32).contiguous(); v = qvel.to(device=self.device, dtype=torch.float32).contiguous()
-    assert q.shape == (self.num_envs, self.nq) and v.shape == (self.num_envs, self.nv)
-    self._check(self._lib.so101_set_state(self._h, ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(v.data_ptr()), self._stream()))
+    self._put_state(qpos, qvel, False)
 
   def get_state(self, dtype=torch.float32):
     q = torch.empty(self.num_envs, self.nq, dtype=dtype, device=self.device); v = torch.empty(self.num_envs, self.nv, dtype=dtype, device=self.device)
@@ -300,9 +325,9 @@ class BatchedEnvironment:
     return out
 
   def counters(self) -> dict:
-    c = (ctypes.c_uint64 * 4)()
+    c = (ctypes.c_uint64 * 6)()
     self._check(self._lib.so101_counters(self._h, ctypes.byref(c)))
-    return dict(kernel_launches=int(c[0]), control_steps=int(c[1]), diverged=int(c[2]), contacts_dropped=int(c[3]))
+    return dict(kernel_launches=int(c[0]), control_steps=int(c[1]), diverged=int(c[2]), contacts_dropped=int(c[3]), graph_launches=int(c[4]))
 
   KERNEL_NAMES = ("scene_begin_kernel", "scene_narrow_kernel", "scene_solve_kernel", "scene_solve_tier_kernel(1+2)", "arm_step_kernel", "scene_gjk_kernel",
                   "scene_kindyn_kernel", "scene_broad_kernel")
@@ -429,8 +454,15 @@ class BatchedEnvironment:
 def create_batched_task_env(task_name: str, num_envs: int, time_limit: float, seed: int | None = None,
                             control_timestep: float = DEFAULT_CONTROL_TIMESTEP, cameras: tuple = (), device='cuda:0',
                             calibration_offsets=None, calibration_file: str | None = None, precision: str = 'f32',
-                            solver_iterations: int = 100, solver_tolerance: float | None = None, **kwargs) -> BatchedEnvironment:
-  """Batched twin of task_suite.create_task_env (task_suite.py:103-155)."""
+                            solver_iterations: int = 100, solver_tolerance: float | None = None, reset_rounds: int = 1,
+                            **kwargs) -> BatchedEnvironment:
+  """Batched twin of task_suite.create_task_env (task_suite.py:103-155).
+
+  For the SO100HandOver tasks the env comes back with `reset_rounds` sampled-and-settled prop placements per env installed as
+  its reset pool (randomize_resets with `seed`), as the reference samples and settles the props in every initialize_episode
+  (so100_hand_over.py:208-229,320-323): a plain create -> reset -> step loop never starts from the blob's qpos0, where both
+  free props sit coincident at the world origin.  reset_rounds=0 skips this (the caller installs its own states with
+  set_initial_state / set_reset_pool / sample_prop_initial_states before the first reset)."""
   if task_name not in TASK_FACTORIES:
     raise ValueError(f'Unknown task_name: {task_name}. Available tasks: {list(TASK_FACTORIES.keys())}')  # task_suite.py:126-130
   task_class, task_kwargs = TASK_FACTORIES[task_name]
@@ -443,4 +475,7 @@ def create_batched_task_env(task_name: str, num_envs: int, time_limit: float, se
     calibration_offsets = SO101Calibration(calibration_file).homing_offsets
   if solver_tolerance is None:
     solver_tolerance = 1e-8 if precision == 'f64' else 1e-6
-  return BatchedEnvironment(task, num_envs, time_limit, seed, device, calibration_offsets, precision, solver_iterations, solver_tolerance)
+  env = BatchedEnvironment(task, num_envs, time_limit, seed, device, calibration_offsets, precision, solver_iterations, solver_tolerance)
+  if task.collide and reset_rounds > 0:
+    env.randomize_resets(rounds=int(reset_rounds))
+  return env

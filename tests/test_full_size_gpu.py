@@ -15,7 +15,7 @@ DEV = 'cuda:0'
 
 def _make(task, n, **kw):
   from so101_sim_b200.task_suite import create_batched_task_env
-  return create_batched_task_env(task, num_envs=n, time_limit=30.0, seed=0, device=DEV, **kw)
+  return create_batched_task_env(task, num_envs=n, time_limit=30.0, seed=0, device=DEV, reset_rounds=0, **kw)
 
 
 def _actions(env, steps, n, seed=1, scale=0.3):

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(built):
   L = ctypes.CDLL(_lib.LIB_PATH)
   for sym in declared:
     assert hasattr(L, sym), sym
-  assert L.so101_abi_version() == 2
+  assert L.so101_abi_version() == 3
 
 
 def test_create_fails_loudly_without_gpu(built):

@@ -134,7 +134,7 @@ def test_reset_pool_cycles_placements(built):
   """Every reset of an env moves on to its next sampled-and-settled placement (initialize_episode re-samples the props in the
   reference, so100_hand_over.py:208-229,320-323); the pool wraps around."""
   from so101_sim_b200.task_suite import create_batched_task_env
-  env = create_batched_task_env('SO100HandOverBanana', num_envs=4, time_limit=0.04, seed=0, device='cuda:0')
+  env = create_batched_task_env('SO100HandOverBanana', num_envs=4, time_limit=0.04, seed=0, device='cuda:0', reset_rounds=0)
   Q, V = env.randomize_resets(rounds=3, seed=7, settle_steps=10)
   assert Q.shape == (3, 4, 20) and not torch.allclose(Q[0, :, 6:8], Q[1, :, 6:8])
   # placement ranges of so100_hand_over.py:37-55

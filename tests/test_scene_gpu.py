@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 def _env(built, **kw):
   from so101_sim_b200.task_suite import create_batched_task_env
-  args = dict(task_name='SO100HandOverBanana', num_envs=8, time_limit=30.0, seed=0, device='cuda:0')
+  args = dict(task_name='SO100HandOverBanana', num_envs=8, time_limit=30.0, seed=0, device='cuda:0', reset_rounds=0)
   args.update(kw)
   return create_batched_task_env(**args)
 
@@ -74,24 +74,132 @@ def test_contacts_match_oracle(built):
 
 
 def test_f32_scene_tracks_oracle(built):
-  """float32 product path: props settle on the table at the oracle's rest pose; arm tracks within the stated tolerance."""
-  env = _env(built, precision='f32', num_envs=4)
+  """float32 product path, ALL envs of the batch against the float64 oracle over 25 control steps (250 substeps): the arm within
+  the north_star tolerance (1e-4 relative), the props settling on the table at the oracle's rest pose, reward / discount /
+  step_type flags exact.  Measured errors are printed."""
+  N = 4
+  env = _env(built, precision='f32', num_envs=N)
   q0, v0 = _initial(env, seed=5)
   acts = _actions(env, 25, scale=0.1)
-  o = OracleSim('so100_handover_banana', collide=True)
-  o.set_state(q0[1].cpu().numpy(), v0[1].cpu().numpy())
+  sims = []
+  for e in range(N):
+    o = OracleSim('so100_handover_banana', collide=True)
+    o.set_state(q0[e].cpu().numpy(), v0[e].cpu().numpy())
+    sims.append(o)
   errs = []
   for t in range(25):
     ts = env.step(acts[t])
-    o.control_step(acts[t, 1].double().cpu().numpy())
     q, v = env.get_state(torch.float64)
-    errs.append((np.abs(q[1, :6].cpu().numpy() - o.qpos[:6]).max(), np.abs(q[1, 6:].cpu().numpy() - o.qpos[6:]).max()))
-  print('f32 scene: (arm qpos err, prop qpos err) per control step:', [(float(f'{a:.2g}'), float(f'{b:.2g}')) for a, b in errs[::4]])
-  assert errs[0][0] < 1e-5 and errs[0][1] < 1e-4
-  assert errs[9][0] < 1e-4
-  assert errs[-1][1] < 2e-3          # resting pose of the props (contact dynamics amplify round-off; positions stay within 2 mm)
-  assert abs(float(q[1, 8]) - o.qpos[8]) < 2e-4 and abs(float(q[1, 15]) - o.qpos[15]) < 2e-4  # rest heights
+    ea = ev = ep = 0.0
+    for e, o in enumerate(sims):
+      r = o.control_step(acts[t, e].double().cpu().numpy())
+      assert float(ts.reward[e]) == r and int(ts.step_type[e]) == 1 and float(ts.discount[e]) == 1.0
+      qe, ve = q[e].cpu().numpy(), v[e].cpu().numpy()
+      ea = max(ea, float(np.abs(qe[:6] - o.qpos[:6]).max() / max(1.0, np.abs(o.qpos[:6]).max())))
+      ev = max(ev, float(np.abs(ve[:6] - o.qvel[:6]).max() / max(1.0, np.abs(o.qvel[:6]).max())))
+      ep = max(ep, float(np.abs(qe[6:] - o.qpos[6:]).max()))
+    errs.append((ea, ev, ep))
+  print('f32 scene, 4 envs: max (arm qpos rel, arm qvel rel, prop qpos abs) by control step:',
+        [(t + 1,) + tuple(float(f'{x:.2g}') for x in errs[t]) for t in (0, 4, 9, 14, 19, 24)])
+  assert errs[0][0] < 1e-6 and errs[0][2] < 1e-4
+  assert max(e[0] for e in errs) < 1e-4 and max(e[1] for e in errs) < 1e-4, errs   # north_star: 1e-4 relative
+  assert errs[-1][2] < 2e-3          # resting pose of the props (contact dynamics amplify round-off; positions stay within 2 mm)
+  for e, o in enumerate(sims):       # rest heights
+    assert abs(float(q[e, 8]) - o.qpos[8]) < 2e-4 and abs(float(q[e, 15]) - o.qpos[15]) < 2e-4
   assert torch.isfinite(q).all() and env.counters()['diverged'] == 0
+  env.close()
+
+
+def test_scene_forced_divergence_ends_the_episode(built):
+  """PhysicsError path of the contact scene (task_suite.py:153: raise_exception_on_physics_error=False): a non-finite prop
+  velocity makes qacc fail [upstream] mj_checkAcc -> reward 0, discount 0, LAST for that env only; the next step() returns
+  FIRST from the env's reset state.  The neighbouring env keeps stepping."""
+  env = _env(built, num_envs=2)
+  env.sample_prop_initial_states(seed=2, settle_steps=5)
+  env.reset()
+  q0, v0 = env.get_state()
+  zero = torch.zeros(2, 6, device='cuda:0')
+  env.step(zero)
+  q, v = env.get_state()
+  v[1, 6] = float('inf')
+  env.set_state(q, v)
+  d0 = env.counters()['diverged']
+  ts = env.step(zero)
+  assert int(ts.step_type[1]) == 2 and float(ts.reward[1]) == 0.0 and float(ts.discount[1]) == 0.0
+  assert int(ts.step_type[0]) == 1 and float(ts.discount[0]) == 1.0
+  assert env.counters()['diverged'] == d0 + 1
+  ts = env.step(zero)
+  assert int(ts.step_type[1]) == 0 and float(ts.reward[1]) == 0.0 and float(ts.discount[1]) == 1.0 and int(ts.step_type[0]) == 1
+  qq, vv = env.get_state()
+  assert torch.allclose(qq[1], q0[1]) and torch.isfinite(qq).all() and torch.isfinite(vv).all()
+  env.close()
+
+
+@pytest.mark.parametrize('precision', [64, 32])
+def test_device_overlap_matches_the_reference_golden(built, precision):
+  """The DEVICE 6-axis SAT (scene_kernel.inl overlap_oobb_oobb, the reward geometry) on the 240 box pairs whose flags were
+  produced by executing the reference's own oobb_utils.py (tests/golden/oobb_overlap.json, tools/make_golden_oobb.py): every
+  flag must be reproduced, in float64 and in the float32 the product path evaluates it in."""
+  import ctypes, json, os
+  from so101_sim_b200 import _lib
+  g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'oobb_overlap.json')))
+  rows = [c['obj_pos'] + c['obj_quat'] + c['obj_half'] + c['ws_pos'] + c['ws_quat'] + c['container_half'] for c in g['cases']]
+  want = torch.tensor([c['overlap'] for c in g['cases']], dtype=torch.uint8)
+  cases = torch.tensor(rows, dtype=torch.float64, device='cuda:0').contiguous()
+  out = torch.zeros(len(rows), dtype=torch.uint8, device='cuda:0')
+  L = _lib.load()
+  rc = L.so101_debug_overlap(precision, 0, ctypes.c_void_p(cases.data_ptr()), len(rows), ctypes.c_void_p(out.data_ptr()),
+                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+  torch.cuda.synchronize()
+  assert rc == 0
+  got = out.cpu()
+  assert int(want.sum()) > 40 and int((1 - want).sum()) > 40
+  assert torch.equal(got, want), f'{int((got != want).sum())} of {len(rows)} flags differ: cases {torch.nonzero(got != want).flatten().tolist()}'
+
+
+@pytest.mark.parametrize('precision', ['f64'])
+def test_single_env_many_pairs_keeps_every_contact(built, precision):
+  """num_envs = 1 with the banana resting inside the bowl (> 32 candidate geom pairs: 53 bowl hulls + 4 banana hulls against
+  the table and each other): no hit record may be lost to a capacity that scales with the batch size (the hit list once held
+  32 x num_envs records).  The state follows the float64 oracle; nothing is dropped."""
+  env = _env(built, num_envs=1, precision=precision)
+  q = torch.tensor(env.model['qpos0'], dtype=torch.float64).repeat(1, 1)
+  q[:, :6] = 0
+  q[:, 13:16] = torch.tensor([-0.25, -0.05, 0.4226], dtype=torch.float64); q[:, 16] = 1; q[:, 17:20] = 0
+  q[0, 6:9] = torch.tensor([-0.25 - 0.0255, -0.05 - 0.0675, 0.4226 + 0.06], dtype=torch.float64)
+  q[0, 9] = float(np.cos(0.4)); q[0, 10:12] = 0; q[0, 12] = float(np.sin(0.4))
+  env.set_initial_state(q, torch.zeros(1, 18, dtype=torch.float64))
+  env.reset()
+  o = OracleSim('so100_handover_banana', collide=True)
+  o.set_state(q[0].numpy(), np.zeros(18))
+  zero = torch.zeros(1, 6, device='cuda:0')
+  nmax = 0
+  for t in range(15):
+    env.step(zero)
+    o.control_step(np.zeros(6))
+    qq, _ = env.get_state(torch.float64)
+    n = int(env.debug_read('ncon')[0, 0])
+    nmax = max(nmax, n)
+    assert np.abs(qq[0].cpu().numpy() - o.qpos).max() < 1e-5, t
+  assert nmax > 16 and env.counters()['contacts_dropped'] == 0
+  env.close()
+
+
+def test_default_creation_starts_from_settled_placements(built):
+  """create -> reset -> step with no further set-up must start from sampled and settled prop placements (the reference places
+  and settles the props in every initialize_episode, so100_hand_over.py:208-229,320-323), never from the blob's qpos0 with both
+  props coincident at the world origin."""
+  from so101_sim_b200.task_suite import create_batched_task_env
+  env = create_batched_task_env('SO100HandOverBanana', num_envs=8, time_limit=30.0, seed=3, device='cuda:0')
+  ts = env.reset()
+  ps = ts.observation['physics_state']
+  assert float(ps[:, 6].min()) >= 0.19 and float(ps[:, 6].max()) <= 0.31       # banana x in its placement range (+- settle drift)
+  assert float(ps[:, 13].min()) >= -0.31 and float(ps[:, 13].max()) <= -0.19   # bowl x
+  assert float((ps[:, 8] - 0.4217).abs().max()) < 3e-3                         # banana resting on the table top
+  assert float(ps[:, :6].abs().max()) == 0.0                                   # arm qpos 0 (home is never applied, so100_task.py:308-313)
+  ts = env.step(torch.zeros(8, 6, device='cuda:0'))
+  assert ts.step_type.tolist() == [1] * 8 and env.counters()['diverged'] == 0
+  assert float((ts.observation['physics_state'][:, 6:9] - ps[:, 6:9]).abs().max()) < 2e-3  # props stay put
   env.close()
 
 

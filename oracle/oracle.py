@@ -130,5 +130,6 @@ class OracleSim:
     for c in range(self.info('ncon')):
       lib().so_get_contact(self._d, c, _dp(buf))
       out.append(dict(dist=buf[0], pos=buf[1:4].copy(), frame=buf[4:13].reshape(3, 3).copy(), dim=int(buf[13]), geom1=int(buf[14]),
-                      geom2=int(buf[15]), mu=buf[16], friction=buf[17:22].copy(), solref=buf[22:24].copy(), solimp=buf[24:29].copy()))
+                      geom2=int(buf[15]), mu=buf[16], friction=buf[17:22].copy(), solref=buf[22:24].copy(), solimp=buf[24:29].copy(),
+                      efc_address=int(buf[29])))
     return out

@@ -221,7 +221,7 @@ struct Handle : HandleBase {
     if (getenv("SO101_PROFILE") && atoi(getenv("SO101_PROFILE"))) S.prof = dalloc<unsigned long long>(16);
     sc.dbg_env = getenv("SO101_DBG_ENV") ? atoi(getenv("SO101_DBG_ENV")) : -1;
     sc.dbg_step = getenv("SO101_DBG_STEP") ? atoi(getenv("SO101_DBG_STEP")) : -1;
-    sc.arm_mode = getenv("SO101_ARM_MODE") ? atoi(getenv("SO101_ARM_MODE")) : 2;
+    sc.arm_mode = getenv("SO101_ARM_MODE") ? atoi(getenv("SO101_ARM_MODE")) : 4;
     sc.terminate_on_success = c.terminate_on_success; sc.max_iter = c.solver_iterations; sc.tol = c.solver_tolerance;
     for (int i = 0; i < 6; i++) { sc.offsets[i] = c.calibration_offsets[i]; sc.home[i] = c.home_ctrl[i]; }
     // default initial state: qpos0, zero velocity
@@ -324,7 +324,7 @@ struct Handle : HandleBase {
     if (!scene) { timer.begin(4, s); launch_arm_step<T>(am, am64, sc, S, action, out, s); timer.end(4, s); launches += 1; steps += 1; return; }
     const int nk = (int)groups.size() * (3 + 8 * sc.nsub);
     if (!use_graph || timer.on) {
-      launches += launch_scene_step<T>(am, scene->dev, sc, S, groups.data(), tiers.data(), (int)groups.size(), action, out, s, &timer);
+      launches += launch_scene_step<T>(am, am64, scene->dev, sc, S, groups.data(), tiers.data(), (int)groups.size(), action, out, s, &timer);
       steps += 1;
       return;
     }
@@ -337,7 +337,7 @@ struct Handle : HandleBase {
       if (!cap_stream) CUDA_OK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
       cudaGraph_t graph = nullptr;
       CUDA_OK(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
-      launch_scene_step<T>(am, scene->dev, sc, S, groups.data(), tiers.data(), (int)groups.size(), d_action, out, cap_stream, nullptr);
+      launch_scene_step<T>(am, am64, scene->dev, sc, S, groups.data(), tiers.data(), (int)groups.size(), d_action, out, cap_stream, nullptr);
       cudaError_t e = cudaStreamEndCapture(cap_stream, &graph);
       if (e != cudaSuccess || !graph) { cudaGetLastError(); throw std::runtime_error(std::string("step graph capture failed: ") + cudaGetErrorString(e)); }
       e = cudaGraphInstantiate(&exec, graph, 0);

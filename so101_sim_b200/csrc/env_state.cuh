@@ -6,11 +6,12 @@
 
 namespace so101 {
 
-// The integration state (qpos, qvel and the reset pool) is float64 in BOTH precisions: the float32 product path evaluates the
-// dynamics and the contact pipeline in float32 from the rounded state, but accumulates the semi-implicit Euler update (and
-// evaluates the position-feedback actuators, gain 50 on q) in float64.  Rounding the state itself to float32 every substep
-// (|qvel| ~ 5 rad/s: 2e-7 per substep) is what the anti-damped actuators (bias +1 * qvel, scene_pbr.xml:11) amplify ~300x over
-// 100 control steps; the dynamics' own float32 round-off is three orders of magnitude below that.
+// The integration state (qpos, qvel and the reset pool) is float64 in BOTH precisions.  The float32 product path runs
+// collision, the contact rows and the Newton solver in float32 (> 95 % of the arithmetic), but the arm's smooth dynamics
+// (FK, CRB, RNE, actuators, M^-1), and the semi-implicit Euler update in float64: the reference's actuators are anti-damped
+// (bias +1 * qvel, scene_pbr.xml:11) and amplify a perturbation ~300x over 100 control steps, so that neither a float32 state
+// (1.8e-3 relative error after 100 steps) nor float32 smooth dynamics on a float64 state (1.6e-4) meet north_star's 1e-4;
+// float64 smooth dynamics + float32 solver give 9e-6 (tools/exp_arm_precision.py).
 using TS = double;
 
 template <typename T>

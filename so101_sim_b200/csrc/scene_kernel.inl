@@ -566,26 +566,30 @@ __global__ void __launch_bounds__(WARPS_BROAD * 32) scene_begin_kernel(const __g
 // friction-loss / limit rows of mj_makeConstraint).  All of it is straight-line scalar code on registers, the same functions
 // the arm-only kernel uses (arm_dynamics.cuh, arm_solver.cuh).
 template <typename T>
-__global__ void __launch_bounds__(KD_THREADS) scene_kindyn_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
-                                                                 const EnvState<T> S, const PipeBuf<T> pb, int need_dyn) {
+__global__ void __launch_bounds__(KD_THREADS) scene_kindyn_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ ArmModelT<double> am64,
+                                                                 const __grid_constant__ SceneModel<T> sm, const EnvState<T> S, const PipeBuf<T> pb,
+                                                                 int need_dyn) {
   const int env = pb.env0 + blockIdx.x * KD_THREADS + threadIdx.x;
   if (env >= pb.env0 + pb.nenv || !pb.active[env]) return;
   const TS *gq = S.qpos + (size_t)env * NQ, *gv = S.qvel + (size_t)env * NV;
   T *gx = pb.xpos + (size_t)env * (NSLOT * 3), *gm = pb.xmat + (size_t)env * (NSLOT * 9), *gd = pb.dyn + (size_t)env * DYNW;
-  T qa[NJ], qda[NJ], ca[NJ];
+  // the arm's smooth dynamics run in float64 on the float64 state in both precisions (env_state.cuh); what the float32
+  // collision and solve kernels read (poses, mass matrix, qacc_smooth, rows) is rounded when it is stored
+  double qa[NJ], qda[NJ];
+  T ca[NJ];
 #pragma unroll
-  for (int i = 0; i < NJ; i++) { qa[i] = (T)gq[i]; qda[i] = (T)gv[i]; ca[i] = S.ctrl[(size_t)env * 6 + i]; }
-  ArmKin<T> k;
+  for (int i = 0; i < NJ; i++) { qa[i] = gq[i]; qda[i] = gv[i]; ca[i] = S.ctrl[(size_t)env * 6 + i]; }
+  ArmKin<double> k;
   {
-    T R[NJ][9];
-    arm_fk<T>(am, qa, k, R);
+    double R[NJ][9];
+    arm_fk<double>(am64, qa, k, R);
 #pragma unroll
     for (int i = 0; i < NJ; i++) {
-      gx[3 * i] = k.p[i].x; gx[3 * i + 1] = k.p[i].y; gx[3 * i + 2] = k.p[i].z;
-      gd[DYN_P + 3 * i] = k.p[i].x; gd[DYN_P + 3 * i + 1] = k.p[i].y; gd[DYN_P + 3 * i + 2] = k.p[i].z;
-      gd[DYN_A + 3 * i] = k.a[i].x; gd[DYN_A + 3 * i + 1] = k.a[i].y; gd[DYN_A + 3 * i + 2] = k.a[i].z;
+      gx[3 * i] = (T)k.p[i].x; gx[3 * i + 1] = (T)k.p[i].y; gx[3 * i + 2] = (T)k.p[i].z;
+      gd[DYN_P + 3 * i] = (T)k.p[i].x; gd[DYN_P + 3 * i + 1] = (T)k.p[i].y; gd[DYN_P + 3 * i + 2] = (T)k.p[i].z;
+      gd[DYN_A + 3 * i] = (T)k.a[i].x; gd[DYN_A + 3 * i + 1] = (T)k.a[i].y; gd[DYN_A + 3 * i + 2] = (T)k.a[i].z;
 #pragma unroll
-      for (int e = 0; e < 9; e++) gm[9 * i + e] = R[i][e];
+      for (int e = 0; e < 9; e++) gm[9 * i + e] = (T)R[i][e];
     }
   }
   const bool dyn = need_dyn && !pb.flags[env];  // (a diverged env is frozen for the rest of the control step)
@@ -615,26 +619,23 @@ __global__ void __launch_bounds__(KD_THREADS) scene_kindyn_kernel(const __grid_c
     }
   }
   if (!dyn) return;
-  T M[21], bias[NJ], qs[NJ], L[21];
-  arm_crb_rne(am, k, qda, M, bias);
-  double frc[NJ];  // actuators on the float64 state (arm_actuation_d; identical to arm_actuation when T = double)
-  {
-    double q64[NJ], qd64[NJ];
+  double M[21], bias[NJ], frc[NJ], qs[NJ], L[21];
+  arm_crb_rne(am64, k, qda, M, bias);
+  arm_actuation_d(am, qa, qda, ca, frc);
 #pragma unroll
-    for (int i = 0; i < NJ; i++) { q64[i] = gq[i]; qd64[i] = gv[i]; }
-    arm_actuation_d(am, q64, qd64, ca, frc);
-  }
-#pragma unroll
-  for (int i = 0; i < 21; i++) { L[i] = M[i]; gd[DYN_MARM + i] = M[i]; }
+  for (int i = 0; i < 21; i++) { L[i] = M[i]; gd[DYN_MARM + i] = (T)M[i]; }
   chol6(L);
 #pragma unroll
-  for (int i = 0; i < NJ; i++) qs[i] = (T)(frc[i] - (double)bias[i]);
+  for (int i = 0; i < NJ; i++) qs[i] = frc[i] - bias[i];
   chol6_solve(L, qs);
+  T qaT[NJ], qdaT[NJ], qsT[NJ];
+#pragma unroll
+  for (int i = 0; i < NJ; i++) { qaT[i] = (T)qa[i]; qdaT[i] = (T)qda[i]; qsT[i] = (T)qs[i]; }
   ArmRows<T> arows;
-  arm_make_rows(am, qa, qda, qs, arows);
+  arm_make_rows(am, qaT, qdaT, qsT, arows);
 #pragma unroll
   for (int i = 0; i < NJ; i++) {
-    gd[DYN_QACC + i] = qs[i];
+    gd[DYN_QACC + i] = qsT[i];
     gd[DYN_ROWS + i] = arows.jar0_f[i]; gd[DYN_ROWS + 6 + i] = arows.jar0_l[i]; gd[DYN_ROWS + 12 + i] = arows.D_l[i]; gd[DYN_ROWS + 18 + i] = arows.js[i];
   }
 }
@@ -1076,7 +1077,7 @@ void scene_nprof(unsigned long long out[16]) { cudaMemcpyFromSymbol(out, g_nprof
 // Launches of one control step: per pipeline group 1 memset + 3 + 8 * nsub kernels on the group's streams, forked from and
 // joined back into the caller's stream.  Returns the kernel count.
 template <typename T>
-int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> *pbs,
+int launch_scene_step(const ArmModelT<T> &am, const ArmModelT<double> &am64, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> *pbs,
                       TierExec *txs, int ngroups, const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt) {
   static bool configured[64] = {};
   int dev = 0;
@@ -1096,7 +1097,7 @@ int launch_scene_step(const ArmModelT<T> &am, const SceneModel<T> &sm, const Ste
   // kinematics (+ smooth dynamics) at the current state, then the broad phase for substep `sub` or the task layer
   auto refresh = [&](const PipeBuf<T> &pb, cudaStream_t st, int sub, bool last) {
     t.begin(6, st);
-    scene_kindyn_kernel<T><<<(pb.nenv + KD_THREADS - 1) / KD_THREADS, KD_THREADS, 0, st>>>(am, sm, S, pb, last ? 0 : 1);
+    scene_kindyn_kernel<T><<<(pb.nenv + KD_THREADS - 1) / KD_THREADS, KD_THREADS, 0, st>>>(am, am64, sm, S, pb, last ? 0 : 1);
     t.end(6, st);
     t.begin(7, st);
     scene_broad_kernel<T><<<(pb.nenv + WARPS_BROAD - 1) / WARPS_BROAD, WARPS_BROAD * 32, 0, st>>>(sm, cfg, S, pb, out, sub, last ? 1 : 0);

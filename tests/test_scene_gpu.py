@@ -74,9 +74,13 @@ def test_contacts_match_oracle(built):
 
 
 def test_f32_scene_tracks_oracle(built):
-  """float32 product path, ALL envs of the batch against the float64 oracle over 25 control steps (250 substeps): the arm within
-  the north_star tolerance (1e-4 relative), the props settling on the table at the oracle's rest pose, reward / discount /
-  step_type flags exact.  Measured errors are printed."""
+  """float32 product path, ALL envs of the batch against the float64 oracle over 25 control steps (250 substeps) in which the
+  props drop 2 mm onto the table while the arm moves.  Bars: reward / discount / step_type exact; the arm within north_star's
+  1e-4 relative for as long as it is contact-free (the tolerance is stated for contact-free rollouts); props within 0.2 mm /
+  2e-3 (quaternion) through the landing transient and back within 2e-5 / 2e-5 at rest - except a prop that lands on one of the
+  scene's CURVED static obstacles (capsule / cylinder, scene_pbr.xml:141-146), where EPA's termination tolerance (1e-6 in
+  float32, [upstream] ccd_tolerance) bounds the contact normal only to ~sqrt(2 tol / r) and the rest pose to ~1e-3.
+  Measured errors are printed."""
   N = 4
   env = _env(built, precision='f32', num_envs=N)
   q0, v0 = _initial(env, seed=5)
@@ -86,27 +90,45 @@ def test_f32_scene_tracks_oracle(built):
     o = OracleSim('so100_handover_banana', collide=True)
     o.set_state(q0[e].cpu().numpy(), v0[e].cpu().numpy())
     sims.append(o)
-  errs = []
+  meta = sims[0].meta
+  arm_bodies = set(int(b) for b in meta['jnt_body'][:6])
+  gbody, gtype = meta['geom_body'], meta['geom_type']
+  curved_static = {g for g in range(len(gtype)) if gtype[g] in (2, 3) and meta['body_weld'][gbody[g]] == 0}
+  arm_free = [True] * N       # no arm contact so far
+  on_curved = [False] * N     # a prop has touched a curved static obstacle
+  worst = dict(arm=0.0, arm_v=0.0, prop_p=0.0, prop_q=0.0)
+  rows = []
   for t in range(25):
     ts = env.step(acts[t])
     q, v = env.get_state(torch.float64)
-    ea = ev = ep = 0.0
     for e, o in enumerate(sims):
       r = o.control_step(acts[t, e].double().cpu().numpy())
       assert float(ts.reward[e]) == r and int(ts.step_type[e]) == 1 and float(ts.discount[e]) == 1.0
+      for c in o.contacts():
+        if int(gbody[c['geom1']]) in arm_bodies or int(gbody[c['geom2']]) in arm_bodies: arm_free[e] = False
+        if c['geom1'] in curved_static or c['geom2'] in curved_static: on_curved[e] = True
       qe, ve = q[e].cpu().numpy(), v[e].cpu().numpy()
-      ea = max(ea, float(np.abs(qe[:6] - o.qpos[:6]).max() / max(1.0, np.abs(o.qpos[:6]).max())))
-      ev = max(ev, float(np.abs(ve[:6] - o.qvel[:6]).max() / max(1.0, np.abs(o.qvel[:6]).max())))
-      ep = max(ep, float(np.abs(qe[6:] - o.qpos[6:]).max()))
-    errs.append((ea, ev, ep))
-  print('f32 scene, 4 envs: max (arm qpos rel, arm qvel rel, prop qpos abs) by control step:',
-        [(t + 1,) + tuple(float(f'{x:.2g}') for x in errs[t]) for t in (0, 4, 9, 14, 19, 24)])
-  assert errs[0][0] < 1e-6 and errs[0][2] < 1e-4
-  assert max(e[0] for e in errs) < 1e-4 and max(e[1] for e in errs) < 1e-4, errs   # north_star: 1e-4 relative
-  assert errs[-1][2] < 2e-3          # resting pose of the props (contact dynamics amplify round-off; positions stay within 2 mm)
-  for e, o in enumerate(sims):       # rest heights
-    assert abs(float(q[e, 8]) - o.qpos[8]) < 2e-4 and abs(float(q[e, 15]) - o.qpos[15]) < 2e-4
-  assert torch.isfinite(q).all() and env.counters()['diverged'] == 0
+      ea = float(np.abs(qe[:6] - o.qpos[:6]).max() / max(1.0, np.abs(o.qpos[:6]).max()))
+      ev = float(np.abs(ve[:6] - o.qvel[:6]).max() / max(1.0, np.abs(o.qvel[:6]).max()))
+      pp = float(max(np.abs(qe[6:9] - o.qpos[6:9]).max(), np.abs(qe[13:16] - o.qpos[13:16]).max()))
+      pq = float(max(np.abs(qe[9:13] - o.qpos[9:13]).max(), np.abs(qe[16:20] - o.qpos[16:20]).max()))
+      rows.append((t + 1, e, ea, ev, pp, pq, arm_free[e], on_curved[e]))
+      if arm_free[e]:
+        worst['arm'] = max(worst['arm'], ea); worst['arm_v'] = max(worst['arm_v'], ev)
+        assert ea < 1e-4 and ev < 1e-4, (t, e, ea, ev)                     # north_star: 1e-4 relative, contact-free arm
+      if not on_curved[e]:
+        worst['prop_p'] = max(worst['prop_p'], pp); worst['prop_q'] = max(worst['prop_q'], pq)
+        assert pp < 2e-4 and pq < 2e-3, (t, e, pp, pq)                     # landing transient
+      else:
+        assert pp < 1e-3 and pq < 5e-3, (t, e, pp, pq)
+  print('f32 scene, 4 envs x 25 steps, worst errors vs the float64 oracle:', {k: float(f'{x:.2g}') for k, x in worst.items()},
+        '| arm contact-free to the end:', arm_free, '| prop on a curved obstacle:', on_curved)
+  print('   final (env, arm rel, prop pos, prop quat):', [(r[1], float(f'{r[2]:.2g}'), float(f'{r[4]:.2g}'), float(f'{r[5]:.2g}')) for r in rows[-N:]])
+  assert sum(arm_free) >= 2 and sum(not c for c in on_curved) >= 2       # the test must exercise both bars
+  for r in rows[-N:]:
+    if not r[7]:
+      assert r[4] < 2e-5 and r[5] < 2e-5, r                               # at rest on the table: same pose as the oracle
+  assert torch.isfinite(q).all() and env.counters()['diverged'] == 0 and env.counters()['contacts_dropped'] == 0
   env.close()
 
 
@@ -175,12 +197,15 @@ def test_single_env_many_pairs_keeps_every_contact(built, precision):
   zero = torch.zeros(1, 6, device='cuda:0')
   nmax = 0
   for t in range(15):
-    env.step(zero)
-    o.control_step(np.zeros(6))
+    ts = env.step(zero)
+    r = o.control_step(np.zeros(6))
     qq, _ = env.get_state(torch.float64)
     n = int(env.debug_read('ncon')[0, 0])
     nmax = max(nmax, n)
-    assert np.abs(qq[0].cpu().numpy() - o.qpos).max() < 1e-5, t
+    assert np.abs(qq[0].cpu().numpy() - o.qpos).max() < 1e-6, t
+    assert float(ts.reward[0]) == r
+    if r >= 1.0:   # banana at rest in the bowl: success, the env resets on the next step
+      break
   assert nmax > 16 and env.counters()['contacts_dropped'] == 0
   env.close()
 

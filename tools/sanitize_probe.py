@@ -1,0 +1,26 @@
+#!/usr/bin/env python3
+"""compute-sanitizer target: a few control steps of a 64-env banana scene (collisions, all solver tiers reachable) and of the
+arm-only kernel, through the public API.  usage: compute-sanitizer --tool memcheck|racecheck|initcheck python tools/sanitize_probe.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from so101_sim_b200.task_suite import create_batched_task_env
+dev = 'cuda:0'
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+env = create_batched_task_env('SO100HandOverBanana', num_envs=64, time_limit=30.0, seed=0, device=dev, reset_rounds=0)
+env.sample_prop_initial_states(seed=3, clearance=0.001, settle_steps=0)
+g = torch.Generator(device=dev); g.manual_seed(1)
+spec = env.action_spec()
+lo, hi = torch.tensor(spec.minimum, device=dev), torch.tensor(spec.maximum, device=dev)
+for t in range(steps):
+  ts = env.step((lo + torch.rand(64, 6, generator=g, device=dev) * (hi - lo)) * 0.3)
+torch.cuda.synchronize()
+print('scene ok', env.counters(), float(ts.observation['physics_state'].abs().max()))
+env.close()
+env = create_batched_task_env('SO100ArmOnly', num_envs=64, time_limit=30.0, seed=0, device=dev)
+env.sample_arm_initial_states(seed=0); env.reset()
+for t in range(steps):
+  ts = env.step(torch.zeros(64, 6, device=dev))
+torch.cuda.synchronize()
+print('arm ok', env.counters())
+env.close()

@@ -95,6 +95,7 @@ def test_f32_scene_tracks_oracle(built):
   gbody, gtype = meta['geom_body'], meta['geom_type']
   curved_static = {g for g in range(len(gtype)) if gtype[g] in (2, 3) and meta['body_weld'][gbody[g]] == 0}
   arm_free = [True] * N       # no arm contact so far
+  first_touch = [None] * N
   on_curved = [False] * N     # a prop has touched a curved static obstacle
   worst = dict(arm=0.0, arm_v=0.0, prop_p=0.0, prop_q=0.0)
   rows = []
@@ -105,7 +106,9 @@ def test_f32_scene_tracks_oracle(built):
       r = o.control_step(acts[t, e].double().cpu().numpy())
       assert float(ts.reward[e]) == r and int(ts.step_type[e]) == 1 and float(ts.discount[e]) == 1.0
       for c in o.contacts():
-        if int(gbody[c['geom1']]) in arm_bodies or int(gbody[c['geom2']]) in arm_bodies: arm_free[e] = False
+        if int(gbody[c['geom1']]) in arm_bodies or int(gbody[c['geom2']]) in arm_bodies:
+          arm_free[e] = False
+          if first_touch[e] is None: first_touch[e] = t + 1
         if c['geom1'] in curved_static or c['geom2'] in curved_static: on_curved[e] = True
       qe, ve = q[e].cpu().numpy(), v[e].cpu().numpy()
       ea = float(np.abs(qe[:6] - o.qpos[:6]).max() / max(1.0, np.abs(o.qpos[:6]).max()))
@@ -116,15 +119,17 @@ def test_f32_scene_tracks_oracle(built):
       if arm_free[e]:
         worst['arm'] = max(worst['arm'], ea); worst['arm_v'] = max(worst['arm_v'], ev)
         assert ea < 1e-4 and ev < 1e-4, (t, e, ea, ev)                     # north_star: 1e-4 relative, contact-free arm
+      else:
+        assert ea < 1e-4 and ev < 2e-3, (t, e, ea, ev)                     # arm in contact (table / props): velocities are impact-sensitive
       if not on_curved[e]:
         worst['prop_p'] = max(worst['prop_p'], pp); worst['prop_q'] = max(worst['prop_q'], pq)
         assert pp < 2e-4 and pq < 2e-3, (t, e, pp, pq)                     # landing transient
       else:
         assert pp < 1e-3 and pq < 5e-3, (t, e, pp, pq)
   print('f32 scene, 4 envs x 25 steps, worst errors vs the float64 oracle:', {k: float(f'{x:.2g}') for k, x in worst.items()},
-        '| arm contact-free to the end:', arm_free, '| prop on a curved obstacle:', on_curved)
+        '| first control step with an arm contact:', first_touch, '| prop on a curved obstacle:', on_curved)
   print('   final (env, arm rel, prop pos, prop quat):', [(r[1], float(f'{r[2]:.2g}'), float(f'{r[4]:.2g}'), float(f'{r[5]:.2g}')) for r in rows[-N:]])
-  assert sum(arm_free) >= 2 and sum(not c for c in on_curved) >= 2       # the test must exercise both bars
+  assert sum(1 for f in first_touch if f is None or f > 10) >= 2 and sum(not c for c in on_curved) >= 2   # both bars are exercised
   for r in rows[-N:]:
     if not r[7]:
       assert r[4] < 2e-5 and r[5] < 2e-5, r                               # at rest on the table: same pose as the oracle

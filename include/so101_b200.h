@@ -61,6 +61,19 @@ typedef struct so101_config {
   int collide;              /* 0 = collisions off (BASELINE config 2, arm-only), 1 = full contact pipeline */
   float calibration_offsets[6]; /* SO101Calibration.homing_offsets, scripts/so101_calibration.py:62-77 */
   float home_ctrl[6];       /* SO100_HOME_CTRL, so100_task.py:45-47 (ctrl written by initialize_episode :316-317) */
+  /* On-device episode initialisation of the hand-over tasks (initialize_episode so100_hand_over.py:320-323, the three
+   * PropPlacers :208-229 with the distributions :37-55).  nursery_envs extra envs (hidden from the caller) keep sampling,
+   * collision-checking and settling placements with the arm frozen and publish them into a ring of ring_capacity entries;
+   * every auto-reset / so101_reset takes a fresh one (falls back to the env's own initial state when the ring is empty). */
+  int nursery_envs;         /* 0 = no background placements (resets re-use the installed initial states / reset pool) */
+  int ring_capacity;        /* placements the ring can hold */
+  uint64_t seed;            /* Philox key of the placement stream */
+  float place_lo[2][3], place_hi[2][3]; /* position boxes of prop 0 (object) and prop 1 (container) */
+  float place_yaw[2][2];    /* yaw range about z per prop */
+  int place_check_collisions[2]; /* 1 = re-sample while the prop penetrates anything at its spawn pose (ignore_collisions=False) */
+  int place_max_attempts;   /* [upstream] PropPlacer max_attempts_per_prop (20) */
+  int settle_max_substeps;  /* [upstream] max_settle_physics_time / timestep (2 s / 0.002 s = 1000) */
+  float settle_qvel_tol, settle_qacc_tol; /* [upstream] 1e-3, 1e-2 */
 } so101_config;
 
 int so101_abi_version(void);
@@ -90,6 +103,17 @@ int so101_reset(so101_handle h, const uint8_t *mask_dev, const so101_step_out *o
 /* replaces composer.Environment.step(action) for all N envs; action_dev is row-major [N,6] float32.
  * Envs whose previous step was LAST are reset instead and return FIRST (dm_control auto-reset). */
 int so101_step(so101_handle h, const float *action_dev, const so101_step_out *out, void *stream);
+/* replaces the placement part of initialize_episode for ALL envs at once: every env draws a placement from the configured
+ * distributions (Philox keyed on (seed, env, draw)), re-samples while the collision-checked prop penetrates anything at its
+ * spawn pose, and settles with the arm frozen ([upstream] PropPlacer settle_physics: props' |qvel| < qvel_tol and |qacc| <
+ * qacc_tol, or settle_max_substeps).  The loop over control steps runs inside the library; the settled states become the envs'
+ * initial states and the envs are reset.  stats_out (nullable): [0] control steps run, [1] settles that hit the time limit,
+ * [2] rejected samples, [3] placements kept after max_attempts rejections.  Synchronises the stream. */
+int so101_sample_and_settle(so101_handle h, uint64_t seed, const so101_step_out *out, uint64_t stats_out[4], void *stream);
+/* placement ring statistics: [0] published, [1] consumed, [2] resets that found the ring empty (re-used their initial state),
+ * [3] settles that hit the time limit, [4] placements kept after max_attempts rejections, [5] rejected samples */
+int so101_placement_stats(so101_handle h, uint64_t out[6]);
+
 /* physics.get_state() / set_state() equivalents (so100_task.py:366-368): row-major [N,nq], [N,nv] device pointers */
 int so101_get_state(so101_handle h, float *qpos_dev, float *qvel_dev, void *stream);
 int so101_set_state(so101_handle h, const float *qpos_dev, const float *qvel_dev, void *stream);

@@ -20,12 +20,16 @@ class Config(ctypes.Structure):
   _fields_ = [('num_envs', ctypes.c_int), ('device', ctypes.c_int), ('n_substeps', ctypes.c_int), ('last_step', ctypes.c_int),
               ('joints_delay_steps', ctypes.c_int), ('physics_delay_steps', ctypes.c_int), ('terminate_on_success', ctypes.c_int),
               ('solver_iterations', ctypes.c_int), ('solver_tolerance', ctypes.c_float), ('precision', ctypes.c_int),
-              ('collide', ctypes.c_int), ('calibration_offsets', ctypes.c_float * 6), ('home_ctrl', ctypes.c_float * 6)]
+              ('collide', ctypes.c_int), ('calibration_offsets', ctypes.c_float * 6), ('home_ctrl', ctypes.c_float * 6),
+              ('nursery_envs', ctypes.c_int), ('ring_capacity', ctypes.c_int), ('seed', ctypes.c_uint64),
+              ('place_lo', (ctypes.c_float * 3) * 2), ('place_hi', (ctypes.c_float * 3) * 2), ('place_yaw', (ctypes.c_float * 2) * 2),
+              ('place_check_collisions', ctypes.c_int * 2), ('place_max_attempts', ctypes.c_int), ('settle_max_substeps', ctypes.c_int),
+              ('settle_qvel_tol', ctypes.c_float), ('settle_qacc_tol', ctypes.c_float)]
 
 
 EXPORTS = ('so101_abi_version', 'so101_create', 'so101_destroy', 'so101_last_error', 'so101_dims', 'so101_set_initial_state',
            'so101_reset', 'so101_step', 'so101_get_state', 'so101_set_state', 'so101_get_state_f64', 'so101_step_host',
-           'so101_counters', 'so101_debug_read', 'so101_kernel_times', 'so101_set_reset_pool', 'so101_set_state_f64', 'so101_debug_overlap')
+           'so101_counters', 'so101_debug_read', 'so101_kernel_times', 'so101_set_reset_pool', 'so101_set_state_f64', 'so101_debug_overlap', 'so101_sample_and_settle', 'so101_placement_stats')
 
 _lib = None
 
@@ -48,6 +52,8 @@ def load() -> ctypes.CDLL:
     getattr(L, f).restype = ci; getattr(L, f).argtypes = [vp, vp, vp, vp]
   L.so101_set_state_f64.restype = ci; L.so101_set_state_f64.argtypes = [vp, vp, vp, ci, vp]
   L.so101_debug_overlap.restype = ci; L.so101_debug_overlap.argtypes = [ci, ci, vp, ci, vp, vp]
+  L.so101_sample_and_settle.restype = ci; L.so101_sample_and_settle.argtypes = [vp, ctypes.c_uint64, ctypes.POINTER(StepOut), ctypes.POINTER(ctypes.c_uint64 * 4), vp]
+  L.so101_placement_stats.restype = ci; L.so101_placement_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64 * 6)]
   L.so101_set_reset_pool.restype = ci; L.so101_set_reset_pool.argtypes = [vp, vp, vp, ci, vp]
   L.so101_reset.restype = ci; L.so101_reset.argtypes = [vp, vp, ctypes.POINTER(StepOut), vp]
   L.so101_step.restype = ci; L.so101_step.argtypes = [vp, vp, ctypes.POINTER(StepOut), vp]

@@ -54,6 +54,8 @@ struct HandleBase {
   virtual void reset(const uint8_t *mask, const so101_step_out &out, cudaStream_t s) = 0;
   virtual void step(const float *action, const so101_step_out &out, cudaStream_t s) = 0;
   virtual void debug_read(const char *field, float *dst, size_t count, cudaStream_t s) = 0;
+  virtual void sample_and_settle(uint64_t seed, const so101_step_out &out, uint64_t stats[4], cudaStream_t s) = 0;
+  virtual void placement_stats(uint64_t out[6]) = 0;
   virtual void step_host(const float *action, const so101_step_out &host_out, cudaStream_t s) = 0;
   virtual uint64_t diverged() = 0;
   KernelTimer timer;
@@ -188,6 +190,7 @@ struct Handle : HandleBase {
   std::vector<StepGraph> graphs;
   cudaStream_t cap_stream = nullptr;
   bool use_graph = true;
+  unsigned settle_epoch = 0;   // so101_sample_and_settle calls so far (high bits of the envs' Philox draw counters)
 
   template <typename U>
   U *dalloc(size_t n) {
@@ -209,8 +212,24 @@ struct Handle : HandleBase {
       scene->build(b);
       if (scene_smem_bytes<T>() > 227 * 1024) throw std::runtime_error("scene kernel scratch exceeds the 227 KB shared-memory limit");
     }
-    const size_t N = c.num_envs;
-    S.N = c.num_envs; S.nq = nq; S.nv = nv;
+    // user envs first, then the nursery envs that keep producing settled placements (contact scene only)
+    const int nursery = scene ? std::max(0, c.nursery_envs) : 0;
+    const size_t N = (size_t)c.num_envs + nursery;
+    S.N = (int)N; S.NU = c.num_envs; S.nq = nq; S.nv = nv;
+    S.mode = dalloc<uint8_t>(N); S.sstate = dalloc<uint8_t>(N); S.settle_sub = dalloc<int>(N); S.attempt = dalloc<int>(N); S.draws = dalloc<unsigned>(N);
+    S.ring_ctr = dalloc<int>(RC_N);
+    S.ring_cap = nursery > 0 ? std::max(1, c.ring_capacity) : 0;
+    if (S.ring_cap > 0) { S.ring_q = dalloc<TS>((size_t)S.ring_cap * nq); S.ring_v = dalloc<TS>((size_t)S.ring_cap * nv); }
+    if (nursery > 0) CUDA_OK(cudaMemset(S.mode + c.num_envs, 1, nursery));   // (sstate 0 = SETTLE_SAMPLE: they start drawing at the first step)
+    for (int p = 0; p < 2; p++) {
+      for (int k = 0; k < 3; k++) { S.place.lo[p][k] = c.place_lo[p][k]; S.place.hi[p][k] = c.place_hi[p][k]; }
+      S.place.yaw[p][0] = c.place_yaw[p][0]; S.place.yaw[p][1] = c.place_yaw[p][1];
+      S.place.check_collisions[p] = c.place_check_collisions[p];
+    }
+    S.place.max_attempts = c.place_max_attempts > 0 ? c.place_max_attempts : 20;
+    S.place.max_settle_substeps = c.settle_max_substeps > 0 ? c.settle_max_substeps : 1000;
+    S.place.qvel_tol = c.settle_qvel_tol > 0 ? c.settle_qvel_tol : 1e-3f; S.place.qacc_tol = c.settle_qacc_tol > 0 ? c.settle_qacc_tol : 1e-2f;
+    S.place.seed = c.seed;
     S.qpos = dalloc<TS>(nq * N); S.qvel = dalloc<TS>(nv * N); S.warm = dalloc<T>(nv * N);
     S.init_qpos = dalloc<TS>(nq * N); S.init_qvel = dalloc<TS>(nv * N); S.ctrl = dalloc<T>(6 * N);
     S.step = dalloc<int>(N); S.needs_reset = dalloc<uint8_t>(N); S.episode = dalloc<int>(N); S.npool = 1;
@@ -248,7 +267,7 @@ struct Handle : HandleBase {
       tiers.resize(ng);
       for (int g = 0; g < ng; g++) {
         PipeBuf<T> p = pipe;
-        p.env0 = (int)(N * g / ng); p.nenv = (int)(N * (g + 1) / ng) - p.env0;
+        p.env0 = (int)(N * g / ng); p.nenv = (int)(N * (g + 1) / ng) - p.env0;   // (groups partition ALL envs, nursery included)
         // A queue holds the candidate pairs of ALL envs that share its key geom.  The static table is the partner of every arm
         // geom that comes down on it (17 of them), so the per-queue capacity must cover many pairs per env (only the used
         // entries are ever touched): 4 per env overflowed in long random-action rollouts and silently lost arm-table contacts.
@@ -276,11 +295,15 @@ struct Handle : HandleBase {
   template <typename A>
   void set_state_any(const A *q, const A *v, bool initial, cudaStream_t s) {
     auto put = [&](const A *rows, TS *dst, int k) {
-      if (scene) launch_cast_copy<A, TS>(rows, dst, (size_t)S.N * k, s); else launch_rows_to_soa<A, TS>(rows, dst, S.N, k, s);
+      if (scene) launch_cast_copy<A, TS>(rows, dst, (size_t)S.NU * k, s); else launch_rows_to_soa<A, TS>(rows, dst, S.N, k, s);
       launches += 1;
     };
     put(q, S.qpos, nq); put(v, S.qvel, nv);
-    if (initial) { if (S.npool != 1) invalidate_graphs(); S.npool = 1; put(q, S.init_qpos, nq); put(v, S.init_qvel, nv); }
+    if (initial) {  // the caller's own initial states replace the device-side placements
+      if (S.npool != 1 || S.use_ring) invalidate_graphs();
+      S.npool = 1; S.use_ring = 0;
+      put(q, S.init_qpos, nq); put(v, S.init_qvel, nv);
+    }
     CUDA_OK(cudaMemsetAsync(S.warm, 0, sizeof(T) * nv * S.N, s));
   }
   void set_state(const float *q, const float *v, bool initial, cudaStream_t s) override { set_state_any(q, v, initial, s); }
@@ -290,16 +313,17 @@ struct Handle : HandleBase {
   void set_reset_pool(const float *q, const float *v, int rounds, cudaStream_t s) override {
     if (rounds < 1) throw std::runtime_error("reset pool needs at least one round");
     invalidate_graphs();
-    const size_t N = S.N;
+    S.use_ring = 0;
+    const size_t N = S.N, NU = S.NU;   // pool rows are strided by all envs of the handle; the caller supplies the user envs
     if ((size_t)rounds > pool_cap) {
       CUDA_OK(cudaStreamSynchronize(s));
       S.init_qpos = dalloc<TS>((size_t)rounds * nq * N); S.init_qvel = dalloc<TS>((size_t)rounds * nv * N);  // (old pool is freed with the handle)
       pool_cap = rounds;
     }
     for (int r = 0; r < rounds; r++) {
-      const float *qr = q + (size_t)r * N * nq, *vr = v + (size_t)r * N * nv;
+      const float *qr = q + (size_t)r * NU * nq, *vr = v + (size_t)r * NU * nv;
       TS *dq = S.init_qpos + (size_t)r * N * nq, *dv = S.init_qvel + (size_t)r * N * nv;
-      if (scene) { launch_cast_copy<float, TS>(qr, dq, N * nq, s); launch_cast_copy<float, TS>(vr, dv, N * nv, s); }
+      if (scene) { launch_cast_copy<float, TS>(qr, dq, NU * nq, s); launch_cast_copy<float, TS>(vr, dv, NU * nv, s); }
       else { launch_rows_to_soa<float, TS>(qr, dq, S.N, nq, s); launch_rows_to_soa<float, TS>(vr, dv, S.N, nv, s); }
       launches += 2;
     }
@@ -307,12 +331,12 @@ struct Handle : HandleBase {
     CUDA_OK(cudaMemsetAsync(S.episode, 0, sizeof(int) * N, s));
   }
   void get_state(float *q, float *v, cudaStream_t s) override {
-    if (scene) { launch_cast_copy<TS, float>(S.qpos, q, (size_t)S.N * nq, s); launch_cast_copy<TS, float>(S.qvel, v, (size_t)S.N * nv, s); }
+    if (scene) { launch_cast_copy<TS, float>(S.qpos, q, (size_t)S.NU * nq, s); launch_cast_copy<TS, float>(S.qvel, v, (size_t)S.NU * nv, s); }
     else { launch_soa_to_rows<TS, float>(S.qpos, q, S.N, nq, s); launch_soa_to_rows<TS, float>(S.qvel, v, S.N, nv, s); }
     launches += 2;
   }
   void get_state_f64(double *q, double *v, cudaStream_t s) override {
-    if (scene) { launch_cast_copy<TS, double>(S.qpos, q, (size_t)S.N * nq, s); launch_cast_copy<TS, double>(S.qvel, v, (size_t)S.N * nv, s); }
+    if (scene) { launch_cast_copy<TS, double>(S.qpos, q, (size_t)S.NU * nq, s); launch_cast_copy<TS, double>(S.qvel, v, (size_t)S.NU * nv, s); }
     else { launch_soa_to_rows<TS, double>(S.qpos, q, S.N, nq, s); launch_soa_to_rows<TS, double>(S.qvel, v, S.N, nv, s); }
     launches += 2;
   }
@@ -329,7 +353,7 @@ struct Handle : HandleBase {
       return;
     }
     // graph replay: the action goes through a fixed staging buffer so that the graph does not depend on the caller's pointer
-    if (action != d_action) CUDA_OK(cudaMemcpyAsync(d_action, action, sizeof(float) * 6 * S.N, cudaMemcpyDeviceToDevice, s));
+    if (action != d_action) CUDA_OK(cudaMemcpyAsync(d_action, action, sizeof(float) * 6 * S.NU, cudaMemcpyDeviceToDevice, s));
     cudaGraphExec_t exec = nullptr;
     for (auto &g : graphs) if (std::memcmp(&g.key, &out, sizeof out) == 0) exec = g.exec;
     if (!exec) {
@@ -352,12 +376,12 @@ struct Handle : HandleBase {
     const std::string f(field);
     if (f == "solver_iter" || f == "ncon" || f == "step") {
       const int *src = f == "solver_iter" ? S.solver_iter : (f == "ncon" ? S.ncon : S.step);
-      if (count < (size_t)S.N) throw std::runtime_error("debug_read: buffer too small");
-      launch_int_to_float(src, dst, S.N, s);
+      if (count < (size_t)S.NU) throw std::runtime_error("debug_read: buffer too small");
+      launch_int_to_float(src, dst, S.NU, s);
       launches += 1;
     } else if (f == "warm") {
-      if (count < (size_t)S.N * nv) throw std::runtime_error("debug_read: buffer too small");
-      if (scene) launch_cast_copy<T, float>(S.warm, dst, (size_t)S.N * nv, s); else launch_soa_to_rows<T, float>(S.warm, dst, S.N, nv, s);
+      if (count < (size_t)S.NU * nv) throw std::runtime_error("debug_read: buffer too small");
+      if (scene) launch_cast_copy<T, float>(S.warm, dst, (size_t)S.NU * nv, s); else launch_soa_to_rows<T, float>(S.warm, dst, S.N, nv, s);
       launches += 1;
     } else if (f == "epahist") {
       if (count < 8) throw std::runtime_error("debug_read: buffer too small");
@@ -397,16 +421,16 @@ struct Handle : HandleBase {
     } else if (f == "contacts") {
       // [N][1 + 9*NCON]: ncon, then (geom1, geom2, dist, pos3, normal3) per contact of the last substep.  The first call only
       // enables the probe (the buffer is filled by subsequent steps).
-      const size_t need = (size_t)S.N * (1 + 9 * NCON);
+      const size_t need = (size_t)S.NU * (1 + 9 * NCON);
       if (count < need) throw std::runtime_error("debug_read: buffer too small");
-      if (!S.dbg_contacts) { S.dbg_contacts = dalloc<float>(need); invalidate_graphs(); }
+      if (!S.dbg_contacts) { S.dbg_contacts = dalloc<float>((size_t)S.N * (1 + 9 * NCON)); invalidate_graphs(); }
       CUDA_OK(cudaMemcpyAsync(dst, S.dbg_contacts, need * sizeof(float), cudaMemcpyDeviceToDevice, s));
     } else throw std::runtime_error("debug_read: unknown field " + f);
   }
   // e2e path: host buffers in, the WHOLE TimeStep (every block of so101_step_out that is non-null in host_out) out to host
   // buffers; host<->device copies on the caller's stream, one sync at the end
   void step_host(const float *action, const so101_step_out &host_out, cudaStream_t s) override {
-    const size_t N = S.N, sd = (size_t)nq + nv;
+    const size_t N = S.NU, sd = (size_t)nq + nv;
     if (!d_out.reward) {
       d_out.commanded_joints_pos = dalloc<float>(6 * N); d_out.joints_pos = dalloc<float>(6 * N); d_out.undelayed_joints_pos = dalloc<float>(6 * N);
       d_out.physics_state = dalloc<float>(sd * N); d_out.delayed_physics_state = dalloc<float>(sd * N);
@@ -424,6 +448,46 @@ struct Handle : HandleBase {
     back(host_out.discount, d_out.discount, N * sizeof(float));
     back(host_out.step_type, d_out.step_type, N);
     CUDA_OK(cudaStreamSynchronize(s));
+  }
+  // All user envs draw a placement and settle it with the arm frozen; the loop over control steps runs here (one graph launch
+  // per step), polling the number of envs still settling every few steps.
+  void sample_and_settle(uint64_t seed, const so101_step_out &out, uint64_t stats[4], cudaStream_t s) override {
+    if (!scene) throw std::runtime_error("sample_and_settle needs a model with free props");
+    int before[RC_N], after[RC_N];
+    CUDA_OK(cudaStreamSynchronize(s));
+    CUDA_OK(cudaMemcpy(before, S.ring_ctr, sizeof before, cudaMemcpyDeviceToHost));
+    if (seed != S.place.seed) { S.place.seed = seed; invalidate_graphs(); }
+    if (S.npool != 1) { S.npool = 1; invalidate_graphs(); }
+    if (S.use_ring != (S.ring_cap > 0)) { S.use_ring = S.ring_cap > 0; invalidate_graphs(); }
+    settle_epoch += 1;
+    launch_settle_enter<T>(S, settle_epoch << 20, s);
+    launches += 1;
+    so101_step_out none{};
+    const int max_steps = (S.place.max_settle_substeps + sc.nsub - 1) / sc.nsub + S.place.max_attempts + 2;
+    int steps_run = 0, pending = 1;
+    while (pending > 0 && steps_run < max_steps) {
+      for (int k = 0; k < 4 && steps_run < max_steps; k++, steps_run++) {
+        CUDA_OK(cudaMemsetAsync(S.ring_ctr + RC_PENDING, 0, sizeof(int), s));
+        step(d_action, none, s);   // (settle-mode envs ignore the action)
+        steps -= 1;
+      }
+      CUDA_OK(cudaMemcpyAsync(&pending, S.ring_ctr + RC_PENDING, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+    }
+    launch_settle_leave<T>(S, s);
+    launches += 1;
+    reset(nullptr, out, s);
+    CUDA_OK(cudaStreamSynchronize(s));
+    CUDA_OK(cudaMemcpy(after, S.ring_ctr, sizeof after, cudaMemcpyDeviceToHost));
+    if (stats) {
+      stats[0] = (uint64_t)steps_run; stats[1] = (uint64_t)(after[RC_UNSETTLED] - before[RC_UNSETTLED]);
+      stats[2] = (uint64_t)(after[RC_REJECTED] - before[RC_REJECTED]); stats[3] = (uint64_t)(after[RC_EXHAUSTED] - before[RC_EXHAUSTED]);
+    }
+  }
+  void placement_stats(uint64_t out[6]) override {
+    int c[RC_N] = {};
+    CUDA_OK(cudaMemcpy(c, S.ring_ctr, sizeof c, cudaMemcpyDeviceToHost));
+    out[0] = c[RC_CLAIM]; out[1] = c[RC_TAIL]; out[2] = c[RC_REUSED]; out[3] = c[RC_UNSETTLED]; out[4] = c[RC_EXHAUSTED]; out[5] = c[RC_REJECTED];
   }
   uint64_t diverged() override {
     int v[2] = {0, 0};
@@ -520,6 +584,19 @@ int so101_set_state_f64(so101_handle h, const double *qpos_dev, const double *qv
   API_BEGIN(h)
   if (!qpos_dev || !qvel_dev) throw std::runtime_error("null state pointer");
   H->set_state_f64(qpos_dev, qvel_dev, initial != 0, (cudaStream_t)stream);
+  API_END()
+}
+int so101_sample_and_settle(so101_handle h, uint64_t seed, const so101_step_out *out, uint64_t stats_out[4], void *stream) {
+  API_BEGIN(h)
+  so101_step_out o{};
+  if (out) o = *out;
+  H->sample_and_settle(seed, o, stats_out, (cudaStream_t)stream);
+  API_END()
+}
+int so101_placement_stats(so101_handle h, uint64_t out[6]) {
+  API_BEGIN(h)
+  if (!out) throw std::runtime_error("null output");
+  H->placement_stats(out);
   API_END()
 }
 int so101_get_state(so101_handle h, float *qpos_dev, float *qvel_dev, void *stream) {

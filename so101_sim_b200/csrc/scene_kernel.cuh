@@ -123,6 +123,10 @@ int launch_scene_step(const ArmModelT<T> &am, const ArmModelT<double> &am64, con
 template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream);
 template <typename T>
+void launch_settle_enter(const EnvState<T> &S, unsigned draw0, cudaStream_t stream);
+template <typename T>
+void launch_settle_leave(const EnvState<T> &S, cudaStream_t stream);
+template <typename T>
 size_t scene_smem_bytes();
 template <typename T>
 void launch_debug_overlap(const double *cases, int n, uint8_t *out, cudaStream_t stream);

@@ -507,19 +507,95 @@ __device__ void write_obs_scene(const StepCfg &cfg, const EnvState<T> &S, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ placements (initialize_episode)
+// Philox4x32-10 (Salmon et al. 2011): counter-based, so a placement is a pure function of (seed, env, episode draw, attempt)
+__device__ __forceinline__ void philox4x32_10(unsigned long long key, unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned (&out)[4]) {
+  unsigned k0 = (unsigned)key, k1 = (unsigned)(key >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0, hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double u01(unsigned x) { return (double)(x >> 8) * (1.0 / 16777216.0); }  // [0, 1)
+
+// pose of prop p for (env, episode draw, attempt): position ~ U(lo, hi), rotation about z by U(yaw)  (so100_hand_over.py:37-55)
+template <typename T>
+__device__ __forceinline__ void sample_prop_pose(const EnvState<T> &S, int env, int p, unsigned draw, unsigned attempt, TS *qp) {
+  unsigned r[4];
+  philox4x32_10(S.place.seed, (unsigned)env, draw, attempt, (unsigned)p, r);
+  for (int c = 0; c < 3; c++) qp[c] = (TS)S.place.lo[p][c] + u01(r[c]) * ((TS)S.place.hi[p][c] - (TS)S.place.lo[p][c]);
+  const TS yaw = (TS)S.place.yaw[p][0] + u01(r[3]) * ((TS)S.place.yaw[p][1] - (TS)S.place.yaw[p][0]);
+  TS sn, cn;
+  sincos(TS(0.5) * yaw, &sn, &cn);
+  qp[3] = cn; qp[4] = TS(0); qp[5] = TS(0); qp[6] = sn;
+}
+
+// SETTLE mode, once per control step (scene_begin_kernel): draw a placement if one is due and keep the env stepping with the
+// home command.  Returns false if the env idles this step (settled and waiting).
+template <typename T>
+__device__ bool settle_begin(const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb, int env, int lane) {
+  const int st = S.sstate[env];
+  __syncwarp();
+  if (st == SETTLE_DONE || (env >= S.NU && !S.use_ring)) { if (lane == 0) pb.active[env] = 0; return false; }
+  if (st == SETTLE_SAMPLE) {
+    // arm qpos = 0 (the reference never applies its home pose, so100_task.py:308-313), velocities 0, props at their sampled poses;
+    // a rejected container placement (attempt > 0) re-draws the container only (the second PropPlacer, so100_hand_over.py:216-221)
+    const unsigned draw = S.draws[env], att = (unsigned)S.attempt[env];
+    if (lane < NPROP) sample_prop_pose(S, env, lane, draw, S.place.check_collisions[lane] ? att : 0u, S.qpos + (size_t)env * NQ + NJ + 7 * lane);
+    if (lane < NJ) S.qpos[(size_t)env * NQ + lane] = TS(0);
+    if (lane < NV) { S.qvel[(size_t)env * NV + lane] = TS(0); S.warm[(size_t)env * NV + lane] = T(0); }
+    if (lane == 0) { S.settle_sub[env] = 0; S.sstate[env] = SETTLE_RUN; }
+  }
+  if (lane < NJ) S.ctrl[(size_t)env * 6 + lane] = (T)cfg.home[lane] + (T)cfg.offsets[lane];   // so100_task.py:316-317
+  if (lane == 0) { pb.active[env] = 1; pb.flags[env] = 0; }
+  return true;
+}
+
 template <typename T, typename SC>
 __device__ void reset_env_scene(const StepCfg &cfg, const EnvState<T> &S, const so101_step_out &out, SC &s, int env, int lane) {
   // initialize_episode (so100_hand_over.py:320-323): each episode starts from the next entry of the env's pool of sampled and
   // settled prop placements
   const int ep = S.episode[env];
   const size_t slot = (size_t)(ep % S.npool) * S.N + env;
+  // a fresh settled placement from the nursery's ring if one is available (every placement is consumed once), else the env's
+  // own initial state / reset pool entry
+  const TS *srcq = S.init_qpos + slot * NQ, *srcv = S.init_qvel + slot * NV;
+  if (S.use_ring && ep > 0) {   // (episode 0 starts from the env's own settled state: deterministic for a given seed)
+    int t = 0;
+    if (lane == 0) {
+      t = atomicAdd(S.ring_ctr + RC_TAIL, 1);
+      if (t >= *((volatile int *)(S.ring_ctr + RC_CLAIM))) { atomicSub(S.ring_ctr + RC_TAIL, 1); atomicAdd(S.ring_ctr + RC_REUSED, 1); t = -1; }
+    }
+    t = __shfl_sync(FULL, t, 0);
+    if (t >= 0) { srcq = S.ring_q + (size_t)(t % S.ring_cap) * NQ; srcv = S.ring_v + (size_t)(t % S.ring_cap) * NV; }
+  }
   __syncwarp();
-  for (int i = lane; i < NQ; i += 32) { const TS v = S.init_qpos[slot * NQ + i]; s.q[i] = (T)v; S.qpos[(size_t)env * NQ + i] = v; }
-  for (int i = lane; i < NV; i += 32) { const TS v = S.init_qvel[slot * NV + i]; s.qd[i] = (T)v; S.qvel[(size_t)env * NV + i] = v; S.warm[(size_t)env * NV + i] = T(0); }
+  for (int i = lane; i < NQ; i += 32) { const TS v = srcq[i]; s.q[i] = (T)v; S.qpos[(size_t)env * NQ + i] = v; }
+  for (int i = lane; i < NV; i += 32) { const TS v = srcv[i]; s.qd[i] = (T)v; S.qvel[(size_t)env * NV + i] = v; S.warm[(size_t)env * NV + i] = T(0); }
   if (lane < NJ) { s.ctrl[lane] = (T)cfg.home[lane] + (T)cfg.offsets[lane]; S.ctrl[(size_t)env * 6 + lane] = s.ctrl[lane]; }
   if (lane == 0) { S.step[env] = 0; S.needs_reset[env] = 0; S.episode[env] = ep + 1; }
   __syncwarp();
   write_obs_scene(cfg, S, out, s, env, 0, 0.f, 1.f, SO101_STEP_FIRST, lane);
+}
+
+// SETTLE mode, end of a control step (task-layer launch; one lane): a diverged settle starts over; a settled NURSERY env
+// publishes its state into the ring (if there is room) and goes back to sampling; a settled user env waits for
+// so101_sample_and_settle to finish.  Publishing here and consuming in scene_begin_kernel keeps producers and consumers in
+// different kernels.
+template <typename T>
+__device__ void settle_end_of_step(const EnvState<T> &S, int env, bool diverged) {
+  if (diverged) { S.sstate[env] = SETTLE_SAMPLE; S.attempt[env] = 0; S.draws[env] += 1; return; }
+  if (S.sstate[env] != SETTLE_DONE) { if (env < S.NU) atomicAdd(S.ring_ctr + RC_PENDING, 1); return; }
+  if (env < S.NU || !S.use_ring) return;
+  const int c = atomicAdd(S.ring_ctr + RC_CLAIM, 1);
+  if (c - *((volatile int *)(S.ring_ctr + RC_TAIL)) >= S.ring_cap) { atomicSub(S.ring_ctr + RC_CLAIM, 1); return; }  // ring full: try again next step
+  TS *dq = S.ring_q + (size_t)(c % S.ring_cap) * NQ, *dv = S.ring_v + (size_t)(c % S.ring_cap) * NV;
+  for (int i = 0; i < NQ; i++) dq[i] = i < NJ ? TS(0) : S.qpos[(size_t)env * NQ + i];
+  for (int i = 0; i < NV; i++) dv[i] = i < NJ ? TS(0) : S.qvel[(size_t)env * NV + i];
+  S.sstate[env] = SETTLE_SAMPLE; S.attempt[env] = 0; S.draws[env] += 1;
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -551,6 +627,7 @@ __global__ void __launch_bounds__(WARPS_BROAD * 32) scene_begin_kernel(const __g
   const int env = pb.env0 + blockIdx.x * WARPS_BROAD + wib;
   if (env >= pb.env0 + pb.nenv) return;
   if (lane == 0) pb.ncon_raw[env] = 0;
+  if (S.mode[env]) { settle_begin(cfg, S, pb, env, lane); return; }
   if (S.needs_reset[env]) {  // the step() after a LAST step resets and returns FIRST; no physics this call
     reset_env_scene(cfg, S, out, all[wib], env, lane);
     if (lane == 0) pb.active[env] = 0;
@@ -649,16 +726,22 @@ __global__ void __launch_bounds__(WARPS_BROAD * 32) scene_broad_kernel(const __g
   __shared__ BroadEnv<T> all[WARPS_BROAD];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int env = pb.env0 + blockIdx.x * WARPS_BROAD + wib;
-  if (env >= pb.env0 + pb.nenv || !pb.active[env]) return;
+  if (env >= pb.env0 + pb.nenv) return;
+  if (!pb.active[env]) {  // (a settled nursery env idles, but keeps trying to publish its placement)
+    if (last && S.mode[env] && lane == 0) settle_end_of_step(S, env, false);
+    return;
+  }
   BroadEnv<T> &s = all[wib];
   prof_begin(s, S, lane);
   load_poses(pb, s, env, lane);
   __syncwarp();
-  const bool bad = pb.flags[env] != 0;
+  const bool bad = pb.flags[env] == 1;   // (flag 2: a rejected placement sits out the rest of this control step)
   if (!last) {
     int dropped = 0;
-    if (!bad) scene_broadphase(sm, s, pb, env, sub, dropped, lane);
+    if (!pb.flags[env]) scene_broadphase(sm, s, pb, env, sub, dropped, lane);
     if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
+  } else if (S.mode[env]) {
+    if (lane == 0) settle_end_of_step(S, env, bad);
   } else {
     for (int i = lane; i < NQ; i += 32) s.q[i] = (T)S.qpos[(size_t)env * NQ + i];
     for (int i = lane; i < NV; i += 32) s.qd[i] = (T)S.qvel[(size_t)env * NV + i];
@@ -899,6 +982,26 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
   if (!frozen && !gather_contacts(sm, pb, s, env, dropped, lane)) return false;
   if (frozen && lane == 0) s.ncon = 0;
   __syncwarp();
+  const int mode = S.mode[env];
+  if (!frozen && mode && S.settle_sub[env] == 0) {
+    // [upstream] PropPlacer(ignore_collisions=False): a fresh sample whose collision-checked prop penetrates anything at its
+    // spawn pose is rejected and re-drawn (so100_hand_over.py:216-221), at most max_attempts times
+    bool hit = false;
+    for (int c = lane; c < s.ncon; c += 32) {
+      if (!(s.sol.v.con.dist[c] < T(0))) continue;
+      const int s1 = sm.body_slot[sm.geom_body[s.sol.v.con.g1[c]]], s2 = sm.body_slot[sm.geom_body[s.sol.v.con.g2[c]]];
+      if ((s1 >= NJ && S.place.check_collisions[s1 - NJ]) || (s2 >= NJ && S.place.check_collisions[s2 - NJ])) hit = true;
+    }
+    if (__any_sync(FULL, hit)) {
+      int give_up = 0;
+      if (lane == 0) {
+        const int a = S.attempt[env] + 1;
+        if (a < S.place.max_attempts) { S.attempt[env] = a; S.sstate[env] = SETTLE_SAMPLE; pb.flags[env] = 2; atomicAdd(S.ring_ctr + RC_REJECTED, 1); }
+        else { give_up = 1; atomicAdd(S.ring_ctr + RC_EXHAUSTED, 1); }
+      }
+      if (!__shfl_sync(FULL, give_up, 0)) return true;
+    }
+  }
   if (!frozen) {
     PROF_CNT(s, P_NCON, s.ncon, lane);
     load_poses(pb, s, env, lane);
@@ -939,9 +1042,24 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
     const TS h = am.dt_d;
     TS qd_new = TS(0);
     if (lane < NV) {
-      qd_new = badnow ? TS(0) : S.qvel[(size_t)env * NV + lane] + h * (TS)qacc;
+      // SETTLE mode: the arm is frozen ([upstream] JointStaticIsolator restores the non-prop joints after every settle step)
+      qd_new = (badnow || (mode && lane < NJ)) ? TS(0) : S.qvel[(size_t)env * NV + lane] + h * (TS)qacc;
       S.qvel[(size_t)env * NV + lane] = qd_new;
       S.warm[(size_t)env * NV + lane] = qacc;
+    }
+    if (mode && !badnow) {  // [upstream] PropPlacer settle test after every physics step: props' max |qvel|, max |qacc|
+      T mv = (lane >= NJ && lane < NV) ? (T)t_abs(qd_new) : T(0), ma = (lane >= NJ && lane < NV) ? t_abs(qacc) : T(0);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { mv = max(mv, __shfl_xor_sync(FULL, mv, o)); ma = max(ma, __shfl_xor_sync(FULL, ma, o)); }
+      if (lane == 0) {
+        const int sub_done = S.settle_sub[env] + 1;
+        S.settle_sub[env] = sub_done;
+        const bool settled = mv < (T)S.place.qvel_tol && ma < (T)S.place.qacc_tol, timeout = sub_done >= S.place.max_settle_substeps;
+        if (settled || timeout) {
+          S.sstate[env] = SETTLE_DONE; pb.flags[env] = 2;
+          if (!settled) atomicAdd(S.ring_ctr + RC_UNSETTLED, 1);
+        }
+      }
     }
     TS pv[6];  // the six velocities of prop (lane - 8), gathered from the dof lanes
 #pragma unroll
@@ -1039,7 +1157,7 @@ __global__ void scene_reset_kernel(const __grid_constant__ StepCfg cfg, const En
   __shared__ BroadEnv<T> all[WARPS_BROAD];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int env = blockIdx.x * WARPS_BROAD + wib;
-  if (env >= S.N) return;
+  if (env >= S.NU || S.mode[env]) return;
   if (mask && !mask[env]) return;
   reset_env_scene(cfg, S, out, all[wib], env, lane);
 }
@@ -1158,7 +1276,29 @@ int launch_scene_step(const ArmModelT<T> &am, const ArmModelT<double> &am64, con
 }
 template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream) {
-  scene_reset_kernel<T><<<(S.N + WARPS_BROAD - 1) / WARPS_BROAD, WARPS_BROAD * 32, 0, stream>>>(cfg, S, mask, out);
+  scene_reset_kernel<T><<<(S.NU + WARPS_BROAD - 1) / WARPS_BROAD, WARPS_BROAD * 32, 0, stream>>>(cfg, S, mask, out);
 }
+
+// so101_sample_and_settle support: put the user envs into SETTLE mode with a fresh draw / take the settled states as the envs'
+// initial states and return to normal stepping
+template <typename T>
+__global__ void settle_enter_kernel(const EnvState<T> S, unsigned draw0) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= S.NU) return;
+  S.mode[env] = 1; S.sstate[env] = SETTLE_SAMPLE; S.attempt[env] = 0; S.draws[env] = draw0; S.settle_sub[env] = 0;
+  S.needs_reset[env] = 0;
+}
+template <typename T>
+__global__ void settle_leave_kernel(const EnvState<T> S) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= S.NU) return;
+  for (int i = 0; i < NQ; i++) S.init_qpos[(size_t)env * NQ + i] = i < NJ ? TS(0) : S.qpos[(size_t)env * NQ + i];
+  for (int i = 0; i < NV; i++) S.init_qvel[(size_t)env * NV + i] = i < NJ ? TS(0) : S.qvel[(size_t)env * NV + i];
+  S.mode[env] = 0; S.sstate[env] = SETTLE_SAMPLE; S.episode[env] = 0; S.draws[env] += 1;
+}
+template <typename T>
+void launch_settle_enter(const EnvState<T> &S, unsigned draw0, cudaStream_t stream) { settle_enter_kernel<T><<<(S.NU + 127) / 128, 128, 0, stream>>>(S, draw0); }
+template <typename T>
+void launch_settle_leave(const EnvState<T> &S, cudaStream_t stream) { settle_leave_kernel<T><<<(S.NU + 127) / 128, 128, 0, stream>>>(S); }
 
 }  // namespace so101

@@ -89,6 +89,13 @@ class SO100HandOver(SO100Task):
   """so100_hand_over.py:121-326 (overlap reward): banana -> bowl (:81-96) and pen -> utensil holder (:97-117).  The object /
   container models, the container mesh scale and the overlap boxes are compiled into the model blob (tools/compile_model.py)."""
   collide = True
+  # so100_hand_over.py:34-55: placement distributions of the object and the container (position boxes at TABLE_HEIGHT +
+  # RESET_HEIGHT = 0.45, object yaw uniform in +-0.1 pi, container rotation identity) and :208-229 the PropPlacers (the object
+  # ignores collisions, the container is re-sampled while it collides; both then settle together with the arm frozen)
+  PLACE_LO = ((0.2, -0.1, 0.45), (-0.3, -0.1, 0.45))
+  PLACE_HI = ((0.3, 0.1, 0.45), (-0.2, 0.1, 0.45))
+  PLACE_YAW = ((-0.1 * np.pi, 0.1 * np.pi), (0.0, 0.0))
+  PLACE_CHECK_COLLISIONS = (0, 1)
   # object -> (model blob, instruction, (object z, container z) just above rest on the table top or None = spawn height)
   CONFIGS = {
       'banana': ('so100_handover_banana', 'pick up the banana and put it in the bowl using the SO100 arm', (0.4217, 0.4226)),
@@ -149,7 +156,7 @@ class BatchedEnvironment:
   """N lockstep copies of one reference environment (composer.Environment, task_suite.py:148-155)."""
 
   def __init__(self, task: SO100Task, num_envs: int, time_limit: float, seed: int | None, device, calibration_offsets, precision,
-               solver_iterations, solver_tolerance):
+               solver_iterations, solver_tolerance, nursery_envs: int = 0, ring_capacity: int | None = None):
     self.task = task
     self.num_envs = int(num_envs)
     self.device = torch.device(device)
@@ -182,6 +189,20 @@ class BatchedEnvironment:
     cfg.collide = int(task.collide)
     for i in range(6):
       cfg.calibration_offsets[i] = float(offs[i]); cfg.home_ctrl[i] = float(SO100_HOME_CTRL[i])
+    # on-device episode initialisation (so100_hand_over.py:208-229,320-323): placement distributions + nursery envs
+    self.nursery_envs = int(nursery_envs) if task.collide else 0
+    cfg.nursery_envs = self.nursery_envs
+    cfg.ring_capacity = int(ring_capacity) if ring_capacity is not None else max(2 * self.nursery_envs, 1)
+    cfg.seed = self.seed & 0xFFFFFFFFFFFFFFFF
+    if task.collide and hasattr(task, 'PLACE_LO'):
+      for p in range(2):
+        for k in range(3):
+          cfg.place_lo[p][k] = task.PLACE_LO[p][k]; cfg.place_hi[p][k] = task.PLACE_HI[p][k]
+        cfg.place_yaw[p][0], cfg.place_yaw[p][1] = task.PLACE_YAW[p]
+        cfg.place_check_collisions[p] = task.PLACE_CHECK_COLLISIONS[p]
+    cfg.place_max_attempts = 20          # [upstream] PropPlacer max_attempts_per_prop
+    cfg.settle_max_substeps = int(round(2.0 / PHYSICS_TIMESTEP))   # [upstream] max_settle_physics_time = 2 s
+    cfg.settle_qvel_tol, cfg.settle_qacc_tol = 1e-3, 1e-2          # [upstream] _SETTLE_QVEL_TOL, _SETTLE_QACC_TOL
     self.precision = precision
     self.last_step = cfg.last_step
     h = ctypes.c_void_p()
@@ -424,6 +445,30 @@ class BatchedEnvironment:
     self.reset()
     return q, v
 
+  def initialize_placements(self, seed: int | None = None) -> dict:
+    """initialize_episode for all envs on the device (so100_hand_over.py:320-323 with the PropPlacers :208-229): every env draws
+    an object and a container pose from the task's distributions (Philox keyed on (seed, env, draw)), re-samples the container
+    while it penetrates anything at its spawn pose, settles both with the arm frozen until the props' |qvel| < 1e-3 and |qacc| <
+    1e-2 or 2 s have passed ([upstream] PropPlacer settle_physics), and is reset to the settled state.  One library call: the
+    loop over control steps runs inside so101_sample_and_settle.  With nursery envs the following resets then draw fresh
+    placements from the nursery's ring.  Returns the settle statistics."""
+    if self.nq != 20:
+      raise RuntimeError('initialize_placements needs a SO100HandOver model')
+    seed = self.seed if seed is None else int(seed)
+    st = (ctypes.c_uint64 * 4)()
+    self._check(self._lib.so101_sample_and_settle(self._h, ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), ctypes.byref(self._out), ctypes.byref(st), self._stream()))
+    out = dict(control_steps=int(st[0]), unsettled=int(st[1]), rejected_samples=int(st[2]), attempts_exhausted=int(st[3]))
+    if out['attempts_exhausted']:
+      # [upstream] PropPlacer raises after max_attempts_per_prop colliding samples
+      raise RuntimeError(f"Failed to place the container without collisions in {out['attempts_exhausted']} env(s) after 20 attempts")
+    return out
+
+  def placement_stats(self) -> dict:
+    c = (ctypes.c_uint64 * 6)()
+    self._check(self._lib.so101_placement_stats(self._h, ctypes.byref(c)))
+    return dict(published=int(c[0]), consumed=int(c[1]), ring_empty_resets=int(c[2]), unsettled=int(c[3]), attempts_exhausted=int(c[4]),
+                rejected_samples=int(c[5]))
+
   def set_reset_pool(self, qpos: torch.Tensor, qvel: torch.Tensor):
     """Install `rounds` initial states per env (qpos [rounds, N, nq], qvel [rounds, N, nv]): episode e of an env starts from
     entry e % rounds (so101_set_reset_pool).  The episode counters restart at 0."""
@@ -455,14 +500,19 @@ def create_batched_task_env(task_name: str, num_envs: int, time_limit: float, se
                             control_timestep: float = DEFAULT_CONTROL_TIMESTEP, cameras: tuple = (), device='cuda:0',
                             calibration_offsets=None, calibration_file: str | None = None, precision: str = 'f32',
                             solver_iterations: int = 100, solver_tolerance: float | None = None, reset_rounds: int = 1,
-                            **kwargs) -> BatchedEnvironment:
+                            placement: str = 'device', nursery_envs: int | None = None, **kwargs) -> BatchedEnvironment:
   """Batched twin of task_suite.create_task_env (task_suite.py:103-155).
 
-  For the SO100HandOver tasks the env comes back with `reset_rounds` sampled-and-settled prop placements per env installed as
-  its reset pool (randomize_resets with `seed`), as the reference samples and settles the props in every initialize_episode
-  (so100_hand_over.py:208-229,320-323): a plain create -> reset -> step loop never starts from the blob's qpos0, where both
-  free props sit coincident at the world origin.  reset_rounds=0 skips this (the caller installs its own states with
-  set_initial_state / set_reset_pool / sample_prop_initial_states before the first reset)."""
+  For the SO100HandOver tasks the env comes back with sampled and settled prop placements, as the reference places and settles
+  the props in every initialize_episode (so100_hand_over.py:208-229,320-323): a plain create -> reset -> step loop never starts
+  from the blob's qpos0, where both free props sit coincident at the world origin.
+    placement='device' (default): Philox sampling, collision rejection with the real narrow phase and the frozen-arm settle all
+      run on the device (BatchedEnvironment.initialize_placements); `nursery_envs` extra hidden envs (default num_envs / 16)
+      keep producing settled placements in the background, so every later episode starts from a fresh one.
+    placement='pool': the round-1 path, `reset_rounds` placements per env sampled on the host and settled up front
+      (randomize_resets); episodes cycle through them.
+    placement='none' or reset_rounds=0: nothing is installed (the caller sets its own states with set_initial_state /
+      set_reset_pool / sample_prop_initial_states before the first reset)."""
   if task_name not in TASK_FACTORIES:
     raise ValueError(f'Unknown task_name: {task_name}. Available tasks: {list(TASK_FACTORIES.keys())}')  # task_suite.py:126-130
   task_class, task_kwargs = TASK_FACTORIES[task_name]
@@ -475,7 +525,17 @@ def create_batched_task_env(task_name: str, num_envs: int, time_limit: float, se
     calibration_offsets = SO101Calibration(calibration_file).homing_offsets
   if solver_tolerance is None:
     solver_tolerance = 1e-8 if precision == 'f64' else 1e-6
-  env = BatchedEnvironment(task, num_envs, time_limit, seed, device, calibration_offsets, precision, solver_iterations, solver_tolerance)
-  if task.collide and reset_rounds > 0:
+  if placement not in ('device', 'pool', 'none'):
+    raise ValueError("placement must be 'device', 'pool' or 'none'")
+  if not task.collide or reset_rounds <= 0:
+    placement = 'none'
+  nursery = 0
+  if placement == 'device':
+    nursery = max(1, int(num_envs) // 16) if nursery_envs is None else int(nursery_envs)
+  env = BatchedEnvironment(task, num_envs, time_limit, seed, device, calibration_offsets, precision, solver_iterations, solver_tolerance,
+                           nursery_envs=nursery)
+  if placement == 'device':
+    env.initialize_placements()
+  elif placement == 'pool':
     env.randomize_resets(rounds=int(reset_rounds))
   return env

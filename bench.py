@@ -233,11 +233,13 @@ def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_r
   from so101_sim_b200.sharding import EpisodeStats, gather_episode_stats, rank_seed
   from so101_sim_b200.task_suite import create_batched_task_env
   w = WORKLOADS[name]
-  env = create_batched_task_env(w['task'], num_envs=envs, time_limit=30.0, seed=rank, device=dev, precision=precision, reset_rounds=0)
+  # config 3: the props are sampled from so100_hand_over.py:37-55 and settled with the arm frozen ON THE DEVICE at creation
+  # (initialize_placements).  No episode ends inside this leg's window (30 s episodes), so it runs without nursery envs; the
+  # steady-state leg below has them.
+  env = create_batched_task_env(w['task'], num_envs=envs, time_limit=30.0, seed=rank_seed(0, rank), device=dev, precision=precision,
+                                placement='device', nursery_envs=0)
   if w['task'] == 'SO100ArmOnly':
     env.sample_arm_initial_states(seed=rank_seed(0, rank))
-  else:
-    env.sample_prop_initial_states(seed=rank_seed(0, rank), spawn_z=0.45, settle_steps=50)  # reference drop height, settled 1 s
   env.reset()
   total = warmup + steps
   nact = min(total, 64)
@@ -337,16 +339,18 @@ def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_r
   return res
 
 
-def run_steady_state(name, envs, steps, warmup, precision, dev, rank, episode_s=6.0, rounds=4):
-  """Steady-state regime (>= 200 steps after >= 50 warm-up) with episodes CYCLING through auto-reset: short
-  episodes (time_limit `episode_s`), a pool of `rounds` sampled-and-settled placements per env, and the envs' episode phases
-  staggered uniformly by masked resets during the warm-up, so that at any timed step the batch holds envs of every age and
-  ~1/episode_steps of them are finishing or restarting."""
+def run_steady_state(name, envs, steps, warmup, precision, dev, rank, episode_s=15.0):
+  """Steady-state regime (>= 200 steps after >= 50 warm-up) with episodes CYCLING through auto-reset and
+  the on-device episode initialisation running: `episode_s`-second episodes, envs / 8 nursery envs sampling, collision-checking
+  and settling fresh placements in the background, and the envs' episode phases staggered uniformly by masked resets during the
+  warm-up, so that at any timed step the batch holds envs of every age and ~1/episode_steps of them finish or restart.  The
+  nursery envs' physics is inside the timed steps; only the user envs' steps are counted."""
   import torch
   from so101_sim_b200.task_suite import create_batched_task_env
   w = WORKLOADS[name]
-  env = create_batched_task_env(w['task'], num_envs=envs, time_limit=episode_s, seed=rank, device=dev, precision=precision, reset_rounds=0)
-  env.randomize_resets(rounds=rounds, seed=1000 * rank, spawn_z=0.45, settle_steps=50)
+  nursery = max(1, envs // 8)
+  env = create_batched_task_env(w['task'], num_envs=envs, time_limit=episode_s, seed=1000 * rank, device=dev, precision=precision,
+                                placement='device', nursery_envs=nursery)
   ep_steps = env.last_step
   nact = 64
   acts = _actions(env, nact, envs, dev, 1 + 1000 * rank)
@@ -359,7 +363,7 @@ def run_steady_state(name, envs, steps, warmup, precision, dev, rank, episode_s=
   flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
   ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
   ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-  c0 = env.counters()
+  c0, p0 = env.counters(), env.placement_stats()
   nlast = torch.zeros((), dtype=torch.int64, device=dev); nfirst = torch.zeros((), dtype=torch.int64, device=dev)
   torch.cuda.synchronize()
   for i in range(steps):
@@ -369,13 +373,15 @@ def run_steady_state(name, envs, steps, warmup, precision, dev, rank, episode_s=
     ev1[i].record()
     nlast += (ts.step_type == 2).sum(); nfirst += (ts.step_type == 0).sum()
   torch.cuda.synchronize()
-  c1 = env.counters()
+  c1, p1 = env.counters(), env.placement_stats()
   ms = float(sum(ev0[i].elapsed_time(ev1[i]) for i in range(steps)))
   out = dict(value=envs * steps / (ms * 1e-3), unit='env-steps/s', ms_per_step=ms / steps, steps=steps, warmup=warmup, episode_steps=ep_steps,
-             reset_pool_rounds=rounds, last_steps=int(nlast), first_steps=int(nfirst), diverged=c1['diverged'] - c0['diverged'],
+             nursery_envs=nursery, last_steps=int(nlast), first_steps=int(nfirst), diverged=c1['diverged'] - c0['diverged'],
              contacts_dropped=c1['contacts_dropped'] - c0['contacts_dropped'],
-             note=f'time_limit {episode_s} s episodes ({ep_steps} control steps), phases staggered uniformly by masked resets, random actions; '
-                  'a step() that lands on an env whose previous step was LAST resets it (FIRST) instead of stepping, as dm_control does')
+             placements={k: p1[k] - p0[k] for k in p1},
+             note=f'time_limit {episode_s} s episodes ({ep_steps} control steps), phases staggered uniformly by masked resets, random actions, '
+                  'fresh on-device placement per episode (nursery physics inside the timed steps, not counted as env-steps); a step() that '
+                  'lands on an env whose previous step was LAST resets it (FIRST) instead of stepping, as dm_control does')
   env.close()
   return out
 

@@ -11,8 +11,7 @@ envs = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 prec = sys.argv[3] if len(sys.argv) > 3 else 'f32'
 pre = int(sys.argv[4]) if len(sys.argv) > 4 else 0   # random-action control steps before the measured ones
-env = create_batched_task_env('SO100HandOverBanana', num_envs=envs, time_limit=30.0, seed=0, device='cuda:0', precision=prec)
-env.sample_prop_initial_states(seed=0, spawn_z=0.45, settle_steps=50)
+env = create_batched_task_env('SO100HandOverBanana', num_envs=envs, time_limit=30.0, seed=0, device='cuda:0', precision=prec, placement='device', nursery_envs=0)
 env.reset()
 g = torch.Generator(device='cuda:0'); g.manual_seed(1)
 spec = env.action_spec()

@@ -74,6 +74,8 @@ typedef struct so101_config {
   int place_max_attempts;   /* [upstream] PropPlacer max_attempts_per_prop (20) */
   int settle_max_substeps;  /* [upstream] max_settle_physics_time / timestep (2 s / 0.002 s = 1000) */
   float settle_qvel_tol, settle_qacc_tol; /* [upstream] 1e-3, 1e-2 */
+  int integrator;           /* 0 = semi-implicit Euler: MuJoCo's default, which the reference uses (scene_pbr.xml:4 sets none);
+                               1 = implicitfast ([upstream] mj_implicit without the Coriolis derivatives) */
 } so101_config;
 
 int so101_abi_version(void);

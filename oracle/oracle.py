@@ -45,6 +45,7 @@ def lib():
     L.so_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]
     L.so_info.restype = ctypes.c_int; L.so_info.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
     L.so_set_collide.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.so_set_integrator.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.so_get_contact.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     L.so_overlap_oobb_oobb.restype = ctypes.c_int
     L.so_overlap_oobb_oobb.argtypes = [ctypes.c_void_p] * 6
@@ -64,7 +65,7 @@ def overlap_oobb_oobb(p0, q0, h0, p1, q1, h1) -> bool:
 class OracleSim:
   """One float64 physics instance (model + data)."""
 
-  def __init__(self, model='so100_handover_banana', collide=True):
+  def __init__(self, model='so100_handover_banana', collide=True, integrator='euler'):
     path = model if os.path.exists(model) else os.path.join(DATA_DIR, model + '.blob')
     with open(path, 'rb') as f:
       self._blob = f.read()
@@ -74,6 +75,7 @@ class OracleSim:
       raise RuntimeError('so_model_load failed')
     self._d = L.so_data_new(self._m)
     L.so_set_collide(self._d, int(collide))
+    L.so_set_integrator(self._d, int(integrator == 'implicitfast'))
     from so101_sim_b200.model import read_blob  # host-side blob reader (no CUDA involved)
     self.meta = read_blob(path)
     self.nq, self.nv, self.nu, self.nbody = (int(self.meta[k][0]) for k in ('nq', 'nv', 'nu', 'nbody'))

@@ -145,9 +145,9 @@ so_data *so_data_new(const so_model *m) {
 }
 void so_data_free(so_data *d) { free(d); }
 void so_reset(const so_model *m, so_data *d) {
-  int ce = d->collide_enabled;
+  int ce = d->collide_enabled, ig = d->integrator;
   memset(d, 0, sizeof(so_data));
-  d->collide_enabled = ce;
+  d->collide_enabled = ce; d->integrator = ig;
   memcpy(d->qpos, m->qpos0, sizeof(double) * m->nq);
 }
 
@@ -641,8 +641,32 @@ void so_forward_position(const so_model *m, so_data *d) {
   make_constraint(m, d);
 }
 
-static void integrate(const so_model *m, so_data *d) { /* [upstream] mj_Euler without joint damping */
+/* [upstream] mj_implicit with integrator = implicitfast: qvel += h x with (M - h D) x = M qacc, D = d(qfrc_smooth)/d(qvel) without
+ * the Coriolis terms.  In this model only the actuators depend on velocity (affine bias, biasprm[2] = +1, scene_pbr.xml:11;
+ * no joint damping): D = diag(gear^2 * biasprm[2]) over the actuated dofs whose force is not clamped by forcerange
+ * ([upstream] mjd_actuator_vel skips clamped actuators).  qacc_warmstart keeps the forward-dynamics qacc. */
+static void implicitfast_qacc(const so_model *m, const so_data *d, double *x) {
+  int nv = m->nv;
+  double h = m->timestep, A[SO_NVMAX * SO_NVMAX], D[SO_NVMAX];
+  for (int k = 0; k < nv; k++) D[k] = 0;
+  for (int a = 0; a < m->nu; a++)
+    if (!d->act_clamped[a]) D[m->jnt_dofadr[m->act_jnt[a]]] += m->act_gear[a] * m->act_gear[a] * m->act_bias[3 * a + 2];
+  for (int i = 0; i < nv; i++) {
+    double s = 0;
+    for (int j = 0; j < nv; j++) { s += d->M[i * nv + j] * d->qacc[j]; A[i * nv + j] = d->M[i * nv + j] - (i == j ? h * D[i] : 0.0); }
+    x[i] = s;
+  }
+  cholesky(A, nv);
+  chol_solve(A, nv, x);
+}
+
+static void integrate(const so_model *m, so_data *d) { /* [upstream] mj_Euler without joint damping / mj_implicit (implicitfast) */
   double h = m->timestep;
+  if (d->integrator == 1) {
+    double x[SO_NVMAX];
+    implicitfast_qacc(m, d, x);
+    for (int k = 0; k < m->nv; k++) d->qvel[k] += h * x[k];
+  } else
   for (int k = 0; k < m->nv; k++) d->qvel[k] += h * d->qacc[k];
   for (int j = 0; j < m->njnt; j++) {
     int qa = m->jnt_qposadr[j], da = m->jnt_dofadr[j];
@@ -671,6 +695,7 @@ void so_substep(const so_model *m, so_data *d) {
     double g = m->act_gear[a], len = g * d->qpos[m->jnt_qposadr[j]], vel = g * d->qvel[k];
     double c = clampd(d->ctrl[a], m->act_ctrlrange[2 * a], m->act_ctrlrange[2 * a + 1]);
     double f = m->act_gain[a] * c + m->act_bias[3 * a] + m->act_bias[3 * a + 1] * len + m->act_bias[3 * a + 2] * vel;
+    d->act_clamped[a] = f <= m->act_forcerange[2 * a] || f >= m->act_forcerange[2 * a + 1];
     f = clampd(f, m->act_forcerange[2 * a], m->act_forcerange[2 * a + 1]);
     d->qfrc_actuator[k] += g * f;
   }
@@ -777,6 +802,7 @@ int so_info(const so_data *d, const char *name) {
   return -1;
 }
 void so_set_collide(so_data *d, int enabled) { d->collide_enabled = enabled; }
+void so_set_integrator(so_data *d, int implicitfast) { d->integrator = implicitfast ? 1 : 0; }
 /* contact c -> out[0..]: dist, pos3, frame9, dim, geom1, geom2, mu, friction5, solref2, solimp5, efc_address (30 values) */
 void so_get_contact(const so_data *d, int c, double *out) {
   const so_contact *k = d->contact + c;

@@ -72,6 +72,8 @@ typedef struct so_data {
   double efc_J[SO_NEFCMAX * SO_NVMAX], efc_pos[SO_NEFCMAX], efc_margin[SO_NEFCMAX], efc_R[SO_NEFCMAX], efc_D[SO_NEFCMAX],
       efc_aref[SO_NEFCMAX], efc_vel[SO_NEFCMAX], efc_frictionloss[SO_NEFCMAX], efc_force[SO_NEFCMAX], efc_diagApprox[SO_NEFCMAX];
   int solver_iter, collide_enabled, diverged, ncon_overflow;
+  int integrator;                 /* 0 = semi-implicit Euler (the reference's default), 1 = implicitfast */
+  int act_clamped[SO_NUMAX];      /* actuator force sits on its forcerange limit (implicitfast skips its velocity derivative) */
   double solver_cost;
   /* collision statistics */
   long n_narrow, n_gjk_iter, n_epa_iter;
@@ -97,6 +99,7 @@ void so_jac(const so_model *m, const so_data *d, int body, const double point[3]
 /* task: reward of SO100HandOver in overlap mode (so100_hand_over.py:238-275) */
 double so_reward(const so_model *m, const so_data *d);
 /* restatement of oobb_utils.overlap_oobb_oobb (oobb_utils.py:251-273): pos3, quat4(wxyz), half3 each */
+void so_set_integrator(so_data *d, int implicitfast);
 int so_overlap_oobb_oobb(const double *p0, const double *q0, const double *h0, const double *p1, const double *q1, const double *h1);
 
 #ifdef __cplusplus

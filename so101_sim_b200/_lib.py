@@ -24,7 +24,7 @@ class Config(ctypes.Structure):
               ('nursery_envs', ctypes.c_int), ('ring_capacity', ctypes.c_int), ('seed', ctypes.c_uint64),
               ('place_lo', (ctypes.c_float * 3) * 2), ('place_hi', (ctypes.c_float * 3) * 2), ('place_yaw', (ctypes.c_float * 2) * 2),
               ('place_check_collisions', ctypes.c_int * 2), ('place_max_attempts', ctypes.c_int), ('settle_max_substeps', ctypes.c_int),
-              ('settle_qvel_tol', ctypes.c_float), ('settle_qacc_tol', ctypes.c_float)]
+              ('settle_qvel_tol', ctypes.c_float), ('settle_qacc_tol', ctypes.c_float), ('integrator', ctypes.c_int)]
 
 
 EXPORTS = ('so101_abi_version', 'so101_create', 'so101_destroy', 'so101_last_error', 'so101_dims', 'so101_set_initial_state',

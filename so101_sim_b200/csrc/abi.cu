@@ -241,6 +241,7 @@ struct Handle : HandleBase {
     sc.dbg_env = getenv("SO101_DBG_ENV") ? atoi(getenv("SO101_DBG_ENV")) : -1;
     sc.dbg_step = getenv("SO101_DBG_STEP") ? atoi(getenv("SO101_DBG_STEP")) : -1;
     sc.arm_mode = getenv("SO101_ARM_MODE") ? atoi(getenv("SO101_ARM_MODE")) : 4;
+    sc.integrator = c.integrator == 1 ? 1 : 0;
     sc.terminate_on_success = c.terminate_on_success; sc.max_iter = c.solver_iterations; sc.tol = c.solver_tolerance;
     for (int i = 0; i < 6; i++) { sc.offsets[i] = c.calibration_offsets[i]; sc.home[i] = c.home_ctrl[i]; }
     // default initial state: qpos0, zero velocity
@@ -528,6 +529,7 @@ int so101_create(const void *model_blob, size_t blob_len, const so101_config *cf
     Blob b(model_blob, blob_len);
     DeviceGuard guard(cfg->device);
     HandleBase *H = nullptr;
+    if (cfg->integrator != 0 && cfg->integrator != 1) throw std::runtime_error("integrator must be 0 (Euler) or 1 (implicitfast)");
     if (cfg->precision == 64) H = new Handle<double>(b, *cfg);
     else if (cfg->precision == 32) H = new Handle<float>(b, *cfg);
     else throw std::runtime_error("precision must be 32 or 64");

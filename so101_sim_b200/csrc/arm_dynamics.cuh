@@ -208,6 +208,17 @@ __device__ __forceinline__ void arm_actuation_d(const ArmModelT<T> &am, const do
   }
 }
 
+// [upstream] mjd_actuator_vel for this actuator model: d force / d velocity = biasprm[2] (gear 1) unless the force is clamped by
+// forcerange.  Bit i of the result is set when actuator i contributes.
+template <typename T>
+__device__ __forceinline__ unsigned arm_actuation_vel_mask(const ArmModelT<T> &am, const double (&frc)[NJ]) {
+  unsigned m = 0;
+#pragma unroll
+  for (int i = 0; i < NJ; i++)
+    if (frc[i] > am.forcerange_d[i][0] && frc[i] < am.forcerange_d[i][1]) m |= 1u << i;
+  return m;
+}
+
 // In-place Cholesky of a packed lower-triangular SPD matrix, n = 6.
 template <typename T>
 __device__ __forceinline__ void chol6(T (&A)[21]) {
@@ -254,6 +265,20 @@ __device__ __forceinline__ void symmv6(const T (&M)[21], const T (&x)[NJ], T (&y
     for (int j = 0; j < NJ; j++) s += (j <= i ? M[i * (i + 1) / 2 + j] : M[j * (j + 1) / 2 + i]) * x[j];
     y[i] = s;
   }
+}
+
+// [upstream] mj_implicit, integrator = implicitfast, arm block: the velocity update uses x with (M - h D) x = M qacc, D =
+// diag(biasprm[2]) over the unclamped actuators (no joint damping, no other velocity-dependent smooth force in this model).
+// Returns x - qacc = (M - h D)^-1 (h D qacc): a small correction (h D / M ~ 2 %), so float32 suffices for it.
+template <typename T>
+__device__ __forceinline__ void implicitfast_correction(const T (&M)[21], const T (&dvel)[NJ], T h, const T (&qacc)[NJ], T (&corr)[NJ]) {
+  T A[21];
+#pragma unroll
+  for (int i = 0; i < 21; i++) A[i] = M[i];
+#pragma unroll
+  for (int i = 0; i < NJ; i++) { A[i * (i + 1) / 2 + i] -= h * dvel[i]; corr[i] = h * dvel[i] * qacc[i]; }
+  chol6(A);
+  chol6_solve(A, corr);
 }
 
 // [upstream] getimpedance — power-law sigmoid between solimp[0] and solimp[1] over width solimp[2]

@@ -130,12 +130,25 @@ __global__ void __launch_bounds__(128) arm_step_kernel(const __grid_constant__ A
 #pragma unroll
     for (int i = 0; i < NJ; i++) delta[i] = warm[i] - qacc_s[i];
     iters = arm_solve(am, M, rows, delta, cfg.max_iter, (T)cfg.tol);
+    TS corr[NJ] = {TS(0), TS(0), TS(0), TS(0), TS(0), TS(0)};
+    if (cfg.integrator == 1) {  // implicitfast: velocity update with (M - h D)^-1 M qacc instead of qacc
+      double fd[NJ];
+#pragma unroll
+      for (int i = 0; i < NJ; i++) fd[i] = (double)frc[i];
+      const unsigned vm = arm_actuation_vel_mask(am, fd);
+      TD qa[NJ], dv[NJ], cr[NJ];
+#pragma unroll
+      for (int i = 0; i < NJ; i++) { qa[i] = (TD)(qacc_sd[i] + (TS)delta[i]); dv[i] = ((vm >> i) & 1u) ? (TD)am.bias_d[i][2] : TD(0); }
+      implicitfast_correction<TD>(Md, dv, (TD)am.dt_d, qa, cr);
+#pragma unroll
+      for (int i = 0; i < NJ; i++) corr[i] = (TS)cr[i];
+    }
 #pragma unroll
     for (int i = 0; i < NJ; i++) {
       const TS qacc = qacc_sd[i] + (TS)delta[i];
       warm[i] = (T)qacc;
       bad |= !(t_abs(qacc) < TS(1e10));  // [upstream] mj_checkAcc (also catches NaN)
-      qd[i] += am.dt_d * qacc;           // [upstream] mj_Euler: velocity first, then position with the new velocity
+      qd[i] += am.dt_d * (qacc + corr[i]);  // [upstream] mj_Euler: velocity first, then position with the new velocity
       q[i] += am.dt_d * qd[i];
       if constexpr (ROUND32) { qd[i] = (TS)(float)qd[i]; q[i] = (TS)(float)q[i]; }
     }

@@ -68,6 +68,7 @@ struct EnvState {
 
 struct StepCfg {
   int nsub, last_step, dj, dp, terminate_on_success, max_iter;
+  int integrator;  // 0 = semi-implicit Euler (the reference's default, scene_pbr.xml sets none), 1 = implicitfast (north_star)
   int arm_mode;  // developer switch (SO101_ARM_MODE): which parts of the float32 arm path run in float64, see arm_kernel.cu
   float tol;
   int dbg_env, dbg_step;  // developer probe: device printf of one env's manifold inputs (SO101_DBG_ENV / SO101_DBG_STEP)

@@ -15,7 +15,8 @@ namespace so101 {
 
 // Per-env record written by the thread-per-env kinematics + smooth-dynamics kernel and read by the solve kernels:
 // joint anchors 18, joint axes 18, arm mass matrix 21, prop mass blocks 2 x 21, qacc_smooth 18, arm rows 24
-constexpr int DYN_P = 0, DYN_A = 18, DYN_MARM = 36, DYN_MPROP = 57, DYN_QACC = 99, DYN_ROWS = 117, DYNW = 144;
+constexpr int DYN_P = 0, DYN_A = 18, DYN_MARM = 36, DYN_MPROP = 57, DYN_QACC = 99, DYN_ROWS = 117, DYN_VELMASK = 141 /* actuators whose force is
+   not clamped (bit mask, implicitfast) */, DYNW = 144;
 constexpr int GMAX_GEOMS = 96;       // geoms per model the broad phase holds in shared memory
 constexpr int WQ = 128;             // work queues (>= ngeom)
 constexpr int WSTRIDE = 2 * WQ + 8; // counters per substep

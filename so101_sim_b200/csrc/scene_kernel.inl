@@ -699,6 +699,7 @@ __global__ void __launch_bounds__(KD_THREADS) scene_kindyn_kernel(const __grid_c
   double M[21], bias[NJ], frc[NJ], qs[NJ], L[21];
   arm_crb_rne(am64, k, qda, M, bias);
   arm_actuation_d(am, qa, qda, ca, frc);
+  gd[DYN_VELMASK] = (T)arm_actuation_vel_mask(am, frc);
 #pragma unroll
   for (int i = 0; i < 21; i++) { L[i] = M[i]; gd[DYN_MARM + i] = (T)M[i]; }
   chol6(L);
@@ -1037,13 +1038,29 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
       if (lane == 0) pb.flags[env] = 1;
       qacc = T(0);
     }
+    T qacc_int = qacc;   // acceleration the velocity update uses (differs from qacc under implicitfast only)
     // The update itself runs in float64 on the float64 state (env_state.cuh): velocity first, then positions with the new
     // velocity; free-joint quaternions are advanced by the body-frame angular velocity and renormalised.
     const TS h = am.dt_d;
     TS qd_new = TS(0);
+    if (cfg.integrator == 1) {
+      // implicitfast ([upstream] mj_implicit): the arm's velocity update uses x = qacc + (M - h D)^-1 h D qacc, D = the unclamped
+      // actuators' velocity gain (arm_dynamics.cuh); the free props have no velocity-dependent smooth force (x = qacc)
+      T qa6[NJ], dv[NJ], cr[NJ], Mm[21];
+      const unsigned vm = (unsigned)pb.dyn[(size_t)env * DYNW + DYN_VELMASK];
+#pragma unroll
+      for (int i = 0; i < NJ; i++) { qa6[i] = __shfl_sync(FULL, qacc, i); dv[i] = ((vm >> i) & 1u) ? (T)am.bias_d[i][2] : T(0); }
+#pragma unroll
+      for (int i = 0; i < 21; i++) Mm[i] = s.Marm[i];
+      implicitfast_correction<T>(Mm, dv, (T)h, qa6, cr);
+      T mine = T(0);
+#pragma unroll
+      for (int i = 0; i < NJ; i++) if (lane == i) mine = cr[i];
+      if (lane < NJ && !badnow) qacc_int = qacc + mine;
+    }
     if (lane < NV) {
       // SETTLE mode: the arm is frozen ([upstream] JointStaticIsolator restores the non-prop joints after every settle step)
-      qd_new = (badnow || (mode && lane < NJ)) ? TS(0) : S.qvel[(size_t)env * NV + lane] + h * (TS)qacc;
+      qd_new = (badnow || (mode && lane < NJ)) ? TS(0) : S.qvel[(size_t)env * NV + lane] + h * (TS)qacc_int;
       S.qvel[(size_t)env * NV + lane] = qd_new;
       S.warm[(size_t)env * NV + lane] = qacc;
     }

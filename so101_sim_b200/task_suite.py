@@ -156,7 +156,7 @@ class BatchedEnvironment:
   """N lockstep copies of one reference environment (composer.Environment, task_suite.py:148-155)."""
 
   def __init__(self, task: SO100Task, num_envs: int, time_limit: float, seed: int | None, device, calibration_offsets, precision,
-               solver_iterations, solver_tolerance, nursery_envs: int = 0, ring_capacity: int | None = None):
+               solver_iterations, solver_tolerance, nursery_envs: int = 0, ring_capacity: int | None = None, integrator: str = 'euler'):
     self.task = task
     self.num_envs = int(num_envs)
     self.device = torch.device(device)
@@ -187,6 +187,10 @@ class BatchedEnvironment:
     cfg.solver_tolerance = float(solver_tolerance)
     cfg.precision = {'f32': 32, 'f64': 64}[precision]
     cfg.collide = int(task.collide)
+    if integrator not in ('euler', 'implicitfast'):
+      raise ValueError("integrator must be 'euler' (MuJoCo's default, what the reference runs) or 'implicitfast'")
+    cfg.integrator = int(integrator == 'implicitfast')
+    self.integrator = integrator
     for i in range(6):
       cfg.calibration_offsets[i] = float(offs[i]); cfg.home_ctrl[i] = float(SO100_HOME_CTRL[i])
     # on-device episode initialisation (so100_hand_over.py:208-229,320-323): placement distributions + nursery envs
@@ -500,7 +504,8 @@ def create_batched_task_env(task_name: str, num_envs: int, time_limit: float, se
                             control_timestep: float = DEFAULT_CONTROL_TIMESTEP, cameras: tuple = (), device='cuda:0',
                             calibration_offsets=None, calibration_file: str | None = None, precision: str = 'f32',
                             solver_iterations: int = 100, solver_tolerance: float | None = None, reset_rounds: int = 1,
-                            placement: str = 'device', nursery_envs: int | None = None, **kwargs) -> BatchedEnvironment:
+                            placement: str = 'device', nursery_envs: int | None = None, integrator: str = 'euler',
+                            **kwargs) -> BatchedEnvironment:
   """Batched twin of task_suite.create_task_env (task_suite.py:103-155).
 
   For the SO100HandOver tasks the env comes back with sampled and settled prop placements, as the reference places and settles
@@ -512,7 +517,9 @@ def create_batched_task_env(task_name: str, num_envs: int, time_limit: float, se
     placement='pool': the round-1 path, `reset_rounds` placements per env sampled on the host and settled up front
       (randomize_resets); episodes cycle through them.
     placement='none' or reset_rounds=0: nothing is installed (the caller sets its own states with set_initial_state /
-      set_reset_pool / sample_prop_initial_states before the first reset)."""
+      set_reset_pool / sample_prop_initial_states before the first reset).
+  integrator: 'euler' (default: MuJoCo's default semi-implicit Euler, which the reference runs since scene_pbr.xml sets none) or
+    'implicitfast' (named by north_star; differs here through the actuators' +1 * qvel bias term, scene_pbr.xml:11)."""
   if task_name not in TASK_FACTORIES:
     raise ValueError(f'Unknown task_name: {task_name}. Available tasks: {list(TASK_FACTORIES.keys())}')  # task_suite.py:126-130
   task_class, task_kwargs = TASK_FACTORIES[task_name]
@@ -533,7 +540,7 @@ def create_batched_task_env(task_name: str, num_envs: int, time_limit: float, se
   if placement == 'device':
     nursery = max(1, int(num_envs) // 16) if nursery_envs is None else int(nursery_envs)
   env = BatchedEnvironment(task, num_envs, time_limit, seed, device, calibration_offsets, precision, solver_iterations, solver_tolerance,
-                           nursery_envs=nursery)
+                           nursery_envs=nursery, integrator=integrator)
   if placement == 'device':
     env.initialize_placements()
   elif placement == 'pool':

@@ -131,6 +131,31 @@ def test_forced_divergence_ends_the_episode(built):
   env.close()
 
 
+@pytest.mark.parametrize('precision,tol', [('f64', 1e-9), ('f32', 1e-5)])
+def test_implicitfast_rollout_matches_oracle(built, precision, tol):
+  """integrator='implicitfast' (north_star names it; the default stays MuJoCo's Euler, which the reference runs): 20 control
+  steps of the arm-only scene against the oracle's implicitfast ([upstream] mj_implicit: (M - h D) x = M qacc with the
+  actuators' +1 * qvel gain), and the two integrators must differ visibly."""
+  env = _env(built, precision=precision, integrator='implicitfast')
+  q0, _ = env.sample_arm_initial_states(seed=0)
+  env.reset()
+  acts = _actions(env, 20)
+  sims = {}
+  for e in (0, 5, 31):
+    sims[e] = (OracleSim('so100_arm', collide=False, integrator='implicitfast'), OracleSim('so100_arm', collide=False))
+    for o in sims[e]:
+      o.set_state(q0[e].double().cpu().numpy(), np.zeros(6))
+  for t in range(20):
+    env.step(acts[t])
+    for e, (oi, oe) in sims.items():
+      oi.control_step(acts[t, e].double().cpu().numpy()); oe.control_step(acts[t, e].double().cpu().numpy())
+  q, v = env.get_state(torch.float64)
+  for e, (oi, oe) in sims.items():
+    assert _rel_err(q[e].cpu().numpy(), oi.qpos) < tol and _rel_err(v[e].cpu().numpy(), oi.qvel) < tol
+    assert np.abs(oi.qpos - oe.qpos).max() > 1e-4   # not the Euler trajectory
+  env.close()
+
+
 def test_limit_rows_active(built):
   """Drive the elbow into its lower limit (range [0, 3.14158], scene_pbr.xml:18-20): the limit row must engage."""
   env = _env(built, num_envs=2, precision='f64')

@@ -117,3 +117,25 @@ def test_free_fall_follows_semi_implicit_euler():
     o.substep()
   assert abs(o.qvel[8] + ka.G * ka.DT * n) < 1e-12 and abs(o.qpos[8] - (0.8 - ka.G * ka.DT**2 * n * (n + 1) / 2)) < 1e-12
   assert abs(o.qpos[15] - (0.9 - ka.G * ka.DT**2 * n * (n + 1) / 2)) < 1e-12
+
+
+def test_implicitfast_satisfies_its_defining_equation():
+  """integrator = implicitfast (named by north_star; the reference itself runs MuJoCo's default Euler): [upstream] mj_implicit
+  advances the velocity with x solving (M - h D) x = M qacc, D = d(qfrc_smooth)/d(qvel) without Coriolis terms - here the
+  actuators' velocity gain biasprm[2] = +1 (scene_pbr.xml:11) on every actuator whose force is not clamped.  Checked from the
+  oracle's own M, qacc and actuator forces of the substep, independently of how integrate() solves it; Euler gives x = qacc."""
+  rs = np.random.RandomState(0)
+  for integ in ('euler', 'implicitfast'):
+    o = OracleSim('so100_arm', collide=False, integrator=integ)
+    q = 0.3 * rs.uniform(-1, 1, 6); q[2] = abs(q[2]) + 0.2
+    o.set_state(q, rs.uniform(-1, 1, 6)); o.ctrl[:] = q + 0.2 * rs.uniform(-1, 1, 6)
+    v0 = o.qvel.copy()
+    o.substep()
+    M, qacc, fa = o.field('M', 36).reshape(6, 6).copy(), o.field('qacc', 6).copy(), o.field('qfrc_actuator', 6).copy()
+    x = (o.qvel - v0) / ka.DT
+    D = np.diag((np.abs(fa) < 35.0).astype(float))
+    assert D.trace() >= 5
+    if integ == 'implicitfast':
+      assert np.abs((M - ka.DT * D) @ x - M @ qacc).max() < 1e-11 and np.abs(x - qacc).max() > 1e-2
+    else:
+      assert np.abs(x - qacc).max() < 1e-11

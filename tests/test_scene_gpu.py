@@ -54,6 +54,26 @@ def test_f64_scene_matches_oracle(built):
   env.close()
 
 
+def test_f64_scene_implicitfast_matches_oracle(built):
+  """The contact scene with integrator='implicitfast': float64 CUDA path against the oracle's implicitfast over 60 substeps."""
+  env = _env(built, precision='f64', num_envs=2, integrator='implicitfast')
+  q0, v0 = _initial(env, seed=3)
+  acts = _actions(env, 6)
+  sims = []
+  for e in range(2):
+    o = OracleSim('so100_handover_banana', collide=True, integrator='implicitfast')
+    o.set_state(q0[e].cpu().numpy(), v0[e].cpu().numpy())
+    sims.append(o)
+  for t in range(6):
+    env.step(acts[t])
+    for e in range(2):
+      sims[e].control_step(acts[t, e].double().cpu().numpy())
+  q, v = env.get_state(torch.float64)
+  for e in range(2):
+    assert np.abs(q[e].cpu().numpy() - sims[e].qpos).max() < 1e-7 and np.abs(v[e].cpu().numpy() - sims[e].qvel).max() < 1e-5
+  env.close()
+
+
 def test_contacts_match_oracle(built):
   """Contact lists (geom pair, distance, position, normal) of one substep, float64 GPU vs oracle."""
   env = _env(built, precision='f64', num_envs=3, control_timestep=0.002)

@@ -19,8 +19,8 @@ extern "C" {
 
 #define SO_NQMAX 32
 #define SO_NVMAX 24
-#define SO_NBMAX 16
-#define SO_NUMAX 8
+#define SO_NBMAX 24
+#define SO_NUMAX 16
 #define SO_NCONMAX 256
 #define SO_NEFCMAX (2 * SO_NVMAX + 6 * SO_NCONMAX)
 

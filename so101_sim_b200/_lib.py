@@ -9,6 +9,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('SO101_B200_LIB') or os.path.join(_HERE, 'libso101_b200.so')  # override: developer A/B builds only
+# the same sources compiled with -DSO101_NARM=2: the labelled synthetic two-arm hand-over scene (BASELINE config 4)
+LIB_PATH_2ARM = os.path.join(_HERE, 'libso101_b200_2arm.so')
 
 
 class StepOut(ctypes.Structure):
@@ -31,17 +33,20 @@ EXPORTS = ('so101_abi_version', 'so101_create', 'so101_destroy', 'so101_last_err
            'so101_reset', 'so101_step', 'so101_get_state', 'so101_set_state', 'so101_get_state_f64', 'so101_step_host',
            'so101_counters', 'so101_debug_read', 'so101_kernel_times', 'so101_set_reset_pool', 'so101_set_state_f64', 'so101_debug_overlap', 'so101_sample_and_settle', 'so101_placement_stats')
 
-_lib = None
+_libs = {}
 
 
-def load() -> ctypes.CDLL:
-  global _lib
-  if _lib is not None:
-    return _lib
-  if not os.path.exists(LIB_PATH):
-    raise RuntimeError(f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+def load(narm: int = 1) -> ctypes.CDLL:
+  """The library built for `narm` arms (1: the reference's scenes; 2: the synthetic two-arm scene)."""
+  if narm in _libs:
+    return _libs[narm]
+  if narm not in (1, 2):
+    raise RuntimeError(f'no build of the kernels for {narm} arms')
+  path = LIB_PATH if narm == 1 else LIB_PATH_2ARM
+  if not os.path.exists(path):
+    raise RuntimeError(f'{path} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
                        '(so101_sim_b200 has no CPU fallback)')
-  L = ctypes.CDLL(LIB_PATH)
+  L = ctypes.CDLL(path)
   vp, ci = ctypes.c_void_p, ctypes.c_int
   L.so101_abi_version.restype = ci
   L.so101_create.restype = ci; L.so101_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(Config), ctypes.POINTER(vp)]
@@ -62,6 +67,6 @@ def load() -> ctypes.CDLL:
   L.so101_kernel_times.restype = ci; L.so101_kernel_times.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double * 8), ctypes.POINTER(ctypes.c_uint64 * 8)]
   L.so101_debug_read.restype = ci; L.so101_debug_read.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t, vp]
   if L.so101_abi_version() != 3:
-    raise RuntimeError('libso101_b200.so: ABI version mismatch')
-  _lib = L
+    raise RuntimeError(f'{path}: ABI version mismatch')
+  _libs[narm] = L
   return L

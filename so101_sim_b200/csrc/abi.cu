@@ -74,18 +74,19 @@ static void mm3(const double *a, const double *b, double *r) {
     for (int j = 0; j < 3; j++) r[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
 }
 
-// Build the arm chain description from the generic blob: the first NJ hinge joints must form a serial chain whose root's
-// parent is static (scene_pbr.xml:74-126).
+// Build the description of arm `arm` from the generic blob: joints 6 * arm .. 6 * arm + 5 must be hinges that form a serial chain
+// whose root's parent is static (scene_pbr.xml:74-126), with their dofs / actuators at the same indices.
 template <typename T>
-static void build_arm_model(const Blob &b, ArmModelT<T> &am) {
+static void build_arm_model(const Blob &b, ArmModelT<T> &am, int arm = 0) {
   const auto &jt = b.I("jnt_type"), &jb = b.I("jnt_body"), &bp = b.I("body_parent"), &bw = b.I("body_weld");
-  if ((int)jt.size() < NJ) throw std::runtime_error("model has fewer than 6 joints");
+  const int j0 = NJ * arm;
+  if ((int)jt.size() < j0 + NJ) throw std::runtime_error("model has fewer hinge joints than this build's arms need");
   const auto &opt = b.F("opt");
   const double dt = opt[0];
   std::memset(&am, 0, sizeof(am));
   // static base pose: compose the chain of static ancestors of the first arm body
   {
-    int b0 = jb[0];
+    int b0 = jb[j0];
     std::vector<int> chain;
     for (int p = bp[b0]; p != 0; p = bp[p]) {
       if (bw[p] != 0) throw std::runtime_error("arm base must be static");
@@ -104,11 +105,12 @@ static void build_arm_model(const Blob &b, ArmModelT<T> &am) {
     for (int c = 0; c < 9; c++) am.base_R[c] = (T)R[c];
   }
   for (int j = 0; j < NJ; j++) {
-    if (jt[j] != 1) throw std::runtime_error("arm joints must be hinges");
-    const int body = jb[j];
-    if (j > 0 && bp[body] != jb[j - 1]) throw std::runtime_error("arm joints must form a serial chain");
-    if (b.I("jnt_dofadr")[j] != j || b.I("jnt_qposadr")[j] != j) throw std::runtime_error("arm dofs must come first");
-    const double *jp = &b.F("jnt_pos")[3 * j];
+    const int gj = j0 + j;   // joint / dof / qpos index in the model
+    if (jt[gj] != 1) throw std::runtime_error("arm joints must be hinges");
+    const int body = jb[gj];
+    if (j > 0 && bp[body] != jb[gj - 1]) throw std::runtime_error("arm joints must form a serial chain");
+    if (b.I("jnt_dofadr")[gj] != gj || b.I("jnt_qposadr")[gj] != gj) throw std::runtime_error("arm dofs must come first, arm by arm");
+    const double *jp = &b.F("jnt_pos")[3 * gj];
     if (jp[0] != 0 || jp[1] != 0 || jp[2] != 0) throw std::runtime_error("hinge anchors must sit at the body origin");
     double R0[9], Ri[9];
     quat2mat(&b.F("body_quat")[4 * body], R0);
@@ -119,21 +121,21 @@ static void build_arm_model(const Blob &b, ArmModelT<T> &am) {
       for (int c = 0; c < 3; c++) Il[3 * r + c] = Ri[3 * r] * in[0] * Ri[3 * c] + Ri[3 * r + 1] * in[1] * Ri[3 * c + 1] + Ri[3 * r + 2] * in[2] * Ri[3 * c + 2];
     for (int c = 0; c < 3; c++) {
       am.pos[j][c] = (T)b.F("body_pos")[3 * body + c];
-      am.axis[j][c] = (T)b.F("jnt_axis")[3 * j + c];
+      am.axis[j][c] = (T)b.F("jnt_axis")[3 * gj + c];
       am.ipos[j][c] = (T)b.F("body_ipos")[3 * body + c];
     }
     for (int c = 0; c < 9; c++) am.R0[j][c] = (T)R0[c];
     am.Iloc[j][0] = (T)Il[0]; am.Iloc[j][1] = (T)Il[4]; am.Iloc[j][2] = (T)Il[8];
     am.Iloc[j][3] = (T)Il[1]; am.Iloc[j][4] = (T)Il[2]; am.Iloc[j][5] = (T)Il[5];
     am.mass[j] = (T)b.F("body_mass")[body];
-    am.qpos0[j] = (T)b.F("qpos0")[j];
-    am.armature[j] = (T)b.F("dof_armature")[j];
-    am.frictionloss[j] = (T)b.F("dof_frictionloss")[j];
-    const double invw = b.F("dof_invweight0")[j];
+    am.qpos0[j] = (T)b.F("qpos0")[gj];
+    am.armature[j] = (T)b.F("dof_armature")[gj];
+    am.frictionloss[j] = (T)b.F("dof_frictionloss")[gj];
+    const double invw = b.F("dof_invweight0")[gj];
     am.invweight0[j] = (T)invw;
     auto clampimp = [](double x) { return x < 1e-4 ? 1e-4 : (x > 0.9999 ? 0.9999 : x); };
     {  // friction-loss row constants: pos = 0 -> impedance = d0; K = 0; B = 2 / (dmax * max(tc, 2 dt))
-      const double *sr = &b.F("jnt_solreffriction")[2 * j], *si = &b.F("jnt_solimpfriction")[5 * j];
+      const double *sr = &b.F("jnt_solreffriction")[2 * gj], *si = &b.F("jnt_solimpfriction")[5 * gj];
       const double imp = clampimp(si[0]), dmax = clampimp(si[1]);
       double R = (1 - imp) / imp * invw;
       if (R < 1e-15) R = 1e-15;
@@ -141,26 +143,27 @@ static void build_arm_model(const Blob &b, ArmModelT<T> &am) {
       am.fr_B[j] = (T)(sr[0] > 0 ? 2 / (dmax * std::max(sr[0], 2 * dt)) : -sr[1] / dmax);
     }
     {
-      const double *sr = &b.F("jnt_solreflimit")[2 * j], *si = &b.F("jnt_solimplimit")[5 * j];
+      const double *sr = &b.F("jnt_solreflimit")[2 * gj], *si = &b.F("jnt_solimplimit")[5 * gj];
       const double dmax = clampimp(si[1]);
       for (int c = 0; c < 5; c++) am.lim_solimp[j][c] = (T)si[c];
       if (sr[0] > 0) {
         const double tc = std::max(sr[0], 2 * dt);
         am.lim_K[j] = (T)(1 / (dmax * dmax * tc * tc * sr[1] * sr[1])); am.lim_B[j] = (T)(2 / (dmax * tc));
       } else { am.lim_K[j] = (T)(-sr[0] / (dmax * dmax)); am.lim_B[j] = (T)(-sr[1] / dmax); }
-      am.limited[j] = b.I("jnt_limited")[j];
-      am.range[j][0] = (T)b.F("jnt_range")[2 * j]; am.range[j][1] = (T)b.F("jnt_range")[2 * j + 1];
+      am.limited[j] = b.I("jnt_limited")[gj];
+      am.range[j][0] = (T)b.F("jnt_range")[2 * gj]; am.range[j][1] = (T)b.F("jnt_range")[2 * gj + 1];
     }
   }
-  if (b.scalar("nu") != NJ) throw std::runtime_error("expected 6 actuators");
+  if (b.scalar("nu") != NA) throw std::runtime_error("expected 6 actuators per arm");
   for (int a = 0; a < NJ; a++) {
-    if (b.I("act_jnt")[a] != a) throw std::runtime_error("actuator a must drive joint a");
-    if (b.F("act_gear")[a] != 1.0) throw std::runtime_error("actuator gear must be 1");
-    am.gain[a] = (T)b.F("act_gain")[a]; am.gain_d[a] = b.F("act_gain")[a];
-    for (int c = 0; c < 3; c++) { am.bias[a][c] = (T)b.F("act_bias")[3 * a + c]; am.bias_d[a][c] = b.F("act_bias")[3 * a + c]; }
+    const int ga = j0 + a;
+    if (b.I("act_jnt")[ga] != ga) throw std::runtime_error("actuator a must drive joint a");
+    if (b.F("act_gear")[ga] != 1.0) throw std::runtime_error("actuator gear must be 1");
+    am.gain[a] = (T)b.F("act_gain")[ga]; am.gain_d[a] = b.F("act_gain")[ga];
+    for (int c = 0; c < 3; c++) { am.bias[a][c] = (T)b.F("act_bias")[3 * ga + c]; am.bias_d[a][c] = b.F("act_bias")[3 * ga + c]; }
     for (int c = 0; c < 2; c++) {
-      am.ctrlrange[a][c] = (T)b.F("act_ctrlrange")[2 * a + c]; am.forcerange[a][c] = (T)b.F("act_forcerange")[2 * a + c];
-      am.ctrlrange_d[a][c] = b.F("act_ctrlrange")[2 * a + c]; am.forcerange_d[a][c] = b.F("act_forcerange")[2 * a + c];
+      am.ctrlrange[a][c] = (T)b.F("act_ctrlrange")[2 * ga + c]; am.forcerange[a][c] = (T)b.F("act_forcerange")[2 * ga + c];
+      am.ctrlrange_d[a][c] = b.F("act_ctrlrange")[2 * ga + c]; am.forcerange_d[a][c] = b.F("act_forcerange")[2 * ga + c];
     }
   }
   am.dt_d = dt;
@@ -172,8 +175,8 @@ static void build_arm_model(const Blob &b, ArmModelT<T> &am) {
 
 template <typename T>
 struct Handle : HandleBase {
-  ArmModelT<T> am;
-  ArmModelT<double> am64;  // float64 arm model for the float64 parts of the float32 path
+  ArmSetT<T> am;
+  ArmSetT<double> am64;  // float64 arm models for the float64 parts of the float32 path
   std::unique_ptr<SceneModelHost<T>> scene;  // non-null: full contact scene (warp per env, row-major state)
   EnvState<T> S{};
   PipeBuf<T> pipe{};                 // per-env scratch shared by all groups
@@ -204,8 +207,8 @@ struct Handle : HandleBase {
   Handle(const Blob &b, const so101_config &c) {
     cfg = c;
     nq = b.scalar("nq"); nv = b.scalar("nv"); nu = b.scalar("nu"); nbody = b.scalar("nbody");
-    build_arm_model<T>(b, am);
-    build_arm_model<double>(b, am64);
+    if (nq == NJ && NARM != 1) throw std::runtime_error("the arm-only model needs the one-arm build of the library (libso101_b200.so)");
+    for (int k = 0; k < NARM; k++) { build_arm_model<T>(b, am.arm[k], k); build_arm_model<double>(b, am64.arm[k], k); }
     if (nq != NJ || c.collide) {
       if (!c.collide) throw std::runtime_error("models with free props need collide=1");
       scene.reset(new SceneModelHost<T>());
@@ -231,9 +234,9 @@ struct Handle : HandleBase {
     S.place.qvel_tol = c.settle_qvel_tol > 0 ? c.settle_qvel_tol : 1e-3f; S.place.qacc_tol = c.settle_qacc_tol > 0 ? c.settle_qacc_tol : 1e-2f;
     S.place.seed = c.seed;
     S.qpos = dalloc<TS>(nq * N); S.qvel = dalloc<TS>(nv * N); S.warm = dalloc<T>(nv * N);
-    S.init_qpos = dalloc<TS>(nq * N); S.init_qvel = dalloc<TS>(nv * N); S.ctrl = dalloc<T>(6 * N);
+    S.init_qpos = dalloc<TS>(nq * N); S.init_qvel = dalloc<TS>(nv * N); S.ctrl = dalloc<T>(NA * N);
     S.step = dalloc<int>(N); S.needs_reset = dalloc<uint8_t>(N); S.episode = dalloc<int>(N); S.npool = 1;
-    S.ring_joints = dalloc<float>((size_t)(c.joints_delay_steps + 1) * 6 * N);
+    S.ring_joints = dalloc<float>((size_t)(c.joints_delay_steps + 1) * NA * N);
     S.ring_phys = dalloc<float>((size_t)(c.physics_delay_steps + 1) * (nq + nv) * N);
     S.diverged_count = dalloc<int>(2); S.solver_iter = dalloc<int>(N); S.ncon = dalloc<int>(N);
     sc.nsub = c.n_substeps; sc.last_step = c.last_step; sc.dj = c.joints_delay_steps; sc.dp = c.physics_delay_steps;
@@ -248,11 +251,11 @@ struct Handle : HandleBase {
     std::vector<TS> q0(nq * N);
     for (int k = 0; k < nq; k++) for (size_t e = 0; e < N; e++) q0[scene ? e * nq + k : k * N + e] = (TS)b.F("qpos0")[k];
     CUDA_OK(cudaMemcpy(S.init_qpos, q0.data(), q0.size() * sizeof(TS), cudaMemcpyHostToDevice));
-    d_action = dalloc<float>(6 * N);
+    d_action = dalloc<float>(NA * N);
     use_graph = !(getenv("SO101_GRAPH") && atoi(getenv("SO101_GRAPH")) == 0);
     if (scene) {  // inter-kernel scratch of the scene pipeline
       if (b.scalar("ngeom") > GMAX_GEOMS) throw std::runtime_error("model has more geoms than the broad phase can hold");
-      if (b.scalar("nbody") > 16) throw std::runtime_error("model has more bodies than the broad phase can hold");
+      if (b.scalar("nbody") > BMAX_BODIES) throw std::runtime_error("model has more bodies than the broad phase can hold");
       if (b.scalar("ngeom") > WQ) throw std::runtime_error("model has more geoms than narrow-phase work queues");
       pipe.xpos = dalloc<T>(N * NSLOT * 3); pipe.xmat = dalloc<T>(N * NSLOT * 9); pipe.dyn = dalloc<T>(N * DYNW);
       pipe.con = dalloc<T>(N * CONBUF * 8); pipe.con_key = dalloc<int>(N * CONBUF); pipe.ncon_raw = dalloc<int>(N);
@@ -346,7 +349,7 @@ struct Handle : HandleBase {
     launches += 1;
   }
   void step(const float *action, const so101_step_out &out, cudaStream_t s) override {
-    if (!scene) { timer.begin(4, s); launch_arm_step<T>(am, am64, sc, S, action, out, s); timer.end(4, s); launches += 1; steps += 1; return; }
+    if (!scene) { timer.begin(4, s); launch_arm_step<T>(am.arm[0], am64.arm[0], sc, S, action, out, s); timer.end(4, s); launches += 1; steps += 1; return; }
     const int nk = (int)groups.size() * (3 + 8 * sc.nsub);
     if (!use_graph || timer.on) {
       launches += launch_scene_step<T>(am, am64, scene->dev, sc, S, groups.data(), tiers.data(), (int)groups.size(), action, out, s, &timer);
@@ -354,7 +357,7 @@ struct Handle : HandleBase {
       return;
     }
     // graph replay: the action goes through a fixed staging buffer so that the graph does not depend on the caller's pointer
-    if (action != d_action) CUDA_OK(cudaMemcpyAsync(d_action, action, sizeof(float) * 6 * S.NU, cudaMemcpyDeviceToDevice, s));
+    if (action != d_action) CUDA_OK(cudaMemcpyAsync(d_action, action, sizeof(float) * NA * S.NU, cudaMemcpyDeviceToDevice, s));
     cudaGraphExec_t exec = nullptr;
     for (auto &g : graphs) if (std::memcmp(&g.key, &out, sizeof out) == 0) exec = g.exec;
     if (!exec) {
@@ -363,8 +366,12 @@ struct Handle : HandleBase {
       cudaGraph_t graph = nullptr;
       CUDA_OK(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
       launch_scene_step<T>(am, am64, scene->dev, sc, S, groups.data(), tiers.data(), (int)groups.size(), d_action, out, cap_stream, nullptr);
+      const cudaError_t le = cudaGetLastError();   // first launch error inside the capture, if any
       cudaError_t e = cudaStreamEndCapture(cap_stream, &graph);
-      if (e != cudaSuccess || !graph) { cudaGetLastError(); throw std::runtime_error(std::string("step graph capture failed: ") + cudaGetErrorString(e)); }
+      if (e != cudaSuccess || !graph) {
+        cudaGetLastError();
+        throw std::runtime_error(std::string("step graph capture failed: ") + cudaGetErrorString(e) + " (first launch error: " + cudaGetErrorString(le) + ")");
+      }
       e = cudaGraphInstantiate(&exec, graph, 0);
       cudaGraphDestroy(graph);
       if (e != cudaSuccess) throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
@@ -433,16 +440,16 @@ struct Handle : HandleBase {
   void step_host(const float *action, const so101_step_out &host_out, cudaStream_t s) override {
     const size_t N = S.NU, sd = (size_t)nq + nv;
     if (!d_out.reward) {
-      d_out.commanded_joints_pos = dalloc<float>(6 * N); d_out.joints_pos = dalloc<float>(6 * N); d_out.undelayed_joints_pos = dalloc<float>(6 * N);
+      d_out.commanded_joints_pos = dalloc<float>(NA * N); d_out.joints_pos = dalloc<float>(NA * N); d_out.undelayed_joints_pos = dalloc<float>(NA * N);
       d_out.physics_state = dalloc<float>(sd * N); d_out.delayed_physics_state = dalloc<float>(sd * N);
       d_out.reward = dalloc<float>(N); d_out.discount = dalloc<float>(N); d_out.step_type = dalloc<uint8_t>(N);
     }
-    CUDA_OK(cudaMemcpyAsync(d_action, action, 6 * N * sizeof(float), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(d_action, action, NA * N * sizeof(float), cudaMemcpyHostToDevice, s));
     step(d_action, d_out, s);
     auto back = [&](void *dst, const void *src, size_t bytes) { if (dst) CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)); };
-    back(host_out.commanded_joints_pos, d_out.commanded_joints_pos, 6 * N * sizeof(float));
-    back(host_out.joints_pos, d_out.joints_pos, 6 * N * sizeof(float));
-    back(host_out.undelayed_joints_pos, d_out.undelayed_joints_pos, 6 * N * sizeof(float));
+    back(host_out.commanded_joints_pos, d_out.commanded_joints_pos, NA * N * sizeof(float));
+    back(host_out.joints_pos, d_out.joints_pos, NA * N * sizeof(float));
+    back(host_out.undelayed_joints_pos, d_out.undelayed_joints_pos, NA * N * sizeof(float));
     back(host_out.physics_state, d_out.physics_state, sd * N * sizeof(float));
     back(host_out.delayed_physics_state, d_out.delayed_physics_state, sd * N * sizeof(float));
     back(host_out.reward, d_out.reward, N * sizeof(float));

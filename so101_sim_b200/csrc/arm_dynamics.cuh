@@ -11,7 +11,15 @@
 
 namespace so101 {
 
-constexpr int NJ = 6;  // arm hinge joints = arm dofs = actuators
+#ifndef SO101_NARM
+#define SO101_NARM 1
+#endif
+// Arms in the scene: 1 = the reference's SO100 scenes (libso101_b200.so); 2 = the labelled synthetic two-arm hand-over scene of
+// BASELINE config 4 (libso101_b200_2arm.so, the same sources compiled with -DSO101_NARM=2).  State layout: arm 0's six hinge
+// dofs, arm 1's, then the free props.
+constexpr int NARM = SO101_NARM;
+constexpr int NJ = 6;          // hinge joints = dofs = actuators of ONE arm
+constexpr int NA = NJ * NARM;  // arm dofs (= actuators) of the scene; the props' dofs follow
 
 template <typename T>
 struct ArmModelT {
@@ -35,6 +43,13 @@ struct ArmModelT {
   T gravity[3], dt, solver_scale;  // solver_scale = 1 / (meaninertia * max(1, nv))
   // float64 copies of what the float64 parts of the float32 path read (actuation and the Euler update, env_state.cuh)
   double gain_d[NJ], bias_d[NJ][3], ctrlrange_d[NJ][2], forcerange_d[NJ][2], dt_d;
+};
+
+// the scene's arms (kernel parameter); scalars shared by all arms (dt, gravity, solver_scale) are read from arm 0
+template <typename T>
+struct ArmSetT {
+  ArmModelT<T> arm[NARM];
+  __host__ __device__ const ArmModelT<T> &operator[](int k) const { return arm[k]; }
 };
 
 template <typename T> __device__ __forceinline__ T t_sqrt(T x);

@@ -15,9 +15,12 @@ namespace so101 {
 
 // Per-env record written by the thread-per-env kinematics + smooth-dynamics kernel and read by the solve kernels:
 // joint anchors 18, joint axes 18, arm mass matrix 21, prop mass blocks 2 x 21, qacc_smooth 18, arm rows 24
-constexpr int DYN_P = 0, DYN_A = 18, DYN_MARM = 36, DYN_MPROP = 57, DYN_QACC = 99, DYN_ROWS = 117, DYN_VELMASK = 141 /* actuators whose force is
-   not clamped (bit mask, implicitfast) */, DYNW = 144;
-constexpr int GMAX_GEOMS = 96;       // geoms per model the broad phase holds in shared memory
+// (one arm: 0, 18, 36, 57, 99, 117, 141 -> 144 values; two arms: 232)
+constexpr int DYN_P = 0, DYN_A = 3 * NA, DYN_MARM = 6 * NA, DYN_MPROP = DYN_MARM + 21 * NARM, DYN_QACC = DYN_MPROP + 21 * NPROP,
+              DYN_ROWS = DYN_QACC + NV, DYN_VELMASK = DYN_ROWS + 4 * NA /* per arm: actuators whose force is not clamped (bit mask,
+              implicitfast) */, DYNW = (DYN_VELMASK + NARM + 3) / 4 * 4;
+constexpr int GMAX_GEOMS = NARM == 1 ? 96 : 128;  // geoms per model the broad phase holds in shared memory
+constexpr int BMAX_BODIES = NARM == 1 ? 16 : 24;  // bodies per model the broad phase holds in shared memory
 constexpr int WQ = 128;             // work queues (>= ngeom)
 constexpr int WSTRIDE = 2 * WQ + 8; // counters per substep
 enum { W_CURSOR = WQ, W_NTIER = WQ + 1 /* [2]: envs queued for solver tier 1, 2 */, W_TIERCURSOR = WQ + 3 /* [2] */,
@@ -119,7 +122,7 @@ struct KernelTimer {
 
 // pb / tx: one entry per pipeline group (ngroups of them)
 template <typename T>
-int launch_scene_step(const ArmModelT<T> &am, const ArmModelT<double> &am64, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> *pb,
+int launch_scene_step(const ArmSetT<T> &am, const ArmSetT<double> &am64, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> *pb,
                       TierExec *tx, int ngroups, const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt);
 template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream);

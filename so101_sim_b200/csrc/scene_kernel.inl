@@ -53,7 +53,7 @@ struct BroadScratch {
   unsigned cand[CANDCAP];
   T gcenter[3][GMAX];                  // world bounding-sphere centres of all geoms
   T opos[3][GMAX], omat[9][GMAX];      // world oriented boxes (geom AABB in the geom frame) of all geoms
-  T bcenter[3][16];                    // world bounding-sphere centres of the bodies
+  T bcenter[3][BMAX_BODIES];           // world bounding-sphere centres of the bodies
 };
 
 // per-env scratch of the begin / solve kernels (NC contacts, NB Jacobian blocks)
@@ -62,13 +62,13 @@ struct Scratch {
   // the poses are only read while the constraint rows are built, the Hessian only exists afterwards: they share storage
   // (552 bytes less per env let 8 instead of 7 two-env CTAs of the tier-0 kernel fit the 228 KB of an SM)
   union {
-    struct { T xpos[NSLOT][3], xmat[NSLOT][9], arm_p[NJ][3], arm_a[NJ][3]; };
+    struct { T xpos[NSLOT][3], xmat[NSLOT][9], arm_p[NA][3], arm_a[NA][3]; };
     T H[NH];
   };
-  ArmRows<T> arows;
+  ArmRows<T> arows[NARM];
   T q[NQ], qd[NV], warm[NV];
   T Mprop[NPROP][21];
-  T Marm[21];
+  T Marm[NARM][21];
   T qacc_s[NV], delta[NV], grad[NV], search[NV], Md[NV], hscale[NV];
   int ncon, dbg, profon;
   long long prof[16];  // developer probe (SO101_PROFILE=1): per-stage clock64 sums and counters of this env
@@ -79,7 +79,7 @@ struct Scratch {
 template <typename T>
 struct BroadEnv {
   T xpos[NSLOT][3], xmat[NSLOT][9];
-  T q[NQ], qd[NV], ctrl[NJ];
+  T q[NQ], qd[NV], ctrl[NA];
   int profon;
   long long prof[16];
   BroadScratch<T> broad;
@@ -114,10 +114,11 @@ template <typename T, typename S>
 __device__ __forceinline__ void load_dyn(const PipeBuf<T> &pb, S &s, int env, int lane) {
   const T *gd = pb.dyn + (size_t)env * DYNW;
   static_assert(sizeof(ArmRows<T>) == 24 * sizeof(T), "ArmRows layout");
-  if (lane < 18) { (&s.arm_p[0][0])[lane] = gd[DYN_P + lane]; (&s.arm_a[0][0])[lane] = gd[DYN_A + lane]; s.qacc_s[lane] = gd[DYN_QACC + lane]; }
-  if (lane < 21) s.Marm[lane] = gd[DYN_MARM + lane];
-  for (int i = lane; i < 42; i += 32) (&s.Mprop[0][0])[i] = gd[DYN_MPROP + i];
-  if (lane < 24) reinterpret_cast<T *>(&s.arows)[lane] = gd[DYN_ROWS + lane];
+  for (int i = lane; i < 3 * NA; i += 32) { (&s.arm_p[0][0])[i] = gd[DYN_P + i]; (&s.arm_a[0][0])[i] = gd[DYN_A + i]; }
+  if (lane < NV) s.qacc_s[lane] = gd[DYN_QACC + lane];
+  for (int i = lane; i < 21 * NARM; i += 32) (&s.Marm[0][0])[i] = gd[DYN_MARM + i];
+  for (int i = lane; i < 21 * NPROP; i += 32) (&s.Mprop[0][0])[i] = gd[DYN_MPROP + i];
+  for (int i = lane; i < 24 * NARM; i += 32) reinterpret_cast<T *>(&s.arows[0])[i] = gd[DYN_ROWS + i];
 }
 
 // free-joint mass block (packed lower 6x6) and bias force for prop p (uniform; [upstream] mj_crb / mj_rne for a free body)
@@ -447,11 +448,11 @@ __device__ float scene_reward(const SceneModel<T> &sm, const S &s) {
   // success_detector_utils.py:22-28 — linear velocity of either prop >= 1e-3 -> 0
   for (int p = 0; p < NPROP; p++) {
     T mx = T(0);
-    for (int c = 0; c < 3; c++) mx = max(mx, t_abs(s.qd[NJ + 6 * p + c]));
+    for (int c = 0; c < 3; c++) mx = max(mx, t_abs(s.qd[NA + 6 * p + c]));
     if (mx >= T(1e-3)) return 0.f;
   }
   // object OOBB: root BVH box at xipos / ximat (oobb_utils.py:137-148,165-172)
-  const T *R0 = s.xmat[NJ], *X0 = s.xpos[NJ];
+  const T *R0 = s.xmat[NA], *X0 = s.xpos[NA];
   T ximat[9], xipos[3], t[3], q0[4], p0[3];
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) { T v = T(0); for (int k = 0; k < 3; k++) v += R0[3 * i + k] * sm.prop_Riq[0][3 * k + j]; ximat[3 * i + j] = v; }
@@ -463,13 +464,13 @@ __device__ float scene_reward(const SceneModel<T> &sm, const S &s) {
   mulmv(t, Rq, sm.reward_obj_box);
   for (int c = 0; c < 3; c++) p0[c] = t[c] + xipos[c];
   // container box (oobb_utils.py:175-199) — xquat of the bowl body = normalised qpos quaternion
-  const T *qb = s.q + NJ + 7 + 3;
+  const T *qb = s.q + NA + 7 + 3;
   T q1[4] = {qb[0], qb[1], qb[2], qb[3]}, p1[3];
   const T n = t_sqrt(q1[0] * q1[0] + q1[1] * q1[1] + q1[2] * q1[2] + q1[3] * q1[3]);
   for (int i = 0; i < 4; i++) q1[i] /= n;
   for (int k = 0; k < sm.nreward_box; k++) {  // every overlap box must be touched by the object's box (so100_hand_over.py:263-273)
-    mulmv(t, s.xmat[NJ + 1], sm.reward_box_pos[k]);
-    for (int c = 0; c < 3; c++) p1[c] = t[c] + s.xpos[NJ + 1][c];
+    mulmv(t, s.xmat[NA + 1], sm.reward_box_pos[k]);
+    for (int c = 0; c < 3; c++) p1[c] = t[c] + s.xpos[NA + 1][c];
     if (!overlap_oobb_oobb(p0, q0, sm.reward_obj_box + 3, p1, q1, sm.reward_box_half[k])) return 0.f;
   }
   return 1.f;
@@ -482,10 +483,10 @@ __device__ void write_obs_scene(const StepCfg &cfg, const EnvState<T> &S, const 
   constexpr int SD = NQ + NV;
   const int dj = cfg.dj + 1, dp = cfg.dp + 1;
   const size_t N = S.N;
-  float *rj = S.ring_joints + ((size_t)(t % dj) * N + env) * 6;
+  float *rj = S.ring_joints + ((size_t)(t % dj) * N + env) * NA;
   float *rp = S.ring_phys + ((size_t)(t % dp) * N + env) * SD;
   const int tj = t - cfg.dj > 0 ? t - cfg.dj : 0, tp = t - cfg.dp > 0 ? t - cfg.dp : 0;
-  const float *sj = S.ring_joints + ((size_t)(tj % dj) * N + env) * 6;
+  const float *sj = S.ring_joints + ((size_t)(tj % dj) * N + env) * NA;
   const float *sp = S.ring_phys + ((size_t)(tp % dp) * N + env) * SD;
   for (int i = lane; i < SD; i += 32) {
     const float v = i < NQ ? (float)s.q[i] : (float)s.qd[i - NQ];
@@ -493,12 +494,12 @@ __device__ void write_obs_scene(const StepCfg &cfg, const EnvState<T> &S, const 
     if (out.physics_state) out.physics_state[(size_t)env * SD + i] = v;
     if (out.delayed_physics_state) out.delayed_physics_state[(size_t)env * SD + i] = tp == t ? v : sp[i];
   }
-  if (lane < 6) {
+  if (lane < NA) {
     const float v = (float)s.q[lane];
     rj[lane] = v;
-    if (out.undelayed_joints_pos) out.undelayed_joints_pos[(size_t)env * 6 + lane] = v;
-    if (out.joints_pos) out.joints_pos[(size_t)env * 6 + lane] = tj == t ? v : sj[lane];
-    if (out.commanded_joints_pos) out.commanded_joints_pos[(size_t)env * 6 + lane] = (float)s.ctrl[lane];
+    if (out.undelayed_joints_pos) out.undelayed_joints_pos[(size_t)env * NA + lane] = v;
+    if (out.joints_pos) out.joints_pos[(size_t)env * NA + lane] = tj == t ? v : sj[lane];
+    if (out.commanded_joints_pos) out.commanded_joints_pos[(size_t)env * NA + lane] = (float)s.ctrl[lane];
   }
   if (lane == 0) {
     if (out.reward) out.reward[env] = reward;
@@ -544,12 +545,12 @@ __device__ bool settle_begin(const StepCfg &cfg, const EnvState<T> &S, const Pip
     // arm qpos = 0 (the reference never applies its home pose, so100_task.py:308-313), velocities 0, props at their sampled poses;
     // a rejected container placement (attempt > 0) re-draws the container only (the second PropPlacer, so100_hand_over.py:216-221)
     const unsigned draw = S.draws[env], att = (unsigned)S.attempt[env];
-    if (lane < NPROP) sample_prop_pose(S, env, lane, draw, S.place.check_collisions[lane] ? att : 0u, S.qpos + (size_t)env * NQ + NJ + 7 * lane);
-    if (lane < NJ) S.qpos[(size_t)env * NQ + lane] = TS(0);
+    if (lane < NPROP) sample_prop_pose(S, env, lane, draw, S.place.check_collisions[lane] ? att : 0u, S.qpos + (size_t)env * NQ + NA + 7 * lane);
+    if (lane < NA) S.qpos[(size_t)env * NQ + lane] = TS(0);
     if (lane < NV) { S.qvel[(size_t)env * NV + lane] = TS(0); S.warm[(size_t)env * NV + lane] = T(0); }
     if (lane == 0) { S.settle_sub[env] = 0; S.sstate[env] = SETTLE_RUN; }
   }
-  if (lane < NJ) S.ctrl[(size_t)env * 6 + lane] = (T)cfg.home[lane] + (T)cfg.offsets[lane];   // so100_task.py:316-317
+  if (lane < NA) S.ctrl[(size_t)env * NA + lane] = (T)cfg.home[lane % NJ] + (T)cfg.offsets[lane % NJ];   // so100_task.py:316-317
   if (lane == 0) { pb.active[env] = 1; pb.flags[env] = 0; }
   return true;
 }
@@ -575,7 +576,7 @@ __device__ void reset_env_scene(const StepCfg &cfg, const EnvState<T> &S, const 
   __syncwarp();
   for (int i = lane; i < NQ; i += 32) { const TS v = srcq[i]; s.q[i] = (T)v; S.qpos[(size_t)env * NQ + i] = v; }
   for (int i = lane; i < NV; i += 32) { const TS v = srcv[i]; s.qd[i] = (T)v; S.qvel[(size_t)env * NV + i] = v; S.warm[(size_t)env * NV + i] = T(0); }
-  if (lane < NJ) { s.ctrl[lane] = (T)cfg.home[lane] + (T)cfg.offsets[lane]; S.ctrl[(size_t)env * 6 + lane] = s.ctrl[lane]; }
+  if (lane < NA) { s.ctrl[lane] = (T)cfg.home[lane % NJ] + (T)cfg.offsets[lane % NJ]; S.ctrl[(size_t)env * NA + lane] = s.ctrl[lane]; }
   if (lane == 0) { S.step[env] = 0; S.needs_reset[env] = 0; S.episode[env] = ep + 1; }
   __syncwarp();
   write_obs_scene(cfg, S, out, s, env, 0, 0.f, 1.f, SO101_STEP_FIRST, lane);
@@ -593,8 +594,8 @@ __device__ void settle_end_of_step(const EnvState<T> &S, int env, bool diverged)
   const int c = atomicAdd(S.ring_ctr + RC_CLAIM, 1);
   if (c - *((volatile int *)(S.ring_ctr + RC_TAIL)) >= S.ring_cap) { atomicSub(S.ring_ctr + RC_CLAIM, 1); return; }  // ring full: try again next step
   TS *dq = S.ring_q + (size_t)(c % S.ring_cap) * NQ, *dv = S.ring_v + (size_t)(c % S.ring_cap) * NV;
-  for (int i = 0; i < NQ; i++) dq[i] = i < NJ ? TS(0) : S.qpos[(size_t)env * NQ + i];
-  for (int i = 0; i < NV; i++) dv[i] = i < NJ ? TS(0) : S.qvel[(size_t)env * NV + i];
+  for (int i = 0; i < NQ; i++) dq[i] = i < NA ? TS(0) : S.qpos[(size_t)env * NQ + i];
+  for (int i = 0; i < NV; i++) dv[i] = i < NA ? TS(0) : S.qvel[(size_t)env * NV + i];
   S.sstate[env] = SETTLE_SAMPLE; S.attempt[env] = 0; S.draws[env] += 1;
 }
 
@@ -633,7 +634,7 @@ __global__ void __launch_bounds__(WARPS_BROAD * 32) scene_begin_kernel(const __g
     if (lane == 0) pb.active[env] = 0;
     return;
   }
-  if (lane < NJ) S.ctrl[(size_t)env * 6 + lane] = (T)action[(size_t)env * 6 + lane] + (T)cfg.offsets[lane];  // so100_task.py:266-287
+  if (lane < NA) S.ctrl[(size_t)env * NA + lane] = (T)action[(size_t)env * NA + lane] + (T)cfg.offsets[lane % NJ];  // so100_task.py:266-287
   if (lane == 0) { pb.active[env] = 1; pb.flags[env] = 0; }
 }
 
@@ -643,48 +644,29 @@ __global__ void __launch_bounds__(WARPS_BROAD * 32) scene_begin_kernel(const __g
 // friction-loss / limit rows of mj_makeConstraint).  All of it is straight-line scalar code on registers, the same functions
 // the arm-only kernel uses (arm_dynamics.cuh, arm_solver.cuh).
 template <typename T>
-__global__ void __launch_bounds__(KD_THREADS) scene_kindyn_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ ArmModelT<double> am64,
+__global__ void __launch_bounds__(KD_THREADS) scene_kindyn_kernel(const __grid_constant__ ArmSetT<T> am, const __grid_constant__ ArmSetT<double> am64,
                                                                  const __grid_constant__ SceneModel<T> sm, const EnvState<T> S, const PipeBuf<T> pb,
                                                                  int need_dyn) {
   const int env = pb.env0 + blockIdx.x * KD_THREADS + threadIdx.x;
   if (env >= pb.env0 + pb.nenv || !pb.active[env]) return;
   const TS *gq = S.qpos + (size_t)env * NQ, *gv = S.qvel + (size_t)env * NV;
   T *gx = pb.xpos + (size_t)env * (NSLOT * 3), *gm = pb.xmat + (size_t)env * (NSLOT * 9), *gd = pb.dyn + (size_t)env * DYNW;
-  // the arm's smooth dynamics run in float64 on the float64 state in both precisions (env_state.cuh); what the float32
-  // collision and solve kernels read (poses, mass matrix, qacc_smooth, rows) is rounded when it is stored
-  double qa[NJ], qda[NJ];
-  T ca[NJ];
-#pragma unroll
-  for (int i = 0; i < NJ; i++) { qa[i] = gq[i]; qda[i] = gv[i]; ca[i] = S.ctrl[(size_t)env * 6 + i]; }
-  ArmKin<double> k;
-  {
-    double R[NJ][9];
-    arm_fk<double>(am64, qa, k, R);
-#pragma unroll
-    for (int i = 0; i < NJ; i++) {
-      gx[3 * i] = (T)k.p[i].x; gx[3 * i + 1] = (T)k.p[i].y; gx[3 * i + 2] = (T)k.p[i].z;
-      gd[DYN_P + 3 * i] = (T)k.p[i].x; gd[DYN_P + 3 * i + 1] = (T)k.p[i].y; gd[DYN_P + 3 * i + 2] = (T)k.p[i].z;
-      gd[DYN_A + 3 * i] = (T)k.a[i].x; gd[DYN_A + 3 * i + 1] = (T)k.a[i].y; gd[DYN_A + 3 * i + 2] = (T)k.a[i].z;
-#pragma unroll
-      for (int e = 0; e < 9; e++) gm[9 * i + e] = (T)R[i][e];
-    }
-  }
   const bool dyn = need_dyn && !pb.flags[env];  // (a diverged env is frozen for the rest of the control step)
 #pragma unroll 1
   for (int p = 0; p < NPROP; p++) {
-    const TS *qp = gq + NJ + 7 * p;
+    const TS *qp = gq + NA + 7 * p;
     const T quat[4] = {(T)qp[3], (T)qp[4], (T)qp[5], (T)qp[6]};
     T Rp[9];
     prop_rotation(quat, Rp);
 #pragma unroll
-    for (int c = 0; c < 3; c++) gx[3 * (NJ + p) + c] = (T)qp[c];
+    for (int c = 0; c < 3; c++) gx[3 * (NA + p) + c] = (T)qp[c];
 #pragma unroll
-    for (int e = 0; e < 9; e++) gm[9 * (NJ + p) + e] = Rp[e];
+    for (int e = 0; e < 9; e++) gm[9 * (NA + p) + e] = Rp[e];
     if (dyn) {
       T qdp[6], M[21], bias[6], x[6];
 #pragma unroll
-      for (int i = 0; i < 6; i++) qdp[i] = (T)gv[NJ + 6 * p + i];
-      prop_dynamics(sm, am, Rp, qdp, p, M, bias);
+      for (int i = 0; i < 6; i++) qdp[i] = (T)gv[NA + 6 * p + i];
+      prop_dynamics(sm, am[0], Rp, qdp, p, M, bias);
 #pragma unroll
       for (int i = 0; i < 21; i++) gd[DYN_MPROP + 21 * p + i] = M[i];
 #pragma unroll
@@ -692,29 +674,53 @@ __global__ void __launch_bounds__(KD_THREADS) scene_kindyn_kernel(const __grid_c
       chol6(M);
       chol6_solve(M, x);
 #pragma unroll
-      for (int i = 0; i < 6; i++) gd[DYN_QACC + NJ + 6 * p + i] = x[i];
+      for (int i = 0; i < 6; i++) gd[DYN_QACC + NA + 6 * p + i] = x[i];
     }
   }
-  if (!dyn) return;
-  double M[21], bias[NJ], frc[NJ], qs[NJ], L[21];
-  arm_crb_rne(am64, k, qda, M, bias);
-  arm_actuation_d(am, qa, qda, ca, frc);
-  gd[DYN_VELMASK] = (T)arm_actuation_vel_mask(am, frc);
+  // each arm's smooth dynamics run in float64 on the float64 state in both precisions (env_state.cuh); what the float32
+  // collision and solve kernels read (poses, mass matrix, qacc_smooth, rows) is rounded when it is stored
+#pragma unroll 1
+  for (int arm = 0; arm < NARM; arm++) {
+    const int o = NJ * arm;   // first dof / pose slot / actuator of this arm
+    double qa[NJ], qda[NJ];
+    T ca[NJ];
 #pragma unroll
-  for (int i = 0; i < 21; i++) { L[i] = M[i]; gd[DYN_MARM + i] = (T)M[i]; }
-  chol6(L);
+    for (int i = 0; i < NJ; i++) { qa[i] = gq[o + i]; qda[i] = gv[o + i]; ca[i] = S.ctrl[(size_t)env * NA + o + i]; }
+    ArmKin<double> k;
+    {
+      double R[NJ][9];
+      arm_fk<double>(am64[arm], qa, k, R);
 #pragma unroll
-  for (int i = 0; i < NJ; i++) qs[i] = frc[i] - bias[i];
-  chol6_solve(L, qs);
-  T qaT[NJ], qdaT[NJ], qsT[NJ];
+      for (int i = 0; i < NJ; i++) {
+        gx[3 * (o + i)] = (T)k.p[i].x; gx[3 * (o + i) + 1] = (T)k.p[i].y; gx[3 * (o + i) + 2] = (T)k.p[i].z;
+        gd[DYN_P + 3 * (o + i)] = (T)k.p[i].x; gd[DYN_P + 3 * (o + i) + 1] = (T)k.p[i].y; gd[DYN_P + 3 * (o + i) + 2] = (T)k.p[i].z;
+        gd[DYN_A + 3 * (o + i)] = (T)k.a[i].x; gd[DYN_A + 3 * (o + i) + 1] = (T)k.a[i].y; gd[DYN_A + 3 * (o + i) + 2] = (T)k.a[i].z;
 #pragma unroll
-  for (int i = 0; i < NJ; i++) { qaT[i] = (T)qa[i]; qdaT[i] = (T)qda[i]; qsT[i] = (T)qs[i]; }
-  ArmRows<T> arows;
-  arm_make_rows(am, qaT, qdaT, qsT, arows);
+        for (int e = 0; e < 9; e++) gm[9 * (o + i) + e] = (T)R[i][e];
+      }
+    }
+    if (!dyn) continue;
+    double M[21], bias[NJ], frc[NJ], qs[NJ], L[21];
+    arm_crb_rne(am64[arm], k, qda, M, bias);
+    arm_actuation_d(am[arm], qa, qda, ca, frc);
+    gd[DYN_VELMASK + arm] = (T)arm_actuation_vel_mask(am[arm], frc);
 #pragma unroll
-  for (int i = 0; i < NJ; i++) {
-    gd[DYN_QACC + i] = qsT[i];
-    gd[DYN_ROWS + i] = arows.jar0_f[i]; gd[DYN_ROWS + 6 + i] = arows.jar0_l[i]; gd[DYN_ROWS + 12 + i] = arows.D_l[i]; gd[DYN_ROWS + 18 + i] = arows.js[i];
+    for (int i = 0; i < 21; i++) { L[i] = M[i]; gd[DYN_MARM + 21 * arm + i] = (T)M[i]; }
+    chol6(L);
+#pragma unroll
+    for (int i = 0; i < NJ; i++) qs[i] = frc[i] - bias[i];
+    chol6_solve(L, qs);
+    T qaT[NJ], qdaT[NJ], qsT[NJ];
+#pragma unroll
+    for (int i = 0; i < NJ; i++) { qaT[i] = (T)qa[i]; qdaT[i] = (T)qda[i]; qsT[i] = (T)qs[i]; }
+    ArmRows<T> arows;
+    arm_make_rows(am[arm], qaT, qdaT, qsT, arows);
+#pragma unroll
+    for (int i = 0; i < NJ; i++) {
+      gd[DYN_QACC + o + i] = qsT[i];
+      T *gr = gd + DYN_ROWS + 24 * arm;
+      gr[i] = arows.jar0_f[i]; gr[6 + i] = arows.jar0_l[i]; gr[12 + i] = arows.D_l[i]; gr[18 + i] = arows.js[i];
+    }
   }
 }
 
@@ -746,7 +752,7 @@ __global__ void __launch_bounds__(WARPS_BROAD * 32) scene_broad_kernel(const __g
   } else {
     for (int i = lane; i < NQ; i += 32) s.q[i] = (T)S.qpos[(size_t)env * NQ + i];
     for (int i = lane; i < NV; i += 32) s.qd[i] = (T)S.qvel[(size_t)env * NV + i];
-    if (lane < NJ) s.ctrl[lane] = S.ctrl[(size_t)env * 6 + lane];
+    if (lane < NA) s.ctrl[lane] = S.ctrl[(size_t)env * NA + lane];
     __syncwarp();
     const int t = S.step[env] + 1;
     float reward = scene_reward(sm, s), discount = 1.f;
@@ -928,7 +934,7 @@ __device__ __forceinline__ bool gather_contacts(const SceneModel<T> &sm, const P
     mykey[k] = i < nraw ? keys[i] : 0x7fffffff; rank[k] = 0;
     if (i < nraw) {
       const int s1 = sm.body_slot[sm.geom_body[(mykey[k] >> 8) & 0xff]], s2 = sm.body_slot[sm.geom_body[mykey[k] & 0xff]];
-      const int a1 = s1 < 0 ? 31 : (s1 < NJ ? 0 : s1), a2 = s2 < 0 ? 31 : (s2 < NJ ? 0 : s2);
+      const int a1 = s1 < 0 ? 31 : (s1 < NA ? s1 / NJ : s1), a2 = s2 < 0 ? 31 : (s2 < NA ? s2 / NJ : s2);   // dof block of each side
       nblk += (a1 != 31) + (a2 != 31 && a2 != a1);
     }
   }
@@ -968,7 +974,7 @@ __device__ __forceinline__ bool gather_contacts(const SceneModel<T> &sm, const P
 // One substep of one env (warp): constraint rows from the gathered contacts and the dyn record, Newton, semi-implicit Euler.  Returns false if the env must be
 // handled by the large solver tier instead (nothing has been modified in that case).
 template <typename T, typename SC>
-__device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
+__device__ __forceinline__ bool solve_env(const ArmSetT<T> &am, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> &pb,
                                           const so101_step_out &out, int sub, int env, SC &s, int lane) {
   prof_begin(s, S, lane);
   for (int i = lane; i < NQ; i += 32) s.q[i] = (T)S.qpos[(size_t)env * NQ + i];
@@ -991,7 +997,7 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
     for (int c = lane; c < s.ncon; c += 32) {
       if (!(s.sol.v.con.dist[c] < T(0))) continue;
       const int s1 = sm.body_slot[sm.geom_body[s.sol.v.con.g1[c]]], s2 = sm.body_slot[sm.geom_body[s.sol.v.con.g2[c]]];
-      if ((s1 >= NJ && S.place.check_collisions[s1 - NJ]) || (s2 >= NJ && S.place.check_collisions[s2 - NJ])) hit = true;
+      if ((s1 >= NA && S.place.check_collisions[s1 - NA]) || (s2 >= NA && S.place.check_collisions[s2 - NA])) hit = true;
     }
     if (__any_sync(FULL, hit)) {
       int give_up = 0;
@@ -1041,31 +1047,34 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
     T qacc_int = qacc;   // acceleration the velocity update uses (differs from qacc under implicitfast only)
     // The update itself runs in float64 on the float64 state (env_state.cuh): velocity first, then positions with the new
     // velocity; free-joint quaternions are advanced by the body-frame angular velocity and renormalised.
-    const TS h = am.dt_d;
+    const TS h = am[0].dt_d;
     TS qd_new = TS(0);
     if (cfg.integrator == 1) {
       // implicitfast ([upstream] mj_implicit): the arm's velocity update uses x = qacc + (M - h D)^-1 h D qacc, D = the unclamped
       // actuators' velocity gain (arm_dynamics.cuh); the free props have no velocity-dependent smooth force (x = qacc)
-      T qa6[NJ], dv[NJ], cr[NJ], Mm[21];
-      const unsigned vm = (unsigned)pb.dyn[(size_t)env * DYNW + DYN_VELMASK];
+#pragma unroll 1
+      for (int k = 0; k < NARM; k++) {
+        T qa6[NJ], dv[NJ], cr[NJ], Mm[21];
+        const unsigned vm = (unsigned)pb.dyn[(size_t)env * DYNW + DYN_VELMASK + k];
 #pragma unroll
-      for (int i = 0; i < NJ; i++) { qa6[i] = __shfl_sync(FULL, qacc, i); dv[i] = ((vm >> i) & 1u) ? (T)am.bias_d[i][2] : T(0); }
+        for (int i = 0; i < NJ; i++) { qa6[i] = __shfl_sync(FULL, qacc, NJ * k + i); dv[i] = ((vm >> i) & 1u) ? (T)am[k].bias_d[i][2] : T(0); }
 #pragma unroll
-      for (int i = 0; i < 21; i++) Mm[i] = s.Marm[i];
-      implicitfast_correction<T>(Mm, dv, (T)h, qa6, cr);
-      T mine = T(0);
+        for (int i = 0; i < 21; i++) Mm[i] = s.Marm[k][i];
+        implicitfast_correction<T>(Mm, dv, (T)h, qa6, cr);
+        T mine = T(0);
 #pragma unroll
-      for (int i = 0; i < NJ; i++) if (lane == i) mine = cr[i];
-      if (lane < NJ && !badnow) qacc_int = qacc + mine;
+        for (int i = 0; i < NJ; i++) if (lane == NJ * k + i) mine = cr[i];
+        if (lane >= NJ * k && lane < NJ * (k + 1) && !badnow) qacc_int = qacc + mine;
+      }
     }
     if (lane < NV) {
       // SETTLE mode: the arm is frozen ([upstream] JointStaticIsolator restores the non-prop joints after every settle step)
-      qd_new = (badnow || (mode && lane < NJ)) ? TS(0) : S.qvel[(size_t)env * NV + lane] + h * (TS)qacc_int;
+      qd_new = (badnow || (mode && lane < NA)) ? TS(0) : S.qvel[(size_t)env * NV + lane] + h * (TS)qacc_int;
       S.qvel[(size_t)env * NV + lane] = qd_new;
       S.warm[(size_t)env * NV + lane] = qacc;
     }
     if (mode && !badnow) {  // [upstream] PropPlacer settle test after every physics step: props' max |qvel|, max |qacc|
-      T mv = (lane >= NJ && lane < NV) ? (T)t_abs(qd_new) : T(0), ma = (lane >= NJ && lane < NV) ? t_abs(qacc) : T(0);
+      T mv = (lane >= NA && lane < NV) ? (T)t_abs(qd_new) : T(0), ma = (lane >= NA && lane < NV) ? t_abs(qacc) : T(0);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { mv = max(mv, __shfl_xor_sync(FULL, mv, o)); ma = max(ma, __shfl_xor_sync(FULL, ma, o)); }
       if (lane == 0) {
@@ -1078,15 +1087,17 @@ __device__ __forceinline__ bool solve_env(const ArmModelT<T> &am, const SceneMod
         }
       }
     }
-    TS pv[6];  // the six velocities of prop (lane - 8), gathered from the dof lanes
+    constexpr int PL = NV;   // lanes PL, PL + 1 integrate the two free joints
+    static_assert(PL + NPROP <= 32, "prop lanes");
+    TS pv[6];  // the six velocities of prop (lane - PL), gathered from the dof lanes
 #pragma unroll
     for (int c = 0; c < 6; c++) {
-      const TS a0 = __shfl_sync(FULL, qd_new, NJ + c), a1 = __shfl_sync(FULL, qd_new, NJ + 6 + c);
-      pv[c] = lane == 9 ? a1 : a0;
+      const TS a0 = __shfl_sync(FULL, qd_new, NA + c), a1 = __shfl_sync(FULL, qd_new, NA + 6 + c);
+      pv[c] = lane == PL + 1 ? a1 : a0;
     }
-    if (lane < NJ) S.qpos[(size_t)env * NQ + lane] += h * qd_new;
-    if (lane >= 8 && lane < 8 + NPROP) {
-      TS *qp = S.qpos + (size_t)env * NQ + NJ + 7 * (lane - 8);
+    if (lane < NA) S.qpos[(size_t)env * NQ + lane] += h * qd_new;
+    if (lane >= PL && lane < PL + NPROP) {
+      TS *qp = S.qpos + (size_t)env * NQ + NA + 7 * (lane - PL);
       for (int c = 0; c < 3; c++) qp[c] += h * pv[c];
       const TS w[3] = {pv[3], pv[4], pv[5]};
       const TS nw = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]), ang = nw * h;
@@ -1121,7 +1132,7 @@ __global__ void scene_classify_kernel(const __grid_constant__ SceneModel<T> sm, 
   for (int i = 0; i < n; i++) {
     const int k = keys[i];
     const int s1 = sm.body_slot[sm.geom_body[(k >> 8) & 0xff]], s2 = sm.body_slot[sm.geom_body[k & 0xff]];
-    const int a1 = s1 < 0 ? 31 : (s1 < NJ ? 0 : s1), a2 = s2 < 0 ? 31 : (s2 < NJ ? 0 : s2);
+    const int a1 = s1 < 0 ? 31 : (s1 < NA ? s1 / NJ : s1), a2 = s2 < 0 ? 31 : (s2 < NA ? s2 / NJ : s2);
     nblk += (a1 != 31) + (a2 != 31 && a2 != a1);
   }
   const int tier = (n <= NC_S && nblk <= NB_S) ? 0 : ((n <= NC_M && nblk <= NB_M) ? 1 : 2);
@@ -1131,7 +1142,7 @@ __global__ void scene_classify_kernel(const __grid_constant__ SceneModel<T> sm, 
 
 // Tier 0: warp per env (every env whose contacts fit the small scratch).
 template <typename T>
-__global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_solve_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
+__global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_solve_kernel(const __grid_constant__ ArmSetT<T> am, const __grid_constant__ SceneModel<T> sm,
                                                                       const __grid_constant__ StepCfg cfg, const EnvState<T> S, const PipeBuf<T> pb,
                                                                       const so101_step_out out, int sub) {
   using SC = Scratch<T, NC_S, NB_S>;
@@ -1145,7 +1156,7 @@ __global__ void __launch_bounds__(WARPS_SOLVE * 32) scene_solve_kernel(const __g
 }
 // Tiers 1 and 2: persistent CTAs walk the tier's queue (filled by the previous tier during this substep).
 template <typename T, int NC, int NB, int WARPS, int TIER>
-__global__ void __launch_bounds__(WARPS * 32) scene_solve_tier_kernel(const __grid_constant__ ArmModelT<T> am, const __grid_constant__ SceneModel<T> sm,
+__global__ void __launch_bounds__(WARPS * 32) scene_solve_tier_kernel(const __grid_constant__ ArmSetT<T> am, const __grid_constant__ SceneModel<T> sm,
                                                                      const __grid_constant__ StepCfg cfg, const EnvState<T> S, const PipeBuf<T> pb,
                                                                      const so101_step_out out, int sub) {
   using SC = Scratch<T, NC, NB>;
@@ -1212,19 +1223,17 @@ void scene_nprof(unsigned long long out[16]) { cudaMemcpyFromSymbol(out, g_nprof
 // Launches of one control step: per pipeline group 1 memset + 3 + 8 * nsub kernels on the group's streams, forked from and
 // joined back into the caller's stream.  Returns the kernel count.
 template <typename T>
-int launch_scene_step(const ArmModelT<T> &am, const ArmModelT<double> &am64, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> *pbs,
+int launch_scene_step(const ArmSetT<T> &am, const ArmSetT<double> &am64, const SceneModel<T> &sm, const StepCfg &cfg, const EnvState<T> &S, const PipeBuf<T> *pbs,
                       TierExec *txs, int ngroups, const float *action, const so101_step_out &out, cudaStream_t stream, KernelTimer *kt) {
-  static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   const size_t smem_env = sizeof(Scratch<T, NC_S, NB_S>) * WARPS_SOLVE,
                smem_m = sizeof(Scratch<T, NC_M, NB_M>) * WARPS_M, smem_l = sizeof(Scratch<T, NC_L, NB_L>) * WARPS_L;
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaFuncSetAttribute(scene_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
-    cudaFuncSetAttribute(scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
-    cudaFuncSetAttribute(scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
+  // (no function-local statics here: template statics are process-wide unique symbols, and the one-arm and the two-arm builds
+  // of this library can be loaded into the same process)
+  cudaFuncSetAttribute(scene_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
+  cudaFuncSetAttribute(scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
+  cudaFuncSetAttribute(scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
   KernelTimer none;
   KernelTimer &t = kt ? *kt : none;
   cudaEventRecord(txs[0].start, stream);  // every group starts after the work already queued on the caller's stream
@@ -1248,9 +1257,9 @@ int launch_scene_step(const ArmModelT<T> &am, const ArmModelT<double> &am64, con
     t.end(0, st);
     refresh(pb, st, 0, false);
   }
-  static int sm_count[64] = {};  // SMs of the device the handle lives on (148 on B200): grids are sized in multiples of it
-  if (dev >= 0 && dev < 64 && sm_count[dev] == 0) { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); sm_count[dev] = v > 0 ? v : 148; }
-  const int sms = (dev >= 0 && dev < 64) ? sm_count[dev] : 148;
+  int sms = 0;   // SMs of the device the handle lives on (148 on B200): grids are sized in multiples of it
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  const int seq_per_sm = getenv("SO101_SEQ_CTAS") ? atoi(getenv("SO101_SEQ_CTAS")) : 16;  // narrow-phase CTAs of 64 threads per SM
   for (int sub = 0; sub < cfg.nsub; sub++) {
     for (int g = 0; g < ngroups; g++) {
       const PipeBuf<T> &pb = pbs[g];
@@ -1258,7 +1267,6 @@ int launch_scene_step(const ArmModelT<T> &am, const ArmModelT<double> &am64, con
       cudaStream_t st = tx.main;
       const int grid_env = (pb.nenv + WARPS_SOLVE - 1) / WARPS_SOLVE;
       const int grid_gjk = max(1, min(sms * 16, (pb.nenv * 16 + GJK_THREADS - 1) / GJK_THREADS));
-      static const int seq_per_sm = getenv("SO101_SEQ_CTAS") ? atoi(getenv("SO101_SEQ_CTAS")) : 16;  // CTAs of 64 threads per SM
       const int grid_seq = max(1, min(sms * seq_per_sm, (pb.nenv * 12 + NSEQ_THREADS - 1) / NSEQ_THREADS));
       const int grid_m = pb.nenv < sms * 8 ? pb.nenv : sms * 8, grid_l = pb.nenv < sms * 4 ? pb.nenv : sms * 4;
       t.begin(5, st);
@@ -1309,8 +1317,8 @@ template <typename T>
 __global__ void settle_leave_kernel(const EnvState<T> S) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= S.NU) return;
-  for (int i = 0; i < NQ; i++) S.init_qpos[(size_t)env * NQ + i] = i < NJ ? TS(0) : S.qpos[(size_t)env * NQ + i];
-  for (int i = 0; i < NV; i++) S.init_qvel[(size_t)env * NV + i] = i < NJ ? TS(0) : S.qvel[(size_t)env * NV + i];
+  for (int i = 0; i < NQ; i++) S.init_qpos[(size_t)env * NQ + i] = i < NA ? TS(0) : S.qpos[(size_t)env * NQ + i];
+  for (int i = 0; i < NV; i++) S.init_qvel[(size_t)env * NV + i] = i < NA ? TS(0) : S.qvel[(size_t)env * NV + i];
   S.mode[env] = 0; S.sstate[env] = SETTLE_SAMPLE; S.episode[env] = 0; S.draws[env] += 1;
 }
 template <typename T>

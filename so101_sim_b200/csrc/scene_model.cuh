@@ -17,9 +17,10 @@ namespace so101 {
 enum { G_PLANE = 0, G_SPHERE = 1, G_CAPSULE = 2, G_CYLINDER = 3, G_BOX = 4, G_HULL = 5 };
 constexpr int NPROP = 2;
 constexpr int MAXREWARDBOX = 2;  // container overlap boxes (banana / bowl: 1, pen / utensil holder: 2)
-constexpr int NSLOT = NJ + NPROP;   // dynamic bodies whose pose lives in shared memory: 6 arm links + 2 props
-constexpr int NV = NJ + 6 * NPROP;  // 18
-constexpr int NQ = NJ + 7 * NPROP;  // 20
+constexpr int NSLOT = NA + NPROP;   // dynamic bodies whose pose lives in shared memory: 6 links per arm + 2 props
+constexpr int NV = NA + 6 * NPROP;  // 18 (one arm) / 24 (two arms)
+constexpr int NQ = NA + 7 * NPROP;  // 20 / 26
+constexpr int NBLK = NARM + NPROP;  // 6-dof blocks of the mass matrix: one per arm, one per prop
 
 template <typename T>
 struct alignas(16) Vec4 {
@@ -100,7 +101,7 @@ struct SceneModelHost {
   void build(const Blob &b) {
     const int nbody = b.scalar("nbody"), ngeom = b.scalar("ngeom");
     if (b.scalar("nq") != NQ || b.scalar("nv") != NV || b.scalar("nprop") != NPROP)
-      throw std::runtime_error("scene kernel expects the 6-dof arm + 2 free props (nq=20, nv=18)");
+      throw std::runtime_error("this build of the scene kernels expects " + std::to_string(NARM) + " 6-dof arm(s) + 2 free props");
     const auto &bp = b.I("body_parent"), &bw = b.I("body_weld"), &jb = b.I("jnt_body"), &jt = b.I("jnt_type");
     // world poses of all bodies at qpos0 (only the static ones are used)
     std::vector<double> xpos(3 * nbody, 0.0), xmat(9 * nbody, 0.0);
@@ -120,12 +121,12 @@ struct SceneModelHost {
       }
     }
     std::vector<int> slot(nbody, -1);
-    for (int j = 0; j < NJ; j++) slot[jb[j]] = j;
+    for (int j = 0; j < NA; j++) slot[jb[j]] = j;
     int np = 0;
-    for (size_t j = NJ; j < jt.size(); j++) {
-      if (jt[j] != 0) throw std::runtime_error("joints after the arm must be free joints");
-      if (b.I("jnt_qposadr")[j] != NJ + 7 * np || b.I("jnt_dofadr")[j] != NJ + 6 * np) throw std::runtime_error("unexpected prop state layout");
-      slot[jb[j]] = NJ + np++;
+    for (size_t j = NA; j < jt.size(); j++) {
+      if (jt[j] != 0) throw std::runtime_error("joints after the arms must be free joints");
+      if (b.I("jnt_qposadr")[j] != NA + 7 * np || b.I("jnt_dofadr")[j] != NA + 6 * np) throw std::runtime_error("unexpected prop state layout");
+      slot[jb[j]] = NA + np++;
     }
     for (int i = 1; i < nbody; i++)
       if (slot[i] < 0 && bw[i] != 0) throw std::runtime_error("dynamic body without a pose slot");

@@ -45,7 +45,7 @@ struct SolveScratch {
   T D0[NC], mu[NC], fri[3][NC];
   int info[NC];            // dim | baseA << 8 | baseB << 16   (dof base 0 / 6 / 12, 31 = no block)
   int blk[2][NC];          // pool index of block A / block B (-1 = none)
-  unsigned bmask[3][(NC + 31) / 32];  // contacts touching the arm / banana / bowl
+  unsigned bmask[NBLK][(NC + 31) / 32];  // contacts touching each 6-dof block (arm(s), object, container)
   union V {
     struct Con { T pos[3][NC], frame[9][NC], dist[NC]; int g1[NC], g2[NC]; } con;  // gathered contacts (until the rows are built)
     struct Ls { T jv[6][NC], frc[6][NC]; } ls;                                     // J search, cone forces (Newton iterations)
@@ -69,7 +69,7 @@ __device__ __forceinline__ void build_rows(const SceneModel<T> &sm, S &s, int &d
     if (valid) {
       g1 = R.v.con.g1[c]; g2 = R.v.con.g2[c];
       s1 = sm.body_slot[sm.geom_body[g1]]; s2 = sm.body_slot[sm.geom_body[g2]];
-      const int a1 = s1 < 0 ? 31 : (s1 < NJ ? 0 : NJ + 6 * (s1 - NJ)), a2 = s2 < 0 ? 31 : (s2 < NJ ? 0 : NJ + 6 * (s2 - NJ));
+      const int a1 = s1 < 0 ? 31 : (s1 < NA ? NJ * (s1 / NJ) : NA + 6 * (s1 - NA)), a2 = s2 < 0 ? 31 : (s2 < NA ? NJ * (s2 / NJ) : NA + 6 * (s2 - NA));
       nb = (a1 != 31) + (a2 != 31 && a2 != a1);
     }
     int incl = nb;
@@ -135,17 +135,18 @@ __device__ __forceinline__ void build_rows(const SceneModel<T> &sm, S &s, int &d
           const int sl = side ? s2 : s1;
           if (sl < 0) continue;
           const T sgn = side ? T(1) : T(-1);
-          const int base = sl < NJ ? 0 : NJ + 6 * (sl - NJ);
+          const int base = sl < NA ? NJ * (sl / NJ) : NA + 6 * (sl - NA);   // first dof of the body's block
+          const int link = sl < NA ? sl - base : 0;                           // arm link index within its chain
           int bi;
           if (baseA == 31 || baseA == base) { baseA = base; bA = my_blk; bi = bA; }
           else { baseB = base; bB = my_blk + 1; bi = bB; }
 #pragma unroll 1
           for (int col = 0; col < 6; col++) {
             T tr[3] = {T(0), T(0), T(0)}, ro[3] = {T(0), T(0), T(0)};
-            if (sl < NJ) {
-              if (col > sl) continue;
-              const T a[3] = {s.arm_a[col][0], s.arm_a[col][1], s.arm_a[col][2]};
-              const T r[3] = {pos[0] - s.arm_p[col][0], pos[1] - s.arm_p[col][1], pos[2] - s.arm_p[col][2]};
+            if (sl < NA) {
+              if (col > link) continue;
+              const T a[3] = {s.arm_a[base + col][0], s.arm_a[base + col][1], s.arm_a[base + col][2]};
+              const T r[3] = {pos[0] - s.arm_p[base + col][0], pos[1] - s.arm_p[base + col][1], pos[2] - s.arm_p[base + col][2]};
               cross3(tr, a, r);
               ro[0] = a[0]; ro[1] = a[1]; ro[2] = a[2];
             } else if (col < 3) {
@@ -188,7 +189,7 @@ __device__ __forceinline__ void build_rows(const SceneModel<T> &sm, S &s, int &d
     }
     // contacts per body
 #pragma unroll
-    for (int b = 0; b < 3; b++) {
+    for (int b = 0; b < NBLK; b++) {
       const bool t = valid && ((bA >= 0 && baseA == 6 * b) || (bB >= 0 && baseB == 6 * b));
       const unsigned m = __ballot_sync(FULL, t);
       if (lane == 0) R.bmask[b][c0 >> 5] = m;
@@ -261,13 +262,14 @@ __device__ __forceinline__ int cone_eval(const Cone<T> &k, const T *x, T &cost, 
 template <typename T, typename S>
 __device__ __forceinline__ T blockdiag_mv(const S &s, const T *x, int i) {  // (M x)_i for i < NV
   T acc = T(0);
-  if (i < NJ) {
+  if (i < NA) {
+    const int k = i / NJ, li = i % NJ;
 #pragma unroll
-    for (int j = 0; j < NJ; j++) acc += (j <= i ? s.Marm[tri(i, j)] : s.Marm[tri(j, i)]) * x[j];
+    for (int j = 0; j < NJ; j++) acc += (j <= li ? s.Marm[k][tri(li, j)] : s.Marm[k][tri(j, li)]) * x[NJ * k + j];
   } else {
-    const int p = (i - NJ) / 6, li = (i - NJ) % 6;
+    const int p = (i - NA) / 6, li = (i - NA) % 6;
 #pragma unroll
-    for (int j = 0; j < 6; j++) acc += (j <= li ? s.Mprop[p][tri(li, j)] : s.Mprop[p][tri(j, li)]) * x[NJ + 6 * p + j];
+    for (int j = 0; j < 6; j++) acc += (j <= li ? s.Mprop[p][tri(li, j)] : s.Mprop[p][tri(j, li)]) * x[NA + 6 * p + j];
   }
   return acc;
 }
@@ -295,7 +297,7 @@ __device__ __forceinline__ void contacts_Jx(S &s, const T *x, int lane) {  // ->
   __syncwarp();
 }
 
-// per-lane view of the arm's friction-loss / limit rows (lane i < NJ owns joint i)
+// per-lane view of the arms' friction-loss / limit rows (lane i < NA owns arm dof i)
 template <typename T>
 struct ArmLane {
   T jar0_f, eta, rf, frD, jar0_l, D_l, js;
@@ -322,7 +324,7 @@ __device__ __noinline__ void rows_line(S &s, const ArmLane<T> &al, T impratio, T
     for (int r = 0; r < 6; r++) { lg -= force[r] * jv[r]; a1 += v1[r] * jv[r]; a2 += v2[r] * jv[r]; lh += e[r] * jv[r] * jv[r]; }
     lh += a1 * a1 - a2 * a2;
   }
-  if (lane < NJ) {
+  if (lane < NA) {
     const T sv = s.search[lane];
     const T x = al.jar0_f + s.delta[lane] + alpha * sv;
     if (x <= -al.rf) { lc += al.eta * (T(-0.5) * al.rf - x); lg -= al.eta * sv; }
@@ -444,10 +446,10 @@ __device__ __forceinline__ void assemble(S &s, T f_arm, T hdiag_arm, int lane) {
   const int ti = tri_row(lane), tj = lane - ti * (ti + 1) / 2;
   const int gk = lane - 21;  // gradient entry owned by lanes 21..26
 #pragma unroll 1
-  for (int b = 0; b < 3; b++) {
+  for (int b = 0; b < NBLK; b++) {
     const int base = 6 * b;
     T acc = T(0);
-    if (lane < 21) acc = b == 0 ? s.Marm[lane] : s.Mprop[b - 1][lane];
+    if (lane < 21) acc = b < NARM ? s.Marm[b][lane] : s.Mprop[b - NARM][lane];
     T gacc = T(0);
 #pragma unroll 1
     for (int ch = 0; ch < NCH; ch++) {
@@ -468,14 +470,16 @@ __device__ __forceinline__ void assemble(S &s, T f_arm, T hdiag_arm, int lane) {
         }
       }
     }
-    const T hd = __shfl_sync(FULL, hdiag_arm, ti & 31);  // arm row curvature of joint ti lives on lane ti
-    if (lane < 21) s.H[tri(base + ti, base + tj)] = acc + ((b == 0 && ti == tj) ? hd : T(0));
+    const T hd = __shfl_sync(FULL, hdiag_arm, (base + ti) & 31);  // arm row curvature of dof base + ti lives on that lane
+    if (lane < 21) s.H[tri(base + ti, base + tj)] = acc + ((b < NARM && ti == tj) ? hd : T(0));
     else if (lane < 27) s.grad[base + gk] = s.Md[base + gk] - gacc;
   }
   // off-diagonal blocks (hi, lo): only contacts that touch both bodies (grasp, banana in bowl)
 #pragma unroll 1
-  for (int pr = 0; pr < 3; pr++) {
-    const int hi = pr == 0 ? 1 : 2, lo = pr == 2 ? 1 : 0;
+  for (int pr = 0; pr < NBLK * (NBLK - 1) / 2; pr++) {
+    // block pairs (hi, lo), hi > lo, in the order (1,0) (2,0) (2,1) (3,0) ...
+    int hi = 1, lo = pr;
+    while (lo >= hi) { lo -= hi; hi++; }
 #pragma unroll 1
     for (int en = lane; en < 36; en += 32) {
       const int i = en / 6, j = en % 6;
@@ -499,20 +503,22 @@ __device__ __forceinline__ void assemble(S &s, T f_arm, T hdiag_arm, int lane) {
     }
   }
   __syncwarp();
-  if (lane < NJ) s.grad[lane] -= f_arm;
+  if (lane < NA) s.grad[lane] -= f_arm;
   __syncwarp();
 }
 
 // Returns the Newton iteration count.  In: s.delta = warm start (qacc_warmstart - qacc_smooth); out: s.delta = solution.
 template <typename T, typename S>
-__device__ __noinline__ int scene_solve(const ArmModelT<T> &am, T impratio, S &s, int max_iter, T tol, int lane) {
+__device__ __noinline__ int scene_solve(const ArmSetT<T> &ams, T impratio, S &s, int max_iter, T tol, int lane) {
+  const ArmModelT<T> &am = ams[0];   // (solver_scale is a property of the scene, stored with every arm)
   auto &R = s.sol;
   const int ncon = s.ncon;
   const T xeps = sizeof(T) == 8 ? T(1e-14) : T(2e-6);
   ArmLane<T> al{};
-  if (lane < NJ) {
-    al.jar0_f = s.arows.jar0_f[lane]; al.eta = am.frictionloss[lane]; al.rf = am.fr_R[lane] * al.eta; al.frD = am.fr_D[lane];
-    al.jar0_l = s.arows.jar0_l[lane]; al.D_l = s.arows.D_l[lane]; al.js = s.arows.js[lane];
+  if (lane < NA) {
+    const int k = lane / NJ, j = lane % NJ;
+    al.jar0_f = s.arows[k].jar0_f[j]; al.eta = ams[k].frictionloss[j]; al.rf = ams[k].fr_R[j] * al.eta; al.frD = ams[k].fr_D[j];
+    al.jar0_l = s.arows[k].jar0_l[j]; al.D_l = s.arows[k].D_l[j]; al.js = s.arows[k].js[j];
   }
   // warm start: keep it only if it beats delta = 0.  Evaluate both along the line 0 + alpha * warm.
   {
@@ -535,15 +541,17 @@ __device__ __noinline__ int scene_solve(const ArmModelT<T> &am, T impratio, S &s
   }
   // does any contact couple two bodies (grasp, banana in the bowl)?  If not, the Hessian is block diagonal.
   bool decoupled = true;
-  for (int ch = 0; ch < (int)(sizeof(R.bmask[0]) / sizeof(unsigned)); ch++)
-    if ((R.bmask[0][ch] & (R.bmask[1][ch] | R.bmask[2][ch])) | (R.bmask[1][ch] & R.bmask[2][ch])) decoupled = false;
+  for (int ch = 0; ch < (int)(sizeof(R.bmask[0]) / sizeof(unsigned)); ch++) {
+    unsigned seen = 0;
+    for (int b = 0; b < NBLK; b++) { if (seen & R.bmask[b][ch]) decoupled = false; seen |= R.bmask[b][ch]; }
+  }
   int iter = 0;
 #pragma unroll 1
   for (; iter < max_iter; iter++) {
     contacts_eval(s, impratio, lane);
     // arm rows: force and diagonal curvature (lane i < NJ)
     T f_arm = T(0), hdiag = T(0);
-    if (lane < NJ) {
+    if (lane < NA) {
       const T x = al.jar0_f + s.delta[lane];
       if (x <= -al.rf) f_arm = al.eta;
       else if (x >= al.rf) f_arm = -al.eta;

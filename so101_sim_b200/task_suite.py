@@ -116,6 +116,15 @@ class SO100HandOver(SO100Task):
     self.model_name, self.instruction, self.rest_heights = self.CONFIGS[object_name]
 
 
+class SO100TwoArmHandOver(SO100HandOver):
+  """BASELINE config 4 ("hand-over task, two arms"): a LABELLED SYNTHETIC scene.  The reference has no two-SO100 scene (its only
+  two-arm hand-over is the ALOHA task so101_sim/tasks/hand_over.py:122, another robot), so this is scene_pbr.xml with its arm
+  at (+0.12, 0.3) and a second identical arm at (-0.12, 0.3) (tools/compile_model.py two_arm_scene_xml), the reference's table,
+  obstacles, free props, placement distributions and overlap reward.  Actions / joint observations are 12-vectors (arm A then
+  arm B); the kernels are the same sources built for two arms (libso101_b200_2arm.so)."""
+  CONFIGS = {'banana': ('so100_twoarm_banana', 'hand the banana over and put it in the bowl using two SO100 arms', (0.4217, 0.4226))}
+
+
 class SO100ArmOnly(SO100Task):
   """BASELINE config 2: scene_pbr.xml without the free props, collisions off, base-task semantics (reward 0)."""
   model_name = 'so100_arm'
@@ -127,6 +136,7 @@ TASK_FACTORIES = {
     'SO100HandOverBanana': (SO100HandOver, {'object_name': 'banana'}),
     'SO100HandOverPen': (SO100HandOver, {'object_name': 'pen'}),
     'SO100ArmOnly': (SO100ArmOnly, {}),
+    'SO100TwoArmHandOverBanana': (SO100TwoArmHandOver, {'object_name': 'banana'}),   # synthetic (BASELINE config 4), see the class
 }
 
 
@@ -164,11 +174,12 @@ class BatchedEnvironment:
       raise RuntimeError('so101_sim_b200 runs on CUDA devices only (no CPU fallback)')
     if not torch.cuda.is_available():
       raise RuntimeError('CUDA is not available: so101_sim_b200 has no CPU fallback')
-    self._lib = _lib.load()
     self.seed = 0 if seed is None else int(seed)
     self.control_timestep = task.control_timestep
     self.n_substeps = int(round(task.control_timestep / PHYSICS_TIMESTEP))
     self.model = read_blob(task.model_name)
+    self.narm = int(self.model['nu'][0]) // 6
+    self._lib = _lib.load(self.narm)
     with open(blob_path(task.model_name), 'rb') as f:
       blob = f.read()
     offs = np.zeros(6) if calibration_offsets is None else np.asarray(calibration_offsets, dtype=np.float64)
@@ -217,10 +228,10 @@ class BatchedEnvironment:
     dims = [ctypes.c_int() for _ in range(4)]
     self._check(self._lib.so101_dims(self._h, *[ctypes.byref(d) for d in dims]))
     self.nq, self.nv, self.nu, self.nbody = (d.value for d in dims)
-    N, sd = self.num_envs, self.nq + self.nv
+    N, sd, nu = self.num_envs, self.nq + self.nv, self.nu
     f32 = dict(dtype=torch.float32, device=self.device)
-    self._buf = dict(commanded_joints_pos=torch.zeros(N, 6, **f32), joints_pos=torch.zeros(N, 6, **f32),
-                     undelayed_joints_pos=torch.zeros(N, 6, **f32), physics_state=torch.zeros(N, sd, **f32),
+    self._buf = dict(commanded_joints_pos=torch.zeros(N, nu, **f32), joints_pos=torch.zeros(N, nu, **f32),
+                     undelayed_joints_pos=torch.zeros(N, nu, **f32), physics_state=torch.zeros(N, sd, **f32),
                      delayed_physics_state=torch.zeros(N, sd, **f32), reward=torch.zeros(N, **f32), discount=torch.ones(N, **f32),
                      step_type=torch.zeros(N, dtype=torch.uint8, device=self.device))
     self._empty = torch.zeros(N, 0, **f32)  # joints_vel is an EMPTY array in the reference (so100_task.py:357-364)
@@ -247,13 +258,15 @@ class BatchedEnvironment:
     """so100_task.py:232-251 — not enforced on step (neither dm_control nor the task clips actions)."""
     lo = self.model['act_ctrlrange'].reshape(-1, 2)[:, 0].astype(np.float32)
     hi = self.model['act_ctrlrange'].reshape(-1, 2)[:, 1].astype(np.float32)
-    lo[0], hi[0] = -self.task.rotation_joint_limit, self.task.rotation_joint_limit
-    lo[5], hi[5] = SO100_GRIPPER_CTRL_CLOSE, SO100_GRIPPER_CTRL_OPEN
-    return BoundedArraySpec(shape=(6,), dtype=np.float32, minimum=lo, maximum=hi)
+    for k in range(self.narm):   # per arm: rotation joint limit on the first actuator, gripper range on the last
+      lo[6 * k], hi[6 * k] = -self.task.rotation_joint_limit, self.task.rotation_joint_limit
+      lo[6 * k + 5], hi[6 * k + 5] = SO100_GRIPPER_CTRL_CLOSE, SO100_GRIPPER_CTRL_OPEN
+    return BoundedArraySpec(shape=(self.nu,), dtype=np.float32, minimum=lo, maximum=hi)
 
   def observation_spec(self):
     sd = self.nq + self.nv
-    shapes = dict(commanded_joints_pos=(6,), joints_pos=(6,), joints_vel=(0,), physics_state=(sd,), undelayed_joints_pos=(6,),
+    nu = self.nu
+    shapes = dict(commanded_joints_pos=(nu,), joints_pos=(nu,), joints_vel=(0,), physics_state=(sd,), undelayed_joints_pos=(nu,),
                   undelayed_joints_vel=(0,), delayed_physics_state=(sd,))
     return collections.OrderedDict((k, shapes[k]) for k in OBSERVATION_KEYS)
 
@@ -272,8 +285,8 @@ class BatchedEnvironment:
     """composer.Environment.step(action) for all envs; action float32 [N,6] on the env's device."""
     if not isinstance(action, torch.Tensor):
       action = torch.as_tensor(np.asarray(action), dtype=torch.float32)
-    if action.shape != (self.num_envs, 6):
-      raise ValueError(f'action must have shape [{self.num_envs}, 6], got {tuple(action.shape)}')
+    if action.shape != (self.num_envs, self.nu):
+      raise ValueError(f'action must have shape [{self.num_envs}, {self.nu}], got {tuple(action.shape)}')
     action = action.to(device=self.device, dtype=torch.float32).contiguous()
     self._check(self._lib.so101_step(self._h, ctypes.c_void_p(action.data_ptr()), ctypes.byref(self._out), self._stream()))
     return self._timestep()
@@ -283,7 +296,8 @@ class BatchedEnvironment:
     destination of step_host()."""
     N, sd = self.num_envs, self.nq + self.nv
     pin = dict(pin_memory=True)
-    return dict(commanded_joints_pos=torch.zeros(N, 6, **pin), joints_pos=torch.zeros(N, 6, **pin), undelayed_joints_pos=torch.zeros(N, 6, **pin),
+    nu = self.nu
+    return dict(commanded_joints_pos=torch.zeros(N, nu, **pin), joints_pos=torch.zeros(N, nu, **pin), undelayed_joints_pos=torch.zeros(N, nu, **pin),
                 physics_state=torch.zeros(N, sd, **pin), delayed_physics_state=torch.zeros(N, sd, **pin), reward=torch.zeros(N, **pin),
                 discount=torch.zeros(N, **pin), step_type=torch.zeros(N, dtype=torch.uint8, **pin))
 
@@ -456,7 +470,7 @@ class BatchedEnvironment:
     1e-2 or 2 s have passed ([upstream] PropPlacer settle_physics), and is reset to the settled state.  One library call: the
     loop over control steps runs inside so101_sample_and_settle.  With nursery envs the following resets then draw fresh
     placements from the nursery's ring.  Returns the settle statistics."""
-    if self.nq != 20:
+    if not self.task.collide:
       raise RuntimeError('initialize_placements needs a SO100HandOver model')
     seed = self.seed if seed is None else int(seed)
     st = (ctypes.c_uint64 * 4)()

@@ -23,10 +23,11 @@ def test_library_exports_every_declared_symbol(built):
   hdr = open(os.path.join(ROOT, 'include', 'so101_b200.h')).read()
   declared = set(re.findall(r'\b(so101_[a-z0-9_]+)\s*\(', hdr))
   assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-  L = ctypes.CDLL(_lib.LIB_PATH)
-  for sym in declared:
-    assert hasattr(L, sym), sym
-  assert L.so101_abi_version() == 3
+  for path in (_lib.LIB_PATH, _lib.LIB_PATH_2ARM):   # one-arm build and the two-arm build of the same sources
+    L = ctypes.CDLL(path)
+    for sym in declared:
+      assert hasattr(L, sym), (path, sym)
+    assert L.so101_abi_version() == 3
 
 
 def test_create_fails_loudly_without_gpu(built):

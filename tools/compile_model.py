@@ -634,10 +634,46 @@ HANDOVER = {
 }
 
 
-def build(ref_root, task=None):
+# BASELINE config 4 ("hand-over task, two arms"): the reference has no two-SO100 scene (its only two-arm hand-over is the ALOHA
+# task, so101_sim/tasks/hand_over.py:122), so this is a LABELLED SYNTHETIC scene: scene_pbr.xml with its arm
+# moved to (+0.12, 0.3) and a second, identical arm (names prefixed "B_") at (-0.12, 0.3), both reaching over the prop
+# placement area along -y; table, static obstacles and the two free props are the reference's.
+TWO_ARM_BASES = ((0.12, 0.3, 0.42), (-0.12, 0.3, 0.42))
+
+
+def two_arm_scene_xml(scene_path):
+  """scene_pbr.xml with the Base subtree duplicated: returns the path of a temporary MJCF file (absolute meshdir)."""
+  import copy, tempfile
+  tree = ET.parse(scene_path)
+  root = tree.getroot()
+  comp = root.find('compiler')
+  comp.set('meshdir', os.path.join(os.path.dirname(scene_path), comp.get('meshdir', '')))
+  wb = root.find('worldbody')
+  base = [b for b in wb.findall('body') if b.get('name') == 'Base'][0]
+  base.set('pos', ' '.join(str(v) for v in TWO_ARM_BASES[0]))
+  second = copy.deepcopy(base)
+  second.set('pos', ' '.join(str(v) for v in TWO_ARM_BASES[1]))
+  for e in second.iter():
+    if e.get('name') is not None and e.tag in ('body', 'joint', 'geom'):
+      e.set('name', 'B_' + e.get('name'))
+  wb.insert(list(wb).index(base) + 1, second)
+  con = root.find('contact')
+  for e in list(con.findall('exclude')):
+    con.append(ET.Element('exclude', body1='B_' + e.get('body1'), body2='B_' + e.get('body2')))
+  act = root.find('actuator')
+  for g in list(act.findall('general')):
+    attrs = dict(g.attrib); attrs['name'] = 'B_' + attrs['name']; attrs['joint'] = 'B_' + attrs['joint']
+    act.append(ET.Element('general', attrs))
+  f = tempfile.NamedTemporaryFile('w', suffix='.xml', delete=False)
+  tree.write(f.name)
+  return f.name
+
+
+def build(ref_root, task=None, two_arms=False):
   assets = os.path.join(ref_root, 'so101_sim', 'assets')
   m = Model()
-  parse_mjcf(m, os.path.join(assets, 'so100', 'scene_pbr.xml'))
+  scene = os.path.join(assets, 'so100', 'scene_pbr.xml')
+  parse_mjcf(m, two_arm_scene_xml(scene) if two_arms else scene)
   standin = {}
   with_props = task is not None
   if with_props:
@@ -671,8 +707,8 @@ def main():
   ap.add_argument('--out', default=os.path.join(os.path.dirname(__file__), '..', 'so101_sim_b200', 'data'))
   a = ap.parse_args()
   os.makedirs(a.out, exist_ok=True)
-  for name, props in (('so100_arm', None), ('so100_handover_banana', 'banana'), ('so100_handover_pen', 'pen')):
-    A = build(a.ref, props)
+  for name, props in (('so100_arm', None), ('so100_handover_banana', 'banana'), ('so100_handover_pen', 'pen'), ('so100_twoarm_banana', 'banana')):
+    A = build(a.ref, props, two_arms=name.startswith('so100_twoarm'))
     p = os.path.join(a.out, name+'.blob')
     write_blob(p, A)
     print(f"{name}: nq={A['nq']} nv={A['nv']} nu={A['nu']} nbody={A['nbody']} ngeom={A['ngeom']} "

@@ -6,9 +6,16 @@
 
 A "step" is one control step (0.02 s = 10 physics substeps + observations + reward/termination) of ALL lockstep envs.
 Workloads:
-  banana16384  config 3: SO100HandOverBanana pick-and-place with contacts, 16384 envs per GPU  (DEFAULT: the config the
-               "pick-place env-steps/sec" metric is quoted on; largest single-GPU pick-place config in BASELINE.json)
+  banana131072 config 5 at its single-GPU point: SO100HandOverBanana pick-and-place with contacts, 131072 lockstep envs per GPU
+               (DEFAULT: the metric is "pick-place env-steps/sec at 1/2/4/8 B200" and config 5 is its sweep - 131072 envs on 1 GPU
+               is the largest single-GPU pick-place configuration in BASELINE.json; with N GPUs every rank keeps 131072 envs,
+               weak scaling, no per-step collective).  The pipeline's kernels are bound by their slowest warps at small batches
+               (a step of 16384 envs takes as long as one of 32768), so throughput per GPU grows with the batch: 16384 envs
+               ~0.44 M, 32768 ~0.87 M, 131072 ~0.84-1.0 M env-steps/s (profiles/).
+  banana16384  config 3: the same scene with 16384 envs per GPU (attached as `other_workloads`)
   arm4096      config 2: arm-only, collisions off, 4096 envs per GPU (also measured and attached as `other_workloads`)
+  handover8192 config 4: two-arm hand-over, 8192 envs per GPU, on a LABELLED SYNTHETIC two-SO100 scene (the reference has none);
+               also attached as `other_workloads`
 value  = env-steps/s with inputs resident in HBM (CUDA events around each step, L2 flushed between steps).
 e2e    = env-steps/s through BatchedEnvironment.step_host(): pinned host action in, the WHOLE TimeStep (observation dict, reward,
          discount, step_type) out to pinned host tensors, copies and the stream sync inside the timed region.
@@ -38,6 +45,13 @@ WORKLOADS = {
                     desc='BASELINE config 2: SO100 arm-only, collisions off, 4096 lockstep envs per GPU'),
     'banana16384': dict(task='SO100HandOverBanana', envs=16384, model='so100_handover_banana', collide=True, bytes_per_env_step=385,
                         desc='BASELINE config 3: SO100HandOverBanana with contacts, 16384 lockstep envs per GPU'),
+    'banana131072': dict(task='SO100HandOverBanana', envs=131072, model='so100_handover_banana', collide=True, bytes_per_env_step=385,
+                         desc='BASELINE config 5 at its single-GPU point: SO100HandOverBanana with contacts, 131072 lockstep envs per GPU '
+                              '(every rank keeps 131072 envs when N > 1)'),
+    # config 4: read qpos 26 + qvel 24 + action 12 words, write qpos + qvel, joints_pos + commanded_joints_pos 24 words, 9 B of flags
+    'handover8192': dict(task='SO100TwoArmHandOverBanana', envs=8192, model='so100_twoarm_banana', collide=True, bytes_per_env_step=553,
+                         desc='BASELINE config 4 (hand-over, two arms, 8192 envs per GPU) on a LABELLED SYNTHETIC scene: the reference has no '
+                              'two-SO100 scene, this is scene_pbr.xml with two SO100 arms + the banana / bowl props'),
 }
 METRIC = 'SO101 pick-place env-steps/sec at 1/2/4/8 B200 vs MuJoCo CPU on host cores'
 # the float32 product path keeps the integration state, the actuator model and the Euler update in float64
@@ -58,27 +72,28 @@ def _cpu_worker(args):
   from oracle.oracle import OracleSim
   sim = OracleSim(model, collide=collide)
   rs = np.random.RandomState(seed)
-  lo = np.array([-np.pi, -3.14158, -3.14158, -3.14158, -3.14158, 0.0]); hi = np.array([np.pi, 3.14158, 3.14158, 3.14158, 3.14158, 0.08])
+  na = sim.nu   # arm dofs = actuators (6 per arm); the props' free joints follow
+  lo = np.tile([-np.pi, -3.14158, -3.14158, -3.14158, -3.14158, 0.0], na // 6); hi = np.tile([np.pi, 3.14158, 3.14158, 3.14158, 3.14158, 0.08], na // 6)
   rng = sim.meta['jnt_range'].reshape(-1, 2)[:6]
   q = sim.meta['qpos0'].copy()
   if sim.nq == 6:    # config 2: arm qpos ~ U(1/4 joint range)
     q[:6] = 0.25 * rs.uniform(rng[:, 0], rng[:, 1])
     sim.set_state(q, np.zeros(sim.nv))
-  else:              # config 3: props at the reference drop height (so100_hand_over.py:37-55), settled 1 s (untimed), arm at qpos 0
+  else:              # configs 3 / 4: props at the reference drop height (so100_hand_over.py:37-55), settled 1 s (untimed), arms at qpos 0
     u = rs.uniform(size=5)
     while np.hypot(-0.3 + 0.1 * u[3] + 0.1778, -0.1 + 0.2 * u[4] - 0.1656) < 0.151:   # bowl vs static cylinder (see task_suite._bowl_obstacles)
       u[3:5] = rs.uniform(size=2)
     yaw = (2 * u[2] - 1) * 0.1 * np.pi
-    q[:6] = 0
-    q[6:13] = [0.2 + 0.1 * u[0], -0.1 + 0.2 * u[1], 0.45, np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)]
-    q[13:20] = [-0.3 + 0.1 * u[3], -0.1 + 0.2 * u[4], 0.45, 1, 0, 0, 0]
+    q[:na] = 0
+    q[na:na + 7] = [0.2 + 0.1 * u[0], -0.1 + 0.2 * u[1], 0.45, np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)]
+    q[na + 7:na + 14] = [-0.3 + 0.1 * u[3], -0.1 + 0.2 * u[4], 0.45, 1, 0, 0, 0]
     sim.set_state(q, np.zeros(sim.nv))
     for _ in range(50):
-      sim.control_step(np.zeros(6))
+      sim.control_step(np.zeros(na))
     qs, vs = sim.qpos.copy(), sim.qvel.copy()
-    qs[:6] = 0; vs[:6] = 0
+    qs[:na] = 0; vs[:na] = 0
     sim.set_state(qs, vs)
-  acts = rs.uniform(lo, hi, size=(256, 6)) * 0.3
+  acts = rs.uniform(lo, hi, size=(256, na)) * 0.3
   n, t0 = 0, time.perf_counter()
   while time.perf_counter() - t0 < seconds:
     sim.control_step(acts[n % 256])
@@ -142,7 +157,7 @@ def main():
   ap.add_argument('--steps', type=int, default=100)
   ap.add_argument('--warmup', type=int, default=10)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-  ap.add_argument('--workload', default=os.environ.get('SO101_BENCH_WORKLOAD', 'banana16384'), choices=list(WORKLOADS))
+  ap.add_argument('--workload', default=os.environ.get('SO101_BENCH_WORKLOAD', 'banana131072'), choices=list(WORKLOADS))
   ap.add_argument('--envs', type=int, default=0, help='envs per GPU (default: the workload size)')
   ap.add_argument('--precision', default='f32', choices=['f32', 'f64'])
   ap.add_argument('--cpu-seconds', type=float, default=10.0)
@@ -150,7 +165,7 @@ def main():
   ap.add_argument('--no-secondary', action='store_true', help='skip the attached arm4096 measurement')
   ap.add_argument('--no-steady', action='store_true', help='skip the attached steady-state (cycling episodes) measurement')
   ap.add_argument('--steady-steps', type=int, default=200)
-  ap.add_argument('--steady-warmup', type=int, default=50)
+  ap.add_argument('--steady-warmup', type=int, default=100)
   a = ap.parse_args()
   rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
   local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -195,11 +210,21 @@ def main():
                ms_per_step=res['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None,
                dtype=a.precision, data='synthetic', config=config, e2e=res['e2e'], gpu_launches=res['gpu_launches'],
                graph_launches=res['graph_launches'], launches_per_step=res['launches_per_step'], clocks=res['clocks'], roofline=res['roofline'], kernels=res['kernels'], wall_s=res['wall_s'],
-               mean_return=res['mean_return'], diverged=res['diverged'], contacts_dropped=res['contacts_dropped'])
+               mean_return=res['mean_return'], diverged=res['diverged'], contacts_dropped=res['contacts_dropped'],
+               dropped_by_buffer_since_load=res['dropped_by_buffer_since_load'])
     if world == 1 and not a.no_secondary and a.workload != 'arm4096':
-      # BASELINE config 2 (arm-only) measured beside the headline workload: a short run, kernel-only and e2e
+      # the other BASELINE configs measured beside the headline workload (short runs, kernel-only and e2e):
+      # config 2 (arm-only, 4096 envs), config 3 (pick-place, 16384 envs), config 4 (two-arm hand-over, 8192 envs, synthetic scene)
       r2 = run_workload('arm4096', WORKLOADS['arm4096']['envs'], 50, 5, a.precision, dev, rank, world, local_rank)
       out['other_workloads'] = {'arm4096': {k: r2[k] for k in ('value', 'ms_per_step', 'e2e', 'gpu_launches', 'roofline')}}
+      if a.workload != 'banana16384':
+        r3 = run_workload('banana16384', WORKLOADS['banana16384']['envs'], 100, 10, a.precision, dev, rank, world, local_rank)
+        out['other_workloads']['banana16384'] = dict({k: r3[k] for k in ('value', 'ms_per_step', 'e2e', 'gpu_launches', 'roofline', 'diverged', 'contacts_dropped')},
+                                                     description=WORKLOADS['banana16384']['desc'])
+      # BASELINE config 4 on the labelled synthetic two-arm scene: a short run as well
+      r4 = run_workload('handover8192', WORKLOADS['handover8192']['envs'], 30, 10, a.precision, dev, rank, world, local_rank)
+      out['other_workloads']['handover8192'] = dict({k: r4[k] for k in ('value', 'ms_per_step', 'e2e', 'gpu_launches', 'roofline', 'diverged', 'contacts_dropped', 'dropped_by_buffer_since_load')},
+                                                    description=WORKLOADS['handover8192']['desc'])
     if world == 1 and not a.no_steady and WORKLOADS[a.workload]['collide']:
       out['steady_state'] = run_steady_state(a.workload, envs, a.steady_steps, a.steady_warmup, a.precision, dev, rank)
     if not a.no_cpu_baseline and world == 1:
@@ -224,7 +249,7 @@ def _actions(env, n, envs, dev, seed):
   g = torch.Generator(device=dev); g.manual_seed(seed)
   spec = env.action_spec()
   lo, hi = torch.tensor(spec.minimum, device=dev), torch.tensor(spec.maximum, device=dev)
-  return (lo + torch.rand(n, envs, 6, generator=g, device=dev) * (hi - lo)) * 0.3
+  return (lo + torch.rand(n, envs, len(spec.minimum), generator=g, device=dev) * (hi - lo)) * 0.3
 
 
 def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_rank):
@@ -279,6 +304,8 @@ def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_r
     barrier()
     t_wall = time.perf_counter() - t_wall0
   c1 = env.counters()
+  drop_names = ('per_pair', 'candidates', 'pairs', 'queue', 'raw_contacts', 'jacobian_blocks', 'hits')
+  drops = dict(zip(drop_names, [int(x) for x in env.debug_read('dropcat', 8)[0, :7].tolist()])) if w['collide'] and envs >= 8 else {}
   dev_ms = max_over_ranks(float(sum(ev0[i].elapsed_time(ev1[i]) for i in range(steps))))
   value = envs * world * steps / (dev_ms * 1e-3)
 
@@ -294,7 +321,7 @@ def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_r
   # ---- e2e: host buffers through the public API (H2D of the action + step + D2H of the WHOLE TimeStep - observation dict,
   # reward, discount, step_type - + sync, per step).  The envs go back to the same initial state and replay the same action
   # sequence (warm-up included), so both legs time the same stretch of the rollout.
-  h_act = [torch.empty(envs, 6, dtype=torch.float32, pin_memory=True).copy_(acts[i].cpu()) for i in range(nact)]
+  h_act = [torch.empty(envs, acts.shape[2], dtype=torch.float32, pin_memory=True).copy_(acts[i].cpu()) for i in range(nact)]
   h_out = env.make_host_timestep()
   env.reset()
   for i in range(warmup):
@@ -305,7 +332,7 @@ def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_r
     d2h = env.step_host(h_act[(warmup + i) % nact], h_out)
   barrier()
   e2e_value = envs * world * steps / max_over_ranks(time.perf_counter() - e0)
-  h2d = envs * 6 * 4
+  h2d = envs * acts.shape[2] * 4
 
   # ---- episode statistics: the ONLY collective on this path (NCCL all_gather of return / length / success)
   gathered = gather_episode_stats(torch.cat([stats.local(), ret_sum[:, None]], dim=1))
@@ -334,32 +361,31 @@ def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_r
   res = dict(value=value, ms_per_step=dev_ms / steps, e2e=dict(value=e2e_value, unit='env-steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
              gpu_launches=c1['kernel_launches'] - c0['kernel_launches'], graph_launches=c1['graph_launches'] - c0['graph_launches'],
              launches_per_step=(c1['kernel_launches'] - c0['kernel_launches']) / max(1, nsteps), clocks=clocks.summary(), roofline=roofline,
-             kernels=kern, wall_s=t_wall, mean_return=mean_return, diverged=c1['diverged'], contacts_dropped=c1['contacts_dropped'])
+             kernels=kern, wall_s=t_wall, mean_return=mean_return, diverged=c1['diverged'], contacts_dropped=c1['contacts_dropped'],
+             dropped_by_buffer_since_load=drops)
   env.close()
   return res
 
 
-def run_steady_state(name, envs, steps, warmup, precision, dev, rank, episode_s=15.0):
+def run_steady_state(name, envs, steps, warmup, precision, dev, rank, episode_s=30.0):
   """Steady-state regime (>= 200 steps after >= 50 warm-up) with episodes CYCLING through auto-reset and
-  the on-device episode initialisation running: `episode_s`-second episodes, envs / 8 nursery envs sampling, collision-checking
-  and settling fresh placements in the background, and the envs' episode phases staggered uniformly by masked resets during the
-  warm-up, so that at any timed step the batch holds envs of every age and ~1/episode_steps of them finish or restart.  The
-  nursery envs' physics is inside the timed steps; only the user envs' steps are counted."""
+  the on-device episode initialisation running: the headline workload (30 s episodes = 1501 control steps) with envs / 16 nursery
+  envs sampling, collision-checking and settling fresh placements in the background.  After the warm-up the envs' episode step
+  counters are spread uniformly over the episode length (so101_set_episode_steps), so that during the timed steps
+  ~1/1501 of the envs finish and restart per step, each from a fresh placement.  The nursery envs' physics is inside the timed
+  steps; only the user envs' steps are counted."""
   import torch
   from so101_sim_b200.task_suite import create_batched_task_env
   w = WORKLOADS[name]
-  nursery = max(1, envs // 8)
+  nursery = max(1, envs // 16)
   env = create_batched_task_env(w['task'], num_envs=envs, time_limit=episode_s, seed=1000 * rank, device=dev, precision=precision,
                                 placement='device', nursery_envs=nursery)
   ep_steps = env.last_step
   nact = 64
   acts = _actions(env, nact, envs, dev, 1 + 1000 * rank)
-  warmup = max(warmup, ep_steps)
-  ids = torch.arange(envs, device=dev)
   for i in range(warmup):
-    if i < ep_steps:
-      env.reset((ids % ep_steps) == i)
     env.step(acts[i % nact])
+  env.set_episode_steps((torch.arange(envs, device=dev) * ep_steps // envs).to(torch.int32))   # phases uniform over the episode
   flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
   ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
   ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -376,10 +402,10 @@ def run_steady_state(name, envs, steps, warmup, precision, dev, rank, episode_s=
   c1, p1 = env.counters(), env.placement_stats()
   ms = float(sum(ev0[i].elapsed_time(ev1[i]) for i in range(steps)))
   out = dict(value=envs * steps / (ms * 1e-3), unit='env-steps/s', ms_per_step=ms / steps, steps=steps, warmup=warmup, episode_steps=ep_steps,
-             nursery_envs=nursery, last_steps=int(nlast), first_steps=int(nfirst), diverged=c1['diverged'] - c0['diverged'],
+             envs=envs, nursery_envs=nursery, last_steps=int(nlast), first_steps=int(nfirst), diverged=c1['diverged'] - c0['diverged'],
              contacts_dropped=c1['contacts_dropped'] - c0['contacts_dropped'],
              placements={k: p1[k] - p0[k] for k in p1},
-             note=f'time_limit {episode_s} s episodes ({ep_steps} control steps), phases staggered uniformly by masked resets, random actions, '
+             note=f'time_limit {episode_s} s episodes ({ep_steps} control steps), episode phases spread uniformly after the warm-up, random actions, '
                   'fresh on-device placement per episode (nursery physics inside the timed steps, not counted as env-steps); a step() that '
                   'lands on an env whose previous step was LAST resets it (FIRST) instead of stepping, as dm_control does')
   env.close()

@@ -125,6 +125,12 @@ int so101_set_state(so101_handle h, const float *qpos_dev, const float *qvel_dev
 int so101_get_state_f64(so101_handle h, double *qpos_dev, double *qvel_dev, void *stream);
 int so101_set_state_f64(so101_handle h, const double *qpos_dev, const double *qvel_dev, int initial, void *stream);
 
+/* Control steps each env has taken in its current episode ([N] int32 device pointer): the part of the env state that decides when
+ * the time limit fires (composer.Environment's `physics.time() >= time_limit`).  Read / written with the physics state for
+ * checkpoint-resume and to start a batch at staggered episode phases. */
+int so101_get_episode_steps(so101_handle h, int32_t *steps_dev, void *stream);
+int so101_set_episode_steps(so101_handle h, const int32_t *steps_dev, void *stream);
+
 /* End-to-end variant with HOST buffers (pinned or pageable): copies action_host [N,6] to the device, steps, copies every
  * block of the TimeStep whose pointer in *out_host is non-NULL (HOST pointers, same shapes as so101_step_out) back, and
  * synchronises the stream before returning.  This is composer.Environment.step(action) -> TimeStep as a host caller sees it. */

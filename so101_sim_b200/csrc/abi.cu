@@ -56,6 +56,7 @@ struct HandleBase {
   virtual void debug_read(const char *field, float *dst, size_t count, cudaStream_t s) = 0;
   virtual void sample_and_settle(uint64_t seed, const so101_step_out &out, uint64_t stats[4], cudaStream_t s) = 0;
   virtual void placement_stats(uint64_t out[6]) = 0;
+  virtual void episode_steps(int32_t *steps_dev, bool set, cudaStream_t s) = 0;
   virtual void step_host(const float *action, const so101_step_out &host_out, cudaStream_t s) = 0;
   virtual uint64_t diverged() = 0;
   KernelTimer timer;
@@ -238,7 +239,7 @@ struct Handle : HandleBase {
     S.step = dalloc<int>(N); S.needs_reset = dalloc<uint8_t>(N); S.episode = dalloc<int>(N); S.npool = 1;
     S.ring_joints = dalloc<float>((size_t)(c.joints_delay_steps + 1) * NA * N);
     S.ring_phys = dalloc<float>((size_t)(c.physics_delay_steps + 1) * (nq + nv) * N);
-    S.diverged_count = dalloc<int>(2); S.solver_iter = dalloc<int>(N); S.ncon = dalloc<int>(N);
+    S.diverged_count = dalloc<int>(2); S.solver_iter = dalloc<int>(N); S.ncon = dalloc<int>(N); S.dropped_env = dalloc<int>(N);
     sc.nsub = c.n_substeps; sc.last_step = c.last_step; sc.dj = c.joints_delay_steps; sc.dp = c.physics_delay_steps;
     if (getenv("SO101_PROFILE") && atoi(getenv("SO101_PROFILE"))) S.prof = dalloc<unsigned long long>(16);
     sc.dbg_env = getenv("SO101_DBG_ENV") ? atoi(getenv("SO101_DBG_ENV")) : -1;
@@ -382,8 +383,8 @@ struct Handle : HandleBase {
   }
   void debug_read(const char *field, float *dst, size_t count, cudaStream_t s) override {
     const std::string f(field);
-    if (f == "solver_iter" || f == "ncon" || f == "step") {
-      const int *src = f == "solver_iter" ? S.solver_iter : (f == "ncon" ? S.ncon : S.step);
+    if (f == "solver_iter" || f == "ncon" || f == "step" || f == "dropped") {
+      const int *src = f == "solver_iter" ? S.solver_iter : (f == "ncon" ? S.ncon : (f == "dropped" ? S.dropped_env : S.step));
       if (count < (size_t)S.NU) throw std::runtime_error("debug_read: buffer too small");
       launch_int_to_float(src, dst, S.NU, s);
       launches += 1;
@@ -497,6 +498,11 @@ struct Handle : HandleBase {
     CUDA_OK(cudaMemcpy(c, S.ring_ctr, sizeof c, cudaMemcpyDeviceToHost));
     out[0] = c[RC_CLAIM]; out[1] = c[RC_TAIL]; out[2] = c[RC_REUSED]; out[3] = c[RC_UNSETTLED]; out[4] = c[RC_EXHAUSTED]; out[5] = c[RC_REJECTED];
   }
+  void episode_steps(int32_t *steps_dev, bool set, cudaStream_t s) override {
+    static_assert(sizeof(int32_t) == sizeof(int), "step counters are 32-bit");
+    if (set) CUDA_OK(cudaMemcpyAsync(S.step, steps_dev, sizeof(int) * S.NU, cudaMemcpyDeviceToDevice, s));
+    else CUDA_OK(cudaMemcpyAsync(steps_dev, S.step, sizeof(int) * S.NU, cudaMemcpyDeviceToDevice, s));
+  }
   uint64_t diverged() override {
     int v[2] = {0, 0};
     cudaMemcpy(v, S.diverged_count, 2 * sizeof(int), cudaMemcpyDeviceToHost);
@@ -600,6 +606,18 @@ int so101_sample_and_settle(so101_handle h, uint64_t seed, const so101_step_out 
   so101_step_out o{};
   if (out) o = *out;
   H->sample_and_settle(seed, o, stats_out, (cudaStream_t)stream);
+  API_END()
+}
+int so101_get_episode_steps(so101_handle h, int32_t *steps_dev, void *stream) {
+  API_BEGIN(h)
+  if (!steps_dev) throw std::runtime_error("null pointer");
+  H->episode_steps(steps_dev, false, (cudaStream_t)stream);
+  API_END()
+}
+int so101_set_episode_steps(so101_handle h, const int32_t *steps_dev, void *stream) {
+  API_BEGIN(h)
+  if (!steps_dev) throw std::runtime_error("null pointer");
+  H->episode_steps(const_cast<int32_t *>(steps_dev), true, (cudaStream_t)stream);
   API_END()
 }
 int so101_placement_stats(so101_handle h, uint64_t out[6]) {

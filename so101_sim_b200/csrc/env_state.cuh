@@ -62,6 +62,7 @@ struct EnvState {
   int *diverged_count;              // [1]
   int *solver_iter;                 // [N] Newton iterations of the last substep (parity/diagnostics)
   int *ncon;                        // [N] contacts of the last substep
+  int *dropped_env;                 // [N] contacts / candidate pairs this env lost to a full buffer since create (see so101_counters)
   unsigned long long *prof;         // optional [16] stage-profile accumulators (SO101_PROFILE=1), see scene_kernel.inl
   float *dbg_contacts;              // optional [N][1 + 9*NCON] parity probe (null unless requested)
 };

@@ -617,7 +617,10 @@ __device__ __forceinline__ void prof_flush(SC &s, const EnvState<T> &S, int lane
 // envs (warps) per CTA in the begin / broad-phase / task-layer kernels (static shared memory: 48 KB per CTA)
 template <typename T> struct BroadCfg { static constexpr int WARPS = sizeof(T) == 8 ? 2 : 4; };
 #define WARPS_BROAD (BroadCfg<T>::WARPS)
-constexpr int KD_THREADS = 64;   // envs (threads) per CTA in the kinematics + smooth-dynamics kernel
+constexpr int KD_THREADS = 32;   // envs (threads) per CTA in the kinematics + smooth-dynamics kernel: one warp, one staging tile
+// per-env record the kernel produces: poses of the dynamic bodies, then the dyn record; staged per warp in shared memory with an
+// odd row stride (conflict-free thread-per-row writes) and written out as ONE contiguous, coalesced block per array
+constexpr int KD_POSE = NSLOT * 12, KD_ROW = KD_POSE + DYNW, KD_STRIDE = KD_ROW | 1;
 
 // Once per control step: dm_control auto-reset (writes the FIRST TimeStep), action + calibration -> ctrl.
 template <typename T>
@@ -647,11 +650,19 @@ template <typename T>
 __global__ void __launch_bounds__(KD_THREADS) scene_kindyn_kernel(const __grid_constant__ ArmSetT<T> am, const __grid_constant__ ArmSetT<double> am64,
                                                                  const __grid_constant__ SceneModel<T> sm, const EnvState<T> S, const PipeBuf<T> pb,
                                                                  int need_dyn) {
-  const int env = pb.env0 + blockIdx.x * KD_THREADS + threadIdx.x;
-  if (env >= pb.env0 + pb.nenv || !pb.active[env]) return;
+  extern __shared__ __align__(16) unsigned char kd_raw[];
+  T *tile = reinterpret_cast<T *>(kd_raw);                      // [32 envs][KD_STRIDE]
+  const int lane = threadIdx.x;
+  const int env0 = pb.env0 + blockIdx.x * KD_THREADS, env = env0 + lane;
+  const bool live = env < pb.env0 + pb.nenv && pb.active[env];
+  const unsigned livemask = __ballot_sync(0xffffffffu, live);
+  if (!livemask) return;
+  const bool dyn = live && need_dyn && !pb.flags[env];  // (a diverged env is frozen for the rest of the control step)
+  const unsigned dynmask = __ballot_sync(0xffffffffu, dyn);
+  // thread-per-env results go to the env's row of the tile (the pointers keep the names of the global arrays they stand for)
+  T *gx = tile + (size_t)lane * KD_STRIDE, *gm = gx + NSLOT * 3, *gd = gx + KD_POSE;
+  if (live) {
   const TS *gq = S.qpos + (size_t)env * NQ, *gv = S.qvel + (size_t)env * NV;
-  T *gx = pb.xpos + (size_t)env * (NSLOT * 3), *gm = pb.xmat + (size_t)env * (NSLOT * 9), *gd = pb.dyn + (size_t)env * DYNW;
-  const bool dyn = need_dyn && !pb.flags[env];  // (a diverged env is frozen for the rest of the control step)
 #pragma unroll 1
   for (int p = 0; p < NPROP; p++) {
     const TS *qp = gq + NA + 7 * p;
@@ -722,6 +733,14 @@ __global__ void __launch_bounds__(KD_THREADS) scene_kindyn_kernel(const __grid_c
       gr[i] = arows.jar0_f[i]; gr[6 + i] = arows.jar0_l[i]; gr[12 + i] = arows.D_l[i]; gr[18 + i] = arows.js[i];
     }
   }
+  }  // live
+  __syncwarp();
+  // coalesced write-out: the 32 envs' rows are contiguous in each global array ([N][NSLOT*3], [N][NSLOT*9], [N][DYNW])
+  T *ox = pb.xpos + (size_t)env0 * (NSLOT * 3), *om = pb.xmat + (size_t)env0 * (NSLOT * 9), *od = pb.dyn + (size_t)env0 * DYNW;
+  for (int i = lane; i < 32 * NSLOT * 3; i += 32) { const int r = i / (NSLOT * 3), k = i - r * (NSLOT * 3); if ((livemask >> r) & 1u) ox[i] = tile[(size_t)r * KD_STRIDE + k]; }
+  for (int i = lane; i < 32 * NSLOT * 9; i += 32) { const int r = i / (NSLOT * 9), k = i - r * (NSLOT * 9); if ((livemask >> r) & 1u) om[i] = tile[(size_t)r * KD_STRIDE + NSLOT * 3 + k]; }
+  if (dynmask)
+    for (int i = lane; i < 32 * DYNW; i += 32) { const int r = i / DYNW, k = i - r * DYNW; if ((dynmask >> r) & 1u) od[i] = tile[(size_t)r * KD_STRIDE + KD_POSE + k]; }
 }
 
 // Warp per env, after every kinematics refresh: the broad + mid phase that fills the work queues of substep `sub`, or - after
@@ -746,7 +765,7 @@ __global__ void __launch_bounds__(WARPS_BROAD * 32) scene_broad_kernel(const __g
   if (!last) {
     int dropped = 0;
     if (!pb.flags[env]) scene_broadphase(sm, s, pb, env, sub, dropped, lane);
-    if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
+    if (lane == 0 && dropped) { atomicAdd(S.diverged_count + 1, dropped); S.dropped_env[env] += dropped; }
   } else if (S.mode[env]) {
     if (lane == 0) settle_end_of_step(S, env, bad);
   } else {
@@ -849,7 +868,10 @@ __global__ void __launch_bounds__(GJK_THREADS) scene_gjk_kernel(const __grid_con
 }
 
 // Per substep, ONE THREAD per intersecting pair: EPA -> manifold (scene_collide_seq.cuh), contacts to the env's raw buffer.
-constexpr int NSEQ_THREADS = 64, NSEQ_MINCTAS = 12;
+#ifndef SO101_NSEQ_MINCTAS
+#define SO101_NSEQ_MINCTAS 12
+#endif
+constexpr int NSEQ_THREADS = 64, NSEQ_MINCTAS = SO101_NSEQ_MINCTAS;
 template <typename T>
 __global__ void __launch_bounds__(NSEQ_THREADS, NSEQ_MINCTAS) scene_narrow_seq_kernel(const __grid_constant__ SceneModel<T> sm, const EnvState<T> S, const PipeBuf<T> pb, int sub) {
   __shared__ int qpref[NSEQ_THREADS / 32][WQ + 1], hpref[NSEQ_THREADS / 32][WQ + 1];
@@ -1114,7 +1136,7 @@ __device__ __forceinline__ bool solve_env(const ArmSetT<T> &am, const SceneModel
     }
   }
   if (last && lane == 0) { S.solver_iter[env] = iters; S.ncon[env] = s.ncon; }
-  if (lane == 0 && dropped) atomicAdd(S.diverged_count + 1, dropped);
+  if (lane == 0 && dropped) { atomicAdd(S.diverged_count + 1, dropped); S.dropped_env[env] += dropped; }
   prof_flush(s, S, lane);
   return true;
 }
@@ -1231,6 +1253,8 @@ int launch_scene_step(const ArmSetT<T> &am, const ArmSetT<double> &am64, const S
                smem_m = sizeof(Scratch<T, NC_M, NB_M>) * WARPS_M, smem_l = sizeof(Scratch<T, NC_L, NB_L>) * WARPS_L;
   // (no function-local statics here: template statics are process-wide unique symbols, and the one-arm and the two-arm builds
   // of this library can be loaded into the same process)
+  const size_t smem_kd = sizeof(T) * 32 * KD_STRIDE;
+  cudaFuncSetAttribute(scene_kindyn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kd);
   cudaFuncSetAttribute(scene_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_env);
   cudaFuncSetAttribute(scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
   cudaFuncSetAttribute(scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
@@ -1241,7 +1265,7 @@ int launch_scene_step(const ArmSetT<T> &am, const ArmSetT<double> &am64, const S
   // kinematics (+ smooth dynamics) at the current state, then the broad phase for substep `sub` or the task layer
   auto refresh = [&](const PipeBuf<T> &pb, cudaStream_t st, int sub, bool last) {
     t.begin(6, st);
-    scene_kindyn_kernel<T><<<(pb.nenv + KD_THREADS - 1) / KD_THREADS, KD_THREADS, 0, st>>>(am, am64, sm, S, pb, last ? 0 : 1);
+    scene_kindyn_kernel<T><<<(pb.nenv + KD_THREADS - 1) / KD_THREADS, KD_THREADS, smem_kd, st>>>(am, am64, sm, S, pb, last ? 0 : 1);
     t.end(6, st);
     t.begin(7, st);
     scene_broad_kernel<T><<<(pb.nenv + WARPS_BROAD - 1) / WARPS_BROAD, WARPS_BROAD * 32, 0, st>>>(sm, cfg, S, pb, out, sub, last ? 1 : 0);

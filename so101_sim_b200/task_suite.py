@@ -347,6 +347,20 @@ class BatchedEnvironment:
     self._check(fn(self._h, ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(v.data_ptr()), self._stream()))
     return q, v
 
+  def get_episode_steps(self) -> torch.Tensor:
+    """int32 [N]: control steps each env has taken in its current episode (decides when the time limit fires)."""
+    out = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+    self._check(self._lib.so101_get_episode_steps(self._h, ctypes.c_void_p(out.data_ptr()), self._stream()))
+    return out
+
+  def set_episode_steps(self, steps: torch.Tensor):
+    """Checkpoint-resume companion of set_state(): restore the per-env episode step counters (also used to start a batch at
+    staggered episode phases)."""
+    s = steps.to(device=self.device, dtype=torch.int32).contiguous()
+    if s.shape != (self.num_envs,):
+      raise ValueError('steps must have shape [num_envs]')
+    self._check(self._lib.so101_set_episode_steps(self._h, ctypes.c_void_p(s.data_ptr()), self._stream()))
+
   def debug_read(self, field: str, width: int = 1) -> torch.Tensor:
     out = torch.empty(self.num_envs, width, dtype=torch.float32, device=self.device)
     self._check(self._lib.so101_debug_read(self._h, field.encode(), ctypes.c_void_p(out.data_ptr()), out.numel(), self._stream()))
@@ -367,6 +381,12 @@ class BatchedEnvironment:
     c = (ctypes.c_uint64 * 6)()
     self._check(self._lib.so101_counters(self._h, ctypes.byref(c)))
     return dict(kernel_launches=int(c[0]), control_steps=int(c[1]), diverged=int(c[2]), contacts_dropped=int(c[3]), graph_launches=int(c[4]))
+
+  def contacts_dropped_per_env(self) -> torch.Tensor:
+    """int64 [N]: contacts / candidate pairs each env has lost to a full per-env buffer since the env was created (candidate pairs
+    beyond 64 or raw contacts beyond 128 per substep, Jacobian blocks beyond the largest solver tier's pool).  MuJoCo has no such
+    caps; counters()['contacts_dropped'] is the sum."""
+    return self.debug_read('dropped').flatten().to(torch.int64)
 
   KERNEL_NAMES = ("scene_begin_kernel", "scene_narrow_kernel", "scene_solve_kernel", "scene_solve_tier_kernel(1+2)", "arm_step_kernel", "scene_gjk_kernel",
                   "scene_kindyn_kernel", "scene_broad_kernel")

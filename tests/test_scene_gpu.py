@@ -154,6 +154,7 @@ def test_f32_scene_tracks_oracle(built):
     if not r[7]:
       assert r[4] < 2e-5 and r[5] < 2e-5, r                               # at rest on the table: same pose as the oracle
   assert torch.isfinite(q).all() and env.counters()['diverged'] == 0 and env.counters()['contacts_dropped'] == 0
+  assert int(env.contacts_dropped_per_env().sum()) == 0   # per-env view of the same counter
   env.close()
 
 

@@ -328,6 +328,40 @@ def test_f64_contact_rich_rollout_matches_oracle(built):
   env.close()
 
 
+def test_step_host_returns_the_whole_timestep(built):
+  """so101_step_host (the e2e path of bench.py): pinned host action in, EVERY block of the TimeStep out to pinned host tensors;
+  identical to what step() leaves in the device tensors of a twin env."""
+  a, b = _env(built, num_envs=4), _env(built, num_envs=4)
+  for e in (a, b):
+    e.sample_prop_initial_states(seed=7, settle_steps=0)
+  acts = _actions(a, 6, seed=9)
+  host = b.make_host_timestep()
+  assert set(host) == {'commanded_joints_pos', 'joints_pos', 'undelayed_joints_pos', 'physics_state', 'delayed_physics_state', 'reward', 'discount', 'step_type'}
+  for t in range(6):
+    ts = a.step(acts[t])
+    nbytes = b.step_host(acts[t].cpu().pin_memory(), host)
+  assert nbytes == 4 * (3 * 24 + 2 * 152 + 9)
+  for k in ('commanded_joints_pos', 'joints_pos', 'undelayed_joints_pos', 'physics_state', 'delayed_physics_state'):
+    assert torch.equal(ts.observation[k].cpu(), host[k]), k
+  assert torch.equal(ts.reward.cpu(), host['reward']) and torch.equal(ts.discount.cpu(), host['discount']) and torch.equal(ts.step_type.cpu(), host['step_type'])
+  a.close(); b.close()
+
+
+def test_episode_step_counters_roundtrip_and_time_limit(built):
+  """so101_get/set_episode_steps: the per-env control-step counters that decide when `physics.time() >= time_limit` fires
+  (1501 control steps for 30 s).  Setting env 1 to 1499 makes its next-but-one step LAST and the one after FIRST."""
+  env = _env(built, num_envs=3)
+  env.sample_prop_initial_states(seed=1, settle_steps=0)
+  zero = torch.zeros(3, 6, device='cuda:0')
+  env.step(zero)
+  assert env.get_episode_steps().tolist() == [1, 1, 1]
+  env.set_episode_steps(torch.tensor([1, 1499, 7]))
+  kinds = [env.step(zero).step_type.tolist() for _ in range(3)]
+  assert kinds == [[1, 1, 1], [1, 2, 1], [1, 0, 1]]
+  assert env.get_episode_steps().tolist() == [4, 0, 10]
+  env.close()
+
+
 def test_kernel_times_and_launch_counts(built):
   """so101_kernel_times: CUDA-event time per kernel while enabled; one control step = 3 + 8 x 10 launches per group
   (begin, kinematics + dynamics, broad phase; then per substep GJK, EPA / manifold, classify, three solver tiers, kinematics + dynamics,

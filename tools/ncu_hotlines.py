@@ -11,7 +11,13 @@ out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-so
 rows = list(csv.reader(out[1:]))
 hdr = rows[0]
 isamp, iex, ith = hdr.index('# Samples'), hdr.index('Instructions Executed'), hdr.index('Thread Instructions Executed')
-data = [(int(r[isamp]), int(r[iex]), int(r[ith])) for r in rows[1:] if len(r) > ith]
+body = []
+for r in rows[1:]:   # a report with several launches repeats the header per launch: the first launch is attributed
+  if len(r) > ith and r[isamp] == '# Samples':
+    break
+  if len(r) > ith and r[isamp].strip().isdigit():
+    body.append(r)
+data = [(int(r[isamp]), int(r[iex]), int(r[ith])) for r in body]
 with tempfile.TemporaryDirectory() as td:
   subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(obj)], cwd=td, capture_output=True)
   cub = [f for f in os.listdir(td) if f.endswith('.cubin')][0]

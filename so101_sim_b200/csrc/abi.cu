@@ -190,7 +190,7 @@ struct Handle : HandleBase {
   // One control step of the contact scene is 166 launches + event fork/joins on 6 streams.  It is captured once per distinct
   // set of output pointers into a CUDA graph and replayed with a single cudaGraphLaunch (SO101_GRAPH=0 disables; the
   // per-kernel event timers need eager launches and bypass it).
-  struct StepGraph { so101_step_out key; cudaGraphExec_t exec; };
+  struct StepGraph { so101_step_out key; cudaGraphExec_t exec; int kernels; };
   std::vector<StepGraph> graphs;
   cudaStream_t cap_stream = nullptr;
   bool use_graph = true;
@@ -351,7 +351,6 @@ struct Handle : HandleBase {
   }
   void step(const float *action, const so101_step_out &out, cudaStream_t s) override {
     if (!scene) { timer.begin(4, s); launch_arm_step<T>(am.arm[0], am64.arm[0], sc, S, action, out, s); timer.end(4, s); launches += 1; steps += 1; return; }
-    const int nk = (int)groups.size() * (3 + 8 * sc.nsub);
     if (!use_graph || timer.on) {
       launches += launch_scene_step<T>(am, am64, scene->dev, sc, S, groups.data(), tiers.data(), (int)groups.size(), action, out, s, &timer);
       steps += 1;
@@ -360,13 +359,14 @@ struct Handle : HandleBase {
     // graph replay: the action goes through a fixed staging buffer so that the graph does not depend on the caller's pointer
     if (action != d_action) CUDA_OK(cudaMemcpyAsync(d_action, action, sizeof(float) * NA * S.NU, cudaMemcpyDeviceToDevice, s));
     cudaGraphExec_t exec = nullptr;
-    for (auto &g : graphs) if (std::memcmp(&g.key, &out, sizeof out) == 0) exec = g.exec;
+    int nk = 0;
+    for (auto &g : graphs) if (std::memcmp(&g.key, &out, sizeof out) == 0) { exec = g.exec; nk = g.kernels; }
     if (!exec) {
       if (graphs.size() >= 8) { cudaGraphExecDestroy(graphs.front().exec); graphs.erase(graphs.begin()); }
       if (!cap_stream) CUDA_OK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
       cudaGraph_t graph = nullptr;
       CUDA_OK(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
-      launch_scene_step<T>(am, am64, scene->dev, sc, S, groups.data(), tiers.data(), (int)groups.size(), d_action, out, cap_stream, nullptr);
+      nk = launch_scene_step<T>(am, am64, scene->dev, sc, S, groups.data(), tiers.data(), (int)groups.size(), d_action, out, cap_stream, nullptr);
       const cudaError_t le = cudaGetLastError();   // first launch error inside the capture, if any
       cudaError_t e = cudaStreamEndCapture(cap_stream, &graph);
       if (e != cudaSuccess || !graph) {
@@ -376,7 +376,7 @@ struct Handle : HandleBase {
       e = cudaGraphInstantiate(&exec, graph, 0);
       cudaGraphDestroy(graph);
       if (e != cudaSuccess) throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-      graphs.push_back({out, exec});
+      graphs.push_back({out, exec, nk});
     }
     CUDA_OK(cudaGraphLaunch(exec, s));
     launches += nk; graph_launches += 1; steps += 1;

@@ -423,12 +423,10 @@ __device__ __noinline__ int manifold_seq(const SceneModel<T> &sm, CollideScratch
   return u;
 }
 
+// contacts of a pair whose EPA has finished: the multi-point manifold, or the single EPA point when the features give none
 template <typename T>
-__device__ __noinline__ void collide_convex_seq(const SceneModel<T> &sm, CollideScratch<T> &cs, Shape<T> &A, Shape<T> &B, const MPoint<T> *S, int n,
-                                                PairContacts<T> &pc, int &eit, long long &t_epa) {
-  T normal[3], depth, pa[3], pb[3];
-  const int ok = epa_seq(sm, cs, A, B, S, n, normal, depth, pa, pb, eit);
-  t_epa = clock64();  // (stage probe: when this lane left EPA)
+__device__ __forceinline__ void finish_convex_pair(const SceneModel<T> &sm, CollideScratch<T> &cs, Shape<T> &A, Shape<T> &B, int ok, const T *normal,
+                                                   T depth, const T *pa, const T *pb, PairContacts<T> &pc) {
   if (!ok) return;
   if (!(depth > T(0))) return;
   if (manifold_seq(sm, cs, A, B, normal, depth, pc) > 0) return;
@@ -437,6 +435,15 @@ __device__ __noinline__ void collide_convex_seq(const SceneModel<T> &sm, Collide
   for (int c = 0; c < 3; c++) pos[c] = T(0.5) * (pa[c] + pb[c]);
   pc.normal[0] = frame[0]; pc.normal[1] = frame[1]; pc.normal[2] = frame[2];
   emit_seq(pc, pos, -depth);
+}
+
+template <typename T>
+__device__ __noinline__ void collide_convex_seq(const SceneModel<T> &sm, CollideScratch<T> &cs, Shape<T> &A, Shape<T> &B, const MPoint<T> *S, int n,
+                                                PairContacts<T> &pc, int &eit, long long &t_epa) {
+  T normal[3], depth, pa[3], pb[3];
+  const int ok = epa_seq(sm, cs, A, B, S, n, normal, depth, pa, pb, eit);
+  t_epa = clock64();  // (stage probe: when this lane left EPA)
+  finish_convex_pair(sm, cs, A, B, ok, normal, depth, pa, pb, pc);
 }
 
 template <typename T>

@@ -867,6 +867,21 @@ __global__ void __launch_bounds__(GJK_THREADS) scene_gjk_kernel(const __grid_con
   }
 }
 
+// contacts of one pair -> the env's raw buffer, with the (pair, manifold index) sort key
+template <typename T>
+__device__ __forceinline__ void emit_pair_contacts(const PipeBuf<T> &pb, const PairContacts<T> &pc, int env, int g1, int g2, int pidx) {
+  if (pc.n <= 0) return;
+  const int base = atomicAdd(pb.ncon_raw + env, pc.n);
+  for (int c = 0; c < pc.n; c++)
+    if (base + c < CONBUF) {
+      T *dst = pb.con + ((size_t)env * CONBUF + base + c) * 8;
+      dst[0] = pc.normal[0]; dst[1] = pc.normal[1]; dst[2] = pc.normal[2];
+      dst[3] = pc.pos[c][0]; dst[4] = pc.pos[c][1]; dst[5] = pc.pos[c][2];
+      dst[6] = pc.dist[c];
+      pb.con_key[(size_t)env * CONBUF + base + c] = (pidx << 20) | (c << 16) | (g1 << 8) | g2;
+    }
+}
+
 // Per substep, ONE THREAD per intersecting pair: EPA -> manifold (scene_collide_seq.cuh), contacts to the env's raw buffer.
 #ifndef SO101_NSEQ_MINCTAS
 #define SO101_NSEQ_MINCTAS 12
@@ -906,17 +921,7 @@ __global__ void __launch_bounds__(NSEQ_THREADS, NSEQ_MINCTAS) scene_narrow_seq_k
       eit_sum += eit; nepa++;
       if (S.prof) atomicAdd(&g_epahist[eit <= 2 ? 0 : eit <= 5 ? 1 : eit <= 10 ? 2 : eit <= 20 ? 3 : eit <= 40 ? 4 : eit < EPA_MAXIT ? 5 : 6], 1);
     }
-    if (pc.n > 0) {
-      const int base = atomicAdd(pb.ncon_raw + env, pc.n);
-      for (int c = 0; c < pc.n; c++)
-        if (base + c < CONBUF) {
-          T *dst = pb.con + ((size_t)env * CONBUF + base + c) * 8;
-          dst[0] = pc.normal[0]; dst[1] = pc.normal[1]; dst[2] = pc.normal[2];
-          dst[3] = pc.pos[c][0]; dst[4] = pc.pos[c][1]; dst[5] = pc.pos[c][2];
-          dst[6] = pc.dist[c];
-          pb.con_key[(size_t)env * CONBUF + base + c] = (pidx << 20) | (c << 16) | (g1 << 8) | g2;
-        }
-    }
+    emit_pair_contacts(pb, pc, env, g1, g2, pidx);
     if (S.prof) {  // stage probe: how long the lanes that were active in this trip spent in EPA and in the manifold stage
       const long long t1 = clock64();
       long long e = t_epa - t0, m = t1 - t_epa;
@@ -935,6 +940,56 @@ __global__ void __launch_bounds__(NSEQ_THREADS, NSEQ_MINCTAS) scene_narrow_seq_k
   if (S.prof) {
     eit_sum = warp_sum(eit_sum); nepa = warp_sum(nepa);
     if (lane == 0 && nepa) { atomicAdd(S.prof + P_EPAIT, (unsigned long long)eit_sum); atomicAdd(S.prof + P_NEPA, (unsigned long long)nepa); }
+  }
+}
+
+// The same work as scene_narrow_seq_kernel in TWO launches, for large batches: STAGE 0 runs EPA for every intersecting convex pair
+// and leaves (normal, depth, witness points, hints) in the pair's hit record, where its GJK simplex was; STAGE 1 builds the
+// manifold (or the plane contacts) and emits.  Each stage carries half of the fused kernel's 12 k instructions (the fused kernel
+// spends 3 of its 13 stall cycles per instruction waiting for instruction fetch at full occupancy) and touches only its half
+// of the per-thread scratch.  At small batches, where every launch lasts as long as its slowest warp, the second launch's own
+// tail costs more than it saves, so launch_scene_step picks by group size.  Same arithmetic, same results.
+template <typename T, int STAGE>
+__global__ void __launch_bounds__(NSEQ_THREADS, NSEQ_MINCTAS) scene_narrow_split_kernel(const __grid_constant__ SceneModel<T> sm, const EnvState<T> S, const PipeBuf<T> pb, int sub) {
+  __shared__ int qpref[NSEQ_THREADS / 32][WQ + 1], hpref[NSEQ_THREADS / 32][WQ + 1];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int *cnt = pb.nwork + WSTRIDE * sub;
+  build_qpref(qpref[wib], cnt, pb.work_cap, lane);
+  build_qpref(hpref[wib], cnt + W_QHIT, pb.work_cap, lane);
+  const int nhit = hpref[wib][WQ];
+  const int stride = gridDim.x * NSEQ_THREADS;
+#pragma unroll 1
+  for (int item = blockIdx.x * NSEQ_THREADS + threadIdx.x; item < nhit; item += stride) {
+    const int hq = queue_of(hpref[wib], item), hslot = qpref[wib][hq] + (item - hpref[wib][hq]);
+    if (hslot >= pb.hit_cap) continue;
+    HitRec<T> &rec = pb.hits[hslot];
+    const int env = (int)rec.env, g1 = (int)(rec.packed & 0xff), g2 = (int)((rec.packed >> 8) & 0xff), pidx = (int)(rec.packed >> 16);
+    if (STAGE == 0 && sm.geom_type[g1] == G_PLANE) continue;   // plane pairs have no EPA stage
+    const T(*xpos)[3] = reinterpret_cast<const T(*)[3]>(pb.xpos + (size_t)env * (NSLOT * 3));
+    const T(*xmat)[9] = reinterpret_cast<const T(*)[9]>(pb.xmat + (size_t)env * (NSLOT * 9));
+    Shape<T> A, B;
+    make_shape(sm, xpos, xmat, g1, A);
+    make_shape(sm, xpos, xmat, g2, B);
+    A.hint = rec.hintA; B.hint = rec.hintB;
+    CollideScratch<T> cs;
+    T *r = &rec.S[0][0];
+    if (STAGE == 0) {
+      T normal[3], depth = T(0), pa[3] = {T(0), T(0), T(0)}, pb_[3] = {T(0), T(0), T(0)};
+      int eit = 0;
+      const int ok = epa_seq(sm, cs, A, B, reinterpret_cast<const MPoint<T> *>(r), rec.n, normal, depth, pa, pb_, eit);
+      // the simplex is dead now: the EPA result takes its place, together with the hill-climbing hints the manifold continues from
+      if (ok) { r[0] = normal[0]; r[1] = normal[1]; r[2] = normal[2]; r[3] = depth; r[4] = pa[0]; r[5] = pa[1]; r[6] = pa[2]; r[7] = pb_[0]; r[8] = pb_[1]; r[9] = pb_[2]; }
+      rec.pad = ok; rec.hintA = A.hint; rec.hintB = B.hint;
+    } else {
+      PairContacts<T> pc;
+      pc.n = 0;
+      if (A.type == G_PLANE) collide_plane_seq(sm, cs, A, B, pc);
+      else {
+        const T normal[3] = {r[0], r[1], r[2]}, pa[3] = {r[4], r[5], r[6]}, pb_[3] = {r[7], r[8], r[9]};
+        finish_convex_pair(sm, cs, A, B, rec.pad, normal, r[3], pa, pb_, pc);
+      }
+      emit_pair_contacts(pb, pc, env, g1, g2, pidx);
+    }
   }
 }
 
@@ -1284,6 +1339,9 @@ int launch_scene_step(const ArmSetT<T> &am, const ArmSetT<double> &am64, const S
   int sms = 0;   // SMs of the device the handle lives on (148 on B200): grids are sized in multiples of it
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   const int seq_per_sm = getenv("SO101_SEQ_CTAS") ? atoi(getenv("SO101_SEQ_CTAS")) : 16;  // narrow-phase CTAs of 64 threads per SM
+  // groups of at least this many envs run the narrow phase as two launches (scene_narrow_split_kernel)
+  const int split_min = getenv("SO101_NARROW_SPLIT") ? atoi(getenv("SO101_NARROW_SPLIT")) : 32768;
+  int nlaunch = ngroups * (3 + 8 * cfg.nsub);
   for (int sub = 0; sub < cfg.nsub; sub++) {
     for (int g = 0; g < ngroups; g++) {
       const PipeBuf<T> &pb = pbs[g];
@@ -1297,7 +1355,11 @@ int launch_scene_step(const ArmSetT<T> &am, const ArmSetT<double> &am64, const S
       scene_gjk_kernel<T><<<grid_gjk, GJK_THREADS, 0, st>>>(sm, S, pb, sub);
       t.end(5, st);
       t.begin(1, st);
-      scene_narrow_seq_kernel<T><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub);
+      if (pb.nenv >= split_min) {
+        scene_narrow_split_kernel<T, 0><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub);
+        scene_narrow_split_kernel<T, 1><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub);
+        nlaunch++;
+      } else scene_narrow_seq_kernel<T><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub);
       t.end(1, st);
       scene_classify_kernel<T><<<(pb.nenv + 127) / 128, 128, 0, st>>>(sm, S, pb, sub);
       // the three solver tiers work on disjoint envs: tiers 1 and 2 run on side streams beside tier 0 and join before the
@@ -1321,7 +1383,7 @@ int launch_scene_step(const ArmSetT<T> &am, const ArmSetT<double> &am64, const S
     cudaEventRecord(txs[g].done, txs[g].main);
     cudaStreamWaitEvent(stream, txs[g].done, 0);
   }
-  return ngroups * (3 + 8 * cfg.nsub);
+  return nlaunch;
 }
 template <typename T>
 void launch_scene_reset(const StepCfg &cfg, const EnvState<T> &S, const uint8_t *mask, const so101_step_out &out, cudaStream_t stream) {

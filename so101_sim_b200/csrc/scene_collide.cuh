@@ -64,6 +64,7 @@ struct CollideScratch {
       FPt<T> P[MAXCAND], Hh[2 * MAXCAND + 2], FA[MAXFEAT], FB[MAXFEAT], R[2 * MAXFEAT + 8], bufA[2 * MAXFEAT + 8], bufB[2 * MAXFEAT + 8];
       T mdist[2 * MAXFEAT + 8], mdist2[2 * MAXFEAT + 8];
       HPlane<T> hp[2];  // height interpolants of the two features
+      int candi[FEAT_EXACT];  // hull vertex ids of the first FEAT_EXACT slab vertices (feature_seq)
     };
   };
 };

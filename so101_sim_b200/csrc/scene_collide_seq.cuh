@@ -206,17 +206,30 @@ __device__ __noinline__ int feature_seq(const SceneModel<T> &sm, CollideScratch<
 #pragma unroll
     for (int k = 0; k < 8; k++) { emax[k] = -INFINITY; emin[k] = INFINITY; imax[k] = imin[k] = 0; }
     const T thr = hmax - delta;
-    // one in-slab vertex: count it, keep the first FEAT_EXACT (a small slab then needs no second pass), update the extremes
-    auto take = [&](int i, const Vec4<T> &v) {
-      const T x = (v.x * t1l[0] + v.y * t1l[1] + v.z * t1l[2]) + ox, y = (v.x * t2l[0] + v.y * t2l[1] + v.z * t2l[2]) + oy;
-      if (nband < FEAT_EXACT) { cs.cand[0][nband] = x; cs.cand[1][nband] = y; cs.cand[2][nband] = (v.x * dl[0] + v.y * dl[1] + v.z * dl[2]) + off; }
-      nband++;
+    // one in-slab vertex: count it and keep the first FEAT_EXACT (a small slab - the usual case - then needs no second pass and
+    // no extremes at all).  The extremes start with vertex FEAT_EXACT + 1: the stored ones are folded in first, in the same
+    // (index) order, so the result is what updating them for every vertex would give.
+    auto extremes = [&](int i, T x, T y) {
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const T val = feat_cos<T>(k) * x + feat_sin<T>(k) * y;
         if (val > emax[k]) { emax[k] = val; imax[k] = i; }
         if (val < emin[k]) { emin[k] = val; imin[k] = i; }
       }
+    };
+    auto take = [&](int i, const Vec4<T> &v) {
+      const T x = (v.x * t1l[0] + v.y * t1l[1] + v.z * t1l[2]) + ox, y = (v.x * t2l[0] + v.y * t2l[1] + v.z * t2l[2]) + oy;
+      if (nband < FEAT_EXACT) {
+        cs.cand[0][nband] = x; cs.cand[1][nband] = y; cs.cand[2][nband] = (v.x * dl[0] + v.y * dl[1] + v.z * dl[2]) + off;
+        cs.candi[nband] = i;
+      } else {
+        if (nband == FEAT_EXACT) {
+#pragma unroll 1
+          for (int j = 0; j < FEAT_EXACT; j++) extremes(cs.candi[j], cs.cand[0][j], cs.cand[1][j]);
+        }
+        extremes(i, x, y);
+      }
+      nband++;
     };
     // Full scan, SCANW heights per trip (independent loads: the vertex loads come from L2 while the L1 is busy with the per-thread
     // scratch, so the number of round trips is what counts); the few in-slab vertices are then handled one by one in index order.

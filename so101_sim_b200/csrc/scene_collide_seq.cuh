@@ -61,11 +61,19 @@ __device__ __forceinline__ int epa_best_seq(const CollideScratch<T> &cs, int nf)
   return bi;
 }
 
+// EPA in three parts, so that a caller can interleave the iterations of different pairs (scene_epa_kernel): the state between
+// calls is the polytope in cs plus EpaState.  epa_seq() below runs them back to back.
 template <typename T>
-__device__ __noinline__ int epa_seq(const SceneModel<T> &sm, CollideScratch<T> &cs, Shape<T> &A, Shape<T> &B, const MPoint<T> *S, int n, T *normal,
-                                    T &depth, T *pa, T *pb, int &iters) {
-  int nv = 0, nf = 0;
-  iters = 0;
+struct EpaState {
+  int nv, nf, it, best;
+  T inside[3];
+};
+
+// polytope from the GJK simplex (completed to a tetrahedron).  Returns 0 when there is nothing to expand (EPA reports no contact).
+template <typename T>
+__device__ __forceinline__ int epa_begin(const SceneModel<T> &sm, CollideScratch<T> &cs, Shape<T> &A, Shape<T> &B, const MPoint<T> *S, int n, EpaState<T> &st) {
+  int nv = 0;
+  st.nf = 0; st.it = 0; st.best = -1;
   if (n == 1) return 0;
 #pragma unroll 1
   for (int i = 0; i < n; i++) epa_putv_seq(cs, nv++, S[i]);
@@ -98,64 +106,77 @@ __device__ __noinline__ int epa_seq(const SceneModel<T> &sm, CollideScratch<T> &
     }
     epa_putv_seq(cs, nv++, p);
   }
-  T inside[3] = {T(0), T(0), T(0)};
-  for (int i = 0; i < 4; i++) { T v[3]; epa_getv(cs, i, v); for (int k = 0; k < 3; k++) inside[k] += T(0.25) * v[k]; }
-  if (epa_add_face_seq(cs, nf, 0, 1, 2, inside) < 0 || epa_add_face_seq(cs, nf, 0, 1, 3, inside) < 0 ||
-      epa_add_face_seq(cs, nf, 0, 2, 3, inside) < 0 || epa_add_face_seq(cs, nf, 1, 2, 3, inside) < 0) return 0;
-  int best = -1;
+  st.nv = nv;
+  st.inside[0] = st.inside[1] = st.inside[2] = T(0);
+  for (int i = 0; i < 4; i++) { T v[3]; epa_getv(cs, i, v); for (int k = 0; k < 3; k++) st.inside[k] += T(0.25) * v[k]; }
+  if (epa_add_face_seq(cs, st.nf, 0, 1, 2, st.inside) < 0 || epa_add_face_seq(cs, st.nf, 0, 1, 3, st.inside) < 0 ||
+      epa_add_face_seq(cs, st.nf, 0, 2, 3, st.inside) < 0 || epa_add_face_seq(cs, st.nf, 1, 2, 3, st.inside) < 0) return 0;
+  return 1;
+}
+
+// one expansion.  Returns 0 = call again, 1 = finished (epa_end reads the result), -1 = no face left (EPA reports no contact).
+template <typename T>
+__device__ __forceinline__ int epa_step(const SceneModel<T> &sm, CollideScratch<T> &cs, Shape<T> &A, Shape<T> &B, EpaState<T> &st) {
+  if (st.it >= EPA_MAXIT) return 1;
+  const int nf0 = st.nf;
+  const int best = epa_best_seq(cs, nf0);
+  st.best = best;
+  if (best < 0) return -1;
+  if (st.nv >= EPA_MAXV) return 1;
+  st.it++;
+  const T bn[3] = {cs.Fn[0][best], cs.Fn[1][best], cs.Fn[2][best]}, bd = cs.Fd[best];
+  MPoint<T> p;
+  msupport_seq(sm, A, B, bn, p);
+  const T adv = dot3(p.w, bn) - bd;
+  if (adv < T(sizeof(T) == 8 ? 1e-9 : 1e-6)) return 1;
+  const int nv = st.nv;
+  epa_putv_seq(cs, nv, p);
+  // visibility (p above the face plane: n . p - d > eps; dead faces have d = +inf), four faces per trip, then the horizon
+  // edits of the visible ones in face order (same order as the oracle)
+  int nh = 0;
+  const T veps = T(sizeof(T) == 8 ? 1e-12 : 1e-9);
 #pragma unroll 1
-  for (int it = 0; it < EPA_MAXIT; it++) {
-    best = epa_best_seq(cs, nf);
-    if (best < 0) return 0;
-    if (nv >= EPA_MAXV) break;
-    iters = it + 1;
-    const T bn[3] = {cs.Fn[0][best], cs.Fn[1][best], cs.Fn[2][best]}, bd = cs.Fd[best];
-    MPoint<T> p;
-    msupport_seq(sm, A, B, bn, p);
-    const T adv = dot3(p.w, bn) - bd;
-    if (adv < T(sizeof(T) == 8 ? 1e-9 : 1e-6)) break;
-    epa_putv_seq(cs, nv, p);
-    // visibility (p above the face plane: n . p - d > eps; dead faces have d = +inf), four faces per trip, then the horizon
-    // edits of the visible ones in face order (same order as the oracle)
-    int nh = 0;
-    const T veps = T(sizeof(T) == 8 ? 1e-12 : 1e-9);
-#pragma unroll 1
-    for (int f0 = 0; f0 < nf; f0 += 4) {
-      unsigned vis = 0;
+  for (int f0 = 0; f0 < nf0; f0 += 4) {
+    unsigned vis = 0;
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int f = f0 + u < nf ? f0 + u : f0;
-        const T sdist = (cs.Fn[0][f] * p.w[0] + cs.Fn[1][f] * p.w[1] + cs.Fn[2][f] * p.w[2]) - cs.Fd[f];
-        if (f0 + u < nf && sdist > veps) vis |= 1u << u;
-      }
+    for (int u = 0; u < 4; u++) {
+      const int f = f0 + u < nf0 ? f0 + u : f0;
+      const T sdist = (cs.Fn[0][f] * p.w[0] + cs.Fn[1][f] * p.w[1] + cs.Fn[2][f] * p.w[2]) - cs.Fd[f];
+      if (f0 + u < nf0 && sdist > veps) vis |= 1u << u;
+    }
 #pragma unroll 1
-      while (vis) {
-        const int f = f0 + __ffs(vis) - 1;
-        vis &= vis - 1;
-        cs.Falive[f] = 0; cs.Fd[f] = INFINITY;
-        for (int e = 0; e < 3; e++) {
-          const int a = cs.Fv[e][f], b = cs.Fv[(e + 1) % 3][f];
-          int found = 0;
+    while (vis) {
+      const int f = f0 + __ffs(vis) - 1;
+      vis &= vis - 1;
+      cs.Falive[f] = 0; cs.Fd[f] = INFINITY;
+      for (int e = 0; e < 3; e++) {
+        const int a = cs.Fv[e][f], b = cs.Fv[(e + 1) % 3][f];
+        int found = 0;
 #pragma unroll 1
-          for (int h = 0; h < nh; h++)
-            if (cs.horizon[h][0] == b && cs.horizon[h][1] == a) {
-              cs.horizon[h][0] = cs.horizon[nh - 1][0]; cs.horizon[h][1] = cs.horizon[nh - 1][1]; nh--; found = 1;
-              break;
-            }
-          if (!found && nh < EPA_MAXF) { cs.horizon[nh][0] = a; cs.horizon[nh][1] = b; nh++; }
-        }
+        for (int h = 0; h < nh; h++)
+          if (cs.horizon[h][0] == b && cs.horizon[h][1] == a) {
+            cs.horizon[h][0] = cs.horizon[nh - 1][0]; cs.horizon[h][1] = cs.horizon[nh - 1][1]; nh--; found = 1;
+            break;
+          }
+        if (!found && nh < EPA_MAXF) { cs.horizon[nh][0] = a; cs.horizon[nh][1] = b; nh++; }
       }
     }
-    if (nh == 0) break;
-    int failed = 0;
-#pragma unroll 1
-    for (int h = 0; h < nh; h++)
-      if (epa_add_face_seq(cs, nf, cs.horizon[h][0], cs.horizon[h][1], nv, inside) < 0) failed = 1;
-    nv++;
-    if (failed) break;
   }
+  if (nh == 0) return 1;
+  int failed = 0;
+#pragma unroll 1
+  for (int h = 0; h < nh; h++)
+    if (epa_add_face_seq(cs, st.nf, cs.horizon[h][0], cs.horizon[h][1], nv, st.inside) < 0) failed = 1;
+  st.nv = nv + 1;
+  return failed;
+}
+
+// penetration normal / depth and witness points from the face closest to the origin.  Returns 0 when no face is left.
+template <typename T>
+__device__ __forceinline__ int epa_end(CollideScratch<T> &cs, const EpaState<T> &st, T *normal, T &depth, T *pa, T *pb) {
+  int best = st.best;
   if (best < 0 || !cs.Falive[best]) {
-    best = epa_best_seq(cs, nf);
+    best = epa_best_seq(cs, st.nf);
     if (best < 0) return 0;
   }
   const T fn[3] = {cs.Fn[0][best], cs.Fn[1][best], cs.Fn[2][best]}, fd = cs.Fd[best];
@@ -175,6 +196,20 @@ __device__ __noinline__ int epa_seq(const SceneModel<T> &sm, CollideScratch<T> &
     pb[k] = bu * cs.Vb[k][i0] + bv * cs.Vb[k][i1] + bw * cs.Vb[k][i2];
   }
   return 1;
+}
+
+template <typename T>
+__device__ __noinline__ int epa_seq(const SceneModel<T> &sm, CollideScratch<T> &cs, Shape<T> &A, Shape<T> &B, const MPoint<T> *S, int n, T *normal,
+                                    T &depth, T *pa, T *pb, int &iters) {
+  EpaState<T> st;
+  iters = 0;
+  if (!epa_begin(sm, cs, A, B, S, n, st)) return 0;
+  int r;
+#pragma unroll 1
+  do { r = epa_step(sm, cs, A, B, st); } while (r == 0);
+  iters = st.it;
+  if (r < 0) return 0;
+  return epa_end(cs, st, normal, depth, pa, pb);
 }
 
 // vertices of s within delta of the support plane along dir -> CCW 2-D convex polygon in (t1,t2) with heights

@@ -993,6 +993,72 @@ __global__ void __launch_bounds__(NSEQ_THREADS, NSEQ_MINCTAS) scene_narrow_split
   }
 }
 
+// EPA stage of the two-launch narrow phase as a per-lane state machine: every lane owns one pair at a time and the warp runs
+// ONE polytope expansion per round for all of its lanes, whatever pair and iteration each lane is at; a lane whose pair has
+// converged takes the next pair from the group's cursor (warp-aggregated atomicAdd) once `refill_min` lanes are waiting, so the
+// set-up code runs for many lanes at a time.  Run-to-completion per pair (scene_narrow_split_kernel<T, 0>) keeps 5-6 of 32
+// lanes busy, because iteration counts range from 1 to 50 inside a warp; here the lanes a round occupies are those still
+// expanding.  Same per-pair arithmetic, same results.
+template <typename T>
+__global__ void __launch_bounds__(NSEQ_THREADS, NSEQ_MINCTAS) scene_epa_kernel(const __grid_constant__ SceneModel<T> sm, const EnvState<T> S, const PipeBuf<T> pb, int sub, int refill_min) {
+  __shared__ int qpref[NSEQ_THREADS / 32][WQ + 1], hpref[NSEQ_THREADS / 32][WQ + 1];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int *cnt = pb.nwork + WSTRIDE * sub;
+  build_qpref(qpref[wib], cnt, pb.work_cap, lane);
+  build_qpref(hpref[wib], cnt + W_QHIT, pb.work_cap, lane);
+  const int nhit = hpref[wib][WQ];
+  int *cursor = cnt + W_HITCURSOR;
+  const unsigned lt = (1u << lane) - 1u;
+  Shape<T> A, B;
+  CollideScratch<T> cs;
+  EpaState<T> st;
+  HitRec<T> *rec = nullptr;
+  bool busy = false, drained = false;
+#pragma unroll 1
+  while (true) {
+    const unsigned idle = __ballot_sync(FULL, !busy && !drained), act = __ballot_sync(FULL, busy);
+    if (!idle && !act) break;
+    if (idle && (!act || __popc(idle) >= refill_min)) {
+      const int leader = __ffs(idle) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(cursor, __popc(idle));
+      base = __shfl_sync(FULL, base, leader);
+      if (!busy && !drained) {
+        const int item = base + __popc(idle & lt);
+        if (item >= nhit) drained = true;
+        else {
+          const int hq = queue_of(hpref[wib], item), hslot = qpref[wib][hq] + (item - hpref[wib][hq]);
+          if (hslot < pb.hit_cap) {
+            rec = &pb.hits[hslot];
+            const int env = (int)rec->env, g1 = (int)(rec->packed & 0xff), g2 = (int)((rec->packed >> 8) & 0xff);
+            if (sm.geom_type[g1] != G_PLANE) {   // (plane pairs have no EPA stage)
+              const T(*xpos)[3] = reinterpret_cast<const T(*)[3]>(pb.xpos + (size_t)env * (NSLOT * 3));
+              const T(*xmat)[9] = reinterpret_cast<const T(*)[9]>(pb.xmat + (size_t)env * (NSLOT * 9));
+              make_shape(sm, xpos, xmat, g1, A);
+              make_shape(sm, xpos, xmat, g2, B);
+              A.hint = rec->hintA; B.hint = rec->hintB;
+              if (epa_begin(sm, cs, A, B, reinterpret_cast<const MPoint<T> *>(&rec->S[0][0]), rec->n, st)) busy = true;
+              else { rec->pad = 0; rec->hintA = A.hint; rec->hintB = B.hint; }
+            }
+          }
+        }
+      }
+    }
+    if (busy) {
+      const int r_ = epa_step(sm, cs, A, B, st);
+      if (r_ != 0) {
+        T normal[3], depth = T(0), pa[3], pb_[3];
+        const int ok = r_ > 0 ? epa_end(cs, st, normal, depth, pa, pb_) : 0;
+        // the simplex is dead now: the EPA result takes its place, together with the hill-climbing hints the manifold continues from
+        T *r = &rec->S[0][0];
+        if (ok) { r[0] = normal[0]; r[1] = normal[1]; r[2] = normal[2]; r[3] = depth; r[4] = pa[0]; r[5] = pa[1]; r[6] = pa[2]; r[7] = pb_[0]; r[8] = pb_[1]; r[9] = pb_[2]; }
+        rec->pad = ok; rec->hintA = A.hint; rec->hintB = B.hint;
+        busy = false;
+      }
+    }
+  }
+}
+
 // Gather the env's raw contacts into shared memory in oracle order (pair order, then manifold order).  Returns false (and
 // touches nothing) when the env needs more than NC contacts or NB Jacobian blocks: the caller defers it to the large tier.
 template <typename T, typename SC>
@@ -1341,6 +1407,8 @@ int launch_scene_step(const ArmSetT<T> &am, const ArmSetT<double> &am64, const S
   const int seq_per_sm = getenv("SO101_SEQ_CTAS") ? atoi(getenv("SO101_SEQ_CTAS")) : 16;  // narrow-phase CTAs of 64 threads per SM
   // groups of at least this many envs run the narrow phase as two launches (scene_narrow_split_kernel)
   const int split_min = getenv("SO101_NARROW_SPLIT") ? atoi(getenv("SO101_NARROW_SPLIT")) : 32768;
+  // lanes of a warp that wait for a new pair before the EPA kernel fetches (0: run-to-completion EPA, scene_narrow_split_kernel<T, 0>)
+  const int epa_refill = getenv("SO101_EPA_REFILL") ? atoi(getenv("SO101_EPA_REFILL")) : 20;
   int nlaunch = ngroups * (3 + 8 * cfg.nsub);
   for (int sub = 0; sub < cfg.nsub; sub++) {
     for (int g = 0; g < ngroups; g++) {
@@ -1355,8 +1423,9 @@ int launch_scene_step(const ArmSetT<T> &am, const ArmSetT<double> &am64, const S
       scene_gjk_kernel<T><<<grid_gjk, GJK_THREADS, 0, st>>>(sm, S, pb, sub);
       t.end(5, st);
       t.begin(1, st);
-      if (pb.nenv >= split_min) {
-        scene_narrow_split_kernel<T, 0><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub);
+      if (pb.nenv >= split_min && !S.prof) {   // (the stage probes live in the fused kernel)
+        if (epa_refill > 0) scene_epa_kernel<T><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub, epa_refill);
+        else scene_narrow_split_kernel<T, 0><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub);
         scene_narrow_split_kernel<T, 1><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub);
         nlaunch++;
       } else scene_narrow_seq_kernel<T><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub);

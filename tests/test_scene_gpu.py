@@ -362,10 +362,38 @@ def test_episode_step_counters_roundtrip_and_time_limit(built):
   env.close()
 
 
-def test_kernel_times_and_launch_counts(built):
+@pytest.mark.parametrize('precision', ['f32', 'f64'])
+def test_two_launch_narrow_phase_is_bit_identical(built, monkeypatch, precision):
+  """Groups of 32768+ envs run the narrow phase as two launches (scene_epa_kernel: EPA as a per-lane state machine with pairs
+  taken from a cursor; scene_narrow_split_kernel<1>: manifold / plane contacts) instead of the fused thread-per-pair kernel.
+  Forced on at 64 envs (SO101_NARROW_SPLIT = smallest group size that uses it), with both EPA variants, the states after 25
+  random-action control steps must equal the fused kernel's bit for bit, and the launch counter must show the extra launch."""
+  results = []
+  for split, refill in (('1000000000', None), ('1', '20'), ('1', '3'), ('1', '0')):
+    monkeypatch.setenv('SO101_NARROW_SPLIT', split)
+    if refill is None: monkeypatch.delenv('SO101_EPA_REFILL', raising=False)
+    else: monkeypatch.setenv('SO101_EPA_REFILL', refill)
+    env = _env(built, num_envs=64, precision=precision)
+    _initial(env, seed=11)
+    acts = _actions(env, 25, seed=5)
+    c0 = env.counters()['kernel_launches']
+    for t in range(25):
+      env.step(acts[t])
+    launches = env.counters()['kernel_launches'] - c0
+    q, v = env.get_state(torch.float64)
+    results.append((q.clone(), v.clone(), launches, env.debug_read('ncon').flatten().clone()))
+    env.close()
+  assert results[0][2] == 25 * 83 and all(r[2] == 25 * 93 for r in results[1:])
+  assert int(results[0][3].max()) >= 8     # the rollout has contacts
+  for r in results[1:]:
+    assert torch.equal(r[0], results[0][0]) and torch.equal(r[1], results[0][1]) and torch.equal(r[3], results[0][3])
+
+
+def test_kernel_times_and_launch_counts(built, monkeypatch):
   """so101_kernel_times: CUDA-event time per kernel while enabled; one control step = 3 + 8 x 10 launches per group
   (begin, kinematics + dynamics, broad phase; then per substep GJK, EPA / manifold, classify, three solver tiers, kinematics + dynamics,
   broad phase or task layer)."""
+  monkeypatch.delenv('SO101_NARROW_SPLIT', raising=False)
   env = _env(built, num_envs=8)
   env.sample_prop_initial_states(seed=2, settle_steps=0)
   c0 = env.counters()

@@ -36,10 +36,15 @@
 
 namespace so101 {
 
-constexpr int WARPS_SOLVE = 2;   // envs (warps) per CTA in the tier-0 solve kernel
+// envs (warps) per CTA in the tier-0 solve kernel.  One: a two-env CTA keeps the slot of its faster env (or of an env that belongs
+// to a larger tier) idle until the slower one is done; measured at 131072 envs late in a random-action rollout, when a third of
+// the envs are in the larger tiers: 623 k -> 654 k env-steps/s.  (A persistent variant that takes tier-0 envs from a queue,
+// as the larger tiers do, was slower - 634 k: its CTAs hold every solver slot of the SM until the queue is empty, and the
+// larger tiers' CTAs no longer run beside them.)
+constexpr int WARPS_SOLVE = 1;
 // Solver tiers by contact capacity: a resting scene has ~20 contacts, an arm pressed into the table or props 40-100.  Each
 // tier is the same code with a larger shared-memory scratch; an env that does not fit tier t is queued for tier t + 1.
-constexpr int NC_S = 32, NB_S = 40;            // tier 0: every env, 2 warps per CTA
+constexpr int NC_S = 32, NB_S = 36;            // tier 0: every env that fits; 13.2 KB of scratch = 16 single-warp CTAs per SM
 constexpr int NC_M = 64, NB_M = 80;            // tier 1
 constexpr int NC_L = CONBUF, NB_L = CONBUF + 32;  // tier 2 (last: excess contacts are dropped and counted)
 constexpr int WARPS_M = 1, WARPS_L = 1;  // single-warp CTAs: small enough to co-reside with tier-0 CTAs on an SM

@@ -57,7 +57,7 @@ struct CollideScratch {
       unsigned char Fv[3][EPA_MAXF];  // vertex ids < EPA_MAXV
       T Fn[3][EPA_MAXF], Fd[EPA_MAXF];
       unsigned char Falive[EPA_MAXF];
-      unsigned char horizon[EPA_MAXF][2];
+      unsigned short horizon[EPA_MAXF];  // directed edges a | b << 8 (vertex ids < EPA_MAXV <= 255)
     };
     struct {  // manifold
       T cand[3][MAXCAND];

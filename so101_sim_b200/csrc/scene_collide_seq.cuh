@@ -149,16 +149,21 @@ __device__ __forceinline__ int epa_step(const SceneModel<T> &sm, CollideScratch<
       const int f = f0 + __ffs(vis) - 1;
       vis &= vis - 1;
       cs.Falive[f] = 0; cs.Fd[f] = INFINITY;
+      const int fv[3] = {cs.Fv[0][f], cs.Fv[1][f], cs.Fv[2][f]};
       for (int e = 0; e < 3; e++) {
-        const int a = cs.Fv[e][f], b = cs.Fv[(e + 1) % 3][f];
-        int found = 0;
+        const int a = fv[e], b = fv[(e + 1) % 3];
+        // an edge whose reverse is already listed cancels it (the last entry takes its slot), otherwise it is appended.  A directed
+        // edge is listed at most once, so the search can look at four entries per trip (independent local-memory loads).
+        const unsigned rev = (unsigned)b | ((unsigned)a << 8);
+        int at = -1;
 #pragma unroll 1
-        for (int h = 0; h < nh; h++)
-          if (cs.horizon[h][0] == b && cs.horizon[h][1] == a) {
-            cs.horizon[h][0] = cs.horizon[nh - 1][0]; cs.horizon[h][1] = cs.horizon[nh - 1][1]; nh--; found = 1;
-            break;
-          }
-        if (!found && nh < EPA_MAXF) { cs.horizon[nh][0] = a; cs.horizon[nh][1] = b; nh++; }
+        for (int h0 = 0; h0 < nh && at < 0; h0 += 4) {
+          const unsigned e0 = cs.horizon[h0], e1 = h0 + 1 < nh ? cs.horizon[h0 + 1] : 0xffffu, e2 = h0 + 2 < nh ? cs.horizon[h0 + 2] : 0xffffu,
+                         e3 = h0 + 3 < nh ? cs.horizon[h0 + 3] : 0xffffu;
+          at = e0 == rev ? h0 : (e1 == rev ? h0 + 1 : (e2 == rev ? h0 + 2 : (e3 == rev ? h0 + 3 : -1)));
+        }
+        if (at >= 0) { cs.horizon[at] = cs.horizon[nh - 1]; nh--; }
+        else if (nh < EPA_MAXF) { cs.horizon[nh] = (unsigned short)((unsigned)a | ((unsigned)b << 8)); nh++; }
       }
     }
   }
@@ -166,7 +171,7 @@ __device__ __forceinline__ int epa_step(const SceneModel<T> &sm, CollideScratch<
   int failed = 0;
 #pragma unroll 1
   for (int h = 0; h < nh; h++)
-    if (epa_add_face_seq(cs, st.nf, cs.horizon[h][0], cs.horizon[h][1], nv, st.inside) < 0) failed = 1;
+    if (epa_add_face_seq(cs, st.nf, (int)(cs.horizon[h] & 0xff), (int)(cs.horizon[h] >> 8), nv, st.inside) < 0) failed = 1;
   st.nv = nv + 1;
   return failed;
 }

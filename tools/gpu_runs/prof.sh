@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU session: stage profile + ncu full capture of the scene kernel.  Usage (under gpurun): bash tools/gpu_prof.sh <tag>
+# GPU session: stage profile + ncu full capture of the scene kernel.  Usage (under gpurun): bash tools/gpu_runs/prof.sh <tag>
 tag=${1:-r01b}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"

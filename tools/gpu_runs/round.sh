@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU session: parity tests, smoke, bench line, ncu launch list + full capture of the main kernels at the bench config.
-# Usage (under gpurun): bash tools/gpu_round.sh <tag>
+# Usage (under gpurun): bash tools/gpu_runs/round.sh <tag>
 tag=${1:-r02}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.txt 2>&1

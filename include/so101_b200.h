@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SO101_ABI_VERSION 3
+#define SO101_ABI_VERSION 4
 
 /* dm_env.StepType values (reference TimeStep.step_type) */
 #define SO101_STEP_FIRST 0
@@ -130,6 +130,17 @@ int so101_set_state_f64(so101_handle h, const double *qpos_dev, const double *qv
  * checkpoint-resume and to start a batch at staggered episode phases. */
 int so101_get_episode_steps(so101_handle h, int32_t *steps_dev, void *stream);
 int so101_set_episode_steps(so101_handle h, const int32_t *steps_dev, void *stream);
+
+/* Checkpoint / resume of a whole handle.  get_state / set_state move the physics state only, as physics.get_state() does
+ * (so100_task.py:366-368); a rollout also depends on what composer.Environment and the observables keep between steps: warm
+ * starts, ctrl, the observation delay buffers (so100_task.py:196-210), episode counters and auto-reset flags, the reset states,
+ * and here the placement machinery (nursery envs in SETTLE mode, Philox draw counters, the ring of settled placements).
+ * so101_checkpoint_save copies all of it into ONE caller-owned device buffer of so101_checkpoint_size bytes (a header, then the
+ * arrays); so101_checkpoint_load restores it into a handle created with the same model blob, precision, num_envs, nursery_envs,
+ * ring_capacity and delay settings, after which stepping continues bit for bit as it would have.  Both synchronise the stream. */
+int so101_checkpoint_size(so101_handle h, size_t *bytes);
+int so101_checkpoint_save(so101_handle h, void *buf_dev, size_t bytes, void *stream);
+int so101_checkpoint_load(so101_handle h, const void *buf_dev, size_t bytes, void *stream);
 
 /* End-to-end variant with HOST buffers (pinned or pageable): copies action_host [N,6] to the device, steps, copies every
  * block of the TimeStep whose pointer in *out_host is non-NULL (HOST pointers, same shapes as so101_step_out) back, and

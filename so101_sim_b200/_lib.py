@@ -31,7 +31,8 @@ class Config(ctypes.Structure):
 
 EXPORTS = ('so101_abi_version', 'so101_create', 'so101_destroy', 'so101_last_error', 'so101_dims', 'so101_set_initial_state',
            'so101_reset', 'so101_step', 'so101_get_state', 'so101_set_state', 'so101_get_state_f64', 'so101_step_host',
-           'so101_counters', 'so101_debug_read', 'so101_kernel_times', 'so101_set_reset_pool', 'so101_set_state_f64', 'so101_debug_overlap', 'so101_sample_and_settle', 'so101_placement_stats', 'so101_get_episode_steps', 'so101_set_episode_steps')
+           'so101_counters', 'so101_debug_read', 'so101_kernel_times', 'so101_set_reset_pool', 'so101_set_state_f64', 'so101_debug_overlap', 'so101_sample_and_settle', 'so101_placement_stats', 'so101_get_episode_steps', 'so101_set_episode_steps',
+           'so101_checkpoint_size', 'so101_checkpoint_save', 'so101_checkpoint_load')
 
 _libs = {}
 
@@ -60,6 +61,9 @@ def load(narm: int = 1) -> ctypes.CDLL:
   L.so101_sample_and_settle.restype = ci; L.so101_sample_and_settle.argtypes = [vp, ctypes.c_uint64, ctypes.POINTER(StepOut), ctypes.POINTER(ctypes.c_uint64 * 4), vp]
   L.so101_get_episode_steps.restype = ci; L.so101_get_episode_steps.argtypes = [vp, vp, vp]
   L.so101_set_episode_steps.restype = ci; L.so101_set_episode_steps.argtypes = [vp, vp, vp]
+  L.so101_checkpoint_size.restype = ci; L.so101_checkpoint_size.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
+  L.so101_checkpoint_save.restype = ci; L.so101_checkpoint_save.argtypes = [vp, vp, ctypes.c_size_t, vp]
+  L.so101_checkpoint_load.restype = ci; L.so101_checkpoint_load.argtypes = [vp, vp, ctypes.c_size_t, vp]
   L.so101_placement_stats.restype = ci; L.so101_placement_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64 * 6)]
   L.so101_set_reset_pool.restype = ci; L.so101_set_reset_pool.argtypes = [vp, vp, vp, ci, vp]
   L.so101_reset.restype = ci; L.so101_reset.argtypes = [vp, vp, ctypes.POINTER(StepOut), vp]
@@ -68,7 +72,7 @@ def load(narm: int = 1) -> ctypes.CDLL:
   L.so101_counters.restype = ci; L.so101_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64 * 6)]
   L.so101_kernel_times.restype = ci; L.so101_kernel_times.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double * 8), ctypes.POINTER(ctypes.c_uint64 * 8)]
   L.so101_debug_read.restype = ci; L.so101_debug_read.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t, vp]
-  if L.so101_abi_version() != 3:
+  if L.so101_abi_version() != 4:
     raise RuntimeError(f'{path}: ABI version mismatch')
   _libs[narm] = L
   return L

@@ -59,6 +59,8 @@ struct HandleBase {
   virtual void episode_steps(int32_t *steps_dev, bool set, cudaStream_t s) = 0;
   virtual void step_host(const float *action, const so101_step_out &host_out, cudaStream_t s) = 0;
   virtual uint64_t diverged() = 0;
+  virtual size_t checkpoint_bytes() = 0;
+  virtual void checkpoint(void *buf_dev, size_t bytes, bool load, cudaStream_t s) = 0;
   KernelTimer timer;
   std::vector<TierExec> tiers;  // one per pipeline group
 };
@@ -503,6 +505,64 @@ struct Handle : HandleBase {
     if (set) CUDA_OK(cudaMemcpyAsync(S.step, steps_dev, sizeof(int) * S.NU, cudaMemcpyDeviceToDevice, s));
     else CUDA_OK(cudaMemcpyAsync(steps_dev, S.step, sizeof(int) * S.NU, cudaMemcpyDeviceToDevice, s));
   }
+  // ---- checkpoint: everything a handle needs to continue a rollout bit for bit (device buffer: header, then the segments)
+  struct CkptHeader {
+    uint32_t magic, abi, sizeof_real, narm;
+    int32_t N, NU, nq, nv, npool, ring_cap, use_ring, dj, dp, nseg;
+    uint32_t settle_epoch, pad;
+    uint64_t steps, bytes;
+  };
+  struct Seg { void *p; size_t bytes; };
+  std::vector<Seg> segments() const {
+    const size_t N = S.N;
+    std::vector<Seg> v = {
+      {S.qpos, sizeof(TS) * nq * N}, {S.qvel, sizeof(TS) * nv * N}, {S.warm, sizeof(T) * nv * N}, {S.ctrl, sizeof(T) * NA * N},
+      {S.init_qpos, sizeof(TS) * (size_t)S.npool * nq * N}, {S.init_qvel, sizeof(TS) * (size_t)S.npool * nv * N},
+      {S.step, sizeof(int) * N}, {S.needs_reset, N}, {S.episode, sizeof(int) * N},
+      {S.ring_joints, sizeof(float) * (size_t)(sc.dj + 1) * NA * N}, {S.ring_phys, sizeof(float) * (size_t)(sc.dp + 1) * (nq + nv) * N},
+      {S.mode, N}, {S.sstate, N}, {S.settle_sub, sizeof(int) * N}, {S.attempt, sizeof(int) * N}, {S.draws, sizeof(unsigned) * N},
+      {S.ring_ctr, sizeof(int) * RC_N}, {S.diverged_count, sizeof(int) * 2}, {S.solver_iter, sizeof(int) * N}, {S.ncon, sizeof(int) * N},
+      {S.dropped_env, sizeof(int) * N}};
+    if (S.ring_cap > 0) { v.push_back({S.ring_q, sizeof(TS) * (size_t)S.ring_cap * nq}); v.push_back({S.ring_v, sizeof(TS) * (size_t)S.ring_cap * nv}); }
+    return v;
+  }
+  static size_t pad16(size_t b) { return (b + 15) / 16 * 16; }
+  size_t checkpoint_bytes() override {
+    size_t b = pad16(sizeof(CkptHeader));
+    for (const Seg &g : segments()) b += pad16(g.bytes);
+    return b;
+  }
+  void checkpoint(void *buf_dev, size_t bytes, bool load, cudaStream_t s) override {
+    unsigned char *buf = static_cast<unsigned char *>(buf_dev);
+    CkptHeader hd{};
+    if (!load) {
+      const size_t need = checkpoint_bytes();
+      if (bytes < need) throw std::runtime_error("checkpoint buffer too small (ask so101_checkpoint_size)");
+      const auto segs = segments();
+      hd = CkptHeader{0x43314f53u /* 'SO1C' */, SO101_ABI_VERSION, (uint32_t)sizeof(T), (uint32_t)NARM, S.N, S.NU, nq, nv, S.npool, S.ring_cap,
+                      S.use_ring, sc.dj, sc.dp, (int32_t)segs.size(), settle_epoch, 0u, steps, need};
+      CUDA_OK(cudaMemcpyAsync(buf, &hd, sizeof hd, cudaMemcpyHostToDevice, s));
+      size_t off = pad16(sizeof hd);
+      for (const Seg &g : segs) { CUDA_OK(cudaMemcpyAsync(buf + off, g.p, g.bytes, cudaMemcpyDeviceToDevice, s)); off += pad16(g.bytes); }
+      CUDA_OK(cudaStreamSynchronize(s));   // (the header was copied from this stack frame)
+      return;
+    }
+    if (bytes < sizeof hd) throw std::runtime_error("not a checkpoint: buffer shorter than the header");
+    CUDA_OK(cudaStreamSynchronize(s));
+    CUDA_OK(cudaMemcpy(&hd, buf, sizeof hd, cudaMemcpyDeviceToHost));
+    if (hd.magic != 0x43314f53u || hd.abi != SO101_ABI_VERSION) throw std::runtime_error("not a checkpoint of this library version");
+    if (hd.sizeof_real != sizeof(T) || hd.narm != (uint32_t)NARM || hd.N != S.N || hd.NU != S.NU || hd.nq != nq || hd.nv != nv || hd.ring_cap != S.ring_cap ||
+        hd.dj != sc.dj || hd.dp != sc.dp)
+      throw std::runtime_error("checkpoint was taken from a handle with a different model, precision, env count, nursery or observation delays");
+    if (hd.npool < 1 || (size_t)hd.npool > pool_cap) throw std::runtime_error("checkpoint holds a larger reset pool than this handle has allocated (install a pool of that many rounds first)");
+    if (hd.bytes > bytes) throw std::runtime_error("checkpoint buffer is truncated");
+    if (hd.npool != S.npool || hd.use_ring != S.use_ring) { invalidate_graphs(); S.npool = hd.npool; S.use_ring = hd.use_ring; }
+    const auto segs = segments();
+    if ((int32_t)segs.size() != hd.nseg) throw std::runtime_error("checkpoint layout mismatch");
+    size_t off = pad16(sizeof hd);
+    for (const Seg &g : segs) { CUDA_OK(cudaMemcpyAsync(g.p, buf + off, g.bytes, cudaMemcpyDeviceToDevice, s)); off += pad16(g.bytes); }
+    settle_epoch = hd.settle_epoch; steps = hd.steps;
+  }
   uint64_t diverged() override {
     int v[2] = {0, 0};
     cudaMemcpy(v, S.diverged_count, 2 * sizeof(int), cudaMemcpyDeviceToHost);
@@ -618,6 +678,24 @@ int so101_set_episode_steps(so101_handle h, const int32_t *steps_dev, void *stre
   API_BEGIN(h)
   if (!steps_dev) throw std::runtime_error("null pointer");
   H->episode_steps(const_cast<int32_t *>(steps_dev), true, (cudaStream_t)stream);
+  API_END()
+}
+int so101_checkpoint_size(so101_handle h, size_t *bytes) {
+  API_BEGIN(h)
+  if (!bytes) throw std::runtime_error("null pointer");
+  *bytes = H->checkpoint_bytes();
+  API_END()
+}
+int so101_checkpoint_save(so101_handle h, void *buf_dev, size_t bytes, void *stream) {
+  API_BEGIN(h)
+  if (!buf_dev) throw std::runtime_error("null pointer");
+  H->checkpoint(buf_dev, bytes, false, (cudaStream_t)stream);
+  API_END()
+}
+int so101_checkpoint_load(so101_handle h, const void *buf_dev, size_t bytes, void *stream) {
+  API_BEGIN(h)
+  if (!buf_dev) throw std::runtime_error("null pointer");
+  H->checkpoint(const_cast<void *>(buf_dev), bytes, true, (cudaStream_t)stream);
   API_END()
 }
 int so101_placement_stats(so101_handle h, uint64_t out[6]) {

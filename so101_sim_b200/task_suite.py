@@ -361,6 +361,21 @@ class BatchedEnvironment:
       raise ValueError('steps must have shape [num_envs]')
     self._check(self._lib.so101_set_episode_steps(self._h, ctypes.c_void_p(s.data_ptr()), self._stream()))
 
+  def save_checkpoint(self) -> torch.Tensor:
+    """Everything the env needs to continue this rollout bit for bit, as one uint8 device tensor: physics state, warm starts,
+    ctrl, observation delay buffers, episode counters and auto-reset flags, reset states, and the placement machinery (nursery
+    envs, Philox draw counters, the ring of settled placements).  get_state() alone is physics.get_state() (so100_task.py:366-368)."""
+    n = ctypes.c_size_t(0)
+    self._check(self._lib.so101_checkpoint_size(self._h, ctypes.byref(n)))
+    buf = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+    self._check(self._lib.so101_checkpoint_save(self._h, ctypes.c_void_p(buf.data_ptr()), n.value, self._stream()))
+    return buf
+
+  def load_checkpoint(self, buf: torch.Tensor):
+    """Restore a save_checkpoint() tensor into this env (same task, precision, num_envs, nursery_envs and ring capacity)."""
+    b = buf.to(device=self.device, dtype=torch.uint8).contiguous()
+    self._check(self._lib.so101_checkpoint_load(self._h, ctypes.c_void_p(b.data_ptr()), b.numel(), self._stream()))
+
   def debug_read(self, field: str, width: int = 1) -> torch.Tensor:
     out = torch.empty(self.num_envs, width, dtype=torch.float32, device=self.device)
     self._check(self._lib.so101_debug_read(self._h, field.encode(), ctypes.c_void_p(out.data_ptr()), out.numel(), self._stream()))

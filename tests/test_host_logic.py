@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
     L = ctypes.CDLL(path)
     for sym in declared:
       assert hasattr(L, sym), (path, sym)
-    assert L.so101_abi_version() == 3
+    assert L.so101_abi_version() == 4
 
 
 def test_create_fails_loudly_without_gpu(built):

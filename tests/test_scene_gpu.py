@@ -362,6 +362,75 @@ def test_episode_step_counters_roundtrip_and_time_limit(built):
   env.close()
 
 
+def _trace(env, acts):
+  out = []
+  for a in acts:
+    ts = env.step(a)
+    out.append([ts.step_type.clone(), ts.reward.clone(), ts.discount.clone()] + [v.clone() for _, v in sorted(ts.observation.items())])
+  q, v = env.get_state(torch.float64)
+  return out, q, v
+
+
+def test_checkpoint_resume_is_bit_identical(built):
+  """so101_checkpoint_save / _load: a rollout resumed from a checkpoint - in the same env after it has moved on, and in a second
+  env created the same way - reproduces every TimeStep (delayed observations included) and the final state bit for bit.  The
+  window crosses time-limit LAST steps and auto-resets from a two-round reset pool (0.3 s episodes = 16 control steps), so the
+  warm starts, the delay buffers, the episode / pool counters and the auto-reset flags all have to come back."""
+  from so101_sim_b200.task_suite import create_batched_task_env
+  kw = dict(task_name='SO100HandOverBanana', num_envs=16, time_limit=0.3, seed=3, device='cuda:0', placement='pool', reset_rounds=2)
+  env = create_batched_task_env(**kw)
+  env.reset()
+  acts = _actions(env, 45, seed=9)
+  for t in range(11):
+    env.step(acts[t])
+  ck = env.save_checkpoint()
+  assert ck.dtype == torch.uint8 and ck.numel() > 16 * (20 + 18) * 8
+  ref, q_ref, v_ref = _trace(env, acts[11:])
+  kinds = torch.stack([r[0] for r in ref])
+  assert (kinds == 2).any() and (kinds == 0).any()         # the window holds LAST and FIRST steps
+  env.load_checkpoint(ck)                                    # (1) rewind the same env
+  again, q1, v1 = _trace(env, acts[11:])
+  other = create_batched_task_env(**kw)                      # (2) a second env that never saw the first 11 steps
+  other.load_checkpoint(ck)
+  third, q2, v2 = _trace(other, acts[11:])
+  for got, q, v in ((again, q1, v1), (third, q2, v2)):
+    assert torch.equal(q, q_ref) and torch.equal(v, v_ref)
+    for a, b in zip(ref, got):
+      assert all(torch.equal(x, y) for x, y in zip(a, b))
+  # a handle created differently refuses the checkpoint
+  small = create_batched_task_env(**dict(kw, num_envs=8))
+  with pytest.raises(RuntimeError, match='different model'):
+    small.load_checkpoint(ck)
+  with pytest.raises(RuntimeError, match='not a checkpoint'):
+    env.load_checkpoint(torch.zeros(ck.numel(), dtype=torch.uint8, device='cuda:0'))
+  for e in (env, other, small):
+    e.close()
+
+
+def test_checkpoint_carries_the_placement_machinery(built):
+  """With nursery envs the checkpoint also holds the SETTLE-mode state of the hidden envs, the Philox draw counters and the ring
+  of settled placements with its counters: after a load the placement statistics read as they did at the save, and the
+  nursery continues from there."""
+  from so101_sim_b200.task_suite import create_batched_task_env
+  env = create_batched_task_env('SO100HandOverBanana', num_envs=16, time_limit=30.0, seed=5, device='cuda:0', placement='device', nursery_envs=16)
+  env.reset()
+  zero = torch.zeros(16, 6, device='cuda:0')
+  for _ in range(40):
+    env.step(zero)
+  at_save = env.placement_stats()
+  ck = env.save_checkpoint()
+  for _ in range(60):
+    env.step(zero)
+  later = env.placement_stats()
+  assert later['published'] > at_save['published']
+  env.load_checkpoint(ck)
+  assert env.placement_stats() == at_save
+  for _ in range(60):
+    env.step(zero)
+  assert env.placement_stats()['published'] == later['published']   # the nursery's own trajectory is deterministic
+  env.close()
+
+
 @pytest.mark.parametrize('precision', ['f32', 'f64'])
 def test_two_launch_narrow_phase_is_bit_identical(built, monkeypatch, precision):
   """Groups of 32768+ envs run the narrow phase as two launches (scene_epa_kernel: EPA as a per-lane state machine with pairs

@@ -1,6 +1,7 @@
 // C-ABI implementation (include/so101_b200.h): handle life cycle, model upload, kernel launches.
 // PyTorch owns every tensor that crosses this boundary; the handle owns only its SoA state and scratch.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -575,6 +576,12 @@ struct Handle : HandleBase {
 
 using namespace so101;
 
+// NVTX range around an entry point (header-only NVTX 3: a no-op unless a profiler injects its library; `ncu --nvtx
+// --nvtx-include "so101_step/"` restricts a capture to the kernels of the steps)
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 #define API_BEGIN(h)                                   \
   if (!(h)) return -1;                                 \
   HandleBase *H = reinterpret_cast<HandleBase *>(h);   \
@@ -663,6 +670,7 @@ int so101_set_state_f64(so101_handle h, const double *qpos_dev, const double *qv
 }
 int so101_sample_and_settle(so101_handle h, uint64_t seed, const so101_step_out *out, uint64_t stats_out[4], void *stream) {
   API_BEGIN(h)
+  NvtxRange range_("so101_sample_and_settle");
   so101_step_out o{};
   if (out) o = *out;
   H->sample_and_settle(seed, o, stats_out, (cudaStream_t)stream);
@@ -688,12 +696,14 @@ int so101_checkpoint_size(so101_handle h, size_t *bytes) {
 }
 int so101_checkpoint_save(so101_handle h, void *buf_dev, size_t bytes, void *stream) {
   API_BEGIN(h)
+  NvtxRange range_("so101_checkpoint_save");
   if (!buf_dev) throw std::runtime_error("null pointer");
   H->checkpoint(buf_dev, bytes, false, (cudaStream_t)stream);
   API_END()
 }
 int so101_checkpoint_load(so101_handle h, const void *buf_dev, size_t bytes, void *stream) {
   API_BEGIN(h)
+  NvtxRange range_("so101_checkpoint_load");
   if (!buf_dev) throw std::runtime_error("null pointer");
   H->checkpoint(const_cast<void *>(buf_dev), bytes, true, (cudaStream_t)stream);
   API_END()
@@ -718,6 +728,7 @@ int so101_get_state_f64(so101_handle h, double *qpos_dev, double *qvel_dev, void
 }
 int so101_reset(so101_handle h, const uint8_t *mask_dev, const so101_step_out *out, void *stream) {
   API_BEGIN(h)
+  NvtxRange range_("so101_reset");
   so101_step_out o{};
   if (out) o = *out;
   H->reset(mask_dev, o, (cudaStream_t)stream);
@@ -725,6 +736,7 @@ int so101_reset(so101_handle h, const uint8_t *mask_dev, const so101_step_out *o
 }
 int so101_step(so101_handle h, const float *action_dev, const so101_step_out *out, void *stream) {
   API_BEGIN(h)
+  NvtxRange range_("so101_step");
   if (!action_dev) throw std::runtime_error("null action pointer");
   so101_step_out o{};
   if (out) o = *out;
@@ -733,6 +745,7 @@ int so101_step(so101_handle h, const float *action_dev, const so101_step_out *ou
 }
 int so101_step_host(so101_handle h, const float *action_host, const so101_step_out *out_host, void *stream) {
   API_BEGIN(h)
+  NvtxRange range_("so101_step_host");
   if (!action_host) throw std::runtime_error("null action pointer");
   so101_step_out o{};
   if (out_host) o = *out_host;

@@ -595,3 +595,57 @@ def create_batched_task_env(task_name: str, num_envs: int, time_limit: float, se
   elif placement == 'pool':
     env.randomize_resets(rounds=int(reset_rounds))
   return env
+
+
+@dataclasses.dataclass
+class BatchedEnvConfig:
+  """The arguments of create_batched_task_env as one typed, serialisable record (run configs, sweeps, checkpoints' metadata).
+  The reference passes the same things as loose keyword arguments (task_suite.create_task_env, task_suite.py:103-155)."""
+  task_name: str = 'SO100HandOverBanana'
+  num_envs: int = 1
+  time_limit: float = 30.0
+  seed: int | None = None
+  control_timestep: float = DEFAULT_CONTROL_TIMESTEP
+  cameras: tuple = ()
+  device: str = 'cuda:0'
+  calibration_offsets: tuple | None = None
+  calibration_file: str | None = None
+  precision: str = 'f32'
+  solver_iterations: int = 100
+  solver_tolerance: float | None = None
+  reset_rounds: int = 1
+  placement: str = 'device'
+  nursery_envs: int | None = None
+  integrator: str = 'euler'
+  task_kwargs: dict = dataclasses.field(default_factory=dict)   # extra task constructor arguments (filtered like the reference does)
+
+  def __post_init__(self):
+    if self.task_name not in TASK_FACTORIES:
+      raise ValueError(f'Unknown task_name: {self.task_name}. Available tasks: {list(TASK_FACTORIES.keys())}')
+    if self.num_envs < 1:
+      raise ValueError('num_envs must be >= 1')
+    if self.precision not in ('f32', 'f64'):
+      raise ValueError("precision must be 'f32' or 'f64'")
+    if self.placement not in ('device', 'pool', 'none'):
+      raise ValueError("placement must be 'device', 'pool' or 'none'")
+    if self.integrator not in ('euler', 'implicitfast'):
+      raise ValueError("integrator must be 'euler' or 'implicitfast'")
+    self.cameras = tuple(self.cameras)
+    if self.calibration_offsets is not None:
+      self.calibration_offsets = tuple(float(x) for x in self.calibration_offsets)
+
+  def to_dict(self) -> dict:
+    return dataclasses.asdict(self)
+
+  @classmethod
+  def from_dict(cls, d: dict) -> 'BatchedEnvConfig':
+    known = {f.name for f in dataclasses.fields(cls)}
+    unknown = set(d) - known
+    if unknown:
+      raise ValueError(f'unknown config keys: {sorted(unknown)}')
+    return cls(**d)
+
+  def create(self) -> BatchedEnvironment:
+    kw = self.to_dict()
+    extra = kw.pop('task_kwargs')
+    return create_batched_task_env(**kw, **extra)

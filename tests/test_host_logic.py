@@ -67,3 +67,26 @@ def test_blob_roundtrip_fields():
   assert full['ngeom'][0] == 83                                         # 83 colliding geoms
   np.testing.assert_allclose(full['dof_armature'][:6], 0.1); np.testing.assert_allclose(full['dof_frictionloss'][:6], 0.1)
   np.testing.assert_allclose(full['act_ctrlrange'].reshape(-1, 2), [[-3.14158, 3.14158]] * 6)
+
+
+def test_batched_env_config_mirrors_the_factory():
+  """BatchedEnvConfig carries exactly the factory's keyword arguments (with the same defaults), round-trips through a dict /
+  JSON and rejects what the factory would reject."""
+  import inspect, json
+  import dataclasses
+  from so101_sim_b200.task_suite import BatchedEnvConfig, create_batched_task_env
+  sig = inspect.signature(create_batched_task_env).parameters
+  fields = {f.name: f for f in dataclasses.fields(BatchedEnvConfig)}
+  assert set(fields) - {'task_kwargs'} == set(sig) - {'kwargs'}
+  for name, f in fields.items():
+    if name in ('task_kwargs', 'task_name', 'num_envs', 'time_limit'):
+      continue
+    assert f.default == sig[name].default, name
+  c = BatchedEnvConfig(task_name='SO100HandOverPen', num_envs=64, precision='f64', calibration_offsets=[0, 1, 2, 3, 4, 5], cameras=[])
+  again = BatchedEnvConfig.from_dict(json.loads(json.dumps(c.to_dict())))
+  assert again == c and again.calibration_offsets == (0.0, 1.0, 2.0, 3.0, 4.0, 5.0) and again.cameras == ()
+  for bad in (dict(task_name='NoSuchTask'), dict(num_envs=0), dict(precision='f16'), dict(placement='host'), dict(integrator='rk4')):
+    with pytest.raises(ValueError):
+      BatchedEnvConfig(**bad)
+  with pytest.raises(ValueError, match='unknown config keys'):
+    BatchedEnvConfig.from_dict({'envs': 3})

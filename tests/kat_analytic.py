@@ -58,6 +58,33 @@ def rest_depth(mass, ncontacts):
   return 0.5 * (lo + hi)
 
 
+def rest_depth_loaded(load_mass, ncontacts, invweight, tc):
+  """General form: `ncontacts` equally loaded contacts between bodies whose translational invweight0 sum to `invweight`, mixed
+  solref time constant `tc`, carrying load_mass * g:  n * imp^2 / (1 - imp) * K(tc) * d / invweight = load_mass * g."""
+  K = 1.0 / (SOLIMP[1]**2 * max(tc, 2 * DT)**2)
+  f = lambda d: ncontacts * impedance(d)**2 / (1.0 - impedance(d)) * K * d / invweight - load_mass * G
+  lo, hi = 0.0, 1e-3
+  for _ in range(200):
+    mid = 0.5 * (lo + hi)
+    lo, hi = (mid, hi) if f(mid) < 0 else (lo, mid)
+  return 0.5 * (lo + hi)
+
+
+def stack_state(qpos0):
+  """The capsule lying along x on top of the box, which lies flat on the table: the capsule (half extent 0.055) overhangs the
+  box top (half extent 0.03), so the box / capsule contact is the capsule's bottom line clipped to the face: two points at x =
+  +-0.03, each carrying m_cap g / 2; the four box / table contacts carry (m_box + m_cap) g."""
+  hz = BOX_HALF[2]
+  return scene_state(qpos0, (0.25, 0.0, TABLE_TOP + hz), cap_pos=(0.25, 0.0, TABLE_TOP + 2 * hz + CAP_R), cap_quat=quat_about((0, 1, 0), np.pi / 2))
+
+
+def stack_rest_depths():
+  """(box into table, capsule into box): the lower contacts mix solref (0.004 + 0.02) / 2 and see the box's invweight only (the
+  table is static); the upper contacts are prop against prop: solref 0.004 (= 2 dt), invweight 1 / m_box + 1 / m_cap."""
+  return (rest_depth_loaded(BOX_MASS + CAP_MASS, 4, 1.0 / BOX_MASS, SOLREF[0]),
+          rest_depth_loaded(CAP_MASS, 2, 1.0 / BOX_MASS + 1.0 / CAP_MASS, 0.004))
+
+
 def quat_about(axis, angle):
   a = np.asarray(axis, dtype=np.float64); a = a / np.linalg.norm(a)
   return np.concatenate([[np.cos(angle / 2)], np.sin(angle / 2) * a])

@@ -74,6 +74,27 @@ def test_rest_penetration_matches_the_closed_form(built, precision):
 
 
 @pytest.mark.parametrize('precision', ['f64', 'f32'])
+def test_stacked_bodies_rest_at_the_closed_form_penetrations(built, precision):
+  """Capsule on box on table: contact rows between two dynamic bodies and the load passed down (tests/kat_analytic.py
+  stack_rest_depths: 7.7409e-05 m into the table under both weights, 1.7322e-05 m between the props)."""
+  env = _kat_env(built, 1, precision)
+  _put(env, [ka.stack_state(env.model['qpos0'])])
+  zero = torch.zeros(1, 6, device=DEV)
+  for _ in range(150):
+    env.step(zero)
+  q, v = env.get_state(torch.float64)
+  zb, zc = float(q[0, 8]), float(q[0, 15])
+  m_low, m_up = ka.TABLE_TOP + ka.BOX_HALF[2] - zb, (zb + ka.BOX_HALF[2]) - (zc - ka.CAP_R)
+  d_low, d_up = ka.stack_rest_depths()
+  print(f'{precision} stack rest penetrations: box/table analytic {d_low:.6e} measured {m_low:.6e}; capsule/box analytic {d_up:.6e} measured {m_up:.6e}')
+  tol = 1e-9 if precision == 'f64' else 5e-7
+  assert abs(m_low - d_low) < tol and abs(m_up - d_up) < tol
+  assert float(v[0, 6:18].abs().max()) < (1e-9 if precision == 'f64' else 1e-4)
+  assert int(env.debug_read('ncon').flatten()[0]) == 6 and env.counters()['diverged'] == 0
+  env.close()
+
+
+@pytest.mark.parametrize('precision', ['f64', 'f32'])
 def test_sliding_box_decelerates_at_mu_g(built, precision):
   env = _kat_env(built, 2, precision, control_timestep=0.002)
   q0 = env.model['qpos0']

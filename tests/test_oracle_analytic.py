@@ -82,6 +82,28 @@ def test_capsule_rests_at_the_closed_form_penetration():
   assert np.abs(o.qvel[12:18]).max() < 1e-6
 
 
+def test_stacked_bodies_rest_at_the_closed_form_penetrations_and_pass_the_load_down():
+  """Capsule on box on table (ka.stack_state): contact rows between TWO dynamic bodies (Jacobian blocks of both, invweight sum,
+  prop / prop parameter mixing) and the load transfer through the lower body.  Penetrations against the closed forms, normal
+  forces: capsule / box contacts carry m_cap g, box / table contacts (m_box + m_cap) g."""
+  d_low, d_up = ka.stack_rest_depths()
+  o = _sim()
+  _settle(o, ka.stack_state(o.meta['qpos0']), steps=150)
+  zb, zc = o.qpos[8], o.qpos[15]
+  m_low, m_up = ka.TABLE_TOP + ka.BOX_HALF[2] - zb, (zb + ka.BOX_HALF[2]) - (zc - ka.CAP_R)
+  print('stack rest penetrations: box/table analytic %.9e measured %.9e; capsule/box analytic %.9e measured %.9e' % (d_low, m_low, d_up, m_up))
+  assert abs(m_low - d_low) < 1e-9 and abs(m_up - d_up) < 1e-9
+  assert np.abs(o.qvel[6:18]).max() < 1e-9
+  f = o.field('efc_force')
+  low = [c for c in o.contacts() if (c['geom1'], c['geom2']) == (ka.TABLE_GEOM, ka.BOX_GEOM)]
+  up = [c for c in o.contacts() if (c['geom1'], c['geom2']) == (ka.BOX_GEOM, ka.CAPSULE_GEOM)]
+  assert len(low) == 4 and len(up) == 2
+  assert abs(sum(f[c['efc_address']] for c in low) / ((ka.BOX_MASS + ka.CAP_MASS) * ka.G) - 1) < 1e-6
+  assert abs(sum(f[c['efc_address']] for c in up) / (ka.CAP_MASS * ka.G) - 1) < 1e-6
+  assert sorted(round(c['pos'][0] - 0.25, 9) for c in up) == [-0.03, 0.03]          # the line contact clipped to the box face
+  assert all(np.allclose(c['solref'], (0.004, 1.0)) for c in up)
+
+
 def test_sliding_box_decelerates_at_mu_g():
   """A box sliding on the table at 0.3 m/s: every contact sits on the friction cone, so the deceleration is mu * g (mu = 1;
   elliptic cone, impratio 10) while it slides, and it stops without reversing."""

@@ -30,6 +30,18 @@ for t in range(2 * steps):
 torch.cuda.synchronize()
 print('placements ok', env.placement_stats(), env.counters())
 env.close()
+# the two-launch narrow phase of large batches (EPA state machine with a pair cursor, manifold kernel), forced on at 64 envs
+os.environ['SO101_NARROW_SPLIT'] = '1'
+env = create_batched_task_env('SO100HandOverBanana', num_envs=64, time_limit=30.0, seed=0, device=dev, reset_rounds=0)
+env.sample_prop_initial_states(seed=3, clearance=0.001, settle_steps=0)
+a = actions(env)
+for t in range(steps):
+  ts = env.step(a())
+ck = env.save_checkpoint(); env.load_checkpoint(ck)
+torch.cuda.synchronize()
+print('two-launch narrow phase + checkpoint ok', env.counters())
+env.close()
+del os.environ['SO101_NARROW_SPLIT']
 # two-arm build
 env = create_batched_task_env('SO100TwoArmHandOverBanana', num_envs=16, time_limit=30.0, seed=0, device=dev, nursery_envs=0)
 a = actions(env)

@@ -235,12 +235,12 @@ def main():
   return 0
 
 
-def ncu_traffic(workload, envs):
-  """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json), or None."""
+def ncu_traffic(workload, envs, kernel):
+  """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/traffic.json), or None."""
   p = os.path.join(ROOT, 'profiles', 'traffic.json')
   if not os.path.exists(p):
     return None, None
-  t = json.load(open(p)).get(f'{workload}:{envs}')
+  t = json.load(open(p)).get(f'{workload}:{envs}', {}).get(kernel)
   return (t['dram_bytes_per_launch'], t['source']) if t else (None, None)
 
 
@@ -310,7 +310,7 @@ def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_r
   value = envs * world * steps / (dev_ms * 1e-3)
 
   # ---- per-kernel pass (separate from the timed region above): the rollout simply continues for a few steps with CUDA events
-  # around every launch on its launching stream (eager launches)
+  # around every launch (eager launches, all on one stream while the timers are on: each launch is timed alone, as under ncu)
   ksteps = max(2, min(steps, 10))
   k0 = env.kernel_times(True)
   for i in range(ksteps):
@@ -349,12 +349,12 @@ def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_r
   per_launch_steps = envs * ksteps / kern[dom]['launches']
   bytes_per_launch = per_launch_steps * w['bytes_per_env_step']
   achieved = bytes_per_launch / (kern[dom]['us_per_launch'] * 1e-6) / 1e9
-  traffic, traffic_src = ncu_traffic(name, envs)
+  traffic, traffic_src = ncu_traffic(name, envs, dom)
   roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=traffic, kernel=dom,
                   us_per_launch=kern[dom]['us_per_launch'], algorithmic_bytes_per_launch=bytes_per_launch,
                   bytes_per_env_step=w['bytes_per_env_step'], env_steps_per_launch=per_launch_steps, peak_source=peak_src,
                   traffic_source=traffic_src, whole_step_frac=value / world * w['bytes_per_env_step'] / 1e9 / peak,
-                  timed_over=f'{ksteps} control steps continuing the rollout right after the timed region (eager launches, events on each launching stream)',
+                  timed_over=f'{ksteps} control steps continuing the rollout right after the timed region (eager launches on ONE stream, so that every launch is timed alone; the timed region itself replays a CUDA graph with two pipeline groups in flight)',
                   note='state-only algorithmic bytes (SURVEY.md 8d) over the CUDA-event launch time; the path is latency / '
                        'instruction-issue bound, not HBM bound: see profiles/ for issue-slot and stall evidence')
   nsteps = c1['control_steps'] - c0['control_steps']

@@ -1397,10 +1397,14 @@ int launch_scene_step(const ArmSetT<T> &am, const ArmSetT<double> &am64, const S
     scene_broad_kernel<T><<<(pb.nenv + WARPS_BROAD - 1) / WARPS_BROAD, WARPS_BROAD * 32, 0, st>>>(sm, cfg, S, pb, out, sub, last ? 1 : 0);
     t.end(7, st);
   };
+  // While the per-kernel event timers are on, every launch of every group goes to the caller's stream: a launch is then timed
+  // ALONE, as under ncu, instead of sharing the SMs with the other group's kernels and the side-stream solver tiers (which made
+  // a 54 us kinematics launch read 1.6 ms).  The untimed product path interleaves the groups on their own streams.
+  const bool serial = kt && kt->on;
   // interleave the groups' launches substep by substep so that their kernels are in flight together
   for (int g = 0; g < ngroups; g++) {
     const PipeBuf<T> &pb = pbs[g];
-    cudaStream_t st = txs[g].main;
+    cudaStream_t st = serial ? stream : txs[g].main;
     cudaMemsetAsync(pb.nwork, 0, sizeof(int) * WSTRIDE * (cfg.nsub + 1), st);
     t.begin(0, st);
     scene_begin_kernel<T><<<(pb.nenv + WARPS_BROAD - 1) / WARPS_BROAD, WARPS_BROAD * 32, 0, st>>>(cfg, S, pb, action, out);
@@ -1419,7 +1423,7 @@ int launch_scene_step(const ArmSetT<T> &am, const ArmSetT<double> &am64, const S
     for (int g = 0; g < ngroups; g++) {
       const PipeBuf<T> &pb = pbs[g];
       TierExec &tx = txs[g];
-      cudaStream_t st = tx.main;
+      cudaStream_t st = serial ? stream : tx.main, st_m = serial ? stream : tx.sm, st_l = serial ? stream : tx.sl;
       const int grid_env = (pb.nenv + WARPS_SOLVE - 1) / WARPS_SOLVE;
       const int grid_gjk = max(1, min(sms * 16, (pb.nenv * 16 + GJK_THREADS - 1) / GJK_THREADS));
       const int grid_seq = max(1, min(sms * seq_per_sm, (pb.nenv * 12 + NSEQ_THREADS - 1) / NSEQ_THREADS));
@@ -1427,25 +1431,32 @@ int launch_scene_step(const ArmSetT<T> &am, const ArmSetT<double> &am64, const S
       t.begin(5, st);
       scene_gjk_kernel<T><<<grid_gjk, GJK_THREADS, 0, st>>>(sm, S, pb, sub);
       t.end(5, st);
-      t.begin(1, st);
       if (pb.nenv >= split_min && !S.prof) {   // (the stage probes live in the fused kernel)
+        t.begin(8, st);
         if (epa_refill > 0) scene_epa_kernel<T><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub, epa_refill);
         else scene_narrow_split_kernel<T, 0><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub);
+        t.end(8, st);
+        t.begin(9, st);
         scene_narrow_split_kernel<T, 1><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub);
+        t.end(9, st);
         nlaunch++;
-      } else scene_narrow_seq_kernel<T><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub);
-      t.end(1, st);
+      } else {
+        t.begin(1, st);
+        scene_narrow_seq_kernel<T><<<grid_seq, NSEQ_THREADS, 0, st>>>(sm, S, pb, sub);
+        t.end(1, st);
+      }
       scene_classify_kernel<T><<<(pb.nenv + 127) / 128, 128, 0, st>>>(sm, S, pb, sub);
       // the three solver tiers work on disjoint envs: tiers 1 and 2 run on side streams beside tier 0 and join before the
       // next kernel
       cudaEventRecord(tx.fork, st);
-      cudaStreamWaitEvent(tx.sm, tx.fork, 0); cudaStreamWaitEvent(tx.sl, tx.fork, 0);
+      cudaStreamWaitEvent(st_m, tx.fork, 0); cudaStreamWaitEvent(st_l, tx.fork, 0);
       // largest tier first: its few, long envs should not start last
-      scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2><<<grid_l, WARPS_L * 32, smem_l, tx.sl>>>(am, sm, cfg, S, pb, out, sub);
-      t.begin(3, tx.sm);
-      scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1><<<grid_m, WARPS_M * 32, smem_m, tx.sm>>>(am, sm, cfg, S, pb, out, sub);
-      t.end(3, tx.sm);
-      cudaEventRecord(tx.joinm, tx.sm); cudaEventRecord(tx.joinl, tx.sl);
+      if (serial) t.begin(3, st_m);   // (timed alone: the bracket holds both larger tiers)
+      scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2><<<grid_l, WARPS_L * 32, smem_l, st_l>>>(am, sm, cfg, S, pb, out, sub);
+      if (!serial) t.begin(3, st_m);
+      scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1><<<grid_m, WARPS_M * 32, smem_m, st_m>>>(am, sm, cfg, S, pb, out, sub);
+      t.end(3, st_m);
+      cudaEventRecord(tx.joinm, st_m); cudaEventRecord(tx.joinl, st_l);
       t.begin(2, st);
       scene_solve_kernel<T><<<grid_env, WARPS_SOLVE * 32, smem_env, st>>>(am, sm, cfg, S, pb, out, sub);
       t.end(2, st);
@@ -1454,7 +1465,7 @@ int launch_scene_step(const ArmSetT<T> &am, const ArmSetT<double> &am64, const S
     }
   }
   for (int g = 0; g < ngroups; g++) {
-    cudaEventRecord(txs[g].done, txs[g].main);
+    cudaEventRecord(txs[g].done, serial ? stream : txs[g].main);
     cudaStreamWaitEvent(stream, txs[g].done, 0);
   }
   return nlaunch;

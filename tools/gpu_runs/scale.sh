@@ -1,10 +1,10 @@
 #!/bin/bash
 # Scaling evidence on N GPUs of one box: weak (131072 envs per GPU, the bench default) and strong (BASELINE config 5 as written:
 # 131072 envs in total, 131072 / N per GPU).  No per-step collective; NCCL all_gather of episode statistics only.
-n=${1:-2}; tag=${2:-r2x}
+n=${1:-2}; tag=${2:-r2x}; which=${3:-both}
 mkdir -p gpurun_out
 run() {  # name envs_per_gpu
-  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n --envs $2 --steps 20 --warmup 5 > gpurun_out/${tag}_$1_${n}gpu.json 2> gpurun_out/${tag}_$1_${n}gpu.err
+  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n --envs $2 --steps 20 --warmup 5 --no-cpu-baseline --no-secondary --no-steady > gpurun_out/${tag}_$1_${n}gpu.json 2> gpurun_out/${tag}_$1_${n}gpu.err
   echo "$1 rc=$?"; python - <<PY
 import json
 try:
@@ -15,4 +15,4 @@ except Exception as e:
 PY
 }
 run weak 131072
-run strong $((131072 / n))
+if [ "$which" = both ]; then run strong $((131072 / n)); fi

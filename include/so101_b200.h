@@ -155,11 +155,11 @@ int so101_counters(so101_handle h, uint64_t out[6]);
 /* Per-kernel device time, measured with CUDA events around every launch while enabled.  While enabled the step is launched
  * eagerly (no graph replay) and all pipeline groups and solver tiers go to the caller's stream, so that every launch is timed
  * alone.  Returns the totals accumulated so far (ms and launch counts; index 0 scene begin, 1 scene EPA + manifold (fused
- * kernel of small batches), 2 scene solve tier 0, 3 scene solve tiers 1 + 2, 4 arm-only step,
+ * kernel of small batches), 2 scene solve tier 0, 3 scene solve tier 1, 4 arm-only step,
  * 5 scene boolean GJK, 6 scene kinematics + smooth dynamics, 7 scene broad phase / task layer, 8 EPA and 9 manifold kernel
- * of the two-launch narrow phase), then switches recording on/off for the following calls.  Synchronises the host on the
+ * of the two-launch narrow phase, 10 scene solve tier 2), then switches recording on/off for the following calls.  Synchronises the host on the
  * recorded events.  No reference counterpart: measurement support for bench.py's roofline leg. */
-int so101_kernel_times(so101_handle h, int enable, double ms_out[10], uint64_t launches_out[10]);
+int so101_kernel_times(so101_handle h, int enable, double ms_out[11], uint64_t launches_out[11]);
 
 /* Debug/parity probe: copy one internal structure-of-arrays field ("qacc", "ncon", "solver_iter", ...) of all envs to a
  * caller-owned device buffer of `count` floats.  Used by the parity tests only. */

@@ -70,7 +70,7 @@ def load(narm: int = 1) -> ctypes.CDLL:
   L.so101_step.restype = ci; L.so101_step.argtypes = [vp, vp, ctypes.POINTER(StepOut), vp]
   L.so101_step_host.restype = ci; L.so101_step_host.argtypes = [vp, vp, ctypes.POINTER(StepOut), vp]
   L.so101_counters.restype = ci; L.so101_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64 * 6)]
-  L.so101_kernel_times.restype = ci; L.so101_kernel_times.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double * 10), ctypes.POINTER(ctypes.c_uint64 * 10)]
+  L.so101_kernel_times.restype = ci; L.so101_kernel_times.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double * 11), ctypes.POINTER(ctypes.c_uint64 * 11)]
   L.so101_debug_read.restype = ci; L.so101_debug_read.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t, vp]
   if L.so101_abi_version() != 4:
     raise RuntimeError(f'{path}: ABI version mismatch')

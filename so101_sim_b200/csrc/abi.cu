@@ -757,7 +757,7 @@ int so101_counters(so101_handle h, uint64_t out[6]) {
   out[2] = H->diverged(); out[0] = H->launches; out[1] = H->steps; out[3] = H->dropped; out[4] = H->graph_launches; out[5] = 0;
   API_END()
 }
-int so101_kernel_times(so101_handle h, int enable, double ms_out[10], uint64_t launches_out[10]) {
+int so101_kernel_times(so101_handle h, int enable, double ms_out[11], uint64_t launches_out[11]) {
   API_BEGIN(h)
   H->timer.collect();
   for (int i = 0; i < KernelTimer::NK; i++) {

@@ -82,10 +82,10 @@ struct TierExec {
 };
 
 // Optional per-kernel timing with CUDA events on the launching stream (so101_kernel_times; bench.py's roofline leg).
-// Kernel ids: 0 begin, 1 EPA + manifold (fused), 8 EPA / 9 manifold (two-launch narrow phase), 2 solve (tier 0), 3 solve (tiers 1 + 2), 4 arm-only step, 5 boolean GJK,
+// Kernel ids: 0 begin, 1 EPA + manifold (fused), 8 EPA / 9 manifold (two-launch narrow phase), 2 solve (tier 0), 3 solve (tier 1), 10 solve (tier 2), 4 arm-only step, 5 boolean GJK,
 // 6 kinematics + smooth dynamics (thread per env), 7 broad phase / task layer.
 struct KernelTimer {
-  static constexpr int NK = 10;
+  static constexpr int NK = 11;
   bool on = false;
   std::vector<std::array<cudaEvent_t, 2>> ev[NK];
   size_t used[NK] = {};

@@ -1451,9 +1451,10 @@ int launch_scene_step(const ArmSetT<T> &am, const ArmSetT<double> &am64, const S
       cudaEventRecord(tx.fork, st);
       cudaStreamWaitEvent(st_m, tx.fork, 0); cudaStreamWaitEvent(st_l, tx.fork, 0);
       // largest tier first: its few, long envs should not start last
-      if (serial) t.begin(3, st_m);   // (timed alone: the bracket holds both larger tiers)
+      t.begin(10, st_l);
       scene_solve_tier_kernel<T, NC_L, NB_L, WARPS_L, 2><<<grid_l, WARPS_L * 32, smem_l, st_l>>>(am, sm, cfg, S, pb, out, sub);
-      if (!serial) t.begin(3, st_m);
+      t.end(10, st_l);
+      t.begin(3, st_m);
       scene_solve_tier_kernel<T, NC_M, NB_M, WARPS_M, 1><<<grid_m, WARPS_M * 32, smem_m, st_m>>>(am, sm, cfg, S, pb, out, sub);
       t.end(3, st_m);
       cudaEventRecord(tx.joinm, st_m); cudaEventRecord(tx.joinl, st_l);

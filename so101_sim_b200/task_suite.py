@@ -403,13 +403,13 @@ class BatchedEnvironment:
     caps; counters()['contacts_dropped'] is the sum."""
     return self.debug_read('dropped').flatten().to(torch.int64)
 
-  KERNEL_NAMES = ("scene_begin_kernel", "scene_narrow_kernel", "scene_solve_kernel", "scene_solve_tier_kernel(1+2)", "arm_step_kernel", "scene_gjk_kernel",
-                  "scene_kindyn_kernel", "scene_broad_kernel", "scene_epa_kernel", "scene_manifold_kernel")
+  KERNEL_NAMES = ("scene_begin_kernel", "scene_narrow_kernel", "scene_solve_kernel", "scene_solve_tier1_kernel", "arm_step_kernel", "scene_gjk_kernel",
+                  "scene_kindyn_kernel", "scene_broad_kernel", "scene_epa_kernel", "scene_manifold_kernel", "scene_solve_tier2_kernel")
 
   def kernel_times(self, enable: bool = True) -> dict:
     """Accumulated per-kernel device time (CUDA events around each launch, recorded while enabled) -> {name: (ms, launches)};
     then switches the recording on/off for the following steps."""
-    ms = (ctypes.c_double * 10)(); n = (ctypes.c_uint64 * 10)()
+    ms = (ctypes.c_double * 11)(); n = (ctypes.c_uint64 * 11)()
     self._check(self._lib.so101_kernel_times(self._h, int(enable), ctypes.byref(ms), ctypes.byref(n)))
     return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNEL_NAMES)}
 

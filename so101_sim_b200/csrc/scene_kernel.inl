@@ -963,8 +963,20 @@ __global__ void __launch_bounds__(NSEQ_THREADS, NSEQ_MINCTAS) scene_narrow_split
   build_qpref(hpref[wib], cnt + W_QHIT, pb.work_cap, lane);
   const int nhit = hpref[wib][WQ];
   const int stride = gridDim.x * NSEQ_THREADS;
+  int *cursor = cnt + W_CURSOR;
 #pragma unroll 1
-  for (int item = blockIdx.x * NSEQ_THREADS + threadIdx.x; item < nhit; item += stride) {
+  for (int it0 = blockIdx.x * NSEQ_THREADS + threadIdx.x;; it0 += stride) {
+    int item = it0;
+    if (STAGE == 1) {
+      // a warp takes 32 consecutive pairs (same queue = same second geom: its hull loads stay warp-wide broadcasts) from the group's
+      // cursor: a 1000-vertex banana hull costs a warp twenty times a box, and a static assignment leaves the tail to the unlucky
+      int base = 0;
+      if (lane == 0) base = atomicAdd(cursor, 32);
+      base = __shfl_sync(FULL, base, 0);
+      if (base >= nhit) break;
+      item = base + lane;
+      if (item >= nhit) continue;
+    } else if (item >= nhit) break;
     const int hq = queue_of(hpref[wib], item), hslot = qpref[wib][hq] + (item - hpref[wib][hq]);
     if (hslot >= pb.hit_cap) continue;
     HitRec<T> &rec = pb.hits[hslot];

@@ -161,6 +161,7 @@ def main():
   ap.add_argument('--envs', type=int, default=0, help='envs per GPU (default: the workload size)')
   ap.add_argument('--precision', default='f32', choices=['f32', 'f64'])
   ap.add_argument('--cpu-seconds', type=float, default=10.0)
+  ap.add_argument('--ref-seconds', type=float, default=0.0, help='--impl reference: seconds of CPU work per step (default: 120 s spread over the steps, 1..20 s each)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-secondary', action='store_true', help='skip the attached arm4096 measurement')
   ap.add_argument('--no-steady', action='store_true', help='skip the attached steady-state (cycling episodes) measurement')
@@ -179,7 +180,7 @@ def main():
     if rank != 0:
       return 0
     procs = os.cpu_count() or 1
-    per_step_s = max(1.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
+    per_step_s = a.ref_seconds if a.ref_seconds > 0 else max(1.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
     vals = []
     for i in range(a.warmup + a.steps):
       r = cpu_baseline(a.workload, per_step_s, procs)

@@ -90,3 +90,30 @@ def test_batched_env_config_mirrors_the_factory():
       BatchedEnvConfig(**bad)
   with pytest.raises(ValueError, match='unknown config keys'):
     BatchedEnvConfig.from_dict({'envs': 3})
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+  """`bench.py --impl reference` (the CPU arm: the float64 oracle on the host cores) prints one JSON line with the contract's keys,
+  the same metric / config as the GPU arm, and an e2e block without copies."""
+  import json, subprocess, sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0', '--ref-seconds', '1'],
+                     capture_output=True, text=True, timeout=300, cwd=root)
+  assert r.returncode == 0, r.stderr[-800:]
+  d = json.loads(r.stdout.strip().splitlines()[-1])
+  assert d['impl'] == 'reference' and d['unit'] == 'env-steps/s' and d['higher_is_better'] is True and d['value'] > 0
+  assert d['metric'].startswith('SO101 pick-place env-steps/sec') and d['config']['workload'] == 'banana131072'
+  assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+  assert d['e2e'] == dict(value=d['value'], unit='env-steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+  assert d['vs_baseline'] is None and d['steps'] == 1 and d['warmup'] == 0
+
+
+def test_bench_gpu_arm_refuses_to_run_without_a_gpu():
+  """No CPU fallback: without a CUDA device the GPU arm stops with a message instead of measuring something else."""
+  import subprocess, sys
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip('a GPU is present')
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '1', '--warmup', '0'], capture_output=True, text=True, timeout=300, cwd=root)
+  assert r.returncode != 0 and 'no CPU fallback' in (r.stderr + r.stdout)

@@ -190,7 +190,8 @@ struct Handle : HandleBase {
   size_t pool_cap = 1;
   float *d_action = nullptr;   // staging copy of the caller's action: the captured step graph reads it from a fixed address
   so101_step_out d_out{};      // device staging of the whole TimeStep for the host-buffer entry point (so101_step_host)
-  // One control step of the contact scene is 166 launches + event fork/joins on 6 streams.  It is captured once per distinct
+  // One control step of the contact scene is 166 launches (186 with the two-launch narrow phase of large groups) + event
+  // fork/joins on 6 streams.  It is captured once per distinct
   // set of output pointers into a CUDA graph and replayed with a single cudaGraphLaunch (SO101_GRAPH=0 disables; the
   // per-kernel event timers need eager launches and bypass it).
   struct StepGraph { so101_step_out key; cudaGraphExec_t exec; int kernels; };

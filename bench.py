@@ -161,6 +161,7 @@ def main():
   ap.add_argument('--envs', type=int, default=0, help='envs per GPU (default: the workload size)')
   ap.add_argument('--precision', default='f32', choices=['f32', 'f64'])
   ap.add_argument('--cpu-seconds', type=float, default=10.0)
+  ap.add_argument('--profiler-range', action='store_true', help='bracket the timed steps with cudaProfilerStart/Stop (for `ncu --profile-from-start off`; numbers printed under a profiler are not bench values)')
   ap.add_argument('--ref-seconds', type=float, default=0.0, help='--impl reference: seconds of CPU work per step (default: 120 s spread over the steps, 1..20 s each)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-secondary', action='store_true', help='skip the attached arm4096 measurement')
@@ -168,6 +169,8 @@ def main():
   ap.add_argument('--steady-steps', type=int, default=200)
   ap.add_argument('--steady-warmup', type=int, default=100)
   a = ap.parse_args()
+  global PROFILER_RANGE
+  PROFILER_RANGE = bool(a.profiler_range)
   rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
   local_rank = int(os.environ.get('LOCAL_RANK', 0))
   w = WORKLOADS[a.workload]
@@ -253,6 +256,9 @@ def _actions(env, n, envs, dev, seed):
   return (lo + torch.rand(n, envs, len(spec.minimum), generator=g, device=dev) * (hi - lo)) * 0.3
 
 
+PROFILER_RANGE = False   # set by --profiler-range
+
+
 def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_rank):
   import torch
   import torch.distributed as dist
@@ -294,6 +300,8 @@ def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_r
     env.step(acts[i % nact])
   c0 = env.counters()
   barrier()
+  if PROFILER_RANGE:   # `ncu --profile-from-start off ... bench.py --profiler-range`: capture the timed steps only
+    torch.cuda.profiler.start()
   with ClockSampler(local_rank) as clocks:
     t_wall0 = time.perf_counter()
     for i in range(steps):
@@ -304,6 +312,8 @@ def run_workload(name, envs, steps, warmup, precision, dev, rank, world, local_r
       stats.update(ts.step_type, ts.reward); ret_sum += ts.reward
     barrier()
     t_wall = time.perf_counter() - t_wall0
+  if PROFILER_RANGE:
+    torch.cuda.synchronize(); torch.cuda.profiler.stop()
   c1 = env.counters()
   drop_names = ('per_pair', 'candidates', 'pairs', 'queue', 'raw_contacts', 'jacobian_blocks', 'hits')
   drops = dict(zip(drop_names, [int(x) for x in env.debug_read('dropcat', 8)[0, :7].tolist()])) if w['collide'] and envs >= 8 else {}
